@@ -1,0 +1,219 @@
+/*
+ * b200sim task-program encoding: the integer codes and table layouts shared by the host (Python plugin
+ * classes), the CUDA engine and the CPU oracle.  This header is the single source of truth; the Python side
+ * parses the #defines (ksim_b200/codes.py).
+ *
+ * A "task program" is two flat arrays, ti[] (int32) and tf[] (fp32 on the device, fp64 in the oracle), that
+ * describe the reference's plugin lists -- Actuators / Events / Resets / Observations / Terminations /
+ * Commands / Rewards (ksim/actuators.py, events.py, resets.py, observation.py, terminations.py,
+ * commands.py, rewards.py) and EngineConfig (ksim/engine.py:50-139) -- plus the per-env state / record
+ * layouts derived from them.
+ */
+#ifndef B200SIM_CODES_H
+#define B200SIM_CODES_H
+
+#define B2S_TASK_MAGIC 0x42325354 /* "B2ST" */
+
+/* ---- ti[] header slots ---- */
+#define TI_MAGIC 0
+#define TI_NSUB 1            /* phys_steps_per_ctrl_steps (engine.py:108-109) */
+#define TI_ACT_PERIOD 2      /* phys_steps_per_actuator_step (engine.py:111-115) */
+#define TI_ACT_TYPE 3        /* ACT_* */
+#define TI_ACT_IOFF 4
+#define TI_ACT_FOFF 5
+#define TI_ENGINE_FOFF 6     /* tf: min_latency_step, max_latency_step, drop_prob, zero_offset rv(mean,std,mag),
+                              *     action_clip_max, reward_clip_min, reward_clip_max (NaN = no clip) */
+#define TI_ZERO_OFFSET_KIND 7 /* RV_* */
+#define TI_N_EVENT 8
+#define TI_EVENT_TAB 9
+#define TI_N_RESET 10
+#define TI_RESET_TAB 11
+#define TI_N_OBS 12
+#define TI_OBS_TAB 13
+#define TI_N_TERM 14
+#define TI_TERM_TAB 15
+#define TI_N_CMD 16
+#define TI_CMD_TAB 17
+#define TI_N_REW 18
+#define TI_REW_TAB 19
+#define TI_N_RAND 20         /* per-env model override fields */
+#define TI_RAND_TAB 21
+/* sizes (floats); state/record/key buffers are env-major: buf[env][size] */
+#define TI_STATE_SIZE 22     /* padded to a multiple of 4 */
+#define TI_REC_SIZE 23       /* padded to a multiple of 4 */
+#define TI_RAND_SIZE 24
+#define TI_OBS_SIZE 25
+#define TI_CMD_SIZE 26
+#define TI_EVENT_SIZE 27
+#define TI_OBS_CARRY_SIZE 28
+#define TI_ACT_STATE_SIZE 29
+#define TI_ACTION_SIZE 30
+#define TI_N_REW_COMP 31
+#define TI_REW_CARRY_SIZE 32
+/* state offsets (floats; flags and counters are stored as exactly-representable float values) */
+#define TI_S_QPOS 33
+#define TI_S_QVEL 34
+#define TI_S_QACC 35
+#define TI_S_WARM 36
+#define TI_S_TIME 37
+#define TI_S_CTRL 38
+#define TI_S_LAST_CTRL 39
+#define TI_S_LATENCY 40
+#define TI_S_ZERO_OFF 41
+#define TI_S_EVENT 42
+#define TI_S_ACT_STATE 43
+#define TI_KEY_SIZE 44       /* u32 key buffer per env: [0:2] env rng, [2+2i:4+2i] bias key of observation i */
+#define TI_S_LEVEL 45
+#define TI_S_CMD 46
+#define TI_S_OBS_CARRY 47
+#define TI_REC_PRE_SIZE 48   /* record = [pre-step block | post-step block]; pre = obs, cmd, level */
+#define TI_S_NONFINITE 49    /* per-env flag: 1 if a non-finite qpos/qvel was ever produced */
+/* record offsets */
+#define TI_R_QPOS 50
+#define TI_R_QVEL 51
+#define TI_R_XPOS 52
+#define TI_R_XQUAT 53
+#define TI_R_CTRL 54
+#define TI_R_OBS 55
+#define TI_R_CMD 56
+#define TI_R_EVENT 57
+#define TI_R_ACTION 58
+#define TI_R_DONE 59
+#define TI_R_SUCCESS 60
+#define TI_R_TIME 61
+#define TI_R_LEVEL 62
+#define TI_R_TERM 63
+#define TI_S_XFRC 64         /* 6 floats wrench + body id handled via event params; -1 if unused */
+#define TI_HEADER_SIZE 72
+
+/* ---- plugin table entry: 8 ints each ---- */
+#define TAB_STRIDE 8
+#define TAB_TYPE 0
+#define TAB_IOFF 1
+#define TAB_FOFF 2
+#define TAB_OUT_OFF 3   /* obs: offset inside obs block; cmd/event: offset inside their state block; rew: first comp */
+#define TAB_OUT_DIM 4   /* obs dim / cmd floats / event floats / reward components */
+#define TAB_AUX0 5      /* obs: noisy offset or -1; rew: carry offset or -1; rand: model field code */
+#define TAB_AUX1 6      /* obs: carry offset or -1; rew: carry dim;          rand: count */
+#define TAB_AUX2 7      /* obs: has_bias;           rew: is_penalty */
+
+/* ---- random variables / noise / scales ---- */
+#define RV_ZERO 0
+#define RV_UNIFORM 1
+#define RV_GAUSSIAN 2
+#define RV_UNIFORM_GAUSSIAN 3
+/* noise block: ints [n_links, (mul, kind) x 3]; floats [(mean, std, mag) x 3] */
+#define NOISE_MAX_LINKS 3
+#define NOISE_NI 7
+#define NOISE_NF 9
+/* bias block: ints [kind, mul]; floats [mean, std, mag] (kind RV_ZERO == no bias) */
+#define BIAS_NI 2
+#define BIAS_NF 3
+/* scale block: ints [kind]; floats [scale, bias] */
+#define SCALE_CONST 0
+#define SCALE_LINEAR 1
+#define SCALE_QUADRATIC 2
+#define SCALE_SQRT 3
+#define SCALE_NONZERO 4
+#define SCALE_NI 1
+#define SCALE_NF 2
+
+/* ---- actuators (ksim/actuators.py) ---- */
+#define ACT_TORQUE 0
+#define ACT_POSITION 1
+#define ACT_POSITION_VELOCITY 2
+/* ACT_POSITION ints: [action_noise(NOISE_NI), torque_noise(NOISE_NI), rv kinds: action_bias, torque_bias,
+ *   kp_scale, kd_scale, torque_limit_scale (present flag folded: -1 = absent)]
+ * floats: [action_scale, action_noise(NOISE_NF), torque_noise(NOISE_NF), 5 x rv(3), kp[nu], kd[nu], clip[nu]] */
+
+/* ---- events (ksim/events.py) ---- */
+#define EVENT_LINEAR_PUSH 1
+#define EVENT_ANGULAR_PUSH 2
+#define EVENT_JUMP 3
+#define EVENT_FORCE_PUSH 4
+
+/* ---- resets (ksim/resets.py) ---- */
+#define RESET_RANDOM_JOINT_POSITION 1
+#define RESET_RANDOM_JOINT_VELOCITY 2
+#define RESET_RANDOM_HEADING 3
+#define RESET_RANDOM_BASE_VELOCITY_XY 4
+#define RESET_PLANE_XY_POSITION 5
+#define RESET_RANDOM_HEIGHT 6
+#define RESET_RANDOM_PITCH_ROLL 7
+
+/* ---- observations (ksim/observation.py) ---- */
+#define OBS_BASE_POSITION 1
+#define OBS_BASE_ORIENTATION 2
+#define OBS_BASE_LINEAR_VELOCITY 3
+#define OBS_BASE_ANGULAR_VELOCITY 4
+#define OBS_JOINT_POSITION 5
+#define OBS_JOINT_VELOCITY 6
+#define OBS_CENTER_OF_MASS_INERTIA 7
+#define OBS_CENTER_OF_MASS_VELOCITY 8
+#define OBS_ACTUATOR_FORCE 9
+#define OBS_SENSOR 10
+#define OBS_BASE_LINEAR_ACCELERATION 11
+#define OBS_BASE_ANGULAR_ACCELERATION 12
+#define OBS_ACTUATOR_ACCELERATION 13
+#define OBS_PROJECTED_GRAVITY 14
+#define OBS_FEET_CONTACT 15
+#define OBS_BODY_POSITION 16
+#define OBS_BODY_VELOCITY 17
+#define OBS_FEET_FORCE 18
+#define OBS_FEET_TORQUE 19
+#define OBS_TIMESTEP 20
+#define OBS_CONTACT 21
+#define OBS_FEET_POSITION 22
+
+/* ---- terminations (ksim/terminations.py) ---- */
+#define TERM_NOT_UPRIGHT 1
+#define TERM_MINIMUM_HEIGHT 2
+#define TERM_ILLEGAL_CONTACT 3
+#define TERM_BAD_Z 4
+#define TERM_BAD_VELOCITY 5
+#define TERM_FAR_FROM_ORIGIN 6
+#define TERM_EPISODE_LENGTH 7
+
+/* ---- commands (ksim/commands.py) ---- */
+#define CMD_LINEAR_VELOCITY 1
+#define CMD_ANGULAR_VELOCITY 2
+#define CMD_FLOAT_VECTOR 3
+
+/* ---- rewards (ksim/rewards.py) ---- */
+#define REW_STAY_ALIVE 1
+#define REW_UPRIGHT 2
+#define REW_LINEAR_VELOCITY 3
+#define REW_ANGULAR_VELOCITY 4
+#define REW_FEET_AIR_TIME 5
+#define REW_SPARSE_TARGET_HEIGHT 6
+#define REW_FORCE_PENALTY 7
+#define REW_MOTIONLESS_AT_REST 8
+#define REW_ACTION_VELOCITY 9
+#define REW_ACTION_ACCELERATION 10
+#define REW_ACTION_JERK 11
+#define REW_BASE_HEIGHT 12
+#define REW_BASE_HEIGHT_RANGE 13
+#define REW_OFF_AXIS_VELOCITY 14
+#define REW_SMALL_JOINT_VELOCITY 15
+
+/* ---- per-env model override fields (ksim/randomization.py) ---- */
+#define RAND_DOF_FRICTIONLOSS 1
+#define RAND_DOF_ARMATURE 2
+#define RAND_DOF_DAMPING 3
+#define RAND_BODY_MASS 4
+#define RAND_BODY_INERTIA 5
+#define RAND_BODY_IPOS 6
+
+/* ---- GAE flags (ksim/task/ppo.py:54-121) ---- */
+#define GAE_NORMALIZE_ADVANTAGES 1
+#define GAE_MONTE_CARLO_RETURNS 2
+
+/* ---- error codes ---- */
+#define B2S_OK 0
+#define B2S_ERR_BAD_ARG 1
+#define B2S_ERR_BAD_BLOB 2
+#define B2S_ERR_UNSUPPORTED 3
+#define B2S_ERR_CUDA 4
+#define B2S_ERR_TOO_LARGE 5
+
+#endif
