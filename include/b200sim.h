@@ -1,0 +1,87 @@
+/*
+ * b200sim C-ABI: the drop-in boundary of the B200 batched-rollout engine.
+ *
+ * Every entry point takes an opaque model handle, a CUDA stream (as void*; NULL = default stream) and flat
+ * DEVICE buffers owned by the caller.  No host synchronisation, no exceptions: the return value is a B2S_*
+ * error code (include/b200sim_codes.h; 0 = OK).  This is the shape an XLA-FFI / jax.ffi handler binds
+ * (INTEGRATION.md shows the stub); the repo's own host code binds it with ctypes (ksim_b200/binding.py).
+ *
+ * Per-environment blocks are contiguous and 16-byte aligned (sizes from b200sim_model_info):
+ *   state[N][S] f32, keys[N][K] u32, rand[N][RAND] f32 (per-env model overrides), action[N][NA] f32,
+ *   rec[T(+1)][N][R] f32 (trajectory records: [pre-step block: obs, command, level | post-step block]).
+ *
+ * What each entry point replaces in the reference (kscalelabs/ksim):
+ *   b200sim_init_envs   RLTask._get_env_state -> apply_randomizations -> MjxEngine.reset + initial commands /
+ *                       obs carry / obs bias + first get_observation
+ *                       (ksim/task/rl.py:2175-2313, 361-372; ksim/engine.py:205-246)
+ *   b200sim_step_ctrl   RLTask.step_engine for all envs: MjxEngine.step (5 x mjx.step with actuators + events),
+ *                       get_terminations, Trajectory record, reset-on-done, commands, next get_observation
+ *                       (ksim/task/rl.py:1164-1211, 1023-1136; ksim/engine.py:259-361)
+ *   b200sim_rollout     RLTask._single_unroll's scan over T of the above with given actions (rl.py:1604-1665)
+ *   b200sim_rewards     get_rewards vmapped over envs (ksim/task/rl.py:189-245, 1663; ksim/rewards.py)
+ *   b200sim_gae         compute_ppo_inputs (ksim/task/ppo.py:54-121)
+ */
+#ifndef B200SIM_H
+#define B200SIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200sim_model b200sim_model;
+
+/* b200sim_model_info selectors */
+enum {
+  B2S_INFO_STATE_SIZE = 0, /* S  */
+  B2S_INFO_REC_SIZE = 1,   /* R  */
+  B2S_INFO_KEY_SIZE = 2,   /* K  */
+  B2S_INFO_RAND_SIZE = 3,  /* RAND */
+  B2S_INFO_ACTION_SIZE = 4,
+  B2S_INFO_N_REW_COMP = 5,
+  B2S_INFO_REW_CARRY_SIZE = 6,
+  B2S_INFO_SMEM_PER_ENV = 7,    /* bytes of shared memory one environment (warp) occupies */
+  B2S_INFO_WARPS_PER_CTA = 8,
+  B2S_INFO_VARIANT = 9          /* 0 humanoid-sized, 1 kbot-sized, 2 generic */
+};
+
+/* blob: include/b200sim_model.h layout (host memory).  Uploads the model + task program to the current device. */
+int b200sim_model_create(const void* blob, size_t nbytes, b200sim_model** out);
+void b200sim_model_destroy(b200sim_model* model);
+int b200sim_model_info(const b200sim_model* model, int what);
+const char* b200sim_last_error(void);
+
+/* init_keys[N][10] u32: (reset, command, obs-carry, obs-bias, env) keys; levels[N]; rec0[N][R] receives the first
+ * pre-step block; act_keys[N][2] (may be NULL) receives the key the policy samples its first action with. */
+int b200sim_init_envs(const b200sim_model* model, void* stream, int n_envs, const uint32_t* init_keys,
+                      const float* levels, const float* rand, float* state, uint32_t* keys, float* rec0,
+                      uint32_t* act_keys);
+
+/* one control step for every env; rec_cur gets the post-step block, rec_next the next pre-step block. */
+int b200sim_step_ctrl(const b200sim_model* model, void* stream, int n_envs, const float* action, const float* rand,
+                      float* state, uint32_t* keys, float* rec_cur, float* rec_next, uint32_t* act_keys);
+
+/* T control steps with given actions[T][N][NA]; rec[T+1][N][R] (slot 0's pre-step block must be valid on entry,
+ * slot T's pre-step block is valid on exit).  Environment state stays on chip for the whole rollout. */
+int b200sim_rollout(const b200sim_model* model, void* stream, int n_envs, int n_steps, const float* actions,
+                    const float* rand, float* state, uint32_t* keys, float* rec);
+
+/* rec[T][N][R]; levels[N]; carry[N][C] in/out; total[N][T]; comps[K][N][T]. */
+int b200sim_rewards(const b200sim_model* model, void* stream, int n_envs, int n_steps, const float* rec,
+                    const float* levels, float* carry, float* total, float* comps);
+
+/* all arrays [B][T]; flags: GAE_NORMALIZE_ADVANTAGES | GAE_MONTE_CARLO_RETURNS (include/b200sim_codes.h). */
+int b200sim_gae(void* stream, int batch, int n_steps, const float* values, const float* rewards,
+                const uint8_t* dones, const uint8_t* successes, float gamma, float lam, int flags, float* adv,
+                float* targets, float* returns);
+
+/* done / success flags of a record buffer as bytes: out[N][T] from rec[T][N][R] (feeds b200sim_gae). */
+int b200sim_extract_flags(const b200sim_model* model, void* stream, int n_envs, int n_steps, const float* rec,
+                          uint8_t* dones, uint8_t* successes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

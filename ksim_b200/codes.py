@@ -1,19 +1,22 @@
-"""Integer codes of the task-program encoding, parsed from ``include/b200sim_codes.h`` (single source of truth)."""
+"""Integer codes of the task-program and model-blob encodings, parsed from ``include/b200sim_codes.h`` and
+``include/b200sim_model.h`` (the single source of truth)."""
 
 from __future__ import annotations
 
 import re
 from pathlib import Path
 
-_HEADER = Path(__file__).resolve().parent.parent / "include" / "b200sim_codes.h"
+_INCLUDE = Path(__file__).resolve().parent.parent / "include"
+_HEADERS = (_INCLUDE / "b200sim_codes.h", _INCLUDE / "b200sim_model.h")
 
 
 def _parse() -> dict[str, int]:
     out: dict[str, int] = {}
-    for line in _HEADER.read_text().splitlines():
-        m = re.match(r"#define\s+([A-Z0-9_]+)\s+(-?(?:0x[0-9A-Fa-f]+|\d+))\b", line)
-        if m:
-            out[m.group(1)] = int(m.group(2), 0)
+    for header in _HEADERS:
+        for line in header.read_text().splitlines():
+            m = re.match(r"#define\s+([A-Z0-9_]+)\s+(-?(?:0x[0-9A-Fa-f]+|\d+))\b", line)
+            if m:
+                out[m.group(1)] = int(m.group(2), 0)
     return out
 
 

@@ -1,0 +1,316 @@
+// b200sim: kernels + C-ABI (include/b200sim.h).  sm_100a only; no CPU path -- every entry point launches CUDA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200sim.h"
+#include "b2s_engine.cuh"
+#include "b2s_rewards.cuh"
+
+using namespace b2s;
+
+// ------------------------------------------------------------------------------------------------ kernels
+
+template <class D>
+__global__ void __launch_bounds__(256) k_init_envs(const Mdl m, int n_envs, const uint32_t* __restrict__ init_keys,
+                                                   const float* __restrict__ levels, const float* __restrict__ rand,
+                                                   float* __restrict__ state, uint32_t* __restrict__ keys,
+                                                   float* __restrict__ rec0, uint32_t* __restrict__ act_keys) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int env = blockIdx.x * wpb + warp;
+  if (env >= n_envs) return;
+  Work<D>& w = reinterpret_cast<Work<D>*>(smem)[warp];
+  const int* ti = m.ti;
+  const size_t S = ti[TI_STATE_SIZE], R = ti[TI_REC_SIZE], K = ti[TI_KEY_SIZE], RAND = ti[TI_RAND_SIZE];
+  apply_overrides(m, w, rand + env * RAND, lane);
+  env_init(m, w, init_keys + (size_t)env * 10, levels[env], rec0 + env * R, act_keys ? act_keys + 2 * env : nullptr, lane);
+  env_store(m, w, state + env * S, keys + env * K, lane);
+}
+
+// n_steps control steps per launch; the environment stays in shared memory between them.
+template <class D>
+__global__ void __launch_bounds__(256) k_rollout(const Mdl m, int n_envs, int n_steps, const float* __restrict__ actions,
+                                                 const float* __restrict__ rand, float* __restrict__ state,
+                                                 uint32_t* __restrict__ keys, float* __restrict__ rec,
+                                                 float* __restrict__ rec_next_single, uint32_t* __restrict__ act_keys) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int env = blockIdx.x * wpb + warp;
+  if (env >= n_envs) return;
+  Work<D>& w = reinterpret_cast<Work<D>*>(smem)[warp];
+  const int* ti = m.ti;
+  const size_t S = ti[TI_STATE_SIZE], R = ti[TI_REC_SIZE], K = ti[TI_KEY_SIZE], RAND = ti[TI_RAND_SIZE];
+  const size_t NA = ti[TI_ACTION_SIZE];
+  apply_overrides(m, w, rand + env * RAND, lane);
+  env_load(m, w, state + env * S, keys + env * K, lane);
+  for (int t = 0; t < n_steps; t++) {
+    float* cur = rec + ((size_t)t * n_envs + env) * R;
+    float* nxt = rec_next_single ? rec_next_single + env * R : rec + ((size_t)(t + 1) * n_envs + env) * R;
+    env_step(m, w, actions + ((size_t)t * n_envs + env) * NA, cur, nxt, act_keys ? act_keys + 2 * env : nullptr, lane);
+  }
+  env_store(m, w, state + env * S, keys + env * K, lane);
+}
+
+__global__ void __launch_bounds__(256) k_rewards(const Mdl m, int n_envs, int n_steps, const float* __restrict__ rec,
+                                                 const float* __restrict__ levels, float* __restrict__ carry,
+                                                 float* __restrict__ total, float* __restrict__ comps) {
+  const int lane = threadIdx.x & 31;
+  const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (env >= n_envs) return;
+  const int* ti = m.ti;
+  const size_t R = ti[TI_REC_SIZE], C = ti[TI_REW_CARRY_SIZE];
+  env_rewards(m, rec + env * R, (size_t)n_envs * R, n_steps, levels[env], carry + env * C, total + (size_t)env * n_steps,
+              comps + (size_t)env * n_steps, (size_t)n_envs * n_steps, lane);
+}
+
+__global__ void k_extract_flags(int n_envs, int n_steps, size_t R, int off_done, int off_success,
+                                const float* __restrict__ rec, uint8_t* __restrict__ dones, uint8_t* __restrict__ successes) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n_envs * n_steps) return;
+  const int n = idx / n_steps, t = idx - (size_t)n * n_steps;
+  const float* r = rec + ((size_t)t * n_envs + n) * R;
+  dones[idx] = r[off_done] != 0.0f;
+  successes[idx] = r[off_success] != 0.0f;
+}
+
+// compute_ppo_inputs (ksim/task/ppo.py:54-121): reverse-time scan, one thread per trajectory row.
+__global__ void k_gae(int batch, int n_steps, const float* __restrict__ values, const float* __restrict__ rewards,
+                      const uint8_t* __restrict__ dones, const uint8_t* __restrict__ successes, float gamma, float lam,
+                      int flags, float* __restrict__ adv, float* __restrict__ targets, float* __restrict__ returns) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const size_t base = (size_t)b * n_steps;
+  float ret_next = 0.0f, adv_next = 0.0f;
+  float v_next = values[base + n_steps - 1];
+  for (int s = n_steps - 1; s >= 0; s--) {
+    const float v = values[base + s];
+    const float trunc = successes[base + s] ? 1.0f : 0.0f;
+    const float mask = dones[base + s] ? 0.0f : 1.0f;
+    const float br = __fadd_rn(__fmul_rn(1.0f - gamma, rewards[base + s]), __fmul_rn(__fmul_rn(gamma, v), trunc));
+    const float delta = __fsub_rn(__fadd_rn(br, __fmul_rn(__fmul_rn(gamma, v_next), mask)), v);
+    const float ret = __fadd_rn(br, __fmul_rn(__fmul_rn(gamma, mask), ret_next));
+    const float a = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gamma, lam), mask), adv_next));
+    returns[base + s] = ret;
+    adv[base + s] = a;
+    targets[base + s] = (flags & GAE_MONTE_CARLO_RETURNS) ? ret : __fadd_rn(a, v);
+    ret_next = ret; adv_next = a; v_next = v;
+  }
+}
+
+// advantage normalisation over the whole batch (ppo.py:116-119): deterministic single-CTA two-pass reduction
+__global__ void __launch_bounds__(1024) k_gae_normalize(size_t n, float* __restrict__ adv) {
+  __shared__ double red[1024];
+  const int tid = threadIdx.x;
+  double s = 0.0;
+  for (size_t i = tid; i < n; i += 1024) s += (double)adv[i];
+  red[tid] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  const float mean = (float)(red[0] / (double)n);
+  __syncthreads();
+  s = 0.0;
+  for (size_t i = tid; i < n; i += 1024) { const float d = adv[i] - mean; s += (double)(d * d); }
+  red[tid] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  float sd = sqrtf((float)(red[0] / (double)n));
+  if (sd < 1e-6f) sd = 1e-6f;
+  for (size_t i = tid; i < n; i += 1024) adv[i] = (adv[i] - mean) / sd;
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+
+struct b200sim_model {
+  Mdl mdl;
+  int variant;
+  int warps_per_cta;
+  size_t smem_per_env;
+  void* dev_blob;
+  std::vector<int> ti_host;
+};
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define CUDA_OK(expr)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e_ = (expr);                                                                           \
+    if (e_ != cudaSuccess) return fail(B2S_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char* b200sim_last_error(void) { return g_last_error.c_str(); }
+
+template <class D>
+static bool fits(const int* h) {
+  return h[MH_NQ] <= D::NQ && h[MH_NV] <= D::NV && h[MH_NBODY] <= D::NB && h[MH_NJNT] <= D::NJ && h[MH_NU] <= D::NU &&
+         h[MH_NSITE] <= D::NS && h[MH_NSENSORDATA] <= D::NSD && h[MH_NPAIR] <= D::NPAIR && h[MH_NCON] <= D::NCON &&
+         h[MH_NEFC_DENSE] <= D::NDENSE && h[MH_NLIMIT] <= D::NLIMIT && h[MH_NFRICTION] <= D::NFRIC;
+}
+template <class D>
+static bool task_fits(const int* ti) {
+  return ti[TI_EVENT_SIZE] <= D::EVS && ti[TI_ACT_STATE_SIZE] <= D::ACS && ti[TI_CMD_SIZE] <= D::CMDS &&
+         ti[TI_OBS_CARRY_SIZE] <= D::OCS && ti[TI_N_OBS] <= D::NOBS && ti[TI_ACTION_SIZE] <= D::NA;
+}
+
+static const size_t kSmemBudget = 227 * 1024;
+
+template <class D>
+static int configure(b200sim_model* mo) {
+  mo->smem_per_env = sizeof(Work<D>);
+  const int max_warps = (int)((kSmemBudget - 2048) / sizeof(Work<D>));
+  if (max_warps < 1) return fail(B2S_ERR_TOO_LARGE, "workspace does not fit in shared memory");
+  int wpb = max_warps >= 8 ? max_warps / 2 : max_warps;  // two CTAs per SM when possible
+  if (wpb > 8) wpb = 8;
+  mo->warps_per_cta = wpb;
+  const int bytes = (int)(wpb * sizeof(Work<D>));
+  CUDA_OK(cudaFuncSetAttribute(k_init_envs<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(k_rollout<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return B2S_OK;
+}
+
+extern "C" int b200sim_model_create(const void* blob, size_t nbytes, b200sim_model** out) {
+  if (!blob || !out) return fail(B2S_ERR_BAD_ARG, "null argument");
+  if (nbytes < MH_SIZE * sizeof(int)) return fail(B2S_ERR_BAD_BLOB, "blob smaller than its header");
+  const int* h = (const int*)blob;
+  if (h[MH_MAGIC] != B2S_MODEL_MAGIC || h[MH_VERSION] != B2S_MODEL_VERSION) return fail(B2S_ERR_BAD_BLOB, "bad magic/version");
+  const size_t ni = h[MH_NI], nf = h[MH_NF], nti = h[MH_NTI], ntf = h[MH_NTF];
+  if (nbytes != (MH_SIZE + ni + nf + nti + ntf) * 4) return fail(B2S_ERR_BAD_BLOB, "blob size does not match its header");
+  const int* ti = h + MH_SIZE + ni + nf;
+  if (nti < TI_HEADER_SIZE || ti[TI_MAGIC] != B2S_TASK_MAGIC) return fail(B2S_ERR_BAD_BLOB, "bad task program");
+  if (h[MH_NV] > B2S_MAXNV || h[MH_NBODY] > B2S_MAXNB) return fail(B2S_ERR_TOO_LARGE, "nv / nbody exceed one-per-lane limit");
+  b200sim_model* mo = new b200sim_model();
+  memcpy(mo->mdl.h, h, MH_SIZE * sizeof(int));
+  mo->ti_host.assign(ti, ti + nti);
+  cudaError_t e = cudaMalloc(&mo->dev_blob, nbytes);
+  if (e != cudaSuccess) { delete mo; return fail(B2S_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+  e = cudaMemcpy(mo->dev_blob, blob, nbytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(mo->dev_blob); delete mo; return fail(B2S_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e)); }
+  const int* d = (const int*)mo->dev_blob;
+  mo->mdl.mi = d + MH_SIZE;
+  mo->mdl.mf = (const float*)(d + MH_SIZE + ni);
+  mo->mdl.ti = d + MH_SIZE + ni + nf;
+  mo->mdl.tf = (const float*)(d + MH_SIZE + ni + nf + nti);
+  int rc;
+  if (fits<DimsHumanoid>(h) && task_fits<DimsHumanoid>(ti)) { mo->variant = 0; rc = configure<DimsHumanoid>(mo); }
+  else if (fits<DimsKbot>(h) && task_fits<DimsKbot>(ti)) { mo->variant = 1; rc = configure<DimsKbot>(mo); }
+  else if (fits<DimsGeneric>(h) && task_fits<DimsGeneric>(ti)) { mo->variant = 2; rc = configure<DimsGeneric>(mo); }
+  else rc = fail(B2S_ERR_TOO_LARGE, "model / task sizes exceed the largest kernel instantiation");
+  if (rc != B2S_OK) { cudaFree(mo->dev_blob); delete mo; return rc; }
+  *out = mo;
+  return B2S_OK;
+}
+
+extern "C" void b200sim_model_destroy(b200sim_model* model) {
+  if (!model) return;
+  cudaFree(model->dev_blob);
+  delete model;
+}
+
+extern "C" int b200sim_model_info(const b200sim_model* mo, int what) {
+  if (!mo) return -1;
+  const int* ti = mo->ti_host.data();
+  switch (what) {
+    case B2S_INFO_STATE_SIZE: return ti[TI_STATE_SIZE];
+    case B2S_INFO_REC_SIZE: return ti[TI_REC_SIZE];
+    case B2S_INFO_KEY_SIZE: return ti[TI_KEY_SIZE];
+    case B2S_INFO_RAND_SIZE: return ti[TI_RAND_SIZE];
+    case B2S_INFO_ACTION_SIZE: return ti[TI_ACTION_SIZE];
+    case B2S_INFO_N_REW_COMP: return ti[TI_N_REW_COMP];
+    case B2S_INFO_REW_CARRY_SIZE: return ti[TI_REW_CARRY_SIZE];
+    case B2S_INFO_SMEM_PER_ENV: return (int)mo->smem_per_env;
+    case B2S_INFO_WARPS_PER_CTA: return mo->warps_per_cta;
+    case B2S_INFO_VARIANT: return mo->variant;
+  }
+  return -1;
+}
+
+#define DISPATCH(mo, CALL)                       \
+  switch ((mo)->variant) {                       \
+    case 0: { using D = DimsHumanoid; CALL; } break; \
+    case 1: { using D = DimsKbot; CALL; } break;     \
+    default: { using D = DimsGeneric; CALL; } break; \
+  }
+
+extern "C" int b200sim_init_envs(const b200sim_model* mo, void* stream, int n_envs, const uint32_t* init_keys,
+                                 const float* levels, const float* rand, float* state, uint32_t* keys, float* rec0,
+                                 uint32_t* act_keys) {
+  if (!mo || n_envs < 0 || !init_keys || !levels || !state || !keys || !rec0) return fail(B2S_ERR_BAD_ARG, "null argument");
+  if (n_envs == 0) return B2S_OK;
+  if (!rand && mo->ti_host[TI_RAND_SIZE] > 0) return fail(B2S_ERR_BAD_ARG, "rand is required for this task");
+  const int wpb = mo->warps_per_cta;
+  const dim3 grid((n_envs + wpb - 1) / wpb), block(wpb * 32);
+  const size_t smem = wpb * mo->smem_per_env;
+  DISPATCH(mo, (k_init_envs<D><<<grid, block, smem, (cudaStream_t)stream>>>(mo->mdl, n_envs, init_keys, levels, rand, state, keys, rec0, act_keys)));
+  CUDA_OK(cudaGetLastError());
+  return B2S_OK;
+}
+
+static int launch_rollout(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* actions,
+                          const float* rand, float* state, uint32_t* keys, float* rec, float* rec_next_single,
+                          uint32_t* act_keys) {
+  const int wpb = mo->warps_per_cta;
+  const dim3 grid((n_envs + wpb - 1) / wpb), block(wpb * 32);
+  const size_t smem = wpb * mo->smem_per_env;
+  DISPATCH(mo, (k_rollout<D><<<grid, block, smem, (cudaStream_t)stream>>>(mo->mdl, n_envs, n_steps, actions, rand, state, keys, rec, rec_next_single, act_keys)));
+  CUDA_OK(cudaGetLastError());
+  return B2S_OK;
+}
+
+extern "C" int b200sim_step_ctrl(const b200sim_model* mo, void* stream, int n_envs, const float* action, const float* rand,
+                                 float* state, uint32_t* keys, float* rec_cur, float* rec_next, uint32_t* act_keys) {
+  if (!mo || n_envs < 0 || !action || !state || !keys || !rec_cur || !rec_next) return fail(B2S_ERR_BAD_ARG, "null argument");
+  if (n_envs == 0) return B2S_OK;
+  if (!rand && mo->ti_host[TI_RAND_SIZE] > 0) return fail(B2S_ERR_BAD_ARG, "rand is required for this task");
+  return launch_rollout(mo, stream, n_envs, 1, action, rand, state, keys, rec_cur, rec_next, act_keys);
+}
+
+extern "C" int b200sim_rollout(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* actions,
+                               const float* rand, float* state, uint32_t* keys, float* rec) {
+  if (!mo || n_envs < 0 || n_steps < 0 || !actions || !state || !keys || !rec) return fail(B2S_ERR_BAD_ARG, "null argument");
+  if (n_envs == 0 || n_steps == 0) return B2S_OK;
+  if (!rand && mo->ti_host[TI_RAND_SIZE] > 0) return fail(B2S_ERR_BAD_ARG, "rand is required for this task");
+  return launch_rollout(mo, stream, n_envs, n_steps, actions, rand, state, keys, rec, nullptr, nullptr);
+}
+
+extern "C" int b200sim_rewards(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* rec,
+                               const float* levels, float* carry, float* total, float* comps) {
+  if (!mo || n_envs < 0 || n_steps < 0 || !rec || !levels || !total || !comps) return fail(B2S_ERR_BAD_ARG, "null argument");
+  if (n_envs == 0 || n_steps == 0) return B2S_OK;
+  if (!carry && mo->ti_host[TI_REW_CARRY_SIZE] > 0) return fail(B2S_ERR_BAD_ARG, "carry is required for this task");
+  const int threads = 256;
+  const dim3 grid(((size_t)n_envs * 32 + threads - 1) / threads);
+  k_rewards<<<grid, threads, 0, (cudaStream_t)stream>>>(mo->mdl, n_envs, n_steps, rec, levels, carry, total, comps);
+  CUDA_OK(cudaGetLastError());
+  return B2S_OK;
+}
+
+extern "C" int b200sim_extract_flags(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* rec,
+                                     uint8_t* dones, uint8_t* successes) {
+  if (!mo || !rec || !dones || !successes || n_envs < 0 || n_steps < 0) return fail(B2S_ERR_BAD_ARG, "null argument");
+  const size_t n = (size_t)n_envs * n_steps;
+  if (n == 0) return B2S_OK;
+  const int* ti = mo->ti_host.data();
+  k_extract_flags<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_envs, n_steps, ti[TI_REC_SIZE], ti[TI_R_DONE],
+                                                                                 ti[TI_R_SUCCESS], rec, dones, successes);
+  CUDA_OK(cudaGetLastError());
+  return B2S_OK;
+}
+
+extern "C" int b200sim_gae(void* stream, int batch, int n_steps, const float* values, const float* rewards,
+                           const uint8_t* dones, const uint8_t* successes, float gamma, float lam, int flags, float* adv,
+                           float* targets, float* returns) {
+  if (batch < 0 || n_steps < 0 || !values || !rewards || !dones || !successes || !adv || !targets || !returns)
+    return fail(B2S_ERR_BAD_ARG, "null argument");
+  if (batch == 0 || n_steps == 0) return B2S_OK;
+  k_gae<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(batch, n_steps, values, rewards, dones, successes, gamma, lam,
+                                                               flags, adv, targets, returns);
+  CUDA_OK(cudaGetLastError());
+  if (flags & GAE_NORMALIZE_ADVANTAGES) {
+    k_gae_normalize<<<1, 1024, 0, (cudaStream_t)stream>>>((size_t)batch * n_steps, adv);
+    CUDA_OK(cudaGetLastError());
+  }
+  return B2S_OK;
+}

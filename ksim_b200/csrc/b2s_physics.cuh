@@ -1,0 +1,1228 @@
+// b200sim: warp-cooperative rigid-body dynamics for one environment (one warp).
+//
+// Replaces `mjx.forward` / `mjx.step` at ksim/engine.py:213,257 for the feature subset of SURVEY.md 9.1:
+// free + hinge joints, capsule/sphere/plane contacts from explicit or dynamic pairs, joint limits, dof
+// friction loss, motors, Newton solver with pyramidal cones, implicitfast integration (Euler damping off).
+// Stage by stage it computes what the CPU oracle (oracle/physics.c) computes, in fp32, with lanes mapped to
+// bodies / dofs / constraint rows.
+#pragma once
+
+#include "b2s_work.cuh"
+
+namespace b2s {
+
+#if B2S_DEVICE
+#define LANE_FOR_ALL(i, n) for (int i = lane; i < (((n) + 31) & ~31); i += 32)
+DEV int wcompact(bool pred, int& base, LANE_ARG) {
+  unsigned mask = __ballot_sync(0xffffffffu, pred);
+  int idx = base + __popc(mask & ((1u << lane) - 1u));
+  base += __popc(mask);
+  return idx;
+}
+#else
+#define LANE_FOR_ALL(i, n) for (int i = 0; i < (n); i++)
+DEV int wcompact(bool pred, int& base, LANE_ARG) {
+  int idx = base;
+  if (pred) base++;
+  return idx;
+}
+#endif
+
+#define LD3(arr, i) v3((arr)[0][i], (arr)[1][i], (arr)[2][i])
+#define ST3(arr, i, v) do { (arr)[0][i] = (v).x; (arr)[1][i] = (v).y; (arr)[2][i] = (v).z; } while (0)
+#define LDQ(arr, i) Q4{(arr)[0][i], (arr)[1][i], (arr)[2][i], (arr)[3][i]}
+#define STQ(arr, i, q) do { (arr)[0][i] = (q).w; (arr)[1][i] = (q).x; (arr)[2][i] = (q).y; (arr)[3][i] = (q).z; } while (0)
+
+template <class A> DEV M9 ldm9(const A& arr, int i) {
+  M9 r;
+#pragma unroll
+  for (int k = 0; k < 9; k++) r.m[k] = arr[k][i];
+  return r;
+}
+template <class A> DEV void stm9(A& arr, int i, const M9& m) {
+#pragma unroll
+  for (int k = 0; k < 9; k++) arr[k][i] = m.m[k];
+}
+template <class A> DEV V6 ld6(const A& arr, int i) {
+  V6 r;
+#pragma unroll
+  for (int k = 0; k < 6; k++) r.v[k] = arr[k][i];
+  return r;
+}
+template <class A> DEV void st6(A& arr, int i, const V6& v) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) arr[k][i] = v.v[k];
+}
+DEV V3 ldg3(const float* p) { return v3(p[0], p[1], p[2]); }
+DEV Q4 ldgq(const float* p) { Q4 q; q.w = p[0]; q.x = p[1]; q.y = p[2]; q.z = p[3]; return q; }
+
+// ------------------------------------------------------------------------------------------ position stage
+
+template <class D>
+DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nb = m.h[MH_NBODY];
+  const int* parentid = MI(m, MH_BODY_PARENTID);
+  const int* jntnum = MI(m, MH_BODY_JNTNUM);
+  const int* jntadr = MI(m, MH_BODY_JNTADR);
+  const int* jtype = MI(m, MH_JNT_TYPE);
+  const int* qposadr = MI(m, MH_JNT_QPOSADR);
+  const int* lstart = MI(m, MH_LEVEL_START);
+  const int* lbody = MI(m, MH_LEVEL_BODY);
+  const float* body_pos = MF(m, MH_BODY_POS);
+  const float* body_quat = MF(m, MH_BODY_QUAT);
+  const float* body_iquat = MF(m, MH_BODY_IQUAT);
+  const float* jnt_pos = MF(m, MH_JNT_POS);
+  const float* jnt_axis = MF(m, MH_JNT_AXIS);
+  const float* qpos0 = MF(m, MH_QPOS0);
+  IF_LANE0 {
+    ST3(w.xpos, 0, v3(0, 0, 0));
+    Q4 qi; qi.w = 1; qi.x = qi.y = qi.z = 0;
+    STQ(w.xquat, 0, qi);
+    M9 id = q2mat(qi);
+    stm9(w.xmat, 0, id);
+    stm9(w.ximat, 0, id);
+    ST3(w.xipos, 0, v3(0, 0, 0));
+  }
+  WSYNC();
+  const int nlevel = m.h[MH_NLEVEL];
+  for (int l = 0; l < nlevel; l++) {
+    const int s = lstart[l], e = lstart[l + 1];
+    LANE_FOR(t, e - s) {
+      const int b = lbody[s + t];
+      const int p = parentid[b];
+      const int jn = jntnum[b], ja = jntadr[b];
+      V3 pos;
+      Q4 quat;
+      if (jn == 1 && jtype[ja] == JNT_FREE) {
+        const int qa = qposadr[ja];
+        Q4 q; q.w = w.qpos[qa + 3]; q.x = w.qpos[qa + 4]; q.y = w.qpos[qa + 5]; q.z = w.qpos[qa + 6];
+        q = qnormalize(q);
+        w.qpos[qa + 3] = q.w; w.qpos[qa + 4] = q.x; w.qpos[qa + 5] = q.y; w.qpos[qa + 6] = q.z;
+        pos = v3(w.qpos[qa], w.qpos[qa + 1], w.qpos[qa + 2]);
+        quat = q;
+        ST3(w.xanchor, ja, pos);
+        ST3(w.xaxis, ja, ldg3(jnt_axis + 3 * ja));
+      } else {
+        M9 pm = ldm9(w.xmat, p);
+        pos = LD3(w.xpos, p) + mulv(pm, ldg3(body_pos + 3 * b));
+        quat = qmul(LDQ(w.xquat, p), ldgq(body_quat + 4 * b));
+        for (int j = ja; j < ja + jn; j++) {
+          V3 jp = ldg3(jnt_pos + 3 * j), jax = ldg3(jnt_axis + 3 * j);
+          V3 anchor = qrot(quat, jp) + pos;
+          V3 axis = qrot(quat, jax);
+          ST3(w.xanchor, j, anchor);
+          ST3(w.xaxis, j, axis);
+          const int qa = qposadr[j];
+          Q4 qloc = axis_angle(jax, w.qpos[qa] - qpos0[qa]);
+          quat = qmul(quat, qloc);
+          pos = anchor - qrot(quat, jp);
+        }
+      }
+      quat = qnormalize(quat);
+      ST3(w.xpos, b, pos);
+      STQ(w.xquat, b, quat);
+      M9 xm = q2mat(quat);
+      stm9(w.xmat, b, xm);
+      V3 ip = pos + mulv(xm, LD3(w.body_ipos, b));
+      ST3(w.xipos, b, ip);
+      stm9(w.ximat, b, q2mat(qmul(quat, ldgq(body_iquat + 4 * b))));
+    }
+    WSYNC();
+  }
+  const int ns = m.h[MH_NSITE];
+  const int* site_body = MI(m, MH_SITE_BODYID);
+  const float* site_pos = MF(m, MH_SITE_POS);
+  const float* site_quat = MF(m, MH_SITE_QUAT);
+  LANE_FOR(s, ns) {
+    const int b = site_body[s];
+    V3 p = LD3(w.xpos, b) + mulv(ldm9(w.xmat, b), ldg3(site_pos + 3 * s));
+    ST3(w.site_xpos, s, p);
+    stm9(w.site_xmat, s, q2mat(qmul(LDQ(w.xquat, b), ldgq(site_quat + 4 * s))));
+  }
+  (void)nb;
+  WSYNC();
+}
+
+template <class D>
+DEV void com_pos(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nb = m.h[MH_NBODY], nj = m.h[MH_NJNT];
+  const int* rootid = MI(m, MH_BODY_ROOTID);
+  const int* sub_end = MI(m, MH_BODY_SUBTREE_END);
+  const float* subtreemass = MF(m, MH_BODY_SUBTREEMASS);
+  // mass-weighted positions into cfrc[0..2] (free at this point of the pipeline)
+  LANE_FOR(b, nb) {
+    const float ms = w.body_mass[b];
+    w.cfrc[0][b] = ms * w.xipos[0][b]; w.cfrc[1][b] = ms * w.xipos[1][b]; w.cfrc[2][b] = ms * w.xipos[2][b];
+  }
+  WSYNC();
+  LANE_FOR(b, nb) {
+    float sx = 0, sy = 0, sz = 0;
+    const int e = sub_end[b];
+    for (int c = b; c < e; c++) { sx += w.cfrc[0][c]; sy += w.cfrc[1][c]; sz += w.cfrc[2][c]; }
+    // nominal body_subtreemass even when body_mass is randomised (ksim/randomization.py:351-355)
+    const float sm = fmaxf(subtreemass[b], MINVAL);
+    w.subtree_com[0][b] = sx / sm; w.subtree_com[1][b] = sy / sm; w.subtree_com[2][b] = sz / sm;
+  }
+  WSYNC();
+  LANE_FOR(b, nb) {
+    if (b == 0) {
+#pragma unroll
+      for (int k = 0; k < 10; k++) w.cinert[k][0] = 0.0f;
+    } else {
+      V3 com = LD3(w.subtree_com, rootid[b]);
+      V3 off = LD3(w.xipos, b) - com;
+      const float mass = w.body_mass[b];
+      M9 R = ldm9(w.ximat, b);
+      const float I0 = w.body_inertia[0][b], I1 = w.body_inertia[1][b], I2 = w.body_inertia[2][b];
+      float full[9];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          full[3 * r + c] = R.m[3 * r] * I0 * R.m[3 * c] + R.m[3 * r + 1] * I1 * R.m[3 * c + 1] + R.m[3 * r + 2] * I2 * R.m[3 * c + 2];
+      const float dd = dot(off, off);
+      const float o[3] = {off.x, off.y, off.z};
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) full[3 * r + c] += mass * ((r == c ? dd : 0.0f) - o[r] * o[c]);
+      w.cinert[0][b] = full[0]; w.cinert[1][b] = full[4]; w.cinert[2][b] = full[8];
+      w.cinert[3][b] = full[1]; w.cinert[4][b] = full[2]; w.cinert[5][b] = full[5];
+      w.cinert[6][b] = mass * off.x; w.cinert[7][b] = mass * off.y; w.cinert[8][b] = mass * off.z;
+      w.cinert[9][b] = mass;
+    }
+  }
+  const int* jbody = MI(m, MH_JNT_BODYID);
+  const int* jdof = MI(m, MH_JNT_DOFADR);
+  const int* jtype = MI(m, MH_JNT_TYPE);
+  LANE_FOR(j, nj) {
+    const int b = jbody[j], da = jdof[j];
+    V3 off = LD3(w.subtree_com, rootid[b]) - LD3(w.xanchor, j);
+    if (jtype[j] == JNT_FREE) {
+      M9 xm = ldm9(w.xmat, b);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) w.cdof[c][da + k] = (c == 3 + k) ? 1.0f : 0.0f;
+        V3 ax = v3(xm.m[k], xm.m[3 + k], xm.m[6 + k]);
+        V3 cr = cross(ax, off);
+        w.cdof[0][da + 3 + k] = ax.x; w.cdof[1][da + 3 + k] = ax.y; w.cdof[2][da + 3 + k] = ax.z;
+        w.cdof[3][da + 3 + k] = cr.x; w.cdof[4][da + 3 + k] = cr.y; w.cdof[5][da + 3 + k] = cr.z;
+      }
+    } else {
+      V3 ax = LD3(w.xaxis, j);
+      V3 cr = cross(ax, off);
+      w.cdof[0][da] = ax.x; w.cdof[1][da] = ax.y; w.cdof[2][da] = ax.z;
+      w.cdof[3][da] = cr.x; w.cdof[4][da] = cr.y; w.cdof[5][da] = cr.z;
+    }
+  }
+  WSYNC();
+}
+
+template <class D>
+DEV void crb_mass_matrix(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nb = m.h[MH_NBODY], nv = m.h[MH_NV];
+  const int* sub_end = MI(m, MH_BODY_SUBTREE_END);
+  const int* dof_body = MI(m, MH_DOF_BODYID);
+  const int* dof_parent = MI(m, MH_DOF_PARENTID);
+  // composite inertia: sum of cinert over the (contiguous, depth-first) subtree of each body
+  LANE_FOR(idx, 10 * nb) {
+    const int k = idx / nb, b = idx - k * nb;
+    float s = 0.0f;
+    const int e = (b == 0) ? 1 : sub_end[b];
+    for (int c = b; c < e; c++) s += w.cinert[k][c];
+    w.crb[k][b] = s;
+  }
+  WSYNC();
+  LANE_FOR(i, nv) {
+    float ci[10];
+    const int b = dof_body[i];
+#pragma unroll
+    for (int k = 0; k < 10; k++) ci[k] = w.crb[k][b];
+    V6 buf = mul_inert_vec(ci, ld6(w.cdof, i));
+    for (int j = 0; j < i; j++) { w.M[i][j] = 0.0f; w.M[j][i] = 0.0f; }
+    for (int j = i; j >= 0; j = dof_parent[j]) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 6; k++) s += w.cdof[k][j] * buf.v[k];
+      if (j == i) s += w.armature[i];
+      w.M[i][j] = s;
+      w.M[j][i] = s;
+    }
+  }
+  WSYNC();
+}
+
+// dense Cholesky of (A + diag(add)) into W (lower triangle), one phase per column.
+template <class D>
+DEV void chol_factor(Work<D>& w, const float (*A)[D::NVP], const float* diag_add, float diag_scale, int nv, LANE_ARG) {
+  LANE_FOR(i, nv) {
+    for (int j = 0; j <= i; j++) w.W[i][j] = A[i][j];
+    if (diag_add) w.W[i][i] += diag_scale * diag_add[i];
+  }
+  WSYNC();
+  for (int j = 0; j < nv; j++) {
+    LANE_FOR(i, nv) {
+      if (i >= j) {
+        float t = w.W[i][j], s = w.W[j][j];
+        for (int k = 0; k < j; k++) {
+          const float ljk = w.W[j][k];
+          t -= w.W[i][k] * ljk;
+          s -= ljk * ljk;
+        }
+        if (s < MINVAL) s = MINVAL;
+        const float dj = sqrtf(s);
+        // the diagonal of W keeps A[j][j] (other lanes read it in this phase); the pivot lives in Linv_diag
+        if (i == j) w.Linv_diag[j] = 1.0f / dj;
+        else w.W[i][j] = t / dj;
+      }
+    }
+    WSYNC();
+  }
+}
+
+// solves (L L^T) x = b with the factor in W; x and b may alias.  Uses s_tmp.
+template <class D>
+DEV void chol_solve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
+  float* y = w.s_tmp;
+  LANE_FOR(i, nv) y[i] = b[i];
+  WSYNC();
+  for (int k = 0; k < nv; k++) {
+    const float yk = y[k] * w.Linv_diag[k];
+    LANE_FOR(i, nv) if (i > k) y[i] -= w.W[i][k] * yk;
+    WSYNC();
+  }
+  LANE_FOR(i, nv) y[i] *= w.Linv_diag[i];
+  WSYNC();
+  for (int k = nv - 1; k >= 0; k--) {
+    const float xk = y[k] * w.Linv_diag[k];
+    LANE_FOR(i, nv) if (i < k) y[i] -= w.W[k][i] * xk;
+    WSYNC();
+  }
+  LANE_FOR(i, nv) x[i] = y[i] * w.Linv_diag[i];
+  WSYNC();
+}
+
+// ---------------------------------------------------------------------------------------------- collision
+
+DEV void make_frame(V3 n, float* frame) {
+  float na = sqrtf(dot(n, n));
+  V3 a = n * (1.0f / na);
+  V3 ref = (fabsf(a.y) < 0.5f) ? v3(0, 1, 0) : v3(0, 0, 1);
+  float dp = dot(a, ref);
+  V3 b = ref - a * dp;
+  float nbm = sqrtf(dot(b, b));
+  b = b * (1.0f / nbm);
+  V3 c = cross(a, b);
+  frame[0] = a.x; frame[1] = a.y; frame[2] = a.z; frame[3] = b.x; frame[4] = b.y; frame[5] = b.z;
+  frame[6] = c.x; frame[7] = c.y; frame[8] = c.z;
+}
+
+template <class D>
+DEV void put_contact(Work<D>& w, int c, int pair, float dist, V3 pos, const float* frame) {
+  w.con_pair[c] = pair;
+  w.con_dist[c] = dist;
+  ST3(w.con_pos, c, pos);
+#pragma unroll
+  for (int k = 0; k < 9; k++) w.con_frame[k][c] = frame[k];
+  w.con_efc[c] = -1;
+}
+
+template <class D>
+DEV void collision(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int np = m.h[MH_NPAIR];
+  const int* pg1 = MI(m, MH_PAIR_GEOM1);
+  const int* pg2 = MI(m, MH_PAIR_GEOM2);
+  const int* conadr = MI(m, MH_PAIR_CONADR);
+  const int* gtype = MI(m, MH_GEOM_TYPE);
+  const int* gbody = MI(m, MH_GEOM_BODYID);
+  const float* gpos = MF(m, MH_GEOM_POS);
+  const float* gquat = MF(m, MH_GEOM_QUAT);
+  const float* gsize = MF(m, MH_GEOM_SIZE);
+  LANE_FOR(p, np) {
+    const int g1 = pg1[p], g2 = pg2[p];
+    const int t1 = gtype[g1], t2 = gtype[g2];
+    const int b1 = gbody[g1], b2 = gbody[g2];
+    V3 p1 = LD3(w.xpos, b1) + mulv(ldm9(w.xmat, b1), ldg3(gpos + 3 * g1));
+    V3 p2 = LD3(w.xpos, b2) + mulv(ldm9(w.xmat, b2), ldg3(gpos + 3 * g2));
+    M9 m1 = q2mat(qmul(LDQ(w.xquat, b1), ldgq(gquat + 4 * g1)));
+    M9 m2 = q2mat(qmul(LDQ(w.xquat, b2), ldgq(gquat + 4 * g2)));
+    const int c0 = conadr[p];
+    float frame[9];
+    if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) {
+      V3 n = v3(m1.m[2], m1.m[5], m1.m[8]);
+      const float r = gsize[3 * g2];
+      const float dist = dot(p2 - p1, n) - r;
+      V3 pos = p2 - n * (r + 0.5f * dist);
+      make_frame(n, frame);
+      put_contact(w, c0, p, dist, pos, frame);
+    } else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) {
+      V3 n = v3(m1.m[2], m1.m[5], m1.m[8]);
+      V3 axis = v3(m2.m[2], m2.m[5], m2.m[8]);
+      const float r = gsize[3 * g2], half = gsize[3 * g2 + 1];
+      make_frame(n, frame);
+      // tangent aligned with the capsule axis projected on the plane, when well defined (oracle/physics.c)
+      const float dpa = dot(axis, n);
+      V3 bt = axis - n * dpa;
+      const float nbt = sqrtf(dot(bt, bt));
+      if (nbt > 0.5f) {
+        bt = bt * (1.0f / nbt);
+        V3 cc = cross(n, bt);
+        frame[3] = bt.x; frame[4] = bt.y; frame[5] = bt.z; frame[6] = cc.x; frame[7] = cc.y; frame[8] = cc.z;
+      }
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const float sg = s == 0 ? -1.0f : 1.0f;
+        V3 end = p2 + axis * (half * sg);
+        const float dist = dot(end - p1, n) - r;
+        V3 pos = end - n * (r + 0.5f * dist);
+        put_contact(w, c0 + s, p, dist, pos, frame);
+      }
+    } else {  // sphere-sphere
+      V3 dv = p2 - p1;
+      const float len = sqrtf(dot(dv, dv));
+      V3 n = len < MINVAL ? v3(1, 0, 0) : dv * (1.0f / len);
+      const float r1 = gsize[3 * g1], r2 = gsize[3 * g2];
+      const float dist = len - r1 - r2;
+      V3 pos = p1 + n * (r1 + 0.5f * dist);
+      make_frame(n, frame);
+      put_contact(w, c0, p, dist, pos, frame);
+    }
+  }
+  WSYNC();
+}
+
+// --------------------------------------------------------------------------------------------- constraints
+
+struct KBI { float k, b, imp; };
+
+DEV KBI kbi(const Mdl& m, const float* solref, const float* solimp, float pos) {
+  float timeconst = solref[0], dampratio = solref[1];
+  if (!m.h[MH_DISABLE_REFSAFE] && solref[0] > 0) {
+    const float lo = 2 * m.mf[MF_TIMESTEP];
+    if (timeconst < lo) timeconst = lo;
+  }
+  float dmin = clipf(solimp[0], MINIMP, MAXIMP), dmax = clipf(solimp[1], MINIMP, MAXIMP);
+  float width = fmaxf(solimp[2], MINVAL), mid = clipf(solimp[3], MINIMP, MAXIMP), power = fmaxf(solimp[4], 1.0f);
+  float kk = 1.0f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  float bb = 2.0f / (dmax * timeconst);
+  if (solref[0] <= 0) kk = -solref[0] / (dmax * dmax);
+  if (solref[1] <= 0) bb = -solref[1] / dmax;
+  const float x = fabsf(pos) / width;
+  float y;
+  if (x < mid) y = (1.0f / powf(mid, power - 1)) * powf(x, power);
+  else y = 1.0f - (1.0f / powf(1.0f - mid, power - 1)) * powf(fmaxf(1.0f - x, 0.0f), power);
+  if (x > 1) y = 1;
+  float im = clipf(dmin + y * (dmax - dmin), dmin, dmax);
+  if (x > 1) im = dmax;
+  KBI r; r.k = kk; r.b = bb; r.imp = im;
+  return r;
+}
+
+template <class D>
+DEV void fill_row(const Mdl& m, Work<D>& w, int r, int type, float vel, float pos, float invweight, const float* solref,
+                  const float* solimp, float floss) {
+  KBI q = kbi(m, solref, solimp, pos);
+  float R = invweight * (1.0f - q.imp) / q.imp;
+  if (R < MINVAL) R = MINVAL;
+  w.efc_type[r] = type;
+  w.efc_aref[r] = -q.b * vel - q.k * q.imp * pos;
+  w.efc_R[r] = R;
+  w.efc_D[r] = 1.0f / R;
+  w.efc_floss[r] = floss;
+  w.efc_force[r] = 0.0f;
+}
+
+enum { EFC_FRICTION = 1, EFC_LIMIT = 2, EFC_CONTACT = 3 };
+
+// Row order follows the oracle / MJX make_constraint: friction, limit, contact.  Single-dof rows (friction,
+// limit) are kept in compact form (dof + sign); contact rows are dense in Jd.
+template <class D>
+DEV void make_constraint(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = m.h[MH_NV], nlimit = m.h[MH_NLIMIT], ncon = m.h[MH_NCON];
+  const float* dof_invw = MF(m, MH_DOF_INVWEIGHT0);
+  const float* dof_solref = MF(m, MH_DOF_SOLREF);
+  const float* dof_solimp = MF(m, MH_DOF_SOLIMP);
+  int nrow = 0;
+  LANE_FOR_ALL(i, nv) {
+    const bool on = i < nv && w.frictionloss[i] > 0.0f;
+    const int r = wcompact(on, nrow, LANE_PASS);
+    if (on) {
+      w.efc_dof[r] = i; w.efc_sign[r] = 1.0f;
+      fill_row(m, w, r, EFC_FRICTION, w.qvel[i], 0.0f, dof_invw[i], dof_solref + 2 * i, dof_solimp + 5 * i, w.frictionloss[i]);
+    }
+  }
+  const int* limit_jnt = MI(m, MH_LIMIT_JNT);
+  const int* jqpos = MI(m, MH_JNT_QPOSADR);
+  const int* jdof = MI(m, MH_JNT_DOFADR);
+  const float* jrange = MF(m, MH_JNT_RANGE);
+  const float* jmargin = MF(m, MH_JNT_MARGIN);
+  const float* jsolref = MF(m, MH_JNT_SOLREF);
+  const float* jsolimp = MF(m, MH_JNT_SOLIMP);
+  LANE_FOR_ALL(t, nlimit) {
+    bool on = false;
+    int j = 0, dof = 0;
+    float pos = 0, sign = 1;
+    if (t < nlimit) {
+      j = limit_jnt[t];
+      dof = jdof[j];
+      const float q = w.qpos[jqpos[j]];
+      const float dmin = q - jrange[2 * j], dmax = jrange[2 * j + 1] - q;
+      pos = fminf(dmin, dmax) - jmargin[j];
+      sign = dmin < dmax ? 1.0f : -1.0f;
+      on = pos < 0.0f;
+    }
+    const int r = wcompact(on, nrow, LANE_PASS);
+    if (on) {
+      w.efc_dof[r] = dof; w.efc_sign[r] = sign;
+      fill_row(m, w, r, EFC_LIMIT, sign * w.qvel[dof], pos, dof_invw[dof], jsolref + 2 * j, jsolimp + 5 * j, 0.0f);
+    }
+  }
+  const int nsparse = nrow;
+  // contacts: every lane walks the (few) candidate contacts to agree on row addresses
+  const int* pdim = MI(m, MH_PAIR_DIM);
+  const float* pmargin = MF(m, MH_PAIR_MARGIN);
+  const float* pgap = MF(m, MH_PAIR_GAP);
+  for (int c = 0; c < ncon; c++) {
+    const int p = w.con_pair[c];
+    const float pos = w.con_dist[c] - (pmargin[p] - pgap[p]);
+    int adr = -1;
+    if (pos < 0.0f) { adr = nrow; nrow += (pdim[p] == 1) ? 1 : 4; }
+    IF_LANE0 w.con_efc[c] = adr;
+  }
+  IF_LANE0 { w.nefc = nrow; w.nsparse = nsparse; }
+  WSYNC();
+  if (nrow == nsparse) return;
+  // dense Jacobian rows: lanes over dofs
+  const int* pg1 = MI(m, MH_PAIR_GEOM1);
+  const int* pg2 = MI(m, MH_PAIR_GEOM2);
+  const int* gbody = MI(m, MH_GEOM_BODYID);
+  const int* rootid = MI(m, MH_BODY_ROOTID);
+  const int* bdofmask = MI(m, MH_BODY_DOFMASK);
+  const float* pfric = MF(m, MH_PAIR_FRICTION);
+  LANE_FOR(i, nv) {
+    for (int c = 0; c < ncon; c++) {
+      const int adr = w.con_efc[c];
+      if (adr < 0) continue;
+      const int p = w.con_pair[c];
+      const int b1 = gbody[pg1[p]], b2 = gbody[pg2[p]];
+      V3 cp = LD3(w.con_pos, c);
+      V3 diff = v3(0, 0, 0);
+      V3 ang = v3(w.cdof[0][i], w.cdof[1][i], w.cdof[2][i]), lin = v3(w.cdof[3][i], w.cdof[4][i], w.cdof[5][i]);
+      if (b2 != 0 && ((bdofmask[b2] >> i) & 1)) diff = diff + lin + cross(ang, cp - LD3(w.subtree_com, rootid[b2]));
+      if (b1 != 0 && ((bdofmask[b1] >> i) & 1)) diff = diff - (lin + cross(ang, cp - LD3(w.subtree_com, rootid[b1])));
+      float d[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+        d[r] = w.con_frame[3 * r][c] * diff.x + w.con_frame[3 * r + 1][c] * diff.y + w.con_frame[3 * r + 2][c] * diff.z;
+      const int rd = adr - nsparse;
+      if (pdim[p] == 1) {
+        w.Jd[rd][i] = d[0];
+      } else {
+        const float mu0 = pfric[5 * p], mu1 = pfric[5 * p + 1];
+        w.Jd[rd + 0][i] = d[0] + mu0 * d[1];
+        w.Jd[rd + 1][i] = d[0] - mu0 * d[1];
+        w.Jd[rd + 2][i] = d[0] + mu1 * d[2];
+        w.Jd[rd + 3][i] = d[0] - mu1 * d[2];
+      }
+    }
+  }
+  WSYNC();
+  const float* binvw = MF(m, MH_BODY_INVWEIGHT0);
+  const float* psolref = MF(m, MH_PAIR_SOLREF);
+  const float* psolimp = MF(m, MH_PAIR_SOLIMP);
+  const float impratio = m.mf[MF_IMPRATIO];
+  LANE_FOR(rd, nrow - nsparse) {
+    const int r = nsparse + rd;
+    // owning contact of this row
+    int c = 0;
+    for (int cc = 0; cc < ncon; cc++) if (w.con_efc[cc] >= 0 && w.con_efc[cc] <= r) c = cc;
+    const int p = w.con_pair[c];
+    float vel = 0.0f;
+    for (int i = 0; i < nv; i++) vel += w.Jd[rd][i] * w.qvel[i];
+    const int b1 = gbody[pg1[p]], b2 = gbody[pg2[p]];
+    const float t = binvw[2 * b1] + binvw[2 * b2];
+    const float pos = w.con_dist[c] - (pmargin[p] - pgap[p]);
+    float iw = t;
+    if (pdim[p] != 1) {
+      const float mu0 = pfric[5 * p];
+      iw = (t + mu0 * mu0 * t) * 2 * mu0 * mu0 / impratio;
+    }
+    w.efc_dof[r] = -1; w.efc_sign[r] = 0.0f;
+    fill_row(m, w, r, EFC_CONTACT, vel, pos, iw, psolref + 2 * p, psolimp + 5 * p, 0.0f);
+  }
+  WSYNC();
+}
+
+// ------------------------------------------------------------------------------------------ velocity stage
+
+// Spatial velocity of each body and cdof_dot of each dof, by walking the dof chain instead of recursing over
+// bodies: cvel[b] = sum of cdof*qvel over the dofs between the root and b (same quantity mj_comVel builds).
+template <class D>
+DEV void com_vel(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nb = m.h[MH_NBODY], nv = m.h[MH_NV];
+  const int* dof_parent = MI(m, MH_DOF_PARENTID);
+  const int* dof_velparent = MI(m, MH_DOF_VELPARENT);
+  const int* body_lastdof = MI(m, MH_BODY_LASTDOF);
+  LANE_FOR(b, nb) {
+    V6 v;
+#pragma unroll
+    for (int c = 0; c < 6; c++) v.v[c] = 0.0f;
+    for (int j = body_lastdof[b]; j >= 0; j = dof_parent[j]) {
+      const float qv = w.qvel[j];
+#pragma unroll
+      for (int c = 0; c < 6; c++) v.v[c] += w.cdof[c][j] * qv;
+    }
+    st6(w.cvel, b, v);
+  }
+  LANE_FOR(i, nv) {
+    const int vp = dof_velparent[i];
+    V6 r;
+    if (vp == -2) {  // translational dof of a free joint
+#pragma unroll
+      for (int c = 0; c < 6; c++) r.v[c] = 0.0f;
+    } else {
+      V6 v;
+#pragma unroll
+      for (int c = 0; c < 6; c++) v.v[c] = 0.0f;
+      for (int j = vp; j >= 0; j = dof_parent[j]) {
+        const float qv = w.qvel[j];
+#pragma unroll
+        for (int c = 0; c < 6; c++) v.v[c] += w.cdof[c][j] * qv;
+      }
+      r = cross_motion(v, ld6(w.cdof, i));
+    }
+    st6(w.cdof_dot, i, r);
+  }
+  WSYNC();
+}
+
+template <class D>
+DEV void passive(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = m.h[MH_NV];
+  const int* dof_jnt = MI(m, MH_DOF_JNTID);
+  const int* jtype = MI(m, MH_JNT_TYPE);
+  const int* jqpos = MI(m, MH_JNT_QPOSADR);
+  const float* stiff = MF(m, MH_JNT_STIFFNESS);
+  const float* spring = MF(m, MH_QPOS_SPRING);
+  LANE_FOR(i, nv) {
+    float f = -w.damping[i] * w.qvel[i];
+    const int j = dof_jnt[i];
+    if (jtype[j] == JNT_HINGE) f -= stiff[j] * (w.qpos[jqpos[j]] - spring[jqpos[j]]);
+    w.qfrc_passive[i] = f;
+  }
+}
+
+// cacc[b] = -gravity + sum over the dof chain of cdof_dot*qvel (+ cdof*qacc)
+template <class D>
+DEV void rne_cacc(const Mdl& m, Work<D>& w, bool with_acc, LANE_ARG) {
+  const int nb = m.h[MH_NBODY];
+  const int* dof_parent = MI(m, MH_DOF_PARENTID);
+  const int* body_lastdof = MI(m, MH_BODY_LASTDOF);
+  const float gx = m.mf[MF_GRAVITY], gy = m.mf[MF_GRAVITY + 1], gz = m.mf[MF_GRAVITY + 2];
+  LANE_FOR(b, nb) {
+    V6 a;
+    a.v[0] = a.v[1] = a.v[2] = 0.0f; a.v[3] = -gx; a.v[4] = -gy; a.v[5] = -gz;
+    for (int j = body_lastdof[b]; j >= 0; j = dof_parent[j]) {
+      const float qv = w.qvel[j];
+#pragma unroll
+      for (int c = 0; c < 6; c++) a.v[c] += w.cdof_dot[c][j] * qv;
+      if (with_acc) {
+        const float qa = w.qacc[j];
+#pragma unroll
+        for (int c = 0; c < 6; c++) a.v[c] += w.cdof[c][j] * qa;
+      }
+    }
+    st6(w.cacc, b, a);
+  }
+  WSYNC();
+}
+
+template <class D>
+DEV V6 body_inertial_force(Work<D>& w, int b) {
+  float ci[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) ci[k] = w.cinert[k][b];
+  V6 v = ld6(w.cvel, b);
+  V6 t1 = mul_inert_vec(ci, ld6(w.cacc, b));
+  V6 t2 = mul_inert_vec(ci, v);
+  V6 t3 = cross_force(v, t2);
+  V6 r;
+#pragma unroll
+  for (int c = 0; c < 6; c++) r.v[c] = t1.v[c] + t3.v[c];
+  return r;
+}
+
+template <class D>
+DEV void rne(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nb = m.h[MH_NBODY], nv = m.h[MH_NV];
+  const int* sub_end = MI(m, MH_BODY_SUBTREE_END);
+  const int* dof_body = MI(m, MH_DOF_BODYID);
+  rne_cacc(m, w, false, LANE_PASS);
+  LANE_FOR(b, nb) {
+    V6 f;
+    if (b == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) f.v[c] = 0.0f;
+    } else {
+      f = body_inertial_force(w, b);
+    }
+    st6(w.cfrc, b, f);
+  }
+  WSYNC();
+  LANE_FOR(i, nv) {
+    const int b = dof_body[i], e = sub_end[b];
+    float s = 0.0f;
+    for (int c = b; c < e; c++) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) s += w.cdof[k][i] * w.cfrc[k][c];
+    }
+    w.qfrc_bias[i] = s;
+  }
+  WSYNC();
+}
+
+template <class D>
+DEV void actuation(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = m.h[MH_NV], nu = m.h[MH_NU];
+  const int* trnid = MI(m, MH_ACT_TRNID);
+  const int* climited = MI(m, MH_ACT_CTRLLIMITED);
+  const int* flimited = MI(m, MH_ACT_FORCELIMITED);
+  const int* jdof = MI(m, MH_JNT_DOFADR);
+  const float* gear = MF(m, MH_ACT_GEAR);
+  const float* crange = MF(m, MH_ACT_CTRLRANGE);
+  const float* frange = MF(m, MH_ACT_FORCERANGE);
+  LANE_FOR(u, nu) {
+    float c = w.ctrl[u];
+    if (climited[u]) c = clipf(c, crange[2 * u], crange[2 * u + 1]);
+    float f = c;
+    if (flimited[u]) f = clipf(f, frange[2 * u], frange[2 * u + 1]);
+    w.actuator_force[u] = f;
+  }
+  WSYNC();
+  // one motor per hinge at most in the supported subset, but gather generally
+  LANE_FOR(i, nv) {
+    float s = 0.0f;
+    for (int u = 0; u < nu; u++) if (jdof[trnid[u]] == i) s += gear[u] * w.actuator_force[u];
+    w.qfrc_actuator[i] = s;
+  }
+  WSYNC();
+}
+
+template <class D>
+DEV void acceleration(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = m.h[MH_NV];
+  const int* rootid = MI(m, MH_BODY_ROOTID);
+  const int* bdofmask = MI(m, MH_BODY_DOFMASK);
+  const int xb = w.xfrc_body;
+  LANE_FOR(i, nv) {
+    float s = w.qfrc_passive[i] - w.qfrc_bias[i] + w.qfrc_actuator[i];
+    if (xb > 0 && ((bdofmask[xb] >> i) & 1)) {
+      const bool nz = w.xfrc[0] != 0 || w.xfrc[1] != 0 || w.xfrc[2] != 0 || w.xfrc[3] != 0 || w.xfrc[4] != 0 || w.xfrc[5] != 0;
+      if (nz) {
+        V3 ang = v3(w.cdof[0][i], w.cdof[1][i], w.cdof[2][i]), lin = v3(w.cdof[3][i], w.cdof[4][i], w.cdof[5][i]);
+        V3 jp = lin + cross(ang, LD3(w.xipos, xb) - LD3(w.subtree_com, rootid[xb]));
+        s += jp.x * w.xfrc[0] + ang.x * w.xfrc[3];
+        s += jp.y * w.xfrc[1] + ang.y * w.xfrc[4];
+        s += jp.z * w.xfrc[2] + ang.z * w.xfrc[5];
+      }
+    }
+    w.qfrc_smooth[i] = s;
+  }
+  WSYNC();
+  chol_solve(w, w.qacc_smooth, w.qfrc_smooth, nv, LANE_PASS);
+}
+
+// ------------------------------------------------------------------------------------------------- solver
+
+// J * x for row r
+template <class D>
+DEV float row_dot(const Work<D>& w, int r, int nsparse, const float* x, int nv) {
+  if (r < nsparse) return w.efc_sign[r] * x[w.efc_dof[r]];
+  float s = 0.0f;
+  const float* J = w.Jd[r - nsparse];
+  for (int i = 0; i < nv; i++) s += J[i] * x[i];
+  return s;
+}
+
+// efc_force / active / cost from Jaref; qfrc_constraint = J^T force; returns total cost (gauss + constraint)
+template <class D>
+DEV float solver_update_constraint(const Mdl& m, Work<D>& w, float* gauss_out, LANE_ARG) {
+  const int nv = m.h[MH_NV], ne = w.nefc, nsparse = w.nsparse;
+  float cost = 0.0f;
+  LANE_FOR(r, ne) {
+    const float x = w.efc_Jaref[r], Dr = w.efc_D[r];
+    if (w.efc_type[r] == EFC_FRICTION) {
+      const float f = w.efc_floss[r], rf = w.efc_R[r] * f;
+      if (x <= -rf) { w.efc_force[r] = f; w.efc_active[r] = 0; cost += -f * (0.5f * rf + x); }
+      else if (x >= rf) { w.efc_force[r] = -f; w.efc_active[r] = 0; cost += -f * (0.5f * rf - x); }
+      else { w.efc_force[r] = -Dr * x; w.efc_active[r] = 1; cost += 0.5f * Dr * x * x; }
+    } else {
+      const int act = x < 0.0f;
+      w.efc_active[r] = act;
+      w.efc_force[r] = act ? -Dr * x : 0.0f;
+      if (act) cost += 0.5f * Dr * x * x;
+    }
+  }
+  float gauss = 0.0f;
+  LANE_FOR(i, nv) gauss += (w.s_Ma[i] - w.qfrc_smooth[i]) * (w.s_qacc[i] - w.qacc_smooth[i]);
+  cost = wsum(cost);
+  gauss = 0.5f * wsum(gauss);
+  WSYNC();
+  LANE_FOR(i, nv) {
+    float s = 0.0f;
+    for (int r = 0; r < nsparse; r++) if (w.efc_dof[r] == i) s += w.efc_sign[r] * w.efc_force[r];
+    for (int r = nsparse; r < ne; r++) s += w.Jd[r - nsparse][i] * w.efc_force[r];
+    w.qfrc_constraint[i] = s;
+  }
+  WSYNC();
+  *gauss_out = gauss;
+  return gauss + cost;
+}
+
+// grad = Ma - qfrc_smooth - qfrc_constraint; Mgrad = H^-1 grad with H = M + J^T diag(D*active) J
+template <class D>
+DEV void solver_update_gradient(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = m.h[MH_NV], ne = w.nefc, nsparse = w.nsparse;
+  LANE_FOR(i, nv) {
+    w.s_grad[i] = w.s_Ma[i] - w.qfrc_smooth[i] - w.qfrc_constraint[i];
+    for (int j = 0; j <= i; j++) {
+      float h = w.M[i][j];
+      for (int r = nsparse; r < ne; r++)
+        if (w.efc_active[r]) h += w.efc_D[r] * w.Jd[r - nsparse][i] * w.Jd[r - nsparse][j];
+      w.W[i][j] = h;
+    }
+    float dg = 0.0f;
+    for (int r = 0; r < nsparse; r++) if (w.efc_active[r] && w.efc_dof[r] == i) dg += w.efc_D[r];
+    w.W[i][i] += dg;
+  }
+  WSYNC();
+  // factor in place (W already holds the lower triangle of H)
+  for (int j = 0; j < nv; j++) {
+    LANE_FOR(i, nv) {
+      if (i >= j) {
+        float t = w.W[i][j], s = w.W[j][j];
+        for (int k = 0; k < j; k++) {
+          const float ljk = w.W[j][k];
+          t -= w.W[i][k] * ljk;
+          s -= ljk * ljk;
+        }
+        if (s < MINVAL) s = MINVAL;
+        const float dj = sqrtf(s);
+        // the diagonal of W keeps A[j][j] (other lanes read it in this phase); the pivot lives in Linv_diag
+        if (i == j) w.Linv_diag[j] = 1.0f / dj;
+        else w.W[i][j] = t / dj;
+      }
+    }
+    WSYNC();
+  }
+  chol_solve(w, w.s_Mgrad, w.s_grad, nv, LANE_PASS);
+}
+
+// initialises s_qacc/s_Ma/Jaref from `qacc0`; returns cost
+template <class D>
+DEV float solver_init(const Mdl& m, Work<D>& w, const float* qacc0, float* gauss, LANE_ARG) {
+  const int nv = m.h[MH_NV], ne = w.nefc, nsparse = w.nsparse;
+  LANE_FOR(i, nv) {
+    w.s_qacc[i] = qacc0[i];
+    float s = 0.0f;
+    for (int j = 0; j < nv; j++) s += w.M[i][j] * qacc0[j];
+    w.s_Ma[i] = s;
+  }
+  LANE_FOR(r, ne) w.efc_Jaref[r] = row_dot(w, r, nsparse, qacc0, nv) - w.efc_aref[r];
+  WSYNC();
+  return solver_update_constraint(m, w, gauss, LANE_PASS);
+}
+
+struct LSPoint { float alpha, cost, deriv0, deriv1; };
+
+DEV LSPoint ls_make(float alpha, float q0, float q1, float q2) {
+  LSPoint p;
+  p.alpha = alpha;
+  p.cost = alpha * alpha * q2 + alpha * q1 + q0;
+  p.deriv0 = 2 * alpha * q2 + q1;
+  p.deriv1 = 2 * q2 + (q2 == 0 ? MINVAL : 0.0f);
+  return p;
+}
+DEV bool in_bracket(const LSPoint& x, const LSPoint& y) {
+  return (x.deriv0 < y.deriv0 && y.deriv0 < 0) || (x.deriv0 > y.deriv0 && y.deriv0 > 0);
+}
+
+// evaluates up to three step sizes in one pass over the constraint rows
+template <class D>
+DEV void ls_eval3(const Work<D>& w, int ne, const float* alpha, int n, const float* qg, LSPoint* out, LANE_ARG) {
+  float q[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) q[a][0] = q[a][1] = q[a][2] = 0.0f;
+  LANE_FOR(r, ne) {
+    const float ja = w.efc_Jaref[r], jv = w.efc_jv[r], Dr = w.efc_D[r];
+    const int type = w.efc_type[r];
+    const float f = w.efc_floss[r], rf = w.efc_R[r] * f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (a < n) {
+        const float x = ja + alpha[a] * jv;
+        if (type == EFC_FRICTION) {
+          if (x <= -rf) { q[a][0] += f * (-0.5f * rf - ja); q[a][1] += -f * jv; }
+          else if (x >= rf) { q[a][0] += f * (-0.5f * rf + ja); q[a][1] += f * jv; }
+          else { q[a][0] += 0.5f * Dr * ja * ja; q[a][1] += Dr * jv * ja; q[a][2] += 0.5f * Dr * jv * jv; }
+        } else if (x < 0.0f) {
+          q[a][0] += 0.5f * Dr * ja * ja; q[a][1] += Dr * jv * ja; q[a][2] += 0.5f * Dr * jv * jv;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (a < n) {
+      const float q0 = wsum(q[a][0]) + qg[0], q1 = wsum(q[a][1]) + qg[1], q2 = wsum(q[a][2]) + qg[2];
+      out[a] = ls_make(alpha[a], q0, q1, q2);
+    }
+  }
+}
+
+template <class D>
+DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, LANE_ARG) {
+  const int nv = m.h[MH_NV], ne = w.nefc, nsparse = w.nsparse;
+  float snorm = 0.0f, qg1 = 0.0f, qg2 = 0.0f;
+  LANE_FOR(i, nv) {
+    float s = 0.0f;
+    for (int j = 0; j < nv; j++) s += w.M[i][j] * w.s_search[j];
+    w.s_mv[i] = s;
+    const float si = w.s_search[i];
+    snorm += si * si;
+    qg1 += si * (w.s_Ma[i] - w.qfrc_smooth[i]);
+    qg2 += 0.5f * si * s;
+  }
+  LANE_FOR(r, ne) w.efc_jv[r] = row_dot(w, r, nsparse, w.s_search, nv);
+  snorm = sqrtf(wsum(snorm));
+  const float qg[3] = {gauss, wsum(qg1), wsum(qg2)};
+  WSYNC();
+  const float scale = m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1);
+  const float gtol = m.mf[MF_TOLERANCE] * m.mf[MF_LS_TOLERANCE] * snorm * scale;
+  LSPoint pts[3];
+  float al[3] = {0.0f, 0.0f, 0.0f};
+  ls_eval3(w, ne, al, 1, qg, pts, LANE_PASS);
+  const LSPoint p0 = pts[0];
+  al[0] = p0.alpha - p0.deriv0 / p0.deriv1;
+  ls_eval3(w, ne, al, 1, qg, pts, LANE_PASS);
+  LSPoint lo = pts[0], hi;
+  if (p0.deriv0 < lo.deriv0) { hi = lo; lo = p0; } else { hi = p0; }
+  int swap = 1, it = 0;
+  const int ls_iterations = m.h[MH_LS_ITERATIONS];
+  while (true) {
+    bool done = it >= ls_iterations;
+    done |= !swap;
+    done |= (lo.deriv0 < 0) && (lo.deriv0 > -gtol);
+    done |= (hi.deriv0 > 0) && (hi.deriv0 < gtol);
+    if (done) break;
+    al[0] = lo.alpha - lo.deriv0 / lo.deriv1;
+    al[1] = hi.alpha - hi.deriv0 / hi.deriv1;
+    al[2] = 0.5f * (lo.alpha + hi.alpha);
+    ls_eval3(w, ne, al, 3, qg, pts, LANE_PASS);
+    const LSPoint lo_next = pts[0], hi_next = pts[1], mid = pts[2];
+    const int s1 = in_bracket(lo, lo_next); if (s1) lo = lo_next;
+    const int s2 = in_bracket(lo, mid); if (s2) lo = mid;
+    const int s3 = in_bracket(lo, hi_next); if (s3) lo = hi_next;
+    const int s4 = in_bracket(hi, hi_next); if (s4) hi = hi_next;
+    const int s5 = in_bracket(hi, mid); if (s5) hi = mid;
+    const int s6 = in_bracket(hi, lo_next); if (s6) hi = lo_next;
+    swap = s1 | s2 | s3 | s4 | s5 | s6;
+    it++;
+  }
+  const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+  float alpha = (lo.cost < hi.cost) ? lo.alpha : hi.alpha;
+  if (!improved) alpha = 0.0f;
+  LANE_FOR(i, nv) { w.s_qacc[i] += alpha * w.s_search[i]; w.s_Ma[i] += alpha * w.s_mv[i]; }
+  LANE_FOR(r, ne) w.efc_Jaref[r] += alpha * w.efc_jv[r];
+  WSYNC();
+}
+
+template <class D>
+DEV void solve(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = m.h[MH_NV], ne = w.nefc;
+  if (ne == 0) {
+    // no constraint rows: qacc = qacc_smooth, qacc_warmstart keeps its old value (MJX forward())
+    LANE_FOR(i, nv) { w.qacc[i] = w.qacc_smooth[i]; w.qfrc_constraint[i] = 0.0f; }
+    WSYNC();
+    return;
+  }
+  float gauss;
+  const float* start = w.qacc_smooth;
+  if (!m.h[MH_DISABLE_WARMSTART]) {
+    const float cw = solver_init(m, w, w.warm, &gauss, LANE_PASS);
+    const float cs = solver_init(m, w, w.qacc_smooth, &gauss, LANE_PASS);
+    if (cw < cs) start = w.warm;
+  }
+  float cost = solver_init(m, w, start, &gauss, LANE_PASS);
+  float prev_cost = INFINITY;
+  solver_update_gradient(m, w, LANE_PASS);
+  LANE_FOR(i, nv) w.s_search[i] = -w.s_Mgrad[i];
+  WSYNC();
+  const int iterations = m.h[MH_ITERATIONS];
+  const float tol = m.mf[MF_TOLERANCE];
+  const float scale = 1.0f / (m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1));
+  int niter = 0;
+  while (true) {
+    if (iterations != 1 || niter > 0) {
+      const float improvement = (prev_cost - cost) * scale;
+      float gn = 0.0f;
+      LANE_FOR(i, nv) gn += w.s_grad[i] * w.s_grad[i];
+      const float gradient = sqrtf(wsum(gn)) * scale;
+      bool done = niter >= iterations;
+      done |= improvement < tol;
+      done |= gradient < tol;
+      if (done) break;
+    }
+    linesearch(m, w, gauss, LANE_PASS);
+    prev_cost = cost;
+    cost = solver_update_constraint(m, w, &gauss, LANE_PASS);
+    solver_update_gradient(m, w, LANE_PASS);
+    LANE_FOR(i, nv) w.s_search[i] = -w.s_Mgrad[i];
+    WSYNC();
+    niter++;
+    if (iterations == 1) break;
+  }
+  LANE_FOR(i, nv) { w.qacc[i] = w.s_qacc[i]; w.warm[i] = w.s_qacc[i]; }
+  WSYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ sensors
+
+template <class D>
+DEV void object_frame(const Mdl& m, const Work<D>& w, int objtype, int objid, int* body, V3* pos, M9* rot) {
+  if (objtype == OBJ_SITE) { *body = MI(m, MH_SITE_BODYID)[objid]; *pos = LD3(w.site_xpos, objid); *rot = ldm9(w.site_xmat, objid); }
+  else if (objtype == OBJ_BODY) { *body = objid; *pos = LD3(w.xipos, objid); *rot = ldm9(w.ximat, objid); }
+  else { *body = objid; *pos = LD3(w.xpos, objid); *rot = ldm9(w.xmat, objid); }
+}
+
+// mju_transformSpatial for a motion vector
+DEV V6 transform_motion(const V6& vec, V3 newpos, V3 oldpos, const M9* rot) {
+  V3 dif = newpos - oldpos;
+  V3 ang = v3(vec.v[0], vec.v[1], vec.v[2]);
+  V3 lin = v3(vec.v[3], vec.v[4], vec.v[5]) - cross(dif, ang);
+  if (rot) { ang = mulTv(*rot, ang); lin = mulTv(*rot, lin); }
+  V6 r;
+  r.v[0] = ang.x; r.v[1] = ang.y; r.v[2] = ang.z; r.v[3] = lin.x; r.v[4] = lin.y; r.v[5] = lin.z;
+  return r;
+}
+
+template <class D>
+DEV void sensors_pos_vel(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int ns = m.h[MH_NSENSOR];
+  const int* stype = MI(m, MH_SENSOR_TYPE);
+  const int* sobjt = MI(m, MH_SENSOR_OBJTYPE);
+  const int* sobj = MI(m, MH_SENSOR_OBJID);
+  const int* sadr = MI(m, MH_SENSOR_ADR);
+  const int* rootid = MI(m, MH_BODY_ROOTID);
+  LANE_FOR(s, ns) {
+    const int t = stype[s], ot = sobjt[s], id = sobj[s];
+    float* out = w.sensordata + sadr[s];
+    int body; V3 pos; M9 rot;
+    if (t >= SENS_FRAMEPOS && t <= SENS_FRAMEZAXIS) {
+      object_frame(m, w, ot, id, &body, &pos, &rot);
+      if (t == SENS_FRAMEPOS) { out[0] = pos.x; out[1] = pos.y; out[2] = pos.z; }
+      else if (t == SENS_FRAMEQUAT) {
+        Q4 q = LDQ(w.xquat, body);
+        if (ot == OBJ_SITE) q = qmul(q, ldgq(MF(m, MH_SITE_QUAT) + 4 * id));
+        else if (ot == OBJ_BODY) q = qmul(q, ldgq(MF(m, MH_BODY_IQUAT) + 4 * id));
+        out[0] = q.w; out[1] = q.x; out[2] = q.y; out[3] = q.z;
+      } else {
+        const int col = t - SENS_FRAMEXAXIS;
+        out[0] = rot.m[col]; out[1] = rot.m[3 + col]; out[2] = rot.m[6 + col];
+      }
+    } else if (t == SENS_VELOCIMETER || t == SENS_GYRO || t == SENS_FRAMELINVEL || t == SENS_FRAMEANGVEL) {
+      const bool local = (t == SENS_VELOCIMETER || t == SENS_GYRO);
+      object_frame(m, w, local ? OBJ_SITE : ot, id, &body, &pos, &rot);
+      V6 v = transform_motion(ld6(w.cvel, body), pos, LD3(w.subtree_com, rootid[body]), local ? &rot : nullptr);
+      const int o = (t == SENS_VELOCIMETER || t == SENS_FRAMELINVEL) ? 3 : 0;
+      out[0] = v.v[o]; out[1] = v.v[o + 1]; out[2] = v.v[o + 2];
+    }
+  }
+  WSYNC();
+}
+
+template <class D>
+DEV V3 contact_force_world(const Mdl& m, const Work<D>& w, int c) {
+  const int a = w.con_efc[c];
+  const int p = w.con_pair[c];
+  float f0 = 0, f1 = 0, f2 = 0;
+  if (a >= 0) {
+    if (MI(m, MH_PAIR_DIM)[p] == 1) f0 = w.efc_force[a];
+    else {
+      const float* fr = MF(m, MH_PAIR_FRICTION) + 5 * p;
+      f0 = w.efc_force[a] + w.efc_force[a + 1] + w.efc_force[a + 2] + w.efc_force[a + 3];
+      f1 = (w.efc_force[a] - w.efc_force[a + 1]) * fr[0];
+      f2 = (w.efc_force[a + 2] - w.efc_force[a + 3]) * fr[1];
+    }
+  }
+  return v3(w.con_frame[0][c] * f0 + w.con_frame[3][c] * f1 + w.con_frame[6][c] * f2,
+            w.con_frame[1][c] * f0 + w.con_frame[4][c] * f1 + w.con_frame[7][c] * f2,
+            w.con_frame[2][c] * f0 + w.con_frame[5][c] * f1 + w.con_frame[8][c] * f2);
+}
+
+// rne_postconstraint + acceleration-stage sensors
+template <class D>
+DEV void sensors_acc(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nb = m.h[MH_NBODY], ncon = m.h[MH_NCON], ns = m.h[MH_NSENSOR];
+  const int* rootid = MI(m, MH_BODY_ROOTID);
+  const int* pg1 = MI(m, MH_PAIR_GEOM1);
+  const int* pg2 = MI(m, MH_PAIR_GEOM2);
+  const int* gbody = MI(m, MH_GEOM_BODYID);
+  const int* sub_end = MI(m, MH_BODY_SUBTREE_END);
+  rne_cacc(m, w, true, LANE_PASS);
+  LANE_FOR(b, nb) {
+    V6 e;
+#pragma unroll
+    for (int c = 0; c < 6; c++) e.v[c] = 0.0f;
+    if (b > 0) {
+      V3 com = LD3(w.subtree_com, rootid[b]);
+      if (b == w.xfrc_body) {
+        V3 f = v3(w.xfrc[0], w.xfrc[1], w.xfrc[2]);
+        V3 cr = cross(LD3(w.xipos, b) - com, f);
+        e.v[0] = w.xfrc[3] + cr.x; e.v[1] = w.xfrc[4] + cr.y; e.v[2] = w.xfrc[5] + cr.z;
+        e.v[3] = f.x; e.v[4] = f.y; e.v[5] = f.z;
+      }
+      for (int c = 0; c < ncon; c++) {
+        if (w.con_efc[c] < 0) continue;
+        const int p = w.con_pair[c];
+        const int b1 = gbody[pg1[p]], b2 = gbody[pg2[p]];
+        if (b1 != b && b2 != b) continue;
+        V3 fw = contact_force_world(m, w, c);
+        V3 cr = cross(LD3(w.con_pos, c) - com, fw);
+        const float sg = (b2 == b) ? 1.0f : -1.0f;
+        e.v[0] += sg * cr.x; e.v[1] += sg * cr.y; e.v[2] += sg * cr.z;
+        e.v[3] += sg * fw.x; e.v[4] += sg * fw.y; e.v[5] += sg * fw.z;
+      }
+    }
+    st6(w.cfrc_ext, b, e);
+    V6 f;
+    if (b == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) f.v[c] = 0.0f;
+    } else {
+      f = body_inertial_force(w, b);
+#pragma unroll
+      for (int c = 0; c < 6; c++) f.v[c] -= e.v[c];
+    }
+    st6(w.cfrc, b, f);
+  }
+  WSYNC();
+  const int* stype = MI(m, MH_SENSOR_TYPE);
+  const int* sobjt = MI(m, MH_SENSOR_OBJTYPE);
+  const int* sobj = MI(m, MH_SENSOR_OBJID);
+  const int* sadr = MI(m, MH_SENSOR_ADR);
+  LANE_FOR(s, ns) {
+    const int t = stype[s], ot = sobjt[s], id = sobj[s];
+    float* out = w.sensordata + sadr[s];
+    if (t == SENS_ACCEL || t == SENS_FRAMELINACC || t == SENS_FRAMEANGACC) {
+      const bool local = (t == SENS_ACCEL);
+      int body; V3 pos; M9 rot;
+      object_frame(m, w, local ? OBJ_SITE : ot, id, &body, &pos, &rot);
+      V3 com = LD3(w.subtree_com, rootid[body]);
+      V6 vel = transform_motion(ld6(w.cvel, body), pos, com, local ? &rot : nullptr);
+      V6 acc = transform_motion(ld6(w.cacc, body), pos, com, local ? &rot : nullptr);
+      V3 cr = cross(v3(vel.v[0], vel.v[1], vel.v[2]), v3(vel.v[3], vel.v[4], vel.v[5]));
+      acc.v[3] += cr.x; acc.v[4] += cr.y; acc.v[5] += cr.z;
+      const int o = (t == SENS_FRAMEANGACC) ? 0 : 3;
+      out[0] = acc.v[o]; out[1] = acc.v[o + 1]; out[2] = acc.v[o + 2];
+    } else if (t == SENS_FORCE || t == SENS_TORQUE) {
+      // interaction wrench between the site's body and its parent: subtree sum of cfrc (world excluded)
+      const int b = MI(m, MH_SITE_BODYID)[id];
+      V6 wv;
+#pragma unroll
+      for (int c = 0; c < 6; c++) wv.v[c] = 0.0f;
+      for (int cb = b; cb < sub_end[b]; cb++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) wv.v[c] += w.cfrc[c][cb];
+      V3 com = LD3(w.subtree_com, rootid[b]);
+      V3 dif = LD3(w.site_xpos, id) - com;
+      V3 frc = v3(wv.v[3], wv.v[4], wv.v[5]);
+      V3 tq = v3(wv.v[0], wv.v[1], wv.v[2]) - cross(dif, frc);
+      M9 rot = ldm9(w.site_xmat, id);
+      V3 o = mulTv(rot, t == SENS_FORCE ? frc : tq);
+      out[0] = o.x; out[1] = o.y; out[2] = o.z;
+    } else if (t == SENS_TOUCH) {
+      const int b = MI(m, MH_SITE_BODYID)[id];
+      const float* sz = MF(m, MH_SITE_SIZE) + 3 * id;
+      const int site_type = MI(m, MH_SITE_TYPE)[id];
+      M9 rot = ldm9(w.site_xmat, id);
+      V3 sp = LD3(w.site_xpos, id);
+      float total = 0.0f;
+      for (int c = 0; c < ncon; c++) {
+        const int a = w.con_efc[c];
+        if (a < 0) continue;
+        const int p = w.con_pair[c];
+        const int b1 = gbody[pg1[p]], b2 = gbody[pg2[p]];
+        if (b1 != b && b2 != b) continue;
+        V3 loc = mulTv(rot, LD3(w.con_pos, c) - sp);
+        bool inside;
+        if (site_type == 6) inside = fabsf(loc.x) <= sz[0] && fabsf(loc.y) <= sz[1] && fabsf(loc.z) <= sz[2];
+        else inside = dot(loc, loc) <= sz[0] * sz[0];
+        if (!inside) continue;
+        const int nr = MI(m, MH_PAIR_DIM)[p] == 1 ? 1 : 4;
+        for (int k = 0; k < nr; k++) total += w.efc_force[a + k];
+      }
+      out[0] = total;
+    }
+  }
+  WSYNC();
+}
+
+// --------------------------------------------------------------------------------------------- top level
+
+template <class D>
+DEV void forward(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = m.h[MH_NV];
+  kinematics(m, w, LANE_PASS);
+  com_pos(m, w, LANE_PASS);
+  crb_mass_matrix(m, w, LANE_PASS);
+  collision(m, w, LANE_PASS);
+  com_vel(m, w, LANE_PASS);
+  make_constraint(m, w, LANE_PASS);
+  passive(m, w, LANE_PASS);
+  rne(m, w, LANE_PASS);
+  sensors_pos_vel(m, w, LANE_PASS);
+  actuation(m, w, LANE_PASS);
+  chol_factor(w, w.M, nullptr, 0.0f, nv, LANE_PASS);
+  acceleration(m, w, LANE_PASS);
+  solve(m, w, LANE_PASS);
+  sensors_acc(m, w, LANE_PASS);
+}
+
+// implicitfast with Euler damping disabled: (M + dt*diag(damping)) qacc = qfrc_smooth + qfrc_constraint
+template <class D>
+DEV void physics_step(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = m.h[MH_NV], nj = m.h[MH_NJNT];
+  const float dt = m.mf[MF_TIMESTEP];
+  forward(m, w, LANE_PASS);
+  chol_factor(w, w.M, w.damping, dt, nv, LANE_PASS);
+  LANE_FOR(i, nv) w.s_grad[i] = w.qfrc_smooth[i] + w.qfrc_constraint[i];
+  WSYNC();
+  chol_solve(w, w.s_Mgrad, w.s_grad, nv, LANE_PASS);
+  LANE_FOR(i, nv) w.qvel[i] += w.s_Mgrad[i] * dt;
+  WSYNC();
+  const int* jtype = MI(m, MH_JNT_TYPE);
+  const int* jqpos = MI(m, MH_JNT_QPOSADR);
+  const int* jdof = MI(m, MH_JNT_DOFADR);
+  LANE_FOR(j, nj) {
+    const int qa = jqpos[j], da = jdof[j];
+    if (jtype[j] == JNT_FREE) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) w.qpos[qa + k] += dt * w.qvel[da + k];
+      V3 wv = v3(w.qvel[da + 3], w.qvel[da + 4], w.qvel[da + 5]);
+      const float n = sqrtf(dot(wv, wv));
+      const float inv = 1.0f / (n + (n == 0 ? MINVAL : 0.0f));
+      Q4 qr = axis_angle(wv * inv, dt * n);
+      Q4 q; q.w = w.qpos[qa + 3]; q.x = w.qpos[qa + 4]; q.y = w.qpos[qa + 5]; q.z = w.qpos[qa + 6];
+      q = qnormalize(qmul(q, qr));
+      w.qpos[qa + 3] = q.w; w.qpos[qa + 4] = q.x; w.qpos[qa + 5] = q.y; w.qpos[qa + 6] = q.z;
+    } else {
+      w.qpos[qa] += dt * w.qvel[da];
+    }
+  }
+  IF_LANE0 w.time += dt;
+  WSYNC();
+}
+
+}  // namespace b2s

@@ -1,0 +1,238 @@
+// b200sim: reward evaluation over a finished rollout -- one warp per environment, lanes over time steps.
+//
+// Replaces get_rewards (ksim/task/rl.py:189-245) and the reward plugins of ksim/rewards.py listed in
+// include/b200sim_codes.h (REW_*).  Stateless rewards are evaluated lane-parallel over the T steps; the two
+// stateful ones (FeetAirTimeReward rewards.py:993-1085, SparseTargetHeightReward rewards.py:1149-1192) are
+// short sequential scans done by lane 0.  rec: [T][N][R]; total: [N][T]; comps: [K][N][T]; carry: [N][C].
+#pragma once
+
+#include "b2s_common.cuh"
+
+namespace b2s {
+
+#ifndef TAB
+#define TAB(ti, base, i, f) ((ti)[(ti)[base] + (i) * TAB_STRIDE + (f)])
+#endif
+
+DEV float exp_kernel_pen(float x, float scale, float sq, float ab) {
+  return fabsf(x) * -ab + x * x * -sq + expf(-(x * x) / (2 * scale * scale));
+}
+DEV float exp_kernel(float x, float scale) { return expf(-(x * x) / (2 * scale * scale)); }
+DEV float norm_fn(float x, int l2) { return l2 ? x * x : fabsf(x); }
+
+DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, float level, float* carry, float* total,
+                     float* comps, size_t cstride, LANE_ARG) {
+  const int* ti = m.ti;
+  const float* tf = m.tf;
+  const float* ef = tf + ti[TI_ENGINE_FOFF];
+  const int nq = m.h[MH_NQ], nv = m.h[MH_NV];
+  const int nrew = ti[TI_N_REW];
+  const int QP = ti[TI_R_QPOS], QV = ti[TI_R_QVEL], OB = ti[TI_R_OBS], CM = ti[TI_R_CMD], AC = ti[TI_R_ACTION];
+  const int DN = ti[TI_R_DONE], SC = ti[TI_R_SUCCESS], LV = ti[TI_R_LEVEL];
+  const int na = ti[TI_ACTION_SIZE];
+#define REC(tt, off) rec[(size_t)(tt) * tstride + (off)]
+  const int done_last = REC(T - 1, DN) != 0.0f;
+  LANE_FOR(s, T) total[s] = 0.0f;
+  for (int r = 0; r < nrew; r++) {
+    const int type = TAB(ti, TI_REW_TAB, r, TAB_TYPE);
+    const int* xi = ti + TAB(ti, TI_REW_TAB, r, TAB_IOFF) + SCALE_NI;
+    const float* xf = tf + TAB(ti, TI_REW_TAB, r, TAB_FOFF) + SCALE_NF;
+    const int c0 = TAB(ti, TI_REW_TAB, r, TAB_OUT_OFF), ncomp = TAB(ti, TI_REW_TAB, r, TAB_OUT_DIM);
+    const int coff = TAB(ti, TI_REW_TAB, r, TAB_AUX0), cdim = TAB(ti, TI_REW_TAB, r, TAB_AUX1);
+    float scale = scale_get(ti[TAB(ti, TI_REW_TAB, r, TAB_IOFF)], tf + TAB(ti, TI_REW_TAB, r, TAB_FOFF), level);
+    if (TAB(ti, TI_REW_TAB, r, TAB_AUX2)) scale = -scale;
+    float* o0 = comps + (size_t)c0 * cstride;
+#define OUT(c, s) o0[(size_t)(c) * cstride + (s)]
+    float* cr = coff >= 0 ? carry + coff : nullptr;
+    if (cr && done_last) { LANE_FOR(k, cdim) cr[k] = 0.0f; }
+    WSYNC();
+    switch (type) {
+      case REW_STAY_ALIVE:
+        LANE_FOR(s, T) {
+          const float alive = 1.0f / xf[0];
+          OUT(0, s) = REC(s, DN) != 0.0f ? (REC(s, SC) != 0.0f ? (xi[0] ? xf[1] : alive) : -1.0f) : alive;
+        }
+        break;
+      case REW_UPRIGHT:
+        LANE_FOR(s, T) {
+          Q4 q; q.w = REC(s, QP + 3); q.x = REC(s, QP + 4); q.y = REC(s, QP + 5); q.z = REC(s, QP + 6);
+          V3 zb = rot_vec_quat(v3(0, 0, 1), q, true);
+          OUT(0, s) = exp_kernel_pen(REC(s, QV + 4), xf[0], xf[3], xf[4]);
+          OUT(1, s) = exp_kernel_pen(REC(s, QV + 2), xf[1], xf[5], xf[6]);
+          OUT(2, s) = exp_kernel_pen(atan2f(zb.x, zb.z), xf[2], xf[7], xf[8]);
+        }
+        break;
+      case REW_LINEAR_VELOCITY:
+        LANE_FOR(s, T) {
+          const float* cmd = &REC(s, CM + xi[0]);
+          Q4 q; q.w = REC(s, QP + 3); q.x = REC(s, QP + 4); q.y = REC(s, QP + 5); q.z = REC(s, QP + 6);
+          V3 lv = rot_vec_quat(v3(REC(s, QV), REC(s, QV + 1), REC(s, QV + 2)), q, true);
+          const float vel = sqrtf(lv.x * lv.x + lv.y * lv.y), yaw = atan2f(lv.y, lv.x);
+          const bool is_zero = fabsf(cmd[0]) < xf[2];
+          OUT(0, s) = exp_kernel_pen(vel - cmd[0], xf[0], xf[3], xf[4]);
+          OUT(1, s) = is_zero ? 0.0f : exp_kernel_pen(yaw - cmd[1], xf[1], xf[3], xf[4]);
+          OUT(2, s) = is_zero ? 0.0f : exp_kernel_pen(lv.x - cmd[2], xf[0], xf[3], xf[4]);
+          OUT(3, s) = is_zero ? 0.0f : exp_kernel_pen(lv.y - cmd[3], xf[0], xf[3], xf[4]);
+        }
+        break;
+      case REW_ANGULAR_VELOCITY:
+        LANE_FOR(s, T) {
+          const float cv = REC(s, CM + xi[0]), av = REC(s, QV + 5);
+          const float rs = fabsf(av) < xf[3] ? 0.0f : (av > 0 ? 1.0f : (av < 0 ? -1.0f : 0.0f));
+          const float cs = fabsf(cv) < xf[3] ? 0.0f : (cv > 0 ? 1.0f : (cv < 0 ? -1.0f : 0.0f));
+          OUT(0, s) = exp_kernel_pen(av - cv, xf[0], xf[1], xf[2]);
+          OUT(1, s) = rs == cs ? 1.0f : -1.0f;
+        }
+        break;
+      case REW_FEET_AIR_TIME:
+        IF_LANE0 {
+          const int coffs = xi[0], nf = xi[1], rows = xi[2], lcmd = xi[3], acmd = xi[4], gp_kind = xi[5];
+          const float air_pct = xf[0], ctrl_dt = xf[1], bias = xf[2], gpen = xf[4], lthr = xf[5], athr = xf[6];
+          for (int s = 0; s < T; s++) {
+            const float gp = scale_get(gp_kind, xf + 7, REC(s, LV));
+            const float air_steps = rintf(gp * air_pct / ctrl_dt), gnd_steps = rintf(gp * (1.0f - air_pct) / ctrl_dt);
+            const bool mlin = lcmd < 0 ? (sqrtf(REC(s, QV) * REC(s, QV) + REC(s, QV + 1) * REC(s, QV + 1)) > lthr)
+                                       : (fabsf(REC(s, CM + lcmd)) > lthr);
+            const bool mang = acmd < 0 ? (REC(s, QV + 5) > athr) : (fabsf(REC(s, CM + acmd)) > athr);
+            const bool moving = (mlin || mang) && !(REC(s, DN) != 0.0f);
+            float air_r = -INFINITY, gnd_r = -INFINITY, st_r = -INFINITY;
+            for (int f = 0; f < nf; f++) {
+              bool contact = false;
+              for (int rr = 0; rr < rows; rr++) contact |= REC(s, OB + coffs + rr * nf + f) > 0.5f;
+              float air = cr[f], gnd = cr[nf + f], stg = cr[2 * nf + f];
+              air = (!contact && moving) ? air + 1 : 0.0f;
+              gnd = (contact && moving) ? gnd + 1 : 0.0f;
+              stg = (contact && !moving) ? stg + 1 : 0.0f;
+              cr[f] = air; cr[nf + f] = gnd; cr[2 * nf + f] = stg;
+              const float a = air < air_steps ? air / air_steps + bias : 0.0f;
+              const float g = gnd < gnd_steps ? gnd / gnd_steps + bias : -gpen;
+              const float q = clipf(stg / gnd_steps, 0.0f, 1.0f) + bias;
+              air_r = fmaxf(air_r, a); gnd_r = fmaxf(gnd_r, g); st_r = fmaxf(st_r, q);
+            }
+            OUT(0, s) = air_r; OUT(1, s) = gnd_r; OUT(2, s) = st_r;
+          }
+        }
+        break;
+      case REW_SPARSE_TARGET_HEIGHT:
+        IF_LANE0 {
+          const int coffs = xi[0], poff = xi[1], nbd = xi[2], rows = xi[3];
+          for (int s = 0; s < T; s++) {
+            const bool nm_lin = sqrtf(REC(s, QV) * REC(s, QV) + REC(s, QV + 1) * REC(s, QV + 1)) < xf[1];
+            const bool nm_ang = REC(s, QV + 5) < xf[2];
+            const bool not_moving = (nm_lin && nm_ang) || (REC(s, DN) != 0.0f);
+            float best = -INFINITY;
+            for (int b = 0; b < nbd; b++) {
+              bool contact = false;
+              for (int rr = 0; rr < rows; rr++) contact |= REC(s, OB + coffs + rr * nbd + b) > 0.5f;
+              const float h = REC(s, OB + poff + 3 * b + 2);
+              float rw = contact ? cr[b] : 0.0f;
+              if (rw > xf[0]) rw = xf[0];
+              float mh = cr[b] > h ? cr[b] : h;
+              if (not_moving || contact) mh = 0.0f;
+              cr[b] = mh;
+              best = fmaxf(best, rw);
+            }
+            OUT(0, s) = best;
+          }
+        }
+        break;
+      case REW_FORCE_PENALTY:
+        LANE_FOR(s, T) {
+          float best = -INFINITY;
+          for (int rr = 0; rr < xi[1]; rr++) {
+            float n2 = 0.0f;
+            for (int k = 0; k < xi[2]; k++) { const float v = REC(s, OB + xi[0] + rr * xi[2] + k); n2 += v * v; }
+            float o = sqrtf(n2) - xf[2];
+            if (o < 0) o = 0.0f;
+            const float p = (o / xf[1]) * (o / xf[1]);
+            best = fmaxf(best, p);
+          }
+          OUT(0, s) = best;
+        }
+        break;
+      case REW_MOTIONLESS_AT_REST:
+        LANE_FOR(s, T) {
+          const bool nm_lin = sqrtf(REC(s, QV) * REC(s, QV) + REC(s, QV + 1) * REC(s, QV + 1)) < xf[0];
+          const bool nm_ang = REC(s, QV + 5) < xf[1];
+          float n2 = 0.0f;
+          for (int k = 6; k < nv; k++) n2 += REC(s, QV + k) * REC(s, QV + k);
+          OUT(0, s) = (nm_lin && nm_ang) ? sqrtf(n2) : 0.0f;
+        }
+        break;
+      case REW_ACTION_VELOCITY: case REW_ACTION_ACCELERATION: case REW_ACTION_JERK: {
+        // rewards.py:400-463: edge-padded finite differences with done masking (tests/test_rewards.py:60-271)
+        const int order = type - REW_ACTION_VELOCITY + 1;
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int k = 0; k < na; k++) {
+#define APAD(p) REC(((p) - order) > 0 ? ((p) - order) : 0, AC + k)
+#define DPAD(p) (REC(((p) - order) > 0 ? ((p) - order) : 0, DN) != 0.0f)
+#define VEL(i) (DPAD(i) ? 0.0f : APAD((i) + 1) - APAD(i))
+#define ACC(i) (DPAD((i) + 1) ? 0.0f : VEL((i) + 1) - VEL(i))
+#define JRK(i) (DPAD((i) + 2) ? 0.0f : ACC((i) + 1) - ACC(i))
+            const float v = order == 1 ? VEL(s) : (order == 2 ? ACC(s) : JRK(s));
+            acc += norm_fn(v, xi[0]);
+#undef APAD
+#undef DPAD
+#undef VEL
+#undef ACC
+#undef JRK
+          }
+          OUT(0, s) = s >= order ? acc / (float)na : 0.0f;
+        }
+      } break;
+      case REW_BASE_HEIGHT:
+        LANE_FOR(s, T) OUT(0, s) = exp_kernel(REC(s, QP + 2) - xf[0], xf[1]);
+        break;
+      case REW_BASE_HEIGHT_RANGE:
+        LANE_FOR(s, T) {
+          const float h = REC(s, QP + 2), lo = xf[0] - h, hi = h - xf[1];
+          float mx = fmaxf(fmaxf(lo, hi), 0.0f);
+          const float v = 1.0f - mx * xf[2];
+          OUT(0, s) = v < 0 ? 0.0f : v;
+        }
+        break;
+      case REW_OFF_AXIS_VELOCITY:
+        LANE_FOR(s, T) {
+          OUT(0, s) = exp_kernel(REC(s, QV + 2), xf[0]);
+          OUT(1, s) = exp_kernel(REC(s, QV + 4), xf[1]);
+          OUT(2, s) = exp_kernel(REC(s, QV + 5), xf[1]);
+        }
+        break;
+      case REW_SMALL_JOINT_VELOCITY:
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          const int prev = s > 0 ? s - 1 : 0;
+          const bool dn = REC(prev, DN) != 0.0f;
+          for (int k = 7; k < nq; k++) {
+            const float v = (dn || s == 0) ? 0.0f : REC(s, QP + k) - REC(prev, QP + k);
+            acc += exp_kernel(v, xf[0]);
+          }
+          OUT(0, s) = acc / (float)(nq - 7);
+        }
+        break;
+      default:
+        for (int c = 0; c < ncomp; c++) { LANE_FOR(s, T) OUT(c, s) = 0.0f; }
+        break;
+    }
+    WSYNC();
+    for (int c = 0; c < ncomp; c++) {
+      LANE_FOR(s, T) {
+        const float v = OUT(c, s) * scale;
+        OUT(c, s) = v;
+        total[s] += v;
+      }
+    }
+    WSYNC();
+#undef OUT
+  }
+  LANE_FOR(s, T) {
+    float sum = total[s];
+    if (ef[7] == ef[7] && sum < ef[7]) sum = ef[7];
+    if (ef[8] == ef[8] && sum > ef[8]) sum = ef[8];
+    total[s] = sum;
+  }
+#undef REC
+}
+
+}  // namespace b2s

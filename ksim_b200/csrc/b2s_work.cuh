@@ -1,0 +1,78 @@
+// b200sim: compile-time size traits and the per-warp shared-memory workspace.
+#pragma once
+
+#include "b2s_common.cuh"
+
+namespace b2s {
+
+// Size traits.  A kernel instantiation serves every model whose sizes are <= the traits' (exact match is
+// fastest because lane loops collapse to a single predicated pass).
+template <int NQ_, int NV_, int NB_, int NJ_, int NU_, int NS_, int NSD_, int NPAIR_, int NCON_, int NDENSE_, int NLIMIT_,
+          int NFRIC_>
+struct Dims {
+  static constexpr int NQ = NQ_, NV = NV_, NB = NB_, NJ = NJ_, NU = NU_, NS = NS_, NSD = NSD_;
+  static constexpr int NPAIR = NPAIR_, NCON = NCON_, NDENSE = NDENSE_, NLIMIT = NLIMIT_, NFRIC = NFRIC_;
+  static constexpr int NA = 2 * NU_;          // PositionVelocityActuator doubles the action
+  static constexpr int NVP = NV_ | 1;         // odd row stride: conflict-free column access
+  static constexpr int NSPARSE = NFRIC_ + NLIMIT_;
+  static constexpr int NEFC = NFRIC_ + NLIMIT_ + NDENSE_;
+  static constexpr int EVS = 16;              // event state floats
+  static constexpr int ACS = 2 * NU_ + 3;     // PositionActuators state
+  static constexpr int CMDS = 24;             // command floats
+  static constexpr int OCS = 16;              // observation carry floats
+  static constexpr int NOBS = 32;             // observation plugins (bias keys)
+};
+
+// examples/data/scene.mjcf (walking.py): nq 24 nv 23 nbody 17 njnt 18 nu 17 nsite 3 nsensordata 54,
+// 2 sphere-plane pairs condim 1, 17 limited hinges, no frictionloss.
+using DimsHumanoid = Dims<24, 23, 17, 18, 17, 3, 54, 2, 2, 2, 17, 0>;
+// examples/kbot/robot/kbot-headless/robot.mjcf: nq 27 nv 26 nbody 24 nu 20, 4 capsule-plane pairs condim 3
+// (8 contacts x 4 pyramid rows), 20 limited hinges, 20 frictionloss dofs.
+using DimsKbot = Dims<27, 26, 24, 21, 20, 4, 56, 4, 8, 32, 20, 20>;
+// anything else that fits one dof / body per lane
+using DimsGeneric = Dims<33, 32, 32, 32, 32, 8, 96, 8, 16, 64, 32, 32>;
+
+template <class D>
+struct Work {
+  // ---- persistent per-env state (mirrors the HBM state block) ----
+  float qpos[D::NQ], qvel[D::NV], qacc[D::NV], warm[D::NV], ctrl[D::NU];
+  float last_ctrl[D::NA], zero_off[D::NU], event[D::EVS], act_state[D::ACS], cmd[D::CMDS], obs_carry[D::OCS];
+  float time, latency, level, nonfinite;
+  uint32_t keys[2 + 2 * D::NOBS];
+  // ---- per-env model overrides (ksim/randomization.py); filled from the base model then the rand block ----
+  float armature[D::NV], damping[D::NV], frictionloss[D::NV];
+  float body_mass[D::NB], body_inertia[3][D::NB], body_ipos[3][D::NB];
+  // ---- position stage ----
+  float xpos[3][D::NB], xquat[4][D::NB], xmat[9][D::NB], xipos[3][D::NB], ximat[9][D::NB];
+  float subtree_com[3][D::NB], cinert[10][D::NB], crb[10][D::NB];
+  float xanchor[3][D::NJ], xaxis[3][D::NJ];
+  float cdof[6][D::NV], cdof_dot[6][D::NV];
+  float site_xpos[3][D::NS], site_xmat[9][D::NS];
+  float M[D::NV][D::NVP], W[D::NV][D::NVP];  // mass matrix, work matrix (Cholesky factors)
+  float Linv_diag[D::NV];                     // 1 / diag of the factor in W
+  // ---- contacts ----
+  float con_dist[D::NCON], con_pos[3][D::NCON], con_frame[9][D::NCON];
+  int con_pair[D::NCON], con_efc[D::NCON];
+  // ---- velocity / force stage ----
+  float cvel[6][D::NB], cacc[6][D::NB], cfrc[6][D::NB], cfrc_ext[6][D::NB];
+  float xfrc[6];                              // Cartesian wrench of the ForcePush event (one body)
+  int xfrc_body;
+  float qfrc_passive[D::NV], qfrc_bias[D::NV], qfrc_actuator[D::NV], qfrc_smooth[D::NV], qacc_smooth[D::NV];
+  float qfrc_constraint[D::NV], actuator_force[D::NU];
+  // ---- constraints ----
+  int nefc, nsparse;                          // rows [0,nsparse) are single-dof rows, [nsparse,nefc) dense
+  int efc_type[D::NEFC], efc_dof[D::NEFC];
+  float efc_sign[D::NEFC], efc_aref[D::NEFC], efc_D[D::NEFC], efc_R[D::NEFC], efc_floss[D::NEFC];
+  float efc_force[D::NEFC], efc_Jaref[D::NEFC], efc_jv[D::NEFC];
+  int efc_active[D::NEFC];
+  float Jd[D::NDENSE][D::NVP];
+  // ---- solver vectors ----
+  float s_qacc[D::NV], s_Ma[D::NV], s_grad[D::NV], s_Mgrad[D::NV], s_search[D::NV], s_mv[D::NV], s_tmp[D::NV];
+  float sensordata[D::NSD];
+  float torque[D::NU], action[D::NA], ctrl_blend[D::NA];
+  int drop[D::NA];
+  int scratch_i[8];
+  float scratch_f[8];
+};
+
+}  // namespace b2s

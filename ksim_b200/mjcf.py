@@ -22,7 +22,7 @@ from typing import Any
 
 import numpy as np
 
-__all__ = ["Model", "MjcfError", "load_mjcf", "load_mjcf_string", "GEOM", "JNT", "SENSOR", "OBJ"]
+__all__ = ["Model", "MjcfError", "load_mjcf", "load_mjcf_string", "save_model", "load_model", "GEOM", "JNT", "SENSOR", "OBJ"]
 
 
 class MjcfError(ValueError):
@@ -1091,3 +1091,30 @@ def load_mjcf(path: str | Path) -> Model:
 
 def load_mjcf_string(xml: str) -> Model:
     return _compile(ET.fromstring(xml))
+
+
+# --------------------------------------------------------------------------------------------------
+# compiled-model (de)serialisation: one .npz with every array plus a JSON side-car entry
+# --------------------------------------------------------------------------------------------------
+
+
+def save_model(model: Model, path: str | Path) -> None:
+    """Writes a compiled model as ``.npz`` (arrays) with names / options / constants as a JSON string entry."""
+    import json
+
+    meta = dict(
+        name=model.name, meaninertia=model.meaninertia, names=model.names, custom_numeric=model.custom_numeric,
+        opt={k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in vars(model.opt).items()},
+    )
+    np.savez_compressed(str(path), __meta__=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **model.arrays)
+
+
+def load_model(path: str | Path) -> Model:
+    import json
+
+    with np.load(str(path)) as z:
+        meta = json.loads(bytes(z["__meta__"]).decode())
+        arrays = {k: z[k] for k in z.files if k != "__meta__"}
+    opt = Options(**{k: (np.array(v, dtype=np.float64) if k == "gravity" else v) for k, v in meta["opt"].items()})
+    return Model(name=meta["name"], opt=opt, meaninertia=float(meta["meaninertia"]), arrays=arrays,
+                 names={k: list(v) for k, v in meta["names"].items()}, custom_numeric=dict(meta["custom_numeric"]))

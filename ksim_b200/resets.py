@@ -1,0 +1,129 @@
+"""Reset plugins applied to a fresh state before the reset-time forward pass.  Mirrors ksim/resets.py:36-354."""
+
+from __future__ import annotations
+
+__all__ = [
+    "Reset", "PlaneXYPositionReset", "RandomJointPositionReset", "RandomJointVelocityReset",
+    "RandomBaseVelocityXYReset", "RandomHeadingReset", "RandomHeightReset", "RandomPitchRollReset",
+    "get_xy_position_reset",
+]
+
+from abc import ABC, abstractmethod
+
+import attrs
+
+from ksim_b200 import codes as C
+from ksim_b200.mjcf import GEOM, JNT, Model
+
+
+@attrs.define(frozen=True, kw_only=True)
+class Reset(ABC):
+    @abstractmethod
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]: ...
+
+
+@attrs.define(frozen=True, kw_only=True)
+class PlaneXYPositionReset(Reset):
+    bounds: tuple[float, float, float]
+    padded_bounds: tuple[float, float, float, float]
+    x_range: float = attrs.field(default=5.0)
+    y_range: float = attrs.field(default=5.0)
+    robot_base_height: float = attrs.field(default=0.0)
+
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
+        return C.RESET_PLANE_XY_POSITION, [], [self.bounds[2] + self.robot_base_height, self.x_range, self.y_range, *self.padded_bounds]
+
+
+@attrs.define(frozen=True, kw_only=True)
+class RandomJointPositionReset(Reset):
+    scale: float = attrs.field(default=0.01)
+    scale_by_curriculum: bool = attrs.field(default=True)
+    zeros: tuple[float, ...] | None = attrs.field(default=None)
+    mins: tuple[float, ...] | None = attrs.field(default=None)
+    maxs: tuple[float, ...] | None = attrs.field(default=None)
+
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
+        nj = model.nq - 7
+        def vec(v: tuple[float, ...] | None) -> list[float]:
+            if v is None:
+                return [0.0] * nj
+            if len(v) != nj:
+                raise ValueError(f"expected {nj} joint values, got {len(v)}")
+            return [float(x) for x in v]
+        ints = [int(self.scale_by_curriculum), int(self.zeros is not None), int(self.mins is not None), int(self.maxs is not None)]
+        return C.RESET_RANDOM_JOINT_POSITION, ints, [float(self.scale)] + vec(self.zeros) + vec(self.mins) + vec(self.maxs)
+
+    @classmethod
+    def create(cls, physics_model: Model, zeros: dict[str, float] | None = None, scale: float = 0.01,
+               scale_by_curriculum: bool = True) -> "RandomJointPositionReset":
+        joint_names = physics_model.names["joint"][1:]  # remove the root joint (resets.py:156)
+        rng = physics_model.jnt_range[1:]
+        zeros_values = [0.0] * len(joint_names)
+        mins, maxs = [float(r[0]) for r in rng], [float(r[1]) for r in rng]
+        if zeros is not None:
+            for name, value in zeros.items():
+                if name not in joint_names:
+                    raise ValueError(f"Joint {name} not found in model. Choices are: {joint_names}")
+                index = joint_names.index(name)
+                if value < mins[index] or value > maxs[index]:
+                    raise ValueError(f"Zero value {value} for joint {name} is out of range {mins[index]}, {maxs[index]}")
+                zeros_values[index] = value
+        return cls(scale=scale, zeros=tuple(zeros_values), mins=tuple(mins), maxs=tuple(maxs), scale_by_curriculum=scale_by_curriculum)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class RandomJointVelocityReset(Reset):
+    scale: float = attrs.field(default=0.01)
+    scale_by_curriculum: bool = attrs.field(default=True)
+
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
+        return C.RESET_RANDOM_JOINT_VELOCITY, [int(self.scale_by_curriculum)], [float(self.scale)]
+
+
+@attrs.define(frozen=True, kw_only=True)
+class RandomBaseVelocityXYReset(Reset):
+    """A no-op for the dynamics, exactly as on the reference's MJX path (ksim/resets.py:204-206)."""
+
+    scale: float = attrs.field(default=0.01)
+
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
+        return C.RESET_RANDOM_BASE_VELOCITY_XY, [], [float(self.scale)]
+
+
+@attrs.define(frozen=True, kw_only=True)
+class RandomHeadingReset(Reset):
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
+        return C.RESET_RANDOM_HEADING, [], []
+
+
+@attrs.define(frozen=True, kw_only=True)
+class RandomHeightReset(Reset):
+    range: tuple[float, float] = attrs.field(default=(0.0, 0.1))
+
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
+        return C.RESET_RANDOM_HEIGHT, [], [*self.range]
+
+
+@attrs.define(frozen=True, kw_only=True)
+class RandomPitchRollReset(Reset):
+    pitch_range: tuple[float, float] = attrs.field(default=(-0.1, 0.1))
+    roll_range: tuple[float, float] = attrs.field(default=(-0.1, 0.1))
+
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
+        return C.RESET_RANDOM_PITCH_ROLL, [], [*self.pitch_range, *self.roll_range]
+
+
+def get_xy_position_reset(physics_model: Model, x_range: float = 5.0, y_range: float = 5.0, x_edge_padding: float = 5.0,
+                          y_edge_padding: float = 5.0, robot_base_height: float = 0.0) -> Reset:
+    """Plane-floor variant of ksim/resets.py:210-280 (height fields are outside the supported subset)."""
+    planes = [i for i, t in enumerate(physics_model.geom_type) if t == GEOM.PLANE]
+    if not planes:
+        raise ValueError("No heightfield or plane geom found in the model. MuJoCo scene missing floor!")
+    x_bound = y_bound = 5.0
+    z_pos = float(physics_model.geom_pos[planes[0]][2])
+    padded = (-x_bound + x_edge_padding, x_bound - x_edge_padding, -y_bound + y_edge_padding, y_bound - y_edge_padding)
+    return PlaneXYPositionReset(bounds=(x_bound, y_bound, z_pos), padded_bounds=padded, x_range=x_range, y_range=y_range,
+                                robot_base_height=robot_base_height)
+
+
+_ = JNT  # re-exported for plugin authors

@@ -1,0 +1,265 @@
+"""Reward plugins.  Mirrors ksim/rewards.py:96-1240 for the rewards the B200 reward kernel implements.
+
+Class names, constructor fields and the Reward/Penalty sign rule (rewards.py:118-124) follow the reference;
+evaluation happens in ``ksim_b200/csrc/b2s_rewards.cuh`` over the (T, N) trajectory records.
+``encode(ctx)`` -> (REW_* code, ints, floats, component names, carry floats); ``ctx`` resolves observation /
+command names to record offsets.
+"""
+
+from __future__ import annotations
+
+__all__ = [
+    "Reward", "StatefulReward", "StayAliveReward", "UprightReward", "LinearVelocityReward", "AngularVelocityReward",
+    "FeetAirTimeReward", "SparseTargetHeightReward", "ForcePenalty", "MotionlessAtRestPenalty",
+    "ActionVelocityPenalty", "ActionAccelerationPenalty", "ActionJerkPenalty", "BaseHeightReward",
+    "BaseHeightRangeReward", "OffAxisVelocityReward", "SmallJointVelocityReward", "exp_kernel",
+    "exp_kernel_with_penalty",
+]
+
+import math
+from abc import ABC, abstractmethod
+from typing import Protocol
+
+import attrs
+
+from ksim_b200 import codes as C
+from ksim_b200.scales import Scale, convert_to_scale
+
+Encoded = tuple[int, list[int], list[float], list[str], int]
+
+
+def exp_kernel(x: float, scale: float) -> float:
+    return math.exp(-(x * x) / (2 * scale**2))
+
+
+def exp_kernel_with_penalty(x: float, scale: float, sq_scale: float, abs_scale: float) -> float:
+    return abs(x) * -abs_scale + x * x * -sq_scale + math.exp(-(x * x) / (2 * scale**2))
+
+
+class EncodeContext(Protocol):
+    def obs_offset(self, name: str) -> int: ...
+    def obs_shape(self, name: str) -> tuple[int, ...]: ...
+    def cmd_offset(self, name: str, field: str | None = None) -> int: ...
+    def cmd_type(self, name: str) -> type: ...
+
+
+def _norm_flag(norm: str) -> int:
+    if norm not in ("l1", "l2"):
+        raise ValueError(f"Invalid norm: {norm}")
+    return int(norm == "l2")
+
+
+@attrs.define(frozen=True, kw_only=True)
+class Reward(ABC):
+    scale: Scale = attrs.field(converter=convert_to_scale)
+
+    @abstractmethod
+    def encode(self, ctx: EncodeContext) -> Encoded: ...
+
+    @property
+    def is_penalty(self) -> bool:
+        reward_name = self.__class__.__name__
+        if reward_name.lower().endswith("reward"):
+            return False
+        if reward_name.lower().endswith("penalty"):
+            return True
+        raise ValueError(f"Reward function {reward_name} does not end with 'Reward' or 'Penalty'")
+
+
+@attrs.define(frozen=True, kw_only=True)
+class StatefulReward(Reward):
+    pass
+
+
+@attrs.define(frozen=True, kw_only=True)
+class StayAliveReward(Reward):
+    balance: float = attrs.field(default=100.0)
+    success_reward: float | None = attrs.field(default=None)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        has = self.success_reward is not None
+        return C.REW_STAY_ALIVE, [int(has)], [float(self.balance), float(self.success_reward or 0.0)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class LinearVelocityReward(Reward):
+    cmd: str = attrs.field()
+    vel_length_scale: float = attrs.field(default=0.25)
+    yaw_length_scale: float = attrs.field(default=0.25)
+    zero_threshold: float = attrs.field(default=0.01)
+    vis_height: float = attrs.field(default=0.5)
+    sq_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    abs_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        floats = [self.vel_length_scale, self.yaw_length_scale, self.zero_threshold, self.sq_scale, self.abs_scale]
+        return C.REW_LINEAR_VELOCITY, [ctx.cmd_offset(self.cmd)], [float(f) for f in floats], ["vel", "yaw", "x", "y"], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class AngularVelocityReward(Reward):
+    cmd: str = attrs.field()
+    angvel_length_scale: float = attrs.field(default=0.25)
+    sq_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    abs_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    vis_height: float = attrs.field(default=0.5)
+    zero_threshold: float = attrs.field(default=math.radians(5.0))
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        floats = [self.angvel_length_scale, self.sq_scale, self.abs_scale, self.zero_threshold]
+        return C.REW_ANGULAR_VELOCITY, [ctx.cmd_offset(self.cmd)], [float(f) for f in floats], ["mag", "dir"], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class OffAxisVelocityReward(Reward):
+    lin_length_scale: float = attrs.field(default=0.25)
+    ang_length_scale: float = attrs.field(default=0.25)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_OFF_AXIS_VELOCITY, [], [float(self.lin_length_scale), float(self.ang_length_scale)], ["linz", "angx", "angy"], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class BaseHeightReward(Reward):
+    height_target: float = attrs.field()
+    norm: str = attrs.field(default="l1")
+    kernel_scale: float = attrs.field(default=0.25)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        _norm_flag(self.norm)
+        return C.REW_BASE_HEIGHT, [], [float(self.height_target), float(self.kernel_scale)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class BaseHeightRangeReward(Reward):
+    z_lower: float = attrs.field()
+    z_upper: float = attrs.field()
+    dropoff: float = attrs.field()
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_BASE_HEIGHT_RANGE, [], [float(self.z_lower), float(self.z_upper), float(self.dropoff)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class ActionVelocityPenalty(Reward):
+    norm: str = attrs.field(default="l2")
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_ACTION_VELOCITY, [_norm_flag(self.norm)], [], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class ActionAccelerationPenalty(Reward):
+    norm: str = attrs.field(default="l2")
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_ACTION_ACCELERATION, [_norm_flag(self.norm)], [], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class ActionJerkPenalty(Reward):
+    norm: str = attrs.field(default="l2")
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_ACTION_JERK, [_norm_flag(self.norm)], [], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class SmallJointVelocityReward(Reward):
+    kernel_scale: float = attrs.field(default=0.25)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_SMALL_JOINT_VELOCITY, [], [float(self.kernel_scale)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class UprightReward(Reward):
+    angvel_scale: float = attrs.field(default=0.25)
+    linvel_scale: float = attrs.field(default=0.25)
+    pose_scale: float = attrs.field(default=0.25)
+    angvel_sq_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    angvel_abs_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    linvel_sq_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    linvel_abs_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    pose_sq_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    pose_abs_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        floats = [self.angvel_scale, self.linvel_scale, self.pose_scale, self.angvel_sq_scale, self.angvel_abs_scale,
+                  self.linvel_sq_scale, self.linvel_abs_scale, self.pose_sq_scale, self.pose_abs_scale]
+        return C.REW_UPRIGHT, [], [float(f) for f in floats], ["angvel", "linvel", "pose"], 0
+
+
+def _contact_rows(ctx: EncodeContext, contact_obs: str, n: int) -> int:
+    shape = ctx.obs_shape(contact_obs)
+    if len(shape) != 2 or shape[-1] != n:
+        raise ValueError(f"contact observation {contact_obs} has shape {shape}, expected (rows, {n})")
+    return shape[0]
+
+
+@attrs.define(frozen=True, kw_only=True)
+class FeetAirTimeReward(StatefulReward):
+    gait_period: Scale = attrs.field(converter=convert_to_scale)
+    air_time_percent: float = attrs.field()
+    ctrl_dt: float = attrs.field()
+    contact_obs: str = attrs.field()
+    num_feet: int = attrs.field(default=2)
+    bias: float = attrs.field(default=0.0)
+    alpha: float = attrs.field(default=0.1)
+    ground_penalty: float = attrs.field(default=0.1)
+    linvel_moving_threshold: float = attrs.field(default=0.1)
+    angvel_moving_threshold: float = attrs.field(default=math.radians(10))
+    linvel_cmd: str | None = attrs.field(default=None)
+    angvel_cmd: str | None = attrs.field(default=None)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        rows = _contact_rows(ctx, self.contact_obs, self.num_feet)
+        lcmd = -1 if self.linvel_cmd is None else ctx.cmd_offset(self.linvel_cmd, "vel")
+        acmd = -1 if self.angvel_cmd is None else ctx.cmd_offset(self.angvel_cmd, "vel")
+        gi, gf = self.gait_period.encode()
+        ints = [ctx.obs_offset(self.contact_obs), self.num_feet, rows, lcmd, acmd, gi[0]]
+        floats = [self.air_time_percent, self.ctrl_dt, self.bias, self.alpha, self.ground_penalty,
+                  self.linvel_moving_threshold, self.angvel_moving_threshold, *gf]
+        return C.REW_FEET_AIR_TIME, ints, [float(f) for f in floats], ["air", "gnd", "stationary_gnd"], 3 * self.num_feet
+
+
+@attrs.define(frozen=True, kw_only=True)
+class SparseTargetHeightReward(StatefulReward):
+    contact_obs: str = attrs.field()
+    position_obs: str = attrs.field()
+    height: float = attrs.field()
+    num_bodies: int = attrs.field(default=2)
+    linvel_moving_threshold: float = attrs.field(default=0.5)
+    angvel_moving_threshold: float = attrs.field(default=math.radians(30))
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        rows = _contact_rows(ctx, self.contact_obs, self.num_bodies)
+        if ctx.obs_shape(self.position_obs) != (self.num_bodies, 3):
+            raise ValueError(f"position observation {self.position_obs} must have shape ({self.num_bodies}, 3)")
+        ints = [ctx.obs_offset(self.contact_obs), ctx.obs_offset(self.position_obs), self.num_bodies, rows]
+        floats = [self.height, self.linvel_moving_threshold, self.angvel_moving_threshold]
+        return C.REW_SPARSE_TARGET_HEIGHT, ints, [float(f) for f in floats], [""], self.num_bodies
+
+
+@attrs.define(frozen=True, kw_only=True)
+class MotionlessAtRestPenalty(Reward):
+    linvel_moving_threshold: float = attrs.field(default=0.5)
+    angvel_moving_threshold: float = attrs.field(default=math.radians(30))
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_MOTIONLESS_AT_REST, [], [float(self.linvel_moving_threshold), float(self.angvel_moving_threshold)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class ForcePenalty(Reward):
+    force_obs: str = attrs.field()
+    ctrl_dt: float = attrs.field()
+    expected_weight: float = attrs.field()
+    bias: float = attrs.field(default=0.0)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        shape = ctx.obs_shape(self.force_obs)
+        if len(shape) != 2:
+            raise ValueError(f"force observation {self.force_obs} must be (rows, dim), got {shape}")
+        ints = [ctx.obs_offset(self.force_obs), shape[0], shape[1]]
+        return C.REW_FORCE_PENALTY, ints, [float(self.ctrl_dt), float(self.expected_weight), float(self.bias)], [""], 0

@@ -144,3 +144,93 @@ class OracleData:
             self.lib.o_data_free(self.ptr)
         except Exception:  # noqa: BLE001
             pass
+
+
+# ---------------------------------------------------------------------------------------------------------
+# engine-level entry points (oracle/engine.c): env-major buffers, layouts from the task program ti[]
+# ---------------------------------------------------------------------------------------------------------
+
+
+class OracleEngine:
+    """Batch front-end of o_init_envs / o_step_ctrl / o_rewards / o_gae for a ``ksim_b200.program.TaskProgram``."""
+
+    def __init__(self, program: Any, precision: str = "f32") -> None:  # noqa: ANN401
+        self.program = program
+        self.precision = precision
+        self.real = np.float32 if precision == "f32" else np.float64
+        self.lib = lib(precision)
+        self.model = OracleModel(program.spec.model, precision)
+        self.ti = np.ascontiguousarray(program.ti, dtype=np.int32)
+        self.tf = np.ascontiguousarray(program.tf.astype(self.real))
+        self.S, self.R, self.K = program.state_size, program.rec_size, program.key_size
+        self.RAND, self.NA = program.rand_size, program.action_size
+        for fn in (self.lib.o_init_envs, self.lib.o_step_ctrl, self.lib.o_rewards, self.lib.o_gae):
+            fn.restype = ctypes.c_int
+
+    @staticmethod
+    def _p(a: np.ndarray | None) -> ctypes.c_void_p:
+        return ctypes.c_void_p(None if a is None else a.ctypes.data)
+
+    def init_envs(self, init_keys: np.ndarray, levels: np.ndarray, rand: np.ndarray) -> tuple[np.ndarray, ...]:
+        n = init_keys.shape[0]
+        init_keys = np.ascontiguousarray(init_keys, dtype=np.uint32).reshape(n, 10)
+        levels = np.ascontiguousarray(levels, dtype=self.real)
+        rand = np.ascontiguousarray(rand, dtype=self.real).reshape(n, self.RAND)
+        state = np.zeros((n, self.S), dtype=self.real)
+        keys = np.zeros((n, self.K), dtype=np.uint32)
+        rec0 = np.zeros((n, self.R), dtype=self.real)
+        act_keys = np.zeros((n, 2), dtype=np.uint32)
+        rc = self.lib.o_init_envs(ctypes.c_void_p(self.model.ptr), self._p(self.ti), self._p(self.tf), ctypes.c_int(n),
+                                  self._p(init_keys), self._p(levels), self._p(rand), self._p(state), self._p(keys),
+                                  self._p(rec0), self._p(act_keys))
+        if rc != 0:
+            raise RuntimeError(f"o_init_envs -> {rc}")
+        return state, keys, rec0, act_keys
+
+    def step_ctrl(self, action: np.ndarray, rand: np.ndarray, state: np.ndarray, keys: np.ndarray,
+                  rec_cur: np.ndarray, rec_next: np.ndarray, act_keys: np.ndarray | None = None) -> None:
+        n = state.shape[0]
+        action = np.ascontiguousarray(action, dtype=self.real).reshape(n, self.NA)
+        rand = np.ascontiguousarray(rand, dtype=self.real).reshape(n, self.RAND)
+        for a in (state, keys, rec_cur, rec_next):
+            assert a.flags["C_CONTIGUOUS"]
+        rc = self.lib.o_step_ctrl(ctypes.c_void_p(self.model.ptr), self._p(self.ti), self._p(self.tf), ctypes.c_int(n),
+                                  self._p(action), self._p(rand), self._p(state), self._p(keys), self._p(rec_cur),
+                                  self._p(rec_next), self._p(act_keys))
+        if rc != 0:
+            raise RuntimeError(f"o_step_ctrl -> {rc}")
+
+    def rollout(self, actions: np.ndarray, rand: np.ndarray, state: np.ndarray, keys: np.ndarray, rec: np.ndarray) -> None:
+        """actions [T][N][NA]; rec [T+1][N][R] with slot 0's pre-step block valid."""
+        for t in range(actions.shape[0]):
+            self.step_ctrl(actions[t], rand, state, keys, rec[t], rec[t + 1])
+
+    def rewards(self, rec: np.ndarray, levels: np.ndarray, carry: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        t, n = rec.shape[0], rec.shape[1]
+        k = int(self.ti[31])  # TI_N_REW_COMP
+        rec = np.ascontiguousarray(rec, dtype=self.real)
+        levels = np.ascontiguousarray(levels, dtype=self.real)
+        assert carry.dtype == self.real and carry.flags["C_CONTIGUOUS"]
+        total = np.zeros((n, t), dtype=self.real)
+        comps = np.zeros((k, n, t), dtype=self.real)
+        rc = self.lib.o_rewards(ctypes.c_void_p(self.model.ptr), self._p(self.ti), self._p(self.tf), ctypes.c_int(n),
+                                ctypes.c_int(t), self._p(rec), self._p(levels), self._p(carry), self._p(total), self._p(comps))
+        if rc != 0:
+            raise RuntimeError(f"o_rewards -> {rc}")
+        return total, comps
+
+    def gae(self, values: np.ndarray, rewards: np.ndarray, dones: np.ndarray, successes: np.ndarray, gamma: float,
+            lam: float, flags: int) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        b, t = values.shape
+        values = np.ascontiguousarray(values, dtype=self.real)
+        rewards = np.ascontiguousarray(rewards, dtype=self.real)
+        dones = np.ascontiguousarray(dones, dtype=np.uint8)
+        successes = np.ascontiguousarray(successes, dtype=np.uint8)
+        adv, tgt, ret = (np.zeros((b, t), dtype=self.real) for _ in range(3))
+        real_c = ctypes.c_float if self.precision == "f32" else ctypes.c_double
+        rc = self.lib.o_gae(ctypes.c_int(b), ctypes.c_int(t), self._p(values), self._p(rewards), self._p(dones),
+                            self._p(successes), real_c(gamma), real_c(lam), ctypes.c_int(flags), self._p(adv),
+                            self._p(tgt), self._p(ret))
+        if rc != 0:
+            raise RuntimeError(f"o_gae -> {rc}")
+        return adv, tgt, ret

@@ -694,9 +694,12 @@ static void observe(const Task* t, Env* e, Key rng, REAL* out) {
         for (int k = 0; k < 3; k++) { v[k] = c[k] * c[3] + pg2[k] * ((REAL)1 - c[3]); c[k] = v[k]; }
       } break;
       case OBS_FEET_CONTACT: {
+        /* observation.py:515-521: stack([any_floor(left geoms), any_floor(right geoms)], -1) -> (rows, 2) */
         const int* ids = oi + 3;
-        v[0] = (REAL)geoms_colliding(d, ids, oi[0], ids + oi[0] + oi[1], oi[2]);
-        v[1] = (REAL)geoms_colliding(d, ids + oi[0], oi[1], ids + oi[0] + oi[1], oi[2]);
+        for (int r = 0; r < oi[0]; r++) {
+          v[2 * r + 0] = (REAL)geoms_colliding(d, ids + r, 1, ids + oi[0] + oi[1], oi[2]);
+          v[2 * r + 1] = (REAL)geoms_colliding(d, ids + oi[0] + r, 1, ids + oi[0] + oi[1], oi[2]);
+        }
       } break;
       case OBS_BODY_POSITION: for (int b = 0; b < oi[0]; b++) for (int k = 0; k < 3; k++) v[3 * b + k] = d->xpos[oi[1 + b]][k]; break;
       case OBS_BODY_VELOCITY: for (int b = 0; b < oi[0]; b++) for (int k = 0; k < 6; k++) v[6 * b + k] = d->cvel[oi[1 + b]][k]; break;

@@ -1,0 +1,74 @@
+// Host-side SERIAL EMULATION of the warp kernels -- TEST INFRASTRUCTURE ONLY.
+//
+// The device code in ksim_b200/csrc/*.cuh is written as lane-parallel phases (LANE_FOR / WSYNC).  Compiled
+// with B2S_EMU those phases become plain loops, which lets GPU-less machines run the *same source* against
+// the CPU oracle to catch logic errors before spending GPU time.  It is never imported by ksim_b200, is not a
+// fallback of any product path, and says nothing about races (those are checked on the GPU with
+// compute-sanitizer); only tests/test_emu_vs_oracle.py builds and loads it.
+#define B2S_EMU 1
+#include <string.h>
+
+#include "../../ksim_b200/csrc/b2s_engine.cuh"
+#include "../../ksim_b200/csrc/b2s_rewards.cuh"
+
+using namespace b2s;
+typedef DimsGeneric D;
+
+static Mdl view(const void* blob) {
+  Mdl m;
+  const int* h = (const int*)blob;
+  memcpy(m.h, h, MH_SIZE * sizeof(int));
+  m.mi = h + MH_SIZE;
+  m.mf = (const float*)(h + MH_SIZE + h[MH_NI]);
+  m.ti = h + MH_SIZE + h[MH_NI] + h[MH_NF];
+  m.tf = (const float*)(h + MH_SIZE + h[MH_NI] + h[MH_NF] + h[MH_NTI]);
+  return m;
+}
+
+extern "C" int emu_init_envs(const void* blob, int n, const uint32_t* init_keys, const float* levels, const float* rand,
+                             float* state, uint32_t* keys, float* rec0, uint32_t* act_keys) {
+  Mdl m = view(blob);
+  const int* ti = m.ti;
+  const size_t S = ti[TI_STATE_SIZE], R = ti[TI_REC_SIZE], K = ti[TI_KEY_SIZE], RAND = ti[TI_RAND_SIZE];
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < n; e++) {
+    Work<D>* w = new Work<D>();
+    memset(w, 0, sizeof(*w));
+    apply_overrides(m, *w, rand + e * RAND, 0);
+    env_init(m, *w, init_keys + (size_t)e * 10, levels[e], rec0 + e * R, act_keys ? act_keys + 2 * e : nullptr, 0);
+    env_store(m, *w, state + e * S, keys + e * K, 0);
+    delete w;
+  }
+  return 0;
+}
+
+extern "C" int emu_step_ctrl(const void* blob, int n, const float* action, const float* rand, float* state, uint32_t* keys,
+                             float* rec_cur, float* rec_next, uint32_t* act_keys) {
+  Mdl m = view(blob);
+  const int* ti = m.ti;
+  const size_t S = ti[TI_STATE_SIZE], R = ti[TI_REC_SIZE], K = ti[TI_KEY_SIZE], RAND = ti[TI_RAND_SIZE], NA = ti[TI_ACTION_SIZE];
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < n; e++) {
+    Work<D>* w = new Work<D>();
+    memset(w, 0, sizeof(*w));
+    apply_overrides(m, *w, rand + e * RAND, 0);
+    env_load(m, *w, state + e * S, keys + e * K, 0);
+    env_step(m, *w, action + e * NA, rec_cur + e * R, rec_next + e * R, act_keys ? act_keys + 2 * e : nullptr, 0);
+    env_store(m, *w, state + e * S, keys + e * K, 0);
+    delete w;
+  }
+  return 0;
+}
+
+extern "C" int emu_rewards(const void* blob, int n, int T, const float* rec, const float* levels, float* carry, float* total,
+                           float* comps) {
+  Mdl m = view(blob);
+  const int* ti = m.ti;
+  const size_t R = ti[TI_REC_SIZE], C = ti[TI_REW_CARRY_SIZE];
+  for (int e = 0; e < n; e++)
+    env_rewards(m, rec + e * R, (size_t)n * R, T, levels[e], carry + e * C, total + (size_t)e * T, comps + (size_t)e * T,
+                (size_t)n * T, 0);
+  return 0;
+}
+
+extern "C" int emu_sizeof_work(void) { return (int)sizeof(Work<DimsHumanoid>); }
