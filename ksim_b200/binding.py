@@ -1,0 +1,72 @@
+"""ctypes binding of the C-ABI in ``include/b200sim.h`` (``ksim_b200/csrc/libb200sim.so``).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+
+from __future__ import annotations
+
+__all__ = ["B200SimError", "lib", "library_path", "check", "EXPORTS", "INFO"]
+
+import ctypes
+from pathlib import Path
+
+_CSRC = Path(__file__).resolve().parent / "csrc"
+_LIB: ctypes.CDLL | None = None
+
+# every symbol include/b200sim.h declares (tests assert the library exports exactly these)
+EXPORTS = (
+    "b200sim_model_create", "b200sim_model_destroy", "b200sim_model_info", "b200sim_last_error", "b200sim_init_envs",
+    "b200sim_step_ctrl", "b200sim_rollout", "b200sim_rewards", "b200sim_gae", "b200sim_extract_flags",
+)
+
+INFO = dict(STATE_SIZE=0, REC_SIZE=1, KEY_SIZE=2, RAND_SIZE=3, ACTION_SIZE=4, N_REW_COMP=5, REW_CARRY_SIZE=6,
+            SMEM_PER_ENV=7, WARPS_PER_CTA=8, VARIANT=9)
+
+
+class B200SimError(RuntimeError):
+    pass
+
+
+def library_path() -> Path:
+    return _CSRC / "libb200sim.so"
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not path.exists():
+            raise B200SimError(
+                f"{path} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "There is no CPU fallback."
+            )
+        cdll = ctypes.CDLL(str(path))
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        cdll.b200sim_model_create.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+        cdll.b200sim_model_create.restype = ci
+        cdll.b200sim_model_destroy.argtypes = [vp]
+        cdll.b200sim_model_destroy.restype = None
+        cdll.b200sim_model_info.argtypes = [vp, ci]
+        cdll.b200sim_model_info.restype = ci
+        cdll.b200sim_last_error.argtypes = []
+        cdll.b200sim_last_error.restype = ctypes.c_char_p
+        cdll.b200sim_init_envs.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]
+        cdll.b200sim_init_envs.restype = ci
+        cdll.b200sim_step_ctrl.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]
+        cdll.b200sim_step_ctrl.restype = ci
+        cdll.b200sim_rollout.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
+        cdll.b200sim_rollout.restype = ci
+        cdll.b200sim_rewards.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
+        cdll.b200sim_rewards.restype = ci
+        cdll.b200sim_gae.argtypes = [vp, ci, ci, vp, vp, vp, vp, cf, cf, ci, vp, vp, vp]
+        cdll.b200sim_gae.restype = ci
+        cdll.b200sim_extract_flags.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+        cdll.b200sim_extract_flags.restype = ci
+        _LIB = cdll
+    return _LIB
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().b200sim_last_error()
+        raise B200SimError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")

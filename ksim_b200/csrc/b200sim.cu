@@ -40,9 +40,14 @@ __global__ void __launch_bounds__(256) k_rollout(const Mdl m, int n_envs, int n_
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int env = blockIdx.x * wpb + warp;
-  if (env >= n_envs) return;
-  Work<D>& w = reinterpret_cast<Work<D>*>(smem)[warp];
   const int* ti = m.ti;
+  if (env >= n_envs) {
+    // idle warps of the last CTA still take part in engine_step's per-sub-step CTA barriers
+    const int nbar = n_steps * ti[TI_NSUB];
+    for (int i = 0; i < nbar; i++) __syncthreads();
+    return;
+  }
+  Work<D>& w = reinterpret_cast<Work<D>*>(smem)[warp];
   const size_t S = ti[TI_STATE_SIZE], R = ti[TI_REC_SIZE], K = ti[TI_KEY_SIZE], RAND = ti[TI_RAND_SIZE];
   const size_t NA = ti[TI_ACTION_SIZE];
   apply_overrides(m, w, rand + env * RAND, lane);
@@ -145,6 +150,10 @@ extern "C" const char* b200sim_last_error(void) { return g_last_error.c_str(); }
 
 template <class D>
 static bool fits(const int* h) {
+  if (D::EXACT)
+    return h[MH_NQ] == D::NQ && h[MH_NV] == D::NV && h[MH_NBODY] == D::NB && h[MH_NJNT] == D::NJ && h[MH_NU] == D::NU &&
+           h[MH_NSITE] == D::NS && h[MH_NPAIR] == D::NPAIR && h[MH_NCON] == D::NCON && h[MH_NLIMIT] == D::NLIMIT &&
+           h[MH_NSENSORDATA] <= D::NSD && h[MH_NEFC_DENSE] <= D::NDENSE && h[MH_NFRICTION] <= D::NFRIC;
   return h[MH_NQ] <= D::NQ && h[MH_NV] <= D::NV && h[MH_NBODY] <= D::NB && h[MH_NJNT] <= D::NJ && h[MH_NU] <= D::NU &&
          h[MH_NSITE] <= D::NS && h[MH_NSENSORDATA] <= D::NSD && h[MH_NPAIR] <= D::NPAIR && h[MH_NCON] <= D::NCON &&
          h[MH_NEFC_DENSE] <= D::NDENSE && h[MH_NLIMIT] <= D::NLIMIT && h[MH_NFRICTION] <= D::NFRIC;

@@ -23,6 +23,7 @@
 #define DEVNI __device__ __noinline__
 #define LANE_FOR(i, n) for (int i = lane; i < (n); i += 32)
 #define WSYNC() __syncwarp()
+#define CTA_SYNC() __syncthreads()
 #define IF_LANE0 if (lane == 0)
 #define LANE_ARG const int lane
 #define LANE_PASS lane
@@ -32,6 +33,7 @@
 #define DEVNI static
 #define LANE_FOR(i, n) for (int i = 0; i < (n); i++)
 #define WSYNC() ((void)0)
+#define CTA_SYNC() ((void)0)
 #define IF_LANE0 if (true)
 #define LANE_ARG const int lane
 #define LANE_PASS 0
@@ -134,13 +136,13 @@ DEV V3 mulTv(const M9& m, V3 v) {
             m.m[2] * v.x + m.m[5] * v.y + m.m[8] * v.z);
 }
 DEV V3 qrot(Q4 q, V3 v) { return mulv(q2mat(q), v); }
-DEV Q4 axis_angle(V3 axis, float angle) {
+DEVNI Q4 axis_angle(V3 axis, float angle) {
   float s = sinf(angle * 0.5f);
   Q4 q; q.w = cosf(angle * 0.5f); q.x = axis.x * s; q.y = axis.y * s; q.z = axis.z * s;
   return q;
 }
 // xax.rotate_vector_by_quat (normalises with eps 1e-6); same expression order as the oracle (oracle/physics.c)
-DEV V3 rot_vec_quat(V3 v, Q4 q, bool inverse) {
+DEVNI V3 rot_vec_quat(V3 v, Q4 q, bool inverse) {
   float n = sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z) + 1e-6f;
   float w = q.w / n, x = q.x / n, y = q.y / n, z = q.z / n;
   if (inverse) { x = -x; y = -y; z = -z; }
@@ -153,7 +155,7 @@ DEV V3 rot_vec_quat(V3 v, Q4 q, bool inverse) {
              x * x * vz;
   return v3(xx, yy, zz);
 }
-DEV Q4 euler_to_quat(float roll, float pitch, float yaw) {
+DEVNI Q4 euler_to_quat(float roll, float pitch, float yaw) {
   float cr = cosf(roll * 0.5f), sr = sinf(roll * 0.5f);
   float cp = cosf(pitch * 0.5f), sp = sinf(pitch * 0.5f);
   float cy = cosf(yaw * 0.5f), sy = sinf(yaw * 0.5f);
@@ -198,7 +200,7 @@ struct Key { uint32_t k0, k1; };
 
 DEV uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
 
-DEV void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* o0, uint32_t* o1) {
+DEVNI void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* o0, uint32_t* o1) {
   const uint32_t ks0 = k0, ks1 = k1, ks2 = k0 ^ k1 ^ 0x1BD11BDAu;
   x0 += ks0; x1 += ks1;
 #define B2S_R4A x0 += x1; x1 = rotl32(x1, 13); x1 ^= x0; x0 += x1; x1 = rotl32(x1, 15); x1 ^= x0; \
@@ -280,7 +282,7 @@ DEV float scale_get(int kind, const float* f, float level) {
   }
   return f[0];
 }
-DEV float rv_sample(int kind, const float* f, Key key, int i, float level) {
+DEVNI float rv_sample(int kind, const float* f, Key key, int i, float level) {
   float mean = f[0], std = f[1], mag = f[2];
   switch (kind) {
     case RV_UNIFORM: return key_uniform(key, i, mean - mag * level, mean + mag * level);
@@ -293,7 +295,7 @@ DEV float rv_sample(int kind, const float* f, Key key, int i, float level) {
   }
   return 0.0f;
 }
-DEV float noise_apply(const int* ni, const float* nf, float x, Key key, int i, float level) {
+DEVNI float noise_apply(const int* ni, const float* nf, float x, Key key, int i, float level) {
   int n = ni[0];
   for (int l = 0; l < n; l++) {
     int mul = ni[1 + 2 * l], kind = ni[2 + 2 * l];

@@ -23,7 +23,7 @@ namespace b2s {
 
 template <class D>
 DEV void apply_overrides(const Mdl& m, Work<D>& w, const float* rand, LANE_ARG) {
-  const int nv = m.h[MH_NV], nb = m.h[MH_NBODY];
+  const int nv = DIM(NV, MH_NV), nb = DIM(NB, MH_NBODY);
   const float* arm = MF(m, MH_DOF_ARMATURE);
   const float* damp = MF(m, MH_DOF_DAMPING);
   const float* fl = MF(m, MH_DOF_FRICTIONLOSS);
@@ -59,13 +59,13 @@ DEV void apply_overrides(const Mdl& m, Work<D>& w, const float* rand, LANE_ARG) 
 }
 
 #define B2S_STATE_FIELDS(X)                                        \
-  X(w.qpos, TI_S_QPOS, m.h[MH_NQ])                                 \
-  X(w.qvel, TI_S_QVEL, m.h[MH_NV])                                 \
-  X(w.qacc, TI_S_QACC, m.h[MH_NV])                                 \
-  X(w.warm, TI_S_WARM, m.h[MH_NV])                                 \
-  X(w.ctrl, TI_S_CTRL, m.h[MH_NU])                                 \
+  X(w.qpos, TI_S_QPOS, DIM(NQ, MH_NQ))                                 \
+  X(w.qvel, TI_S_QVEL, DIM(NV, MH_NV))                                 \
+  X(w.qacc, TI_S_QACC, DIM(NV, MH_NV))                                 \
+  X(w.warm, TI_S_WARM, DIM(NV, MH_NV))                                 \
+  X(w.ctrl, TI_S_CTRL, DIM(NU, MH_NU))                                 \
   X(w.last_ctrl, TI_S_LAST_CTRL, ti[TI_ACTION_SIZE])               \
-  X(w.zero_off, TI_S_ZERO_OFF, m.h[MH_NU])                         \
+  X(w.zero_off, TI_S_ZERO_OFF, DIM(NU, MH_NU))                         \
   X(w.event, TI_S_EVENT, ti[TI_EVENT_SIZE])                        \
   X(w.act_state, TI_S_ACT_STATE, ti[TI_ACT_STATE_SIZE])            \
   X(w.cmd, TI_S_CMD, ti[TI_CMD_SIZE])                              \
@@ -106,7 +106,7 @@ DEV void env_store(const Mdl& m, const Work<D>& w, float* s, uint32_t* keys, LAN
 template <class D>
 DEV void actuators_ctrl(const Mdl& m, Work<D>& w, const float* ctrl_in, Key rng, LANE_ARG) {
   const int* ti = m.ti;
-  const int nu = m.h[MH_NU];
+  const int nu = DIM(NU, MH_NU);
   const int* ai = ti + ti[TI_ACT_IOFF];
   const float* af = m.tf + ti[TI_ACT_FOFF];
   const float level = w.level;
@@ -138,7 +138,7 @@ template <class D>
 DEV void actuators_initial_state(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   const int* ti = m.ti;
   if (ti[TI_ACT_TYPE] != ACT_POSITION) return;
-  const int nu = m.h[MH_NU];
+  const int nu = DIM(NU, MH_NU);
   const int* kinds = ti + ti[TI_ACT_IOFF] + 2 * NOISE_NI;
   const float* rvf = m.tf + ti[TI_ACT_FOFF] + 1 + 2 * NOISE_NF;
   const Key k0 = key_split(rng, 0), k1 = key_split(rng, 1);
@@ -165,7 +165,7 @@ DEV uint32_t randint3(Key k) {
 }
 
 template <class D>
-DEV void event_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
+DEVNI void event_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
   const int* ti = m.ti;
   const int type = TAB(ti, TI_EVENT_TAB, idx, TAB_TYPE);
   const int* ei = ti + TAB(ti, TI_EVENT_TAB, idx, TAB_IOFF);
@@ -262,7 +262,7 @@ DEV void event_initial_state(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_AR
 template <class D>
 DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   const int* ti = m.ti;
-  const int na = ti[TI_ACTION_SIZE], nu = m.h[MH_NU], nsub = ti[TI_NSUB], act_period = ti[TI_ACT_PERIOD];
+  const int na = ti[TI_ACTION_SIZE], nu = DIM(NU, MH_NU), nsub = ti[TI_NSUB], act_period = ti[TI_ACT_PERIOD];
   const int nevent = ti[TI_N_EVENT];
   const float* ef = m.tf + ti[TI_ENGINE_FOFF];
   const Key drop_rng = key_split(rng, 0);
@@ -272,6 +272,7 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   LANE_FOR(i, nu) w.torque[i] = 0.0f;
   WSYNC();
   for (int step = 0; step < nsub; step++) {
+    CTA_SYNC();  // keep the CTA's warps on the same code so they share instruction-cache lines
     const float prct = clipf((float)step - w.latency, 0.0f, 1.0f);
     LANE_FOR(i, na) {
       const float lc = w.last_ctrl[i];
@@ -288,7 +289,7 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
       r = key_split(r, 0);
       event_apply(m, w, ev, rng_event, LANE_PASS);
     }
-    physics_step(m, w, LANE_PASS);
+    physics_step(m, w, step == nsub - 1, LANE_PASS);
   }
   LANE_FOR(i, na) w.last_ctrl[i] = w.action[i];
   WSYNC();
@@ -300,7 +301,7 @@ DEV void reset_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
   const int type = TAB(ti, TI_RESET_TAB, idx, TAB_TYPE);
   const int* ri = ti + TAB(ti, TI_RESET_TAB, idx, TAB_IOFF);
   const float* rf = m.tf + TAB(ti, TI_RESET_TAB, idx, TAB_FOFF);
-  const int nj = m.h[MH_NQ] - 7;
+  const int nj = DIM(NQ, MH_NQ) - 7;
   switch (type) {
     case RESET_RANDOM_JOINT_POSITION: {
       const float *zeros = rf + 1, *mins = rf + 1 + nj, *maxs = rf + 1 + 2 * nj;
@@ -314,7 +315,7 @@ DEV void reset_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
       }
     } break;
     case RESET_RANDOM_JOINT_VELOCITY:
-      LANE_FOR(i, m.h[MH_NV] - 6) {
+      LANE_FOR(i, DIM(NV, MH_NV) - 6) {
         float n = key_uniform(rng, i, -rf[0], rf[0]);
         if (ri[0]) n = n * w.level;
         w.qvel[6 + i] = n;
@@ -353,9 +354,9 @@ DEV void reset_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
 }
 
 template <class D>
-DEV void engine_reset(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
+DEVNI void engine_reset(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   const int* ti = m.ti;
-  const int nq = m.h[MH_NQ], nv = m.h[MH_NV], nu = m.h[MH_NU];
+  const int nq = DIM(NQ, MH_NQ), nv = DIM(NV, MH_NV), nu = DIM(NU, MH_NU);
   const float* ef = m.tf + ti[TI_ENGINE_FOFF];
   const float* qpos0 = MF(m, MH_QPOS0);
   // mjx.make_data
@@ -374,7 +375,7 @@ DEV void engine_reset(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
     rng = key_split(rng, 0);
     reset_apply(m, w, i, reset_rng, LANE_PASS);
   }
-  forward(m, w, LANE_PASS);
+  forward(m, w, true, LANE_PASS);
   LANE_FOR(i, nv) { w.qvel[i] = 0.0f; w.qacc[i] = 0.0f; }
   WSYNC();
   actuators_initial_state(m, w, rng, LANE_PASS);
@@ -396,7 +397,7 @@ DEV void engine_reset(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
 // ----------------------------------------------------------------------------------------------- commands
 
 template <class D>
-DEV void cmd_linvel_initial(const int* ci, const float* cf, const Work<D>& w, Key rng, const float* prev, float* out) {
+DEVNI void cmd_linvel_initial(const int* ci, const float* cf, const Work<D>& w, Key rng, const float* prev, float* out) {
   const float lvl = w.level;
   const float min_vel = scale_get(ci[0], cf + 0, lvl), max_vel = scale_get(ci[1], cf + 2, lvl);
   const float max_yaw = scale_get(ci[2], cf + 4, lvl), zero_prob = scale_get(ci[3], cf + 6, lvl);
@@ -491,7 +492,7 @@ DEV void cmd_update(const Mdl& m, Work<D>& w, int idx, Key rng) {
 
 template <class D>
 DEV int geoms_colliding(const Mdl& m, const Work<D>& w, const int* g1, int n1, const int* g2, int n2) {
-  const int ncon = m.h[MH_NCON];
+  const int ncon = DIM(NCON, MH_NCON);
   const int* pg1 = MI(m, MH_PAIR_GEOM1);
   const int* pg2 = MI(m, MH_PAIR_GEOM2);
   for (int c = 0; c < ncon; c++) {
@@ -525,10 +526,10 @@ DEV void obs_carry_initial(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG)
 
 // get_observation: writes the obs block of a record (global memory)
 template <class D>
-DEV void observe(const Mdl& m, Work<D>& w, Key rng, float* out, LANE_ARG) {
+DEVNI void observe(const Mdl& m, Work<D>& w, Key rng, float* out, LANE_ARG) {
   const int* ti = m.ti;
   const int nobs = ti[TI_N_OBS];
-  const int nb = m.h[MH_NBODY];
+  const int nb = DIM(NB, MH_NBODY);
   (void)nb;
   for (int o = 0; o < nobs; o++) {
     const Key noise_rng = key_split(rng, 2);
@@ -623,7 +624,7 @@ DEV int termination(const Mdl& m, const Work<D>& w, int idx) {
     }
     case TERM_MINIMUM_HEIGHT: return w.qpos[2] < xf[0] ? -1 : 0;
     case TERM_ILLEGAL_CONTACT: {
-      const int ncon = m.h[MH_NCON];
+      const int ncon = DIM(NCON, MH_NCON);
       const int* pg1 = MI(m, MH_PAIR_GEOM1);
       const int* pg2 = MI(m, MH_PAIR_GEOM2);
       for (int c = 0; c < ncon; c++) {
@@ -694,7 +695,7 @@ template <class D>
 DEV int env_step(const Mdl& m, Work<D>& w, const float* action_in, float* rec_cur, float* rec_next, uint32_t* act_key,
                  LANE_ARG) {
   const int* ti = m.ti;
-  const int nq = m.h[MH_NQ], nv = m.h[MH_NV], nb = m.h[MH_NBODY], nu = m.h[MH_NU];
+  const int nq = DIM(NQ, MH_NQ), nv = DIM(NV, MH_NV), nb = DIM(NB, MH_NBODY), nu = DIM(NU, MH_NU);
   const float* ef = m.tf + ti[TI_ENGINE_FOFF];
   const int na = ti[TI_ACTION_SIZE];
   const float aclip = ef[6];

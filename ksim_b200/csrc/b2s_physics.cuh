@@ -60,7 +60,7 @@ DEV Q4 ldgq(const float* p) { Q4 q; q.w = p[0]; q.x = p[1]; q.y = p[2]; q.z = p[
 
 template <class D>
 DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nb = m.h[MH_NBODY];
+  const int nb = DIM(NB, MH_NBODY);
   const int* parentid = MI(m, MH_BODY_PARENTID);
   const int* jntnum = MI(m, MH_BODY_JNTNUM);
   const int* jntadr = MI(m, MH_BODY_JNTADR);
@@ -129,7 +129,7 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
     }
     WSYNC();
   }
-  const int ns = m.h[MH_NSITE];
+  const int ns = DIM(NS, MH_NSITE);
   const int* site_body = MI(m, MH_SITE_BODYID);
   const float* site_pos = MF(m, MH_SITE_POS);
   const float* site_quat = MF(m, MH_SITE_QUAT);
@@ -145,7 +145,7 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
 
 template <class D>
 DEV void com_pos(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nb = m.h[MH_NBODY], nj = m.h[MH_NJNT];
+  const int nb = DIM(NB, MH_NBODY), nj = DIM(NJ, MH_NJNT);
   const int* rootid = MI(m, MH_BODY_ROOTID);
   const int* sub_end = MI(m, MH_BODY_SUBTREE_END);
   const float* subtreemass = MF(m, MH_BODY_SUBTREEMASS);
@@ -221,7 +221,7 @@ DEV void com_pos(const Mdl& m, Work<D>& w, LANE_ARG) {
 
 template <class D>
 DEV void crb_mass_matrix(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nb = m.h[MH_NBODY], nv = m.h[MH_NV];
+  const int nb = DIM(NB, MH_NBODY), nv = DIM(NV, MH_NV);
   const int* sub_end = MI(m, MH_BODY_SUBTREE_END);
   const int* dof_body = MI(m, MH_DOF_BODYID);
   const int* dof_parent = MI(m, MH_DOF_PARENTID);
@@ -253,14 +253,10 @@ DEV void crb_mass_matrix(const Mdl& m, Work<D>& w, LANE_ARG) {
   WSYNC();
 }
 
-// dense Cholesky of (A + diag(add)) into W (lower triangle), one phase per column.
+// in-place dense Cholesky of the lower triangle held in W, one phase per column.  The diagonal of W keeps
+// A[j][j] (other lanes read it during the phase); the pivots live in Linv_diag.
 template <class D>
-DEV void chol_factor(Work<D>& w, const float (*A)[D::NVP], const float* diag_add, float diag_scale, int nv, LANE_ARG) {
-  LANE_FOR(i, nv) {
-    for (int j = 0; j <= i; j++) w.W[i][j] = A[i][j];
-    if (diag_add) w.W[i][i] += diag_scale * diag_add[i];
-  }
-  WSYNC();
+DEVNI void chol_inplace(Work<D>& w, int nv, LANE_ARG) {
   for (int j = 0; j < nv; j++) {
     LANE_FOR(i, nv) {
       if (i >= j) {
@@ -272,7 +268,6 @@ DEV void chol_factor(Work<D>& w, const float (*A)[D::NVP], const float* diag_add
         }
         if (s < MINVAL) s = MINVAL;
         const float dj = sqrtf(s);
-        // the diagonal of W keeps A[j][j] (other lanes read it in this phase); the pivot lives in Linv_diag
         if (i == j) w.Linv_diag[j] = 1.0f / dj;
         else w.W[i][j] = t / dj;
       }
@@ -281,9 +276,20 @@ DEV void chol_factor(Work<D>& w, const float (*A)[D::NVP], const float* diag_add
   }
 }
 
+// dense Cholesky of (M + diag_scale * diag_add) into W
+template <class D>
+DEV void chol_factor(Work<D>& w, const float* diag_add, float diag_scale, int nv, LANE_ARG) {
+  LANE_FOR(i, nv) {
+    for (int j = 0; j <= i; j++) w.W[i][j] = w.M[i][j];
+    if (diag_add) w.W[i][i] += diag_scale * diag_add[i];
+  }
+  WSYNC();
+  chol_inplace(w, nv, LANE_PASS);
+}
+
 // solves (L L^T) x = b with the factor in W; x and b may alias.  Uses s_tmp.
 template <class D>
-DEV void chol_solve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
+DEVNI void chol_solve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
   float* y = w.s_tmp;
   LANE_FOR(i, nv) y[i] = b[i];
   WSYNC();
@@ -330,7 +336,7 @@ DEV void put_contact(Work<D>& w, int c, int pair, float dist, V3 pos, const floa
 
 template <class D>
 DEV void collision(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int np = m.h[MH_NPAIR];
+  const int np = DIM(NPAIR, MH_NPAIR);
   const int* pg1 = MI(m, MH_PAIR_GEOM1);
   const int* pg2 = MI(m, MH_PAIR_GEOM2);
   const int* conadr = MI(m, MH_PAIR_CONADR);
@@ -396,7 +402,7 @@ DEV void collision(const Mdl& m, Work<D>& w, LANE_ARG) {
 
 struct KBI { float k, b, imp; };
 
-DEV KBI kbi(const Mdl& m, const float* solref, const float* solimp, float pos) {
+DEVNI KBI kbi(const Mdl& m, const float* solref, const float* solimp, float pos) {
   float timeconst = solref[0], dampratio = solref[1];
   if (!m.h[MH_DISABLE_REFSAFE] && solref[0] > 0) {
     const float lo = 2 * m.mf[MF_TIMESTEP];
@@ -410,7 +416,10 @@ DEV KBI kbi(const Mdl& m, const float* solref, const float* solimp, float pos) {
   if (solref[1] <= 0) bb = -solref[1] / dmax;
   const float x = fabsf(pos) / width;
   float y;
-  if (x < mid) y = (1.0f / powf(mid, power - 1)) * powf(x, power);
+  if (power == 2.0f) {  // MuJoCo's default solimp power: same value without the pow calls
+    if (x < mid) y = (1.0f / mid) * (x * x);
+    else { const float u = fmaxf(1.0f - x, 0.0f); y = 1.0f - (1.0f / (1.0f - mid)) * (u * u); }
+  } else if (x < mid) y = (1.0f / powf(mid, power - 1)) * powf(x, power);
   else y = 1.0f - (1.0f / powf(1.0f - mid, power - 1)) * powf(fmaxf(1.0f - x, 0.0f), power);
   if (x > 1) y = 1;
   float im = clipf(dmin + y * (dmax - dmin), dmin, dmax);
@@ -439,7 +448,7 @@ enum { EFC_FRICTION = 1, EFC_LIMIT = 2, EFC_CONTACT = 3 };
 // limit) are kept in compact form (dof + sign); contact rows are dense in Jd.
 template <class D>
 DEV void make_constraint(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nv = m.h[MH_NV], nlimit = m.h[MH_NLIMIT], ncon = m.h[MH_NCON];
+  const int nv = DIM(NV, MH_NV), nlimit = DIM(NLIMIT, MH_NLIMIT), ncon = DIM(NCON, MH_NCON);
   const float* dof_invw = MF(m, MH_DOF_INVWEIGHT0);
   const float* dof_solref = MF(m, MH_DOF_SOLREF);
   const float* dof_solimp = MF(m, MH_DOF_SOLIMP);
@@ -560,7 +569,7 @@ DEV void make_constraint(const Mdl& m, Work<D>& w, LANE_ARG) {
 // bodies: cvel[b] = sum of cdof*qvel over the dofs between the root and b (same quantity mj_comVel builds).
 template <class D>
 DEV void com_vel(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nb = m.h[MH_NBODY], nv = m.h[MH_NV];
+  const int nb = DIM(NB, MH_NBODY), nv = DIM(NV, MH_NV);
   const int* dof_parent = MI(m, MH_DOF_PARENTID);
   const int* dof_velparent = MI(m, MH_DOF_VELPARENT);
   const int* body_lastdof = MI(m, MH_BODY_LASTDOF);
@@ -599,7 +608,7 @@ DEV void com_vel(const Mdl& m, Work<D>& w, LANE_ARG) {
 
 template <class D>
 DEV void passive(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nv = m.h[MH_NV];
+  const int nv = DIM(NV, MH_NV);
   const int* dof_jnt = MI(m, MH_DOF_JNTID);
   const int* jtype = MI(m, MH_JNT_TYPE);
   const int* jqpos = MI(m, MH_JNT_QPOSADR);
@@ -615,8 +624,8 @@ DEV void passive(const Mdl& m, Work<D>& w, LANE_ARG) {
 
 // cacc[b] = -gravity + sum over the dof chain of cdof_dot*qvel (+ cdof*qacc)
 template <class D>
-DEV void rne_cacc(const Mdl& m, Work<D>& w, bool with_acc, LANE_ARG) {
-  const int nb = m.h[MH_NBODY];
+DEVNI void rne_cacc(const Mdl& m, Work<D>& w, bool with_acc, LANE_ARG) {
+  const int nb = DIM(NB, MH_NBODY);
   const int* dof_parent = MI(m, MH_DOF_PARENTID);
   const int* body_lastdof = MI(m, MH_BODY_LASTDOF);
   const float gx = m.mf[MF_GRAVITY], gy = m.mf[MF_GRAVITY + 1], gz = m.mf[MF_GRAVITY + 2];
@@ -655,7 +664,7 @@ DEV V6 body_inertial_force(Work<D>& w, int b) {
 
 template <class D>
 DEV void rne(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nb = m.h[MH_NBODY], nv = m.h[MH_NV];
+  const int nb = DIM(NB, MH_NBODY), nv = DIM(NV, MH_NV);
   const int* sub_end = MI(m, MH_BODY_SUBTREE_END);
   const int* dof_body = MI(m, MH_DOF_BODYID);
   rne_cacc(m, w, false, LANE_PASS);
@@ -684,7 +693,7 @@ DEV void rne(const Mdl& m, Work<D>& w, LANE_ARG) {
 
 template <class D>
 DEV void actuation(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nv = m.h[MH_NV], nu = m.h[MH_NU];
+  const int nv = DIM(NV, MH_NV), nu = DIM(NU, MH_NU);
   const int* trnid = MI(m, MH_ACT_TRNID);
   const int* climited = MI(m, MH_ACT_CTRLLIMITED);
   const int* flimited = MI(m, MH_ACT_FORCELIMITED);
@@ -711,7 +720,7 @@ DEV void actuation(const Mdl& m, Work<D>& w, LANE_ARG) {
 
 template <class D>
 DEV void acceleration(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nv = m.h[MH_NV];
+  const int nv = DIM(NV, MH_NV);
   const int* rootid = MI(m, MH_BODY_ROOTID);
   const int* bdofmask = MI(m, MH_BODY_DOFMASK);
   const int xb = w.xfrc_body;
@@ -747,8 +756,8 @@ DEV float row_dot(const Work<D>& w, int r, int nsparse, const float* x, int nv) 
 
 // efc_force / active / cost from Jaref; qfrc_constraint = J^T force; returns total cost (gauss + constraint)
 template <class D>
-DEV float solver_update_constraint(const Mdl& m, Work<D>& w, float* gauss_out, LANE_ARG) {
-  const int nv = m.h[MH_NV], ne = w.nefc, nsparse = w.nsparse;
+DEVNI float solver_update_constraint(const Mdl& m, Work<D>& w, float* gauss_out, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
   float cost = 0.0f;
   LANE_FOR(r, ne) {
     const float x = w.efc_Jaref[r], Dr = w.efc_D[r];
@@ -782,8 +791,8 @@ DEV float solver_update_constraint(const Mdl& m, Work<D>& w, float* gauss_out, L
 
 // grad = Ma - qfrc_smooth - qfrc_constraint; Mgrad = H^-1 grad with H = M + J^T diag(D*active) J
 template <class D>
-DEV void solver_update_gradient(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nv = m.h[MH_NV], ne = w.nefc, nsparse = w.nsparse;
+DEVNI void solver_update_gradient(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
   LANE_FOR(i, nv) {
     w.s_grad[i] = w.s_Ma[i] - w.qfrc_smooth[i] - w.qfrc_constraint[i];
     for (int j = 0; j <= i; j++) {
@@ -797,32 +806,14 @@ DEV void solver_update_gradient(const Mdl& m, Work<D>& w, LANE_ARG) {
     w.W[i][i] += dg;
   }
   WSYNC();
-  // factor in place (W already holds the lower triangle of H)
-  for (int j = 0; j < nv; j++) {
-    LANE_FOR(i, nv) {
-      if (i >= j) {
-        float t = w.W[i][j], s = w.W[j][j];
-        for (int k = 0; k < j; k++) {
-          const float ljk = w.W[j][k];
-          t -= w.W[i][k] * ljk;
-          s -= ljk * ljk;
-        }
-        if (s < MINVAL) s = MINVAL;
-        const float dj = sqrtf(s);
-        // the diagonal of W keeps A[j][j] (other lanes read it in this phase); the pivot lives in Linv_diag
-        if (i == j) w.Linv_diag[j] = 1.0f / dj;
-        else w.W[i][j] = t / dj;
-      }
-    }
-    WSYNC();
-  }
+  chol_inplace(w, nv, LANE_PASS);
   chol_solve(w, w.s_Mgrad, w.s_grad, nv, LANE_PASS);
 }
 
 // initialises s_qacc/s_Ma/Jaref from `qacc0`; returns cost
 template <class D>
-DEV float solver_init(const Mdl& m, Work<D>& w, const float* qacc0, float* gauss, LANE_ARG) {
-  const int nv = m.h[MH_NV], ne = w.nefc, nsparse = w.nsparse;
+DEVNI float solver_init(const Mdl& m, Work<D>& w, const float* qacc0, float* gauss, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
   LANE_FOR(i, nv) {
     w.s_qacc[i] = qacc0[i];
     float s = 0.0f;
@@ -850,7 +841,7 @@ DEV bool in_bracket(const LSPoint& x, const LSPoint& y) {
 
 // evaluates up to three step sizes in one pass over the constraint rows
 template <class D>
-DEV void ls_eval3(const Work<D>& w, int ne, const float* alpha, int n, const float* qg, LSPoint* out, LANE_ARG) {
+DEVNI void ls_eval3(const Work<D>& w, int ne, const float* alpha, int n, const float* qg, LSPoint* out, LANE_ARG) {
   float q[3][3];
 #pragma unroll
   for (int a = 0; a < 3; a++) q[a][0] = q[a][1] = q[a][2] = 0.0f;
@@ -883,7 +874,7 @@ DEV void ls_eval3(const Work<D>& w, int ne, const float* alpha, int n, const flo
 
 template <class D>
 DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, LANE_ARG) {
-  const int nv = m.h[MH_NV], ne = w.nefc, nsparse = w.nsparse;
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
   float snorm = 0.0f, qg1 = 0.0f, qg2 = 0.0f;
   LANE_FOR(i, nv) {
     float s = 0.0f;
@@ -940,7 +931,7 @@ DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, LANE_ARG) {
 
 template <class D>
 DEV void solve(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nv = m.h[MH_NV], ne = w.nefc;
+  const int nv = DIM(NV, MH_NV), ne = w.nefc;
   if (ne == 0) {
     // no constraint rows: qacc = qacc_smooth, qacc_warmstart keeps its old value (MJX forward())
     LANE_FOR(i, nv) { w.qacc[i] = w.qacc_smooth[i]; w.qfrc_constraint[i] = 0.0f; }
@@ -1064,7 +1055,7 @@ DEV V3 contact_force_world(const Mdl& m, const Work<D>& w, int c) {
 // rne_postconstraint + acceleration-stage sensors
 template <class D>
 DEV void sensors_acc(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nb = m.h[MH_NBODY], ncon = m.h[MH_NCON], ns = m.h[MH_NSENSOR];
+  const int nb = DIM(NB, MH_NBODY), ncon = DIM(NCON, MH_NCON), ns = m.h[MH_NSENSOR];
   const int* rootid = MI(m, MH_BODY_ROOTID);
   const int* pg1 = MI(m, MH_PAIR_GEOM1);
   const int* pg2 = MI(m, MH_PAIR_GEOM2);
@@ -1171,9 +1162,11 @@ DEV void sensors_acc(const Mdl& m, Work<D>& w, LANE_ARG) {
 
 // --------------------------------------------------------------------------------------------- top level
 
+// `sensors`: also evaluate sensordata / cfrc_ext.  They are pure outputs (recomputed from scratch by every
+// forward pass and read only by observations), so the control step asks for them on its last sub-step only.
 template <class D>
-DEV void forward(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nv = m.h[MH_NV];
+DEVNI void forward(const Mdl& m, Work<D>& w, bool sensors, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV);
   kinematics(m, w, LANE_PASS);
   com_pos(m, w, LANE_PASS);
   crb_mass_matrix(m, w, LANE_PASS);
@@ -1182,21 +1175,21 @@ DEV void forward(const Mdl& m, Work<D>& w, LANE_ARG) {
   make_constraint(m, w, LANE_PASS);
   passive(m, w, LANE_PASS);
   rne(m, w, LANE_PASS);
-  sensors_pos_vel(m, w, LANE_PASS);
+  if (sensors) sensors_pos_vel(m, w, LANE_PASS);
   actuation(m, w, LANE_PASS);
-  chol_factor(w, w.M, nullptr, 0.0f, nv, LANE_PASS);
+  chol_factor(w, nullptr, 0.0f, nv, LANE_PASS);
   acceleration(m, w, LANE_PASS);
   solve(m, w, LANE_PASS);
-  sensors_acc(m, w, LANE_PASS);
+  if (sensors) sensors_acc(m, w, LANE_PASS);
 }
 
 // implicitfast with Euler damping disabled: (M + dt*diag(damping)) qacc = qfrc_smooth + qfrc_constraint
 template <class D>
-DEV void physics_step(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nv = m.h[MH_NV], nj = m.h[MH_NJNT];
+DEV void physics_step(const Mdl& m, Work<D>& w, bool sensors, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), nj = DIM(NJ, MH_NJNT);
   const float dt = m.mf[MF_TIMESTEP];
-  forward(m, w, LANE_PASS);
-  chol_factor(w, w.M, w.damping, dt, nv, LANE_PASS);
+  forward(m, w, sensors, LANE_PASS);
+  chol_factor(w, w.damping, dt, nv, LANE_PASS);
   LANE_FOR(i, nv) w.s_grad[i] = w.qfrc_smooth[i] + w.qfrc_constraint[i];
   WSYNC();
   chol_solve(w, w.s_Mgrad, w.s_grad, nv, LANE_PASS);

@@ -8,8 +8,9 @@ namespace b2s {
 // Size traits.  A kernel instantiation serves every model whose sizes are <= the traits' (exact match is
 // fastest because lane loops collapse to a single predicated pass).
 template <int NQ_, int NV_, int NB_, int NJ_, int NU_, int NS_, int NSD_, int NPAIR_, int NCON_, int NDENSE_, int NLIMIT_,
-          int NFRIC_>
+          int NFRIC_, bool EXACT_>
 struct Dims {
+  static constexpr bool EXACT = EXACT_;       // model sizes equal the traits: lane loops get compile-time bounds
   static constexpr int NQ = NQ_, NV = NV_, NB = NB_, NJ = NJ_, NU = NU_, NS = NS_, NSD = NSD_;
   static constexpr int NPAIR = NPAIR_, NCON = NCON_, NDENSE = NDENSE_, NLIMIT = NLIMIT_, NFRIC = NFRIC_;
   static constexpr int NA = 2 * NU_;          // PositionVelocityActuator doubles the action
@@ -25,12 +26,15 @@ struct Dims {
 
 // examples/data/scene.mjcf (walking.py): nq 24 nv 23 nbody 17 njnt 18 nu 17 nsite 3 nsensordata 54,
 // 2 sphere-plane pairs condim 1, 17 limited hinges, no frictionloss.
-using DimsHumanoid = Dims<24, 23, 17, 18, 17, 3, 54, 2, 2, 2, 17, 0>;
+using DimsHumanoid = Dims<24, 23, 17, 18, 17, 3, 54, 2, 2, 2, 17, 0, true>;
 // examples/kbot/robot/kbot-headless/robot.mjcf: nq 27 nv 26 nbody 24 nu 20, 4 capsule-plane pairs condim 3
 // (8 contacts x 4 pyramid rows), 20 limited hinges, 20 frictionloss dofs.
-using DimsKbot = Dims<27, 26, 24, 21, 20, 4, 56, 4, 8, 32, 20, 20>;
+using DimsKbot = Dims<27, 26, 24, 21, 20, 4, 56, 4, 8, 32, 20, 20, false>;
 // anything else that fits one dof / body per lane
-using DimsGeneric = Dims<33, 32, 32, 32, 32, 8, 96, 8, 16, 64, 32, 32>;
+using DimsGeneric = Dims<33, 32, 32, 32, 32, 8, 96, 8, 16, 64, 32, 32, false>;
+
+// model dimension: compile-time when the traits match the model exactly
+#define DIM(X, H) (D::EXACT ? (int)D::X : m.h[H])
 
 template <class D>
 struct Work {

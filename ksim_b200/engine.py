@@ -1,0 +1,277 @@
+"""B200 rollout engine: the host-side mirror of ksim's ``PhysicsEngine`` for the batched CUDA path.
+
+Reference boundary (ksim/engine.py:171-199): ``PhysicsEngine`` owns ``actuators``, ``resets``, ``events`` and the
+engine config, and exposes ``reset(physics_model, curriculum_level, rng) -> PhysicsState`` and
+``step(action, physics_model, physics_state, curriculum_level, rng) -> PhysicsState``; the rollout driver
+(``RLTask._single_unroll``, ksim/task/rl.py:1604-1665) vmaps it over environments and scans it over time,
+wrapping it with observations, terminations, reset-on-done, commands and finally rewards + GAE.
+
+``B200Engine`` keeps those names and meanings but is *batched*: state for all N environments of this rank
+lives in HBM as flat per-env blocks, and one kernel launch advances every environment by a control step (or a
+whole rollout).  PyTorch is used only for device memory and streams.  No CPU fallback exists: construction
+fails loudly when the CUDA library is missing (ksim_b200/binding.py).
+"""
+
+from __future__ import annotations
+
+__all__ = ["B200Engine", "TrajectoryView", "get_physics_engine"]
+
+import ctypes
+from dataclasses import dataclass
+from typing import Mapping
+
+import numpy as np
+import torch
+
+from ksim_b200 import binding
+from ksim_b200 import codes as C
+from ksim_b200.blob import pack_blob
+from ksim_b200.envinit import EnvInit, make_env_init
+from ksim_b200.program import TaskProgram, TaskSpec, build_program
+from ksim_b200.randomization import PhysicsRandomizer
+
+
+def _ptr(t: torch.Tensor | None) -> ctypes.c_void_p:
+    return ctypes.c_void_p(None if t is None else t.data_ptr())
+
+
+@dataclass
+class TrajectoryView:
+    """Named views into a record buffer ``rec[T][N][R]`` -- the fields of ksim's ``Trajectory`` (types.py:48-76).
+
+    ``obs`` / ``command`` / ``curriculum_level`` are pre-step, everything else post-step (types.py:51-54).
+    """
+
+    rec: torch.Tensor
+    program: TaskProgram
+
+    def _blk(self, slot: str, n: int) -> torch.Tensor:
+        off = self.program[slot]
+        return self.rec[..., off : off + n]
+
+    @property
+    def qpos(self) -> torch.Tensor:
+        return self._blk("TI_R_QPOS", self.program.spec.model.nq)
+
+    @property
+    def qvel(self) -> torch.Tensor:
+        return self._blk("TI_R_QVEL", self.program.spec.model.nv)
+
+    @property
+    def xpos(self) -> torch.Tensor:
+        nb = self.program.spec.model.nbody
+        return self._blk("TI_R_XPOS", 3 * nb).unflatten(-1, (nb, 3))
+
+    @property
+    def xquat(self) -> torch.Tensor:
+        nb = self.program.spec.model.nbody
+        return self._blk("TI_R_XQUAT", 4 * nb).unflatten(-1, (nb, 4))
+
+    @property
+    def ctrl(self) -> torch.Tensor:
+        return self._blk("TI_R_CTRL", self.program.spec.model.nu)
+
+    @property
+    def action(self) -> torch.Tensor:
+        return self._blk("TI_R_ACTION", self.program.action_size)
+
+    @property
+    def done(self) -> torch.Tensor:
+        return self._blk("TI_R_DONE", 1)[..., 0] != 0
+
+    @property
+    def success(self) -> torch.Tensor:
+        return self._blk("TI_R_SUCCESS", 1)[..., 0] != 0
+
+    @property
+    def timestep(self) -> torch.Tensor:
+        return self._blk("TI_R_TIME", 1)[..., 0]
+
+    @property
+    def curriculum_level(self) -> torch.Tensor:
+        return self._blk("TI_R_LEVEL", 1)[..., 0]
+
+    @property
+    def obs_flat(self) -> torch.Tensor:
+        return self._blk("TI_R_OBS", self.program.obs_size)
+
+    @property
+    def obs(self) -> dict[str, torch.Tensor]:
+        flat = self.obs_flat
+        return {k: flat[..., off : off + dim].unflatten(-1, shape) for k, (off, dim, shape) in self.program.obs_slices.items()}
+
+    @property
+    def command(self) -> dict[str, torch.Tensor]:
+        flat = self._blk("TI_R_CMD", self.program["TI_CMD_SIZE"])
+        return {k: flat[..., off : off + dim] for k, (off, dim) in self.program.cmd_slices.items()}
+
+    @property
+    def event_state(self) -> dict[str, torch.Tensor]:
+        flat = self._blk("TI_R_EVENT", self.program["TI_EVENT_SIZE"])
+        return {k: flat[..., off : off + dim] for k, (off, dim) in self.program.event_slices.items()}
+
+    @property
+    def termination_components(self) -> dict[str, torch.Tensor]:
+        names = self.program.termination_names
+        flat = self._blk("TI_R_TERM", len(names))
+        return {k: flat[..., i].to(torch.int32) for i, k in enumerate(names)}
+
+
+class B200Engine:
+    """Batched drop-in for ``MjxEngine`` + the rollout functions around it (see module docstring)."""
+
+    def __init__(self, spec: TaskSpec, num_envs: int, device: torch.device | str = "cuda:0",
+                 randomizers: Mapping[str, PhysicsRandomizer] | None = None, seed: int = 0, curriculum_level: float = 0.0,
+                 env_offset: int = 0, total_envs: int | None = None, program: TaskProgram | None = None) -> None:
+        self.lib = binding.lib()  # raises if the CUDA library is not built
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise binding.B200SimError("B200Engine runs on CUDA devices only; there is no CPU fallback")
+        # mirror of PhysicsEngine's fields (ksim/engine.py:171-178)
+        self.actuators, self.resets, self.events, self.data = spec.actuators, tuple(spec.resets), dict(spec.events), spec.config
+        self.spec = spec
+        self.program = build_program(spec) if program is None else program
+        self.num_envs = int(num_envs)
+        self.randomizers = dict(randomizers or {})
+        self.blob = pack_blob(spec.model, self.program.ti, self.program.tf)
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            buf = (ctypes.c_char * len(self.blob)).from_buffer_copy(self.blob)
+            binding.check(self.lib.b200sim_model_create(buf, len(self.blob), ctypes.byref(self._handle)), "b200sim_model_create")
+        p = self.program
+        self.S, self.R, self.K, self.RAND, self.NA = p.state_size, p.rec_size, p.key_size, p.rand_size, p.action_size
+        for name, want in (("STATE_SIZE", self.S), ("REC_SIZE", self.R), ("KEY_SIZE", self.K), ("RAND_SIZE", self.RAND),
+                           ("ACTION_SIZE", self.NA)):
+            got = self.info(name)
+            if got != want:
+                raise binding.B200SimError(f"layout mismatch for {name}: library {got}, host {want}")
+        n, dev = self.num_envs, self.device
+        self.state = torch.zeros((n, self.S), dtype=torch.float32, device=dev)
+        self.keys = torch.zeros((n, self.K), dtype=torch.int32, device=dev)  # uint32 bit patterns
+        self.rand = torch.zeros((n, max(self.RAND, 1)), dtype=torch.float32, device=dev)
+        self.levels = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self.reward_carry = torch.zeros((n, max(p["TI_REW_CARRY_SIZE"], 1)), dtype=torch.float32, device=dev)
+        self.first_rec = torch.zeros((n, self.R), dtype=torch.float32, device=dev)
+        self.act_keys = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+        self.env_init: EnvInit | None = None
+        self.launches = 0
+        self.reset(seed=seed, curriculum_level=curriculum_level, env_offset=env_offset, total_envs=total_envs)
+
+    def __del__(self) -> None:
+        try:
+            if self._handle:
+                self.lib.b200sim_model_destroy(self._handle)
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def info(self, name: str) -> int:
+        return int(self.lib.b200sim_model_info(self._handle, binding.INFO[name]))
+
+    def _stream(self) -> ctypes.c_void_p:
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, t: torch.Tensor, shape: tuple[int, ...], dtype: torch.dtype, name: str) -> None:
+        if t.device != self.device or t.dtype != dtype or tuple(t.shape) != shape or not t.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous {dtype} {shape} on {self.device}, got {t.dtype} {tuple(t.shape)} on {t.device}")
+
+    def new_record_buffer(self, n_steps: int) -> torch.Tensor:
+        """rec[T+1][N][R]; slot 0 receives the current pre-step block (observations of the next policy call)."""
+        rec = torch.zeros((n_steps + 1, self.num_envs, self.R), dtype=torch.float32, device=self.device)
+        rec[0].copy_(self.first_rec)
+        return rec
+
+    def view(self, rec: torch.Tensor) -> TrajectoryView:
+        return TrajectoryView(rec, self.program)
+
+    # ------------------------------------------------------------------------------------------------- reset
+    def reset(self, seed: int = 0, curriculum_level: float = 0.0, env_offset: int = 0, total_envs: int | None = None) -> None:
+        """(Re)initialises every environment: the batched ``_get_env_state`` + ``engine.reset`` (rl.py:2175-2272)."""
+        init = make_env_init(self.program, self.randomizers, self.num_envs, seed=seed, level=curriculum_level,
+                             env_offset=env_offset, total_envs=total_envs)
+        self.env_init = init
+        dev = self.device
+        if self.RAND > 0:
+            self.rand.copy_(torch.from_numpy(init.rand).to(dev))
+        self.levels.copy_(torch.from_numpy(init.levels).to(dev))
+        ik = torch.from_numpy(init.init_keys.view(np.int32)).to(dev).contiguous()
+        self.reward_carry.zero_()
+        with torch.cuda.device(dev):
+            binding.check(self.lib.b200sim_init_envs(self._handle, self._stream(), self.num_envs, _ptr(ik), _ptr(self.levels),
+                                                     _ptr(self.rand), _ptr(self.state), _ptr(self.keys), _ptr(self.first_rec),
+                                                     _ptr(self.act_keys)), "b200sim_init_envs")
+        self.launches += 1
+        torch.cuda.current_stream(dev).synchronize()  # ik must outlive the launch
+
+    # -------------------------------------------------------------------------------------------------- step
+    def step(self, action: torch.Tensor, rec_cur: torch.Tensor, rec_next: torch.Tensor) -> None:
+        """One control step for every env (``RLTask.step_engine``, rl.py:1164-1211)."""
+        n = self.num_envs
+        self._chk(action, (n, self.NA), torch.float32, "action")
+        self._chk(rec_cur, (n, self.R), torch.float32, "rec_cur")
+        self._chk(rec_next, (n, self.R), torch.float32, "rec_next")
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.b200sim_step_ctrl(self._handle, self._stream(), n, _ptr(action), _ptr(self.rand), _ptr(self.state),
+                                                     _ptr(self.keys), _ptr(rec_cur), _ptr(rec_next), _ptr(self.act_keys)),
+                          "b200sim_step_ctrl")
+        self.launches += 1
+
+    def rollout(self, actions: torch.Tensor, rec: torch.Tensor | None = None) -> torch.Tensor:
+        """T control steps with given ``actions[T][N][NA]`` in one launch (``_single_unroll``'s scan, rl.py:1620)."""
+        t, n = int(actions.shape[0]), self.num_envs
+        self._chk(actions, (t, n, self.NA), torch.float32, "actions")
+        if rec is None:
+            rec = self.new_record_buffer(t)
+        self._chk(rec, (t + 1, n, self.R), torch.float32, "rec")
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.b200sim_rollout(self._handle, self._stream(), n, t, _ptr(actions), _ptr(self.rand), _ptr(self.state),
+                                                   _ptr(self.keys), _ptr(rec)), "b200sim_rollout")
+        self.launches += 1
+        self.first_rec = rec[t]  # pre-step block of the next rollout
+        return rec
+
+    # ----------------------------------------------------------------------------------------------- scoring
+    def rewards(self, rec: torch.Tensor, n_steps: int | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+        """``get_rewards`` for every env (rl.py:189-245): returns total[N][T], components[K][N][T]; updates the carry."""
+        t = int(rec.shape[0]) if n_steps is None else int(n_steps)
+        n, k = self.num_envs, self.program["TI_N_REW_COMP"]
+        total = torch.empty((n, t), dtype=torch.float32, device=self.device)
+        comps = torch.empty((max(k, 1), n, t), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.b200sim_rewards(self._handle, self._stream(), n, t, _ptr(rec), _ptr(self.levels),
+                                                   _ptr(self.reward_carry), _ptr(total), _ptr(comps)), "b200sim_rewards")
+        self.launches += 1
+        return total, comps
+
+    def flags(self, rec: torch.Tensor, n_steps: int) -> tuple[torch.Tensor, torch.Tensor]:
+        n = self.num_envs
+        dones = torch.empty((n, n_steps), dtype=torch.uint8, device=self.device)
+        succ = torch.empty((n, n_steps), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.b200sim_extract_flags(self._handle, self._stream(), n, n_steps, _ptr(rec), _ptr(dones), _ptr(succ)),
+                          "b200sim_extract_flags")
+        self.launches += 1
+        return dones, succ
+
+    def gae(self, values: torch.Tensor, rewards: torch.Tensor, dones: torch.Tensor, successes: torch.Tensor, gamma: float,
+            lam: float, normalize_advantages: bool = False, monte_carlo_returns: bool = False,
+            ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """``compute_ppo_inputs`` (ksim/task/ppo.py:54-121): advantages, value targets, returns, all [B][T]."""
+        b, t = int(values.shape[0]), int(values.shape[1])
+        self._chk(values, (b, t), torch.float32, "values")
+        self._chk(rewards, (b, t), torch.float32, "rewards")
+        self._chk(dones, (b, t), torch.uint8, "dones")
+        self._chk(successes, (b, t), torch.uint8, "successes")
+        adv, tgt, ret = (torch.empty((b, t), dtype=torch.float32, device=self.device) for _ in range(3))
+        flags = (C.GAE_NORMALIZE_ADVANTAGES if normalize_advantages else 0) | (C.GAE_MONTE_CARLO_RETURNS if monte_carlo_returns else 0)
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.b200sim_gae(self._stream(), b, t, _ptr(values), _ptr(rewards), _ptr(dones), _ptr(successes),
+                                               ctypes.c_float(gamma), ctypes.c_float(lam), flags, _ptr(adv), _ptr(tgt), _ptr(ret)),
+                          "b200sim_gae")
+        self.launches += 2 if normalize_advantages else 1
+        return adv, tgt, ret
+
+
+def get_physics_engine(spec: TaskSpec, num_envs: int, **kwargs: object) -> B200Engine:
+    """Counterpart of ``ksim.engine.get_physics_engine`` (engine.py:488-515) for the ``"b200"`` engine type."""
+    return B200Engine(spec, num_envs, **kwargs)  # type: ignore[arg-type]
