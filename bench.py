@@ -1,0 +1,313 @@
+"""Benchmark of the batched-rollout hot path (BASELINE.json metric: humanoid env-steps/sec).
+
+A "step" = one PPO-iteration's worth of the hot path over one batch of synthetic input:
+rollout of `envs` humanoid environments x `rollout` control steps (5 physics sub-steps each, with actuators,
+events, observations, terminations, reset-on-done, commands) -> rewards -> done/success flags -> GAE.
+Workload = BASELINE.json configs[1]: humanoid walking 4096 envs x rollout 64 on 1 B200; with --gpus N each rank owns
+4096 envs (weak scaling, configs[3] at N=8).  Policy = random-init surrogate: a_t = 0.3 N(0,1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+ENVS_PER_GPU = 4096
+ROLLOUT = 64
+METRIC = "humanoid env-steps/sec"
+UNIT = "env-steps/s"
+GAMMA, LAM = 0.97, 0.95
+
+
+def _peaks() -> tuple[float, str]:
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self) -> None:
+        assert self.proc is not None and self.proc.stdout is not None
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _config(n_gpus: int) -> dict:
+    return {"workload": "humanoid walking (examples/walking.py plugin set) 4096 envs x rollout 64 per GPU: physics+obs+termination+"
+                        "reset+reward+GAE", "envs_per_gpu": ENVS_PER_GPU, "rollout": ROLLOUT, "total_envs": ENVS_PER_GPU * n_gpus,
+            "physics_substeps_per_env_step": 5, "policy": "synthetic: a_t = 0.3*N(0,1), values = 0", "parallelism": f"env-sharded x{n_gpus}",
+            "l2_note": "per-step inputs+outputs (record buffer 4096x65x608 fp32 = 648 MB) exceed the 126 MB L2"}
+
+
+def run_reference(args: argparse.Namespace) -> None:
+    """The CPU implementation of the same path (the C oracle, f32, OpenMP over envs) on the host cores.
+
+    The reference's own CPU path is MJX on the JAX CPU backend; neither jax nor mujoco exists in this image
+    (DESIGN.md), so `kind` is "port".  Each step is a bounded sample of the workload: `sample_envs` x `sample_steps`.
+    """
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from ksim_b200.envinit import make_env_init
+    from ksim_b200.examples.walking import RANDOMIZERS, make_spec
+    from ksim_b200.program import build_program
+    from oracle import OracleEngine
+
+    oracle.build()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    spec = make_spec()
+    prog = build_program(spec)
+    rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
+    n, t = max(cores * 8, 64), 16
+    ora = OracleEngine(prog, "f32")
+    init = make_env_init(prog, rz, n, seed=0)
+    st, keys, rec0, _ = ora.init_envs(init.init_keys, init.levels, init.rand)
+    rec = np.zeros((t + 1, n, prog.rec_size), np.float32)
+    rec[0] = rec0
+    actions = (0.3 * np.random.RandomState(1).randn(t, n, prog.action_size)).astype(np.float32)
+    carry = np.zeros((n, prog["TI_REW_CARRY_SIZE"]), np.float32)
+
+    def one() -> None:
+        ora.rollout(actions, init.rand, st, keys, rec)
+        total, _ = ora.rewards(rec[:t], init.levels, carry)
+        d, s = prog["TI_R_DONE"], prog["TI_R_SUCCESS"]
+        ora.gae(np.zeros_like(total), total, (rec[:t, :, d] != 0).T, (rec[:t, :, s] != 0).T, GAMMA, LAM, 0)
+        rec[0] = rec[t]
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n * t / dt
+    sample = f"{n} envs x {t} control steps per step (same plugin set), f32 C oracle, OpenMP over envs"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": _config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_leg() -> dict:
+    """Bounded CPU sample (~10-20 s) of the same workload for the `cpu_baseline` object (rank 0, N=1 only)."""
+    import oracle
+    from ksim_b200.envinit import make_env_init
+    from ksim_b200.examples.walking import RANDOMIZERS, make_spec
+    from ksim_b200.program import build_program
+    from oracle import OracleEngine
+
+    oracle.build()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    spec = make_spec()
+    prog = build_program(spec)
+    rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
+    n, t = max(cores * 8, 64), 16
+    ora = OracleEngine(prog, "f32")
+    init = make_env_init(prog, rz, n, seed=0)
+    st, keys, rec0, _ = ora.init_envs(init.init_keys, init.levels, init.rand)
+    rec = np.zeros((t + 1, n, prog.rec_size), np.float32)
+    rec[0] = rec0
+    actions = (0.3 * np.random.RandomState(1).randn(t, n, prog.action_size)).astype(np.float32)
+    ora.rollout(actions, init.rand, st, keys, rec)  # warm
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 10.0:
+        rec[0] = rec[t]
+        ora.rollout(actions, init.rand, st, keys, rec)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n * t / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} x ({n} envs x {t} control steps), f32 C oracle of the same path, OpenMP over envs, ~10 s"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+
+    from ksim_b200 import distributed as D
+    from ksim_b200.engine import B200Engine
+    from ksim_b200.examples.walking import RANDOMIZERS, make_spec
+
+    rank, local, world = D.init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    spec = make_spec()
+    rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
+    n, t = ENVS_PER_GPU, ROLLOUT
+    lo, _ = D.shard_range(n * world, rank, world)
+    eng = B200Engine(spec, n, device=device, randomizers=rz, seed=0, env_offset=lo, total_envs=n * world)
+    na = eng.NA
+    # synthetic policy outputs for every step of the run, resident in HBM before timing starts
+    gen = torch.Generator(device=device).manual_seed(1 + rank)
+    actions = 0.3 * torch.randn((t, n, na), generator=gen, device=device)
+    values = torch.zeros((n, t), device=device)
+    rec = eng.new_record_buffer(t)
+    stream = torch.cuda.current_stream(device)
+
+    def hot_path(acts: torch.Tensor) -> torch.Tensor:
+        eng.rollout(acts, rec)
+        total, _ = eng.rewards(rec, t)
+        dones, succ = eng.flags(rec, t)
+        adv, tgt, ret = eng.gae(values, total, dones, succ, GAMMA, LAM)
+        rec[0].copy_(rec[t])  # next rollout starts from this rollout's final pre-step block
+        return adv
+
+    def barrier() -> None:
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        hot_path(actions)
+    # ---- device-resident timing (value) + dominant-kernel timing (roofline) ----
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev[0].record(stream)
+    for i in range(args.steps):
+        kev[i][0].record(stream)
+        eng.rollout(actions, rec)
+        kev[i][1].record(stream)
+        total, _ = eng.rewards(rec, t)
+        dones, succ = eng.flags(rec, t)
+        eng.gae(values, total, dones, succ, GAMMA, LAM)
+        rec[0].copy_(rec[t])
+    ev[1].record(stream)
+    barrier()
+    launches = (eng.launches - l0) + args.steps  # + the record hand-over copy
+    ms = ev[0].elapsed_time(ev[1]) / args.steps
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    ms = D.max_over_ranks(ms, device)
+    # ---- end-to-end through the public API with HOST buffers (pinned actions in, rewards+advantages out) ----
+    host_actions = torch.empty((t, n, na), dtype=torch.float32).pin_memory()
+    host_actions.copy_(actions.cpu())
+    host_adv = torch.empty((n, t), dtype=torch.float32).pin_memory()
+    host_total = torch.empty((n, t), dtype=torch.float32).pin_memory()
+    dev_actions = torch.empty_like(actions)
+
+    def e2e_step() -> None:
+        dev_actions.copy_(host_actions, non_blocking=True)
+        eng.rollout(dev_actions, rec)
+        total, _ = eng.rewards(rec, t)
+        dones, succ = eng.flags(rec, t)
+        adv, _, _ = eng.gae(values, total, dones, succ, GAMMA, LAM)
+        rec[0].copy_(rec[t])
+        host_adv.copy_(adv, non_blocking=True)
+        host_total.copy_(total, non_blocking=True)
+        torch.cuda.synchronize(device)  # the caller reads the result
+
+    e2e_step()
+    barrier()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    ev2[1].record(stream)
+    barrier()
+    e2e_ms = D.max_over_ranks(ev2[0].elapsed_time(ev2[1]) / args.steps, device)
+    clocks = sampler.stop() if rank == 0 else {}
+    nonfinite = float(eng.state[:, eng.program["TI_S_NONFINITE"]].sum())
+    if nonfinite:
+        raise SystemExit(f"{nonfinite} environments produced non-finite states")
+    if rank != 0:
+        return
+    env_steps = n * t * world
+    value = env_steps / (ms * 1e-3)
+    # algorithmic HBM bytes per env-step of the rollout kernel: state+keys read & written once per launch
+    # (amortised over the 64 steps), action read, full record written
+    p = eng.program
+    per_launch_env = 4 * (2 * p.state_size + 2 * p.key_size + p.rand_size)
+    bytes_per_env_step = 4 * (p.action_size + p.rec_size) + per_launch_env / t
+    peak, peak_src = _peaks()
+    achieved = n * t * bytes_per_env_step / (kernel_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(world),
+        "e2e": {"value": env_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_actions.numel() * 4),
+                "d2h_bytes_per_step": int((host_adv.numel() + host_total.numel()) * 4), "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "k_rollout<DimsHumanoid>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms,
+                     "algorithmic_bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src,
+                     "note": "latency/issue-bound by design (tiny per-env matrices); see DESIGN.md and profiles/"},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_leg()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+"""One process per GPU: environment sharding and the (few) cross-rank reductions of the rollout path.
+
+Environments are independent, so the data path has NO collective: rank r owns the contiguous slice
+``shard_range(total_envs, r, world)`` and derives the same per-env keys it would get in a single-process run
+(``make_env_init(env_offset=...)``), which makes results invariant to the GPU count.  The only exchanges are
+scalar reductions for reporting (max time over ranks, summed env-steps, optional global advantage statistics).
+Backend: ``nccl`` on GPUs, ``gloo`` in the CPU tests.
+"""
+
+from __future__ import annotations
+
+__all__ = ["shard_range", "init_from_env", "max_over_ranks", "sum_over_ranks", "global_mean_std"]
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced slice [start, stop) of ``total`` items for ``rank``."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of size {world}")
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """(rank, local_rank, world) from torchrun's environment; initialises the process group when world > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, local, world
+
+
+def _reduce(value: float, op: dist.ReduceOp, device: torch.device | str) -> float:
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=op)
+    return float(t.item())
+
+
+def max_over_ranks(value: float, device: torch.device | str = "cpu") -> float:
+    return _reduce(value, dist.ReduceOp.MAX, device)
+
+
+def sum_over_ranks(value: float, device: torch.device | str = "cpu") -> float:
+    return _reduce(value, dist.ReduceOp.SUM, device)
+
+
+def global_mean_std(x: torch.Tensor) -> tuple[float, float]:
+    """Mean / std of a tensor sharded over ranks (for job-wide advantage normalisation): one 3-float all-reduce."""
+    acc = torch.stack([x.sum(dtype=torch.float64), (x.double() ** 2).sum(), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(acc)
+    mean = acc[0] / acc[2]
+    var = torch.clamp(acc[1] / acc[2] - mean * mean, min=0.0)
+    return float(mean), float(var.sqrt())

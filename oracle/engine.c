@@ -1165,3 +1165,27 @@ int o_gae(int B, int T, const REAL* values, const REAL* rewards, const uint8_t* 
   }
   return B2S_OK;
 }
+
+/* ------------------------------------------------------------------------------------------ test hooks */
+
+/* evaluates termination `idx` of the task program on a hand-built state (tests/test_golden_terminations.py);
+ * contacts are given as (geom1, geom2, dist) triples through a one-pair-per-contact scratch model. */
+int o_test_termination(const int* ti, const REAL* tf, int idx, const REAL* qpos, int nq, const REAL* qvel, int nv,
+                       REAL time, REAL level, int ncon, const int* geom1, const int* geom2, const REAL* dist) {
+  Task t;
+  task_init(&t, ti, tf);
+  Env* e = (Env*)calloc(1, sizeof(Env));
+  for (int i = 0; i < nq && i < O_MAXNQ; i++) e->d.qpos[i] = qpos[i];
+  for (int i = 0; i < nv && i < O_MAXNV; i++) e->d.qvel[i] = qvel[i];
+  e->d.time = time;
+  e->level = level;
+  e->d.ncon = ncon < O_MAXCON ? ncon : O_MAXCON;
+  for (int c = 0; c < e->d.ncon; c++) {
+    e->d.contact[c].geom1 = geom1[c];
+    e->d.contact[c].geom2 = geom2[c];
+    e->d.contact[c].dist = dist[c];
+  }
+  int v = termination(&t, e, idx);
+  free(e);
+  return v;
+}

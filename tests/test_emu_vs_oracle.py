@@ -1,0 +1,119 @@
+"""The warp-kernel SOURCE (ksim_b200/csrc/*.cuh), compiled for the host with lanes serialised (tests/emu), against
+the CPU oracle.  This validates the kernel's logic on a GPU-less machine; it is test infrastructure only and is
+never loaded by the package (the -m gpu tests are the parity tests proper)."""
+
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from ksim_b200 import codes as C
+from ksim_b200.blob import pack_blob
+from ksim_b200.envinit import make_env_init
+
+EMU = Path(__file__).resolve().parent / "emu"
+
+
+@pytest.fixture(scope="module")
+def emu() -> ctypes.CDLL:
+    src, out = EMU / "emu.cpp", EMU / "libb2s_emu.so"
+    deps = [src, *sorted((EMU.parent.parent / "ksim_b200" / "csrc").glob("*.cuh")), *sorted((EMU.parent.parent / "include").glob("*.h"))]
+    if not out.exists() or any(d.stat().st_mtime > out.stat().st_mtime for d in deps):
+        subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-x", "c++", "-o", str(out), str(src)], check=True)
+    return ctypes.CDLL(str(out))
+
+
+def _p(a: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _run(emu, prog, rz, n, t, level, seed=0):  # noqa: ANN001, ANN202
+    from oracle import OracleEngine
+
+    blob = np.frombuffer(pack_blob(prog.spec.model, prog.ti, prog.tf), dtype=np.uint8).copy()
+    init = make_env_init(prog, rz, n, seed=seed, level=level)
+    ora = OracleEngine(prog, "f32")
+    st_o, k_o, rec0, ak_o = ora.init_envs(init.init_keys, init.levels, init.rand)
+    st_e, k_e = np.zeros_like(st_o), np.zeros_like(k_o)
+    rec_e = np.zeros((t + 1, n, prog.rec_size), np.float32)
+    ak_e = np.zeros((n, 2), np.uint32)
+    emu.emu_init_envs(_p(blob), n, _p(init.init_keys), _p(init.levels), _p(init.rand), _p(st_e), _p(k_e), _p(rec_e[0]), _p(ak_e))
+    np.testing.assert_array_equal(k_e, k_o)
+    np.testing.assert_array_equal(ak_e, ak_o)
+    np.testing.assert_allclose(st_e, st_o, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(rec_e[0], rec0, rtol=0, atol=1e-3)
+    rec_o = np.zeros_like(rec_e)
+    rec_o[0] = rec0
+    actions = (0.3 * np.random.RandomState(seed + 1).randn(t, n, prog.action_size)).astype(np.float32)
+    for s in range(t):
+        # re-synchronise: both sides step from the ORACLE's state, so the comparison is one control step deep
+        st_e[:], k_e[:] = st_o, k_o
+        emu.emu_step_ctrl(_p(blob), n, _p(actions[s]), _p(init.rand), _p(st_e), _p(k_e), _p(rec_e[s]), _p(rec_e[s + 1]), None)
+        ora.step_ctrl(actions[s], init.rand, st_o, k_o, rec_o[s], rec_o[s + 1])
+        np.testing.assert_array_equal(k_e, k_o)
+    return prog, rec_e, rec_o, st_e, st_o, ora, blob, init
+
+
+def test_walking_single_step_parity(emu, oracle_built, walking_program, walking_randomizers) -> None:  # noqa: ANN001
+    prog, rec_e, rec_o, st_e, st_o, *_ = _run(emu, walking_program, walking_randomizers, n=16, t=12, level=0.0)
+    m = prog.spec.model
+    q, v, d = prog["TI_R_QPOS"], prog["TI_R_QVEL"], prog["TI_R_DONE"]
+    np.testing.assert_allclose(rec_e[:12, :, q : q + m.nq], rec_o[:12, :, q : q + m.nq], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(rec_e[:12, :, v : v + m.nv], rec_o[:12, :, v : v + m.nv], rtol=0, atol=2e-2)
+    np.testing.assert_array_equal(rec_e[:12, :, d], rec_o[:12, :, d])
+    tm = prog["TI_R_TERM"]
+    np.testing.assert_array_equal(rec_e[:12, :, tm : tm + 3], rec_o[:12, :, tm : tm + 3])
+
+
+def test_walking_with_noise_and_resets(emu, oracle_built, walking_program, walking_randomizers) -> None:  # noqa: ANN001
+    """Curriculum level 1: every RandomVariable is live (noise.py:86,102,118); long enough for falls and resets."""
+    prog, rec_e, rec_o, st_e, st_o, *_ = _run(emu, walking_program, walking_randomizers, n=12, t=60, level=1.0, seed=3)
+    d, tm = prog["TI_R_DONE"], prog["TI_R_TIME"]
+    assert rec_o[:60, :, d].sum() > 0, "the test must exercise reset-on-done"
+    np.testing.assert_array_equal(rec_e[:60, :, d], rec_o[:60, :, d])
+    np.testing.assert_allclose(rec_e[:60, :, tm], rec_o[:60, :, tm], rtol=0, atol=1e-5)
+    o = prog["TI_R_OBS"]
+    off, dim, _ = prog.obs_slices["noisy_joint_position"]
+    np.testing.assert_allclose(rec_e[1:61, :, o + off : o + off + dim], rec_o[1:61, :, o + off : o + off + dim], rtol=0, atol=5e-4)
+    np.testing.assert_allclose(st_e, st_o, rtol=5e-3, atol=5e-3)  # state holds qacc (O(1e2)) as well
+
+
+def test_rewards_parity(emu, oracle_built, walking_program, walking_randomizers) -> None:  # noqa: ANN001
+    prog, rec_e, rec_o, _, _, ora, blob, init = _run(emu, walking_program, walking_randomizers, n=6, t=30, level=0.5, seed=5)
+    n, t = 6, 30
+    k, c = prog["TI_N_REW_COMP"], prog["TI_REW_CARRY_SIZE"]
+    carry_o = np.zeros((n, c), np.float32)
+    carry_e = np.zeros((n, c), np.float32)
+    total_o, comps_o = ora.rewards(rec_o[:t], init.levels, carry_o)
+    total_e, comps_e = np.zeros((n, t), np.float32), np.zeros((k, n, t), np.float32)
+    rec_in = np.ascontiguousarray(rec_o[:t])  # same input records: the reward code alone is under test
+    emu.emu_rewards(_p(blob), n, t, _p(rec_in), _p(init.levels), _p(carry_e), _p(total_e), _p(comps_e))
+    np.testing.assert_allclose(comps_e, comps_o, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(total_e, total_o, rtol=1e-5, atol=1e-4)
+    np.testing.assert_array_equal(carry_e, carry_o)
+    assert np.abs(comps_o).sum(axis=(1, 2)).min() >= 0 and np.isfinite(total_o).all()
+
+
+def test_tripod_with_events_and_latency(emu, oracle_built) -> None:  # noqa: ANN001
+    from ksim_b200 import events, terminations
+    from ksim_b200.program import build_program
+    from tests.helpers import tripod_spec
+
+    spec = tripod_spec(
+        events={"push": events.LinearPushEvent(linvel=1.0, interval_range=(0.05, 0.2)),
+                "spin": events.AngularPushEvent(angvel=1.0, interval_range=(0.05, 0.2)),
+                "jump": events.JumpEvent(jump_height_range=(0.05, 0.1), interval_range=(0.1, 0.3))},
+        terminations={"low": terminations.MinimumHeightTermination(min_height=0.2),
+                      "tilt": terminations.NotUprightTermination(max_radians=1.0),
+                      "len": terminations.EpisodeLengthTermination(max_length_sec=0.5)},
+        action_latency_range=(0.004, 0.012), drop_action_prob=0.2, zero_offset_std=0.02, zero_offset_mag=0.02)
+    prog = build_program(spec)
+    prog2, rec_e, rec_o, st_e, st_o, *_ = _run(emu, prog, {}, n=10, t=50, level=1.0, seed=9)
+    d, sc = prog["TI_R_DONE"], prog["TI_R_SUCCESS"]
+    assert rec_o[:50, :, sc].sum() > 0 and rec_o[:50, :, d].sum() > rec_o[:50, :, sc].sum() - 1
+    np.testing.assert_array_equal(rec_e[:50, :, d], rec_o[:50, :, d])
+    np.testing.assert_array_equal(rec_e[:50, :, sc], rec_o[:50, :, sc])
+    q = prog["TI_R_QPOS"]
+    np.testing.assert_allclose(rec_e[:50, :, q : q + 10], rec_o[:50, :, q : q + 10], rtol=0, atol=5e-4)

@@ -1,0 +1,235 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances (fp32 path, stated per north_star):
+  * discrete outputs -- PRNG keys, done / success flags, termination codes, episode time -- bit-exact;
+  * one control step (5 physics sub-steps) from an identical state: |dqpos| <= 2e-4, relative 5e-3 on velocities /
+    accelerations (contact dynamics amplify fp32 round-off by ~1.3x per sub-step; the f32 CPU oracle differs from
+    the f64 CPU oracle by the same amount);
+  * free-running trajectories: the GPU-vs-f64 error must stay within 4x the f32-oracle-vs-f64 error + 1e-4 over a
+    short horizon (contact dynamics are chaotic over longer ones);
+  * rewards on identical records: 1e-5; GAE without normalisation: bit-exact (same fp32 operation order).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(walking_spec, walking_randomizers):  # noqa: ANN001, ANN201
+    import __graft_entry__ as g
+    import oracle
+
+    g.build_cuda()
+    oracle.build()
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+    return walking_spec, walking_randomizers
+
+
+def _engine(spec, rz, n, level=0.0, seed=0, **kw):  # noqa: ANN001, ANN003, ANN202
+    from ksim_b200.engine import B200Engine
+
+    return B200Engine(spec, n, device="cuda:0", randomizers=rz, seed=seed, curriculum_level=level, **kw)
+
+
+def _oracle_init(eng, precision="f32"):  # noqa: ANN001, ANN202
+    from oracle import OracleEngine
+
+    ora = OracleEngine(eng.program, precision)
+    init = eng.env_init
+    st, keys, rec0, ak = ora.init_envs(init.init_keys, init.levels, init.rand)
+    return ora, st, keys, rec0, ak
+
+
+def _np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+def test_native_library_is_the_one_running(ctx) -> None:  # noqa: ANN001
+    from ksim_b200 import binding
+
+    eng = _engine(*ctx, 4)
+    assert binding.library_path().exists() and eng.info("VARIANT") == 0  # humanoid-sized instantiation
+    maps = open("/proc/self/maps").read()
+    assert "libb200sim.so" in maps
+
+
+@pytest.mark.parametrize("level", [0.0, 1.0])
+def test_init_parity(ctx, level) -> None:  # noqa: ANN001
+    eng = _engine(*ctx, 64, level=level, seed=2)
+    ora, st, keys, rec0, ak = _oracle_init(eng)
+    np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
+    np.testing.assert_array_equal(_np(eng.act_keys).view(np.uint32), ak)
+    np.testing.assert_allclose(_np(eng.state), st, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(_np(eng.first_rec), rec0, rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("level,steps,seed", [(0.0, 16, 0), (1.0, 80, 3)])
+def test_single_step_parity_resynchronised(ctx, level, steps, seed) -> None:  # noqa: ANN001
+    """Each control step starts from the oracle's state on both sides, so errors do not compound."""
+    spec, rz = ctx
+    n = 48
+    eng = _engine(spec, rz, n, level=level, seed=seed)
+    ora, st, keys, rec0, _ = _oracle_init(eng)
+    p, m = eng.program, spec.model
+    actions = (0.3 * np.random.RandomState(seed + 1).randn(steps, n, eng.NA)).astype(np.float32)
+    rec_o = np.zeros((2, n, eng.R), np.float32)
+    rec_o[0] = rec0
+    cur, nxt = (torch.zeros((n, eng.R), device="cuda") for _ in range(2))
+    n_done = 0
+    q, v, d, sc, tm, te = p["TI_R_QPOS"], p["TI_R_QVEL"], p["TI_R_DONE"], p["TI_R_SUCCESS"], p["TI_R_TIME"], p["TI_R_TERM"]
+    for s in range(steps):
+        eng.state.copy_(torch.from_numpy(st).cuda())
+        eng.keys.copy_(torch.from_numpy(keys.view(np.int32)).cuda())
+        eng.step(torch.from_numpy(actions[s]).cuda(), cur, nxt)
+        ora.step_ctrl(actions[s], eng.env_init.rand, st, keys, rec_o[0], rec_o[1])
+        g_cur, g_nxt = _np(cur), _np(nxt)
+        np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
+        np.testing.assert_array_equal(g_cur[:, d], rec_o[0][:, d])
+        np.testing.assert_array_equal(g_cur[:, sc], rec_o[0][:, sc])
+        np.testing.assert_array_equal(g_cur[:, te : te + 3], rec_o[0][:, te : te + 3])
+        np.testing.assert_allclose(g_cur[:, tm], rec_o[0][:, tm], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(g_cur[:, q : q + m.nq], rec_o[0][:, q : q + m.nq], rtol=0, atol=2e-4)
+        np.testing.assert_allclose(g_cur[:, v : v + m.nv], rec_o[0][:, v : v + m.nv], rtol=5e-3, atol=2e-2)
+        o = p["TI_R_OBS"]
+        for name in ("joint_position", "noisy_joint_position", "base_orientation", "imu_projected_gravity", "feet_position"):
+            off, dim, _ = p.obs_slices[name]
+            np.testing.assert_allclose(g_nxt[:, o + off : o + off + dim], rec_o[1][:, o + off : o + off + dim], rtol=0, atol=5e-4, err_msg=name)
+        off, dim, _ = p.obs_slices["feet_contact"]
+        np.testing.assert_array_equal(g_nxt[:, o + off : o + off + dim], rec_o[1][:, o + off : o + off + dim])
+        n_done += int(rec_o[0][:, d].sum())
+        rec_o[0] = rec_o[1]
+    if level > 0:
+        assert n_done > 0, "the noisy case must exercise reset-on-done"
+
+
+def test_free_running_error_tracks_f32_oracle(ctx) -> None:  # noqa: ANN001
+    spec, rz = ctx
+    n, t = 64, 6
+    eng = _engine(spec, rz, n, seed=4)
+    p, m = eng.program, spec.model
+    actions = (0.3 * np.random.RandomState(5).randn(t, n, eng.NA)).astype(np.float32)
+    recs = {}
+    for precision in ("f32", "f64"):
+        ora, st, keys, rec0, _ = _oracle_init(eng, precision)
+        rec = np.zeros((t + 1, n, eng.R), ora.real)
+        rec[0] = rec0
+        ora.rollout(actions.astype(ora.real), eng.env_init.rand, st, keys, rec)
+        recs[precision] = rec
+    rec_g = _np(eng.rollout(torch.from_numpy(actions).cuda()))
+    q = p["TI_R_QPOS"]
+    for s in range(t):
+        e_gpu = np.abs(rec_g[s, :, q : q + m.nq] - recs["f64"][s, :, q : q + m.nq]).max(axis=1)
+        e_f32 = np.abs(recs["f32"][s, :, q : q + m.nq] - recs["f64"][s, :, q : q + m.nq]).max(axis=1)
+        # compare error *distributions*: the median env of the GPU run is no worse than 4x the f32 oracle's
+        assert np.median(e_gpu) <= 4 * np.median(e_f32) + 1e-4, (s, np.median(e_gpu), np.median(e_f32))
+    np.testing.assert_allclose(rec_g[0, :, q : q + m.nq], recs["f64"][0, :, q : q + m.nq], rtol=0, atol=2e-4)
+
+
+def test_rewards_and_flags_parity(ctx) -> None:  # noqa: ANN001
+    spec, rz = ctx
+    n, t = 40, 48
+    eng = _engine(spec, rz, n, level=0.7, seed=6)
+    ora, st, keys, rec0, _ = _oracle_init(eng)
+    actions = (0.4 * np.random.RandomState(7).randn(t, n, eng.NA)).astype(np.float32)
+    rec = eng.rollout(torch.from_numpy(actions).cuda())
+    rec_np = _np(rec)[:t]
+    # rewards on IDENTICAL records (the GPU's), two consecutive calls so that the stateful carry is exercised
+    carry = np.zeros((n, eng.program["TI_REW_CARRY_SIZE"]), np.float32)
+    for _ in range(2):
+        total_o, comps_o = ora.rewards(rec_np, eng.env_init.levels, carry)
+        total_g, comps_g = eng.rewards(rec, t)
+        np.testing.assert_allclose(_np(comps_g), comps_o, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(_np(total_g), total_o, rtol=1e-5, atol=1e-4)
+        np.testing.assert_array_equal(_np(eng.reward_carry), carry)
+    dones, succ = eng.flags(rec, t)
+    d, sc = eng.program["TI_R_DONE"], eng.program["TI_R_SUCCESS"]
+    np.testing.assert_array_equal(_np(dones), (rec_np[:, :, d] != 0).T)
+    np.testing.assert_array_equal(_np(succ), (rec_np[:, :, sc] != 0).T)
+    assert _np(dones).sum() > 0
+
+
+@pytest.mark.parametrize("b,t", [(1, 1), (7, 3), (512, 24), (4096, 64)])
+def test_gae_bit_exact(ctx, b, t) -> None:  # noqa: ANN001
+    from oracle import OracleEngine
+
+    eng = _engine(*ctx, 4)
+    ora = OracleEngine(eng.program, "f32")
+    rs = np.random.RandomState(b + t)
+    values, rewards = rs.randn(b, t).astype(np.float32), rs.randn(b, t).astype(np.float32)
+    dones = (rs.rand(b, t) < 0.1)
+    succ = dones & (rs.rand(b, t) < 0.3)
+    tv = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).cuda()  # noqa: E731
+    for mc in (False, True):
+        adv, tgt, ret = eng.gae(tv(values, np.float32), tv(rewards, np.float32), tv(dones, np.uint8), tv(succ, np.uint8), 0.97, 0.95,
+                                monte_carlo_returns=mc)
+        oa, ot, orr = ora.gae(values, rewards, dones, succ, 0.97, 0.95, 2 if mc else 0)
+        np.testing.assert_array_equal(_np(adv), oa)
+        np.testing.assert_array_equal(_np(tgt), ot)
+        np.testing.assert_array_equal(_np(ret), orr)
+    adv, _, _ = eng.gae(tv(values, np.float32), tv(rewards, np.float32), tv(dones, np.uint8), tv(succ, np.uint8), 0.97, 0.95,
+                        normalize_advantages=True)
+    oa, _, _ = ora.gae(values, rewards, dones, succ, 0.97, 0.95, 1)
+    if b * t > 1:
+        np.testing.assert_allclose(_np(adv), oa, rtol=2e-4, atol=2e-5)
+
+
+def test_full_size_properties(ctx) -> None:  # noqa: ANN001
+    """BASELINE config 2 (4096 envs x 64 steps): size-independent properties instead of an oracle replay."""
+    spec, rz = ctx
+    n, t = 4096, 64
+    actions = torch.from_numpy((0.3 * np.random.RandomState(8).randn(t, n, 17)).astype(np.float32)).cuda()
+    eng = _engine(spec, rz, n, seed=9)
+    rec = eng.rollout(actions)
+    view = eng.view(rec[:t])
+    assert torch.isfinite(rec).all() and float(eng.state[:, eng.program["TI_S_NONFINITE"]].sum()) == 0
+    quat = view.qpos[..., 3:7]
+    assert float((quat.norm(dim=-1) - 1).abs().max()) < 1e-5
+    done = view.done
+    assert 0.001 < float(done.float().mean()) < 0.2
+    # after a done step the episode clock restarts: next post-step time is exactly one control step
+    time = view.timestep
+    nxt = time[1:][done[:-1]]
+    assert torch.allclose(nxt, torch.full_like(nxt, 0.02), atol=1e-6)
+    # z termination is consistent with the recorded height (BadZTermination 0.5 < z < 3.0)
+    z = view.qpos[..., 2]
+    bad = (z < 0.5) | (z > 3.0)
+    assert bool((view.termination_components["bad_z"] == -1).eq(bad).all())
+    # determinism: same seed, same bits
+    eng2 = _engine(spec, rz, n, seed=9)
+    rec2 = eng2.rollout(actions)
+    assert torch.equal(rec, rec2) and torch.equal(eng.state, eng2.state) and torch.equal(eng.keys, eng2.keys)
+    # sharding invariance: two half-size engines reproduce the full run bit for bit
+    lo = _engine(spec, rz, n // 2, seed=9, env_offset=0, total_envs=n)
+    hi = _engine(spec, rz, n // 2, seed=9, env_offset=n // 2, total_envs=n)
+    rec_lo, rec_hi = lo.rollout(actions[:, : n // 2].contiguous()), hi.rollout(actions[:, n // 2 :].contiguous())
+    assert torch.equal(torch.cat([rec_lo, rec_hi], dim=1), rec)
+    # step-by-step launches equal the fused rollout launch
+    eng3 = _engine(spec, rz, 256, seed=9, env_offset=0, total_envs=n)
+    rec3 = eng3.new_record_buffer(4)
+    for s in range(4):
+        eng3.step(actions[s, :256].contiguous(), rec3[s], rec3[s + 1])
+    assert torch.equal(rec3[:4], rec[:4, :256])
+
+
+def test_edge_cases(ctx) -> None:  # noqa: ANN001
+    spec, rz = ctx
+    # a single environment (the reference's validation rollout shape) and a ragged count
+    for n in (1, 33):
+        eng = _engine(spec, rz, n, seed=1)
+        acts = torch.zeros((3, n, eng.NA), device="cuda")
+        rec = eng.rollout(acts)
+        assert torch.isfinite(rec).all()
+    # NaN / huge actions are cleaned exactly like rl.py:998-1001
+    eng = _engine(spec, rz, 8, seed=1)
+    acts = torch.full((1, 8, eng.NA), float("nan"), device="cuda")
+    acts[0, 4:] = 1e9
+    rec = eng.rollout(acts)
+    a = eng.view(rec[:1]).action
+    assert torch.equal(a[0, :4], torch.zeros_like(a[0, :4])) and torch.equal(a[0, 4:], torch.full_like(a[0, 4:], 1e3))
+    # zero-length rollout is a no-op
+    eng.rollout(torch.zeros((0, 8, eng.NA), device="cuda"))
+    with pytest.raises(ValueError):
+        eng.step(torch.zeros((7, eng.NA), device="cuda"), rec[0], rec[1])
