@@ -278,8 +278,9 @@ extern "C" int b200sim_step_ctrl(const b200sim_model* mo, void* stream, int n_en
 
 extern "C" int b200sim_rollout(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* actions,
                                const float* rand, float* state, uint32_t* keys, float* rec) {
-  if (!mo || n_envs < 0 || n_steps < 0 || !actions || !state || !keys || !rec) return fail(B2S_ERR_BAD_ARG, "null argument");
+  if (!mo || n_envs < 0 || n_steps < 0) return fail(B2S_ERR_BAD_ARG, "bad argument");
   if (n_envs == 0 || n_steps == 0) return B2S_OK;
+  if (!actions || !state || !keys || !rec) return fail(B2S_ERR_BAD_ARG, "null argument");
   if (!rand && mo->ti_host[TI_RAND_SIZE] > 0) return fail(B2S_ERR_BAD_ARG, "rand is required for this task");
   return launch_rollout(mo, stream, n_envs, n_steps, actions, rand, state, keys, rec, nullptr, nullptr);
 }

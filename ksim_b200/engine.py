@@ -223,6 +223,8 @@ class B200Engine:
         if rec is None:
             rec = self.new_record_buffer(t)
         self._chk(rec, (t + 1, n, self.R), torch.float32, "rec")
+        if t == 0 or n == 0:
+            return rec
         with torch.cuda.device(self.device):
             binding.check(self.lib.b200sim_rollout(self._handle, self._stream(), n, t, _ptr(actions), _ptr(self.rand), _ptr(self.state),
                                                    _ptr(self.keys), _ptr(rec)), "b200sim_rollout")
