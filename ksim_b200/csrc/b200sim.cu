@@ -12,10 +12,13 @@
 
 using namespace b2s;
 
+// CTA barriers one physics sub-step executes (engine_step's + forward's stage barriers)
+#define B2S_BARRIERS_PER_SUBSTEP 7
+
 // ------------------------------------------------------------------------------------------------ kernels
 
 template <class D>
-__global__ void __launch_bounds__(256) k_init_envs(const Mdl m, int n_envs, const uint32_t* __restrict__ init_keys,
+__global__ void __launch_bounds__(512) k_init_envs(const Mdl m, int n_envs, const uint32_t* __restrict__ init_keys,
                                                    const float* __restrict__ levels, const float* __restrict__ rand,
                                                    float* __restrict__ state, uint32_t* __restrict__ keys,
                                                    float* __restrict__ rec0, uint32_t* __restrict__ act_keys) {
@@ -33,7 +36,7 @@ __global__ void __launch_bounds__(256) k_init_envs(const Mdl m, int n_envs, cons
 
 // n_steps control steps per launch; the environment stays in shared memory between them.
 template <class D>
-__global__ void __launch_bounds__(256) k_rollout(const Mdl m, int n_envs, int n_steps, const float* __restrict__ actions,
+__global__ void __launch_bounds__(512) k_rollout(const Mdl m, int n_envs, int n_steps, const float* __restrict__ actions,
                                                  const float* __restrict__ rand, float* __restrict__ state,
                                                  uint32_t* __restrict__ keys, float* __restrict__ rec,
                                                  float* __restrict__ rec_next_single, uint32_t* __restrict__ act_keys) {
@@ -43,7 +46,7 @@ __global__ void __launch_bounds__(256) k_rollout(const Mdl m, int n_envs, int n_
   const int* ti = m.ti;
   if (env >= n_envs) {
     // idle warps of the last CTA still take part in engine_step's per-sub-step CTA barriers
-    const int nbar = n_steps * ti[TI_NSUB];
+    const int nbar = n_steps * ti[TI_NSUB] * B2S_BARRIERS_PER_SUBSTEP;
     for (int i = 0; i < nbar; i++) __syncthreads();
     return;
   }
@@ -171,8 +174,7 @@ static int configure(b200sim_model* mo) {
   mo->smem_per_env = sizeof(Work<D>);
   const int max_warps = (int)((kSmemBudget - 2048) / sizeof(Work<D>));
   if (max_warps < 1) return fail(B2S_ERR_TOO_LARGE, "workspace does not fit in shared memory");
-  int wpb = max_warps >= 8 ? max_warps / 2 : max_warps;  // two CTAs per SM when possible
-  if (wpb > 8) wpb = 8;
+  int wpb = max_warps > 16 ? 16 : max_warps;  // one CTA per SM: all its warps run in lockstep (shared i-cache fills)
   mo->warps_per_cta = wpb;
   const int bytes = (int)(wpb * sizeof(Work<D>));
   CUDA_OK(cudaFuncSetAttribute(k_init_envs<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));

@@ -375,7 +375,7 @@ DEVNI void engine_reset(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
     rng = key_split(rng, 0);
     reset_apply(m, w, i, reset_rng, LANE_PASS);
   }
-  forward(m, w, true, LANE_PASS);
+  forward(m, w, true, false, LANE_PASS);
   LANE_FOR(i, nv) { w.qvel[i] = 0.0f; w.qacc[i] = 0.0f; }
   WSYNC();
   actuators_initial_state(m, w, rng, LANE_PASS);

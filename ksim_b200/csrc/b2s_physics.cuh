@@ -276,17 +276,6 @@ DEVNI void chol_inplace(Work<D>& w, int nv, LANE_ARG) {
   }
 }
 
-// dense Cholesky of (M + diag_scale * diag_add) into W
-template <class D>
-DEV void chol_factor(Work<D>& w, const float* diag_add, float diag_scale, int nv, LANE_ARG) {
-  LANE_FOR(i, nv) {
-    for (int j = 0; j <= i; j++) w.W[i][j] = w.M[i][j];
-    if (diag_add) w.W[i][i] += diag_scale * diag_add[i];
-  }
-  WSYNC();
-  chol_inplace(w, nv, LANE_PASS);
-}
-
 // solves (L L^T) x = b with the factor in W; x and b may alias.  Uses s_tmp.
 template <class D>
 DEVNI void chol_solve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
@@ -307,6 +296,95 @@ DEVNI void chol_solve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
   }
   LANE_FOR(i, nv) x[i] = y[i] * w.Linv_diag[i];
   WSYNC();
+}
+
+enum { FS_MASS = 0, FS_NEWTON = 1, FS_IMPLICIT = 2 };
+
+// Builds A (FS_MASS: M; FS_NEWTON: M + J^T diag(D*active) J; FS_IMPLICIT: M + dt*diag(damping)), factors it and
+// solves A x = b.  The three dense factorisations of a physics sub-step all go through here.
+//
+// Device path: lane i keeps row i of the lower triangle in REGISTERS; column j of the factor needs L[j][k] from
+// lane j, which arrives by warp shuffle, so the whole factorisation and the forward substitution run without
+// shared memory or barriers.  Only the backward substitution needs columns of L: the rows are spilled to W once
+// and read back transposed (conflict-free: lanes read consecutive columns of one row).
+template <class D>
+DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const float* b, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV);
+#if B2S_DEVICE
+  constexpr int N = D::NV;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int i = lane;
+  const bool live = i < nv;
+  float r[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) r[j] = live ? ((j <= i) ? w.M[i][j] : 0.0f) : ((j == i) ? 1.0f : 0.0f);
+  float dg = 0.0f;
+  if (mode == FS_NEWTON) {
+    const int ne = w.nefc, nsparse = w.nsparse;
+    for (int rr = nsparse; rr < ne; rr++) {
+      if (!w.efc_active[rr]) continue;
+      const float* J = w.Jd[rr - nsparse];
+      const float c = live ? w.efc_D[rr] * J[i] : 0.0f;
+#pragma unroll
+      for (int j = 0; j < N; j++) r[j] = fmaf(c, J[j], r[j]);
+    }
+    if (live)
+      for (int rr = 0; rr < nsparse; rr++)
+        if (w.efc_active[rr] && w.efc_dof[rr] == i) dg += w.efc_D[rr];
+  } else if (mode == FS_IMPLICIT) {
+    if (live) dg = m.mf[MF_TIMESTEP] * w.damping[i];
+  }
+#pragma unroll
+  for (int j = 0; j < N; j++) if (j == i) r[j] += dg;
+  float invd = 1.0f;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    float t = r[j];
+#pragma unroll
+    for (int k = 0; k < j; k++) t = fmaf(-r[k], __shfl_sync(FULL, r[k], j), t);
+    float sp = __shfl_sync(FULL, t, j);
+    sp = fmaxf(sp, MINVAL);
+    const float idj = 1.0f / sqrtf(sp);
+    r[j] = t * idj;  // lane j: sqrt(pivot); lanes below: L[i][j]
+    if (i == j) invd = idj;
+  }
+  float y = live ? b[i] : 0.0f;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const float yk = __shfl_sync(FULL, y * invd, k);
+    if (i > k) y = fmaf(-r[k], yk, y);
+  }
+  y *= invd;
+#pragma unroll
+  for (int j = 0; j < N; j++) if (live && j < i) w.W[i][j] = r[j];
+  __syncwarp();
+  float xv = y;
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) {
+    const float xk = __shfl_sync(FULL, xv * invd, k);
+    if (i < k && k < nv) xv = fmaf(-w.W[k][i], xk, xv);
+  }
+  if (live) x[i] = xv * invd;
+  __syncwarp();
+#else
+  LANE_FOR(i, nv) {
+    for (int j = 0; j <= i; j++) w.W[i][j] = w.M[i][j];
+    float dg = 0.0f;
+    if (mode == FS_NEWTON) {
+      const int ne = w.nefc, nsparse = w.nsparse;
+      for (int j = 0; j <= i; j++)
+        for (int rr = nsparse; rr < ne; rr++)
+          if (w.efc_active[rr]) w.W[i][j] += w.efc_D[rr] * w.Jd[rr - nsparse][i] * w.Jd[rr - nsparse][j];
+      for (int rr = 0; rr < nsparse; rr++) if (w.efc_active[rr] && w.efc_dof[rr] == i) dg += w.efc_D[rr];
+    } else if (mode == FS_IMPLICIT) {
+      dg = m.mf[MF_TIMESTEP] * w.damping[i];
+    }
+    w.W[i][i] += dg;
+  }
+  WSYNC();
+  chol_inplace(w, nv, LANE_PASS);
+  chol_solve(w, x, b, nv, LANE_PASS);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- collision
@@ -739,7 +817,7 @@ DEV void acceleration(const Mdl& m, Work<D>& w, LANE_ARG) {
     w.qfrc_smooth[i] = s;
   }
   WSYNC();
-  chol_solve(w, w.qacc_smooth, w.qfrc_smooth, nv, LANE_PASS);
+  factor_solve(m, w, FS_MASS, w.qacc_smooth, w.qfrc_smooth, LANE_PASS);
 }
 
 // ------------------------------------------------------------------------------------------------- solver
@@ -792,22 +870,10 @@ DEVNI float solver_update_constraint(const Mdl& m, Work<D>& w, float* gauss_out,
 // grad = Ma - qfrc_smooth - qfrc_constraint; Mgrad = H^-1 grad with H = M + J^T diag(D*active) J
 template <class D>
 DEVNI void solver_update_gradient(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
-  LANE_FOR(i, nv) {
-    w.s_grad[i] = w.s_Ma[i] - w.qfrc_smooth[i] - w.qfrc_constraint[i];
-    for (int j = 0; j <= i; j++) {
-      float h = w.M[i][j];
-      for (int r = nsparse; r < ne; r++)
-        if (w.efc_active[r]) h += w.efc_D[r] * w.Jd[r - nsparse][i] * w.Jd[r - nsparse][j];
-      w.W[i][j] = h;
-    }
-    float dg = 0.0f;
-    for (int r = 0; r < nsparse; r++) if (w.efc_active[r] && w.efc_dof[r] == i) dg += w.efc_D[r];
-    w.W[i][i] += dg;
-  }
+  const int nv = DIM(NV, MH_NV);
+  LANE_FOR(i, nv) w.s_grad[i] = w.s_Ma[i] - w.qfrc_smooth[i] - w.qfrc_constraint[i];
   WSYNC();
-  chol_inplace(w, nv, LANE_PASS);
-  chol_solve(w, w.s_Mgrad, w.s_grad, nv, LANE_PASS);
+  factor_solve(m, w, FS_NEWTON, w.s_Mgrad, w.s_grad, LANE_PASS);
 }
 
 // initialises s_qacc/s_Ma/Jaref from `qacc0`; returns cost
@@ -1165,21 +1231,30 @@ DEV void sensors_acc(const Mdl& m, Work<D>& w, LANE_ARG) {
 // `sensors`: also evaluate sensordata / cfrc_ext.  They are pure outputs (recomputed from scratch by every
 // forward pass and read only by observations), so the control step asks for them on its last sub-step only.
 template <class D>
-DEVNI void forward(const Mdl& m, Work<D>& w, bool sensors, LANE_ARG) {
+DEVNI void forward(const Mdl& m, Work<D>& w, bool sensors, bool lockstep, LANE_ARG) {
   const int nv = DIM(NV, MH_NV);
+  // `lockstep` (sub-steps of a control step, never the divergent reset path): CTA barriers between stages keep
+  // the CTA's warps on the same code, so one instruction-cache fill serves all of them.
+#define B2S_STAGE_SYNC() do { if (lockstep) CTA_SYNC(); } while (0)
   kinematics(m, w, LANE_PASS);
+  B2S_STAGE_SYNC();
   com_pos(m, w, LANE_PASS);
   crb_mass_matrix(m, w, LANE_PASS);
+  B2S_STAGE_SYNC();
   collision(m, w, LANE_PASS);
   com_vel(m, w, LANE_PASS);
   make_constraint(m, w, LANE_PASS);
+  B2S_STAGE_SYNC();
   passive(m, w, LANE_PASS);
   rne(m, w, LANE_PASS);
   if (sensors) sensors_pos_vel(m, w, LANE_PASS);
   actuation(m, w, LANE_PASS);
-  chol_factor(w, nullptr, 0.0f, nv, LANE_PASS);
+  B2S_STAGE_SYNC();
   acceleration(m, w, LANE_PASS);
+  B2S_STAGE_SYNC();
   solve(m, w, LANE_PASS);
+  B2S_STAGE_SYNC();
+#undef B2S_STAGE_SYNC
   if (sensors) sensors_acc(m, w, LANE_PASS);
 }
 
@@ -1188,11 +1263,10 @@ template <class D>
 DEV void physics_step(const Mdl& m, Work<D>& w, bool sensors, LANE_ARG) {
   const int nv = DIM(NV, MH_NV), nj = DIM(NJ, MH_NJNT);
   const float dt = m.mf[MF_TIMESTEP];
-  forward(m, w, sensors, LANE_PASS);
-  chol_factor(w, w.damping, dt, nv, LANE_PASS);
+  forward(m, w, sensors, true, LANE_PASS);
   LANE_FOR(i, nv) w.s_grad[i] = w.qfrc_smooth[i] + w.qfrc_constraint[i];
   WSYNC();
-  chol_solve(w, w.s_Mgrad, w.s_grad, nv, LANE_PASS);
+  factor_solve(m, w, FS_IMPLICIT, w.s_Mgrad, w.s_grad, LANE_PASS);
   LANE_FOR(i, nv) w.qvel[i] += w.s_Mgrad[i] * dt;
   WSYNC();
   const int* jtype = MI(m, MH_JNT_TYPE);
