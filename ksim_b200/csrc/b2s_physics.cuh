@@ -315,9 +315,12 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
   constexpr unsigned FULL = 0xffffffffu;
   const int i = lane;
   const bool live = i < nv;
+  // Rows / columns >= nv (and the duplicate row idle lanes load) only ever feed entries that are never read
+  // back: column j takes L[j][k] from lane j < nv, and every store / substitution below is guarded.
+  const int ri = i < N ? i : N - 1;
   float r[N];
 #pragma unroll
-  for (int j = 0; j < N; j++) r[j] = live ? ((j <= i) ? w.M[i][j] : 0.0f) : ((j == i) ? 1.0f : 0.0f);
+  for (int j = 0; j < N; j++) r[j] = w.M[ri][j];
   float dg = 0.0f;
   if (mode == FS_NEWTON) {
     const int ne = w.nefc, nsparse = w.nsparse;
@@ -344,7 +347,9 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
     for (int k = 0; k < j; k++) t = fmaf(-r[k], __shfl_sync(FULL, r[k], j), t);
     float sp = __shfl_sync(FULL, t, j);
     sp = fmaxf(sp, MINVAL);
-    const float idj = 1.0f / sqrtf(sp);
+    // rsqrt + one Newton refinement: no slow-path call (a call here would spill the whole row to local memory)
+    float idj = rsqrtf(sp);
+    idj = idj * fmaf(-0.5f * sp, idj * idj, 1.5f);
     r[j] = t * idj;  // lane j: sqrt(pivot); lanes below: L[i][j]
     if (i == j) invd = idj;
   }
@@ -907,7 +912,7 @@ DEV bool in_bracket(const LSPoint& x, const LSPoint& y) {
 
 // evaluates up to three step sizes in one pass over the constraint rows
 template <class D>
-DEVNI void ls_eval3(const Work<D>& w, int ne, const float* alpha, int n, const float* qg, LSPoint* out, LANE_ARG) {
+DEV void ls_eval3(const Work<D>& w, int ne, const float* alpha, int n, const float* qg, LSPoint* out, LANE_ARG) {
   float q[3][3];
 #pragma unroll
   for (int a = 0; a < 3; a++) q[a][0] = q[a][1] = q[a][2] = 0.0f;
