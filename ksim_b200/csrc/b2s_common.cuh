@@ -200,7 +200,10 @@ struct Key { uint32_t k0, k1; };
 
 DEV uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
 
-DEVNI void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* o0, uint32_t* o1) {
+struct U2 { uint32_t a, b; };
+
+// returns by value: out-pointers into a noinline function would go through local memory
+DEVNI U2 threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1) {
   const uint32_t ks0 = k0, ks1 = k1, ks2 = k0 ^ k1 ^ 0x1BD11BDAu;
   x0 += ks0; x1 += ks1;
 #define B2S_R4A x0 += x1; x1 = rotl32(x1, 13); x1 ^= x0; x0 += x1; x1 = rotl32(x1, 15); x1 ^= x0; \
@@ -214,17 +217,17 @@ DEVNI void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint
   B2S_R4A x0 += ks2; x1 += ks0 + 5u;
 #undef B2S_R4A
 #undef B2S_R4B
-  *o0 = x0; *o1 = x1;
+  U2 r; r.a = x0; r.b = x1;
+  return r;
 }
 DEV Key key_split(Key k, int i) {
-  Key o;
-  threefry2x32(k.k0, k.k1, 0u, (uint32_t)i, &o.k0, &o.k1);
+  const U2 r = threefry2x32(k.k0, k.k1, 0u, (uint32_t)i);
+  Key o; o.k0 = r.a; o.k1 = r.b;
   return o;
 }
 DEV uint32_t key_bits(Key k, int i) {
-  uint32_t a, b;
-  threefry2x32(k.k0, k.k1, 0u, (uint32_t)i, &a, &b);
-  return a ^ b;
+  const U2 r = threefry2x32(k.k0, k.k1, 0u, (uint32_t)i);
+  return r.a ^ r.b;
 }
 DEV float bits_to_unit(uint32_t bits) {
   union { uint32_t u; float f; } c;

@@ -337,12 +337,12 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
   } else if (mode == FS_IMPLICIT) {
     if (live) dg = m.mf[MF_TIMESTEP] * w.damping[i];
   }
-#pragma unroll
-  for (int j = 0; j < N; j++) if (j == i) r[j] += dg;
   float invd = 1.0f;
 #pragma unroll
   for (int j = 0; j < N; j++) {
-    float t = r[j];
+    // the diagonal term joins here, on the pivot lane, with a STATIC register index (writing r[i] up front
+    // would be a dynamic index and push the whole row into local memory)
+    float t = r[j] + ((i == j) ? dg : 0.0f);
 #pragma unroll
     for (int k = 0; k < j; k++) t = fmaf(-r[k], __shfl_sync(FULL, r[k], j), t);
     float sp = __shfl_sync(FULL, t, j);
