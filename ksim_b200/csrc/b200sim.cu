@@ -1,6 +1,7 @@
 // b200sim: kernels + C-ABI (include/b200sim.h).  sm_100a only; no CPU path -- every entry point launches CUDA.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -12,8 +13,6 @@
 
 using namespace b2s;
 
-// CTA barriers one physics sub-step executes (engine_step's + forward's stage barriers)
-#define B2S_BARRIERS_PER_SUBSTEP 7
 
 // ------------------------------------------------------------------------------------------------ kernels
 
@@ -45,9 +44,12 @@ __global__ void __launch_bounds__(512) k_rollout(const Mdl m, int n_envs, int n_
   const int env = blockIdx.x * wpb + warp;
   const int* ti = m.ti;
   if (env >= n_envs) {
-    // idle warps of the last CTA still take part in engine_step's per-sub-step CTA barriers
-    const int nbar = n_steps * ti[TI_NSUB] * B2S_BARRIERS_PER_SUBSTEP;
-    for (int i = 0; i < nbar; i++) __syncthreads();
+    // idle warps of the last CTA still take part in the per-sub-step CTA barriers and votes
+    const int nsub = ti[TI_NSUB];
+    for (int i = 0; i < n_steps * nsub; i++) {
+      if ((m.sync_mask >> 6) & 1) __syncthreads();
+      forward_follower(m);
+    }
     return;
   }
   Work<D>& w = reinterpret_cast<Work<D>*>(smem)[warp];
@@ -175,6 +177,7 @@ static int configure(b200sim_model* mo) {
   const int max_warps = (int)((kSmemBudget - 2048) / sizeof(Work<D>));
   if (max_warps < 1) return fail(B2S_ERR_TOO_LARGE, "workspace does not fit in shared memory");
   int wpb = max_warps > 16 ? 16 : max_warps;  // one CTA per SM: all its warps run in lockstep (shared i-cache fills)
+  if (const char* e = getenv("B2S_WPB")) { const int v = atoi(e); if (v >= 1 && v <= max_warps) wpb = v; }  // tuning experiments
   mo->warps_per_cta = wpb;
   const int bytes = (int)(wpb * sizeof(Work<D>));
   CUDA_OK(cudaFuncSetAttribute(k_init_envs<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -204,6 +207,8 @@ extern "C" int b200sim_model_create(const void* blob, size_t nbytes, b200sim_mod
   mo->mdl.mf = (const float*)(d + MH_SIZE + ni);
   mo->mdl.ti = d + MH_SIZE + ni + nf;
   mo->mdl.tf = (const float*)(d + MH_SIZE + ni + nf + nti);
+  mo->mdl.sync_mask = 0xa0;  // measured best on B200: votes inside the solver + the barrier after it (profiles/)
+  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0xff;  // tuning experiments
   int rc;
   if (fits<DimsHumanoid>(h) && task_fits<DimsHumanoid>(ti)) { mo->variant = 0; rc = configure<DimsHumanoid>(mo); }
   else if (fits<DimsKbot>(h) && task_fits<DimsKbot>(ti)) { mo->variant = 1; rc = configure<DimsKbot>(mo); }

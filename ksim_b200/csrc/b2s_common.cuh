@@ -24,6 +24,7 @@
 #define LANE_FOR(i, n) for (int i = lane; i < (n); i += 32)
 #define WSYNC() __syncwarp()
 #define CTA_SYNC() __syncthreads()
+#define CTA_OR(p) __syncthreads_or(p)
 #define IF_LANE0 if (lane == 0)
 #define LANE_ARG const int lane
 #define LANE_PASS lane
@@ -34,6 +35,7 @@
 #define LANE_FOR(i, n) for (int i = 0; i < (n); i++)
 #define WSYNC() ((void)0)
 #define CTA_SYNC() ((void)0)
+#define CTA_OR(p) (p)
 #define IF_LANE0 if (true)
 #define LANE_ARG const int lane
 #define LANE_PASS 0
@@ -87,6 +89,7 @@ struct Mdl {
   const float* mf;
   const int* ti;
   const float* tf;
+  int sync_mask;  // which per-sub-step CTA barriers run (bit 0..5: forward's stages, bit 6: sub-step start)
 };
 #define MI(m, name) ((m).mi + (m).h[name])
 #define MF(m, name) ((m).mf + (m).h[name])

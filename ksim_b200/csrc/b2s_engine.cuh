@@ -272,7 +272,7 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   LANE_FOR(i, nu) w.torque[i] = 0.0f;
   WSYNC();
   for (int step = 0; step < nsub; step++) {
-    CTA_SYNC();  // keep the CTA's warps on the same code so they share instruction-cache lines
+    if ((m.sync_mask >> 6) & 1) CTA_SYNC();  // keep the CTA's warps on the same code so they share instruction-cache lines
     const float prct = clipf((float)step - w.latency, 0.0f, 1.0f);
     LANE_FOR(i, na) {
       const float lc = w.last_ctrl[i];

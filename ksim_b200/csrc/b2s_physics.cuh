@@ -943,8 +943,13 @@ DEV void ls_eval3(const Work<D>& w, int ne, const float* alpha, int n, const flo
   }
 }
 
+// `live` == false (lockstep only): this warp's solve has finished; it only takes part in the CTA votes.
 template <class D>
-DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, LANE_ARG) {
+DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, bool lockstep, bool live, LANE_ARG) {
+  if (!live) {
+    while (CTA_OR(0)) {}
+    return;
+  }
   const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
   float snorm = 0.0f, qg1 = 0.0f, qg2 = 0.0f;
   LANE_FOR(i, nv) {
@@ -977,7 +982,9 @@ DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, LANE_ARG) {
     done |= !swap;
     done |= (lo.deriv0 < 0) && (lo.deriv0 > -gtol);
     done |= (hi.deriv0 > 0) && (hi.deriv0 < gtol);
-    if (done) break;
+    // lockstep: the CTA's warps iterate together (one instruction-cache fill serves all) until none has work left
+    if (lockstep ? !CTA_OR(!done) : done) break;
+    if (done) continue;
     al[0] = lo.alpha - lo.deriv0 / lo.deriv1;
     al[1] = hi.alpha - hi.deriv0 / hi.deriv1;
     al[2] = 0.5f * (lo.alpha + hi.alpha);
@@ -1000,13 +1007,23 @@ DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, LANE_ARG) {
   WSYNC();
 }
 
+// `lockstep` (bit 7 of sync_mask): every warp of the CTA goes through the same sequence of CTA votes -- one per
+// Newton iteration and one per line-search iteration -- so the warps stay on the same code while they iterate.
+// solve_follower() is the vote sequence of a warp that has no environment.
+DEV void solve_follower() {
+  while (CTA_OR(0)) {
+    while (CTA_OR(0)) {}
+  }
+}
+
 template <class D>
-DEV void solve(const Mdl& m, Work<D>& w, LANE_ARG) {
+DEV void solve(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
   const int nv = DIM(NV, MH_NV), ne = w.nefc;
   if (ne == 0) {
     // no constraint rows: qacc = qacc_smooth, qacc_warmstart keeps its old value (MJX forward())
     LANE_FOR(i, nv) { w.qacc[i] = w.qacc_smooth[i]; w.qfrc_constraint[i] = 0.0f; }
     WSYNC();
+    if (lockstep) solve_follower();
     return;
   }
   float gauss;
@@ -1025,25 +1042,27 @@ DEV void solve(const Mdl& m, Work<D>& w, LANE_ARG) {
   const float tol = m.mf[MF_TOLERANCE];
   const float scale = 1.0f / (m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1));
   int niter = 0;
+  bool finished = false;
   while (true) {
-    if (iterations != 1 || niter > 0) {
+    if (!finished && (iterations != 1 || niter > 0)) {
       const float improvement = (prev_cost - cost) * scale;
       float gn = 0.0f;
       LANE_FOR(i, nv) gn += w.s_grad[i] * w.s_grad[i];
       const float gradient = sqrtf(wsum(gn)) * scale;
-      bool done = niter >= iterations;
-      done |= improvement < tol;
-      done |= gradient < tol;
-      if (done) break;
+      finished = niter >= iterations;
+      finished |= improvement < tol;
+      finished |= gradient < tol;
     }
-    linesearch(m, w, gauss, LANE_PASS);
+    if (lockstep ? !CTA_OR(!finished) : finished) break;
+    linesearch(m, w, gauss, lockstep, !finished, LANE_PASS);
+    if (finished) continue;
     prev_cost = cost;
     cost = solver_update_constraint(m, w, &gauss, LANE_PASS);
     solver_update_gradient(m, w, LANE_PASS);
     LANE_FOR(i, nv) w.s_search[i] = -w.s_Mgrad[i];
     WSYNC();
     niter++;
-    if (iterations == 1) break;
+    if (iterations == 1) finished = true;
   }
   LANE_FOR(i, nv) { w.qacc[i] = w.s_qacc[i]; w.warm[i] = w.s_qacc[i]; }
   WSYNC();
@@ -1240,27 +1259,35 @@ DEVNI void forward(const Mdl& m, Work<D>& w, bool sensors, bool lockstep, LANE_A
   const int nv = DIM(NV, MH_NV);
   // `lockstep` (sub-steps of a control step, never the divergent reset path): CTA barriers between stages keep
   // the CTA's warps on the same code, so one instruction-cache fill serves all of them.
-#define B2S_STAGE_SYNC() do { if (lockstep) CTA_SYNC(); } while (0)
+#define B2S_STAGE_SYNC(k) do { if (lockstep && ((m.sync_mask >> (k)) & 1)) CTA_SYNC(); } while (0)
   kinematics(m, w, LANE_PASS);
-  B2S_STAGE_SYNC();
+  B2S_STAGE_SYNC(0);
   com_pos(m, w, LANE_PASS);
   crb_mass_matrix(m, w, LANE_PASS);
-  B2S_STAGE_SYNC();
+  B2S_STAGE_SYNC(1);
   collision(m, w, LANE_PASS);
   com_vel(m, w, LANE_PASS);
   make_constraint(m, w, LANE_PASS);
-  B2S_STAGE_SYNC();
+  B2S_STAGE_SYNC(2);
   passive(m, w, LANE_PASS);
   rne(m, w, LANE_PASS);
   if (sensors) sensors_pos_vel(m, w, LANE_PASS);
   actuation(m, w, LANE_PASS);
-  B2S_STAGE_SYNC();
+  B2S_STAGE_SYNC(3);
   acceleration(m, w, LANE_PASS);
-  B2S_STAGE_SYNC();
-  solve(m, w, LANE_PASS);
-  B2S_STAGE_SYNC();
+  B2S_STAGE_SYNC(4);
+  solve(m, w, lockstep && ((m.sync_mask >> 7) & 1), LANE_PASS);
+  B2S_STAGE_SYNC(5);
 #undef B2S_STAGE_SYNC
   if (sensors) sensors_acc(m, w, LANE_PASS);
+}
+
+// the CTA barriers / votes of one lockstep forward(), for a warp that has no environment (tail of the last CTA)
+DEV void forward_follower(const Mdl& m) {
+#pragma unroll
+  for (int k = 0; k < 5; k++) if ((m.sync_mask >> k) & 1) CTA_SYNC();
+  if ((m.sync_mask >> 7) & 1) solve_follower();
+  if ((m.sync_mask >> 5) & 1) CTA_SYNC();
 }
 
 // implicitfast with Euler damping disabled: (M + dt*diag(damping)) qacc = qfrc_smooth + qfrc_constraint

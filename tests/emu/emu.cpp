@@ -22,6 +22,7 @@ static Mdl view(const void* blob) {
   m.mf = (const float*)(h + MH_SIZE + h[MH_NI]);
   m.ti = h + MH_SIZE + h[MH_NI] + h[MH_NF];
   m.tf = (const float*)(h + MH_SIZE + h[MH_NI] + h[MH_NF] + h[MH_NTI]);
+  m.sync_mask = 0xff;  // barriers / votes are no-ops on the host; the lockstep code paths still run
   return m;
 }
 
