@@ -16,14 +16,54 @@ using namespace b2s;
 
 // ------------------------------------------------------------------------------------------------ kernels
 
+#ifdef B2S_PROFILE_STAGES
+__device__ unsigned long long g_stage_cycles[B2S_NSTAGE];
+extern "C" int b200sim_debug_stage_cycles(unsigned long long* out, int reset) {
+  if (out && cudaMemcpyFromSymbol(out, g_stage_cycles, sizeof(g_stage_cycles)) != cudaSuccess) return 1;
+  if (reset) { unsigned long long z[B2S_NSTAGE] = {0}; if (cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z)) != cudaSuccess) return 1; }
+  return 0;
+}
+#endif
+
+// The model view the device code reads lives in shared memory: the kernel parameter is copied there once per CTA,
+// together with as much of the model / task-program arrays as fits after the per-env workspaces (Mdl::stage), and
+// the view's pointers are redirected to the copies.  Model constants then cost a shared-memory access instead of an
+// L1-thrashed global load on the critical path of every stage.
 template <class D>
-__global__ void __launch_bounds__(512) k_init_envs(const Mdl m, int n_envs, const uint32_t* __restrict__ init_keys,
+__device__ __forceinline__ const Mdl& stage_model(const Mdl& mp, unsigned char* smem, int wpb) {
+  Mdl* ms = reinterpret_cast<Mdl*>(smem + (((size_t)wpb * sizeof(Work<D>) + 15) & ~(size_t)15));
+  int* dst = reinterpret_cast<int*>(ms + 1);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < (int)(sizeof(Mdl) / 4); i += nt) reinterpret_cast<int*>(ms)[i] = reinterpret_cast<const int*>(&mp)[i];
+  const int* src[4] = {mp.mi, reinterpret_cast<const int*>(mp.mf), mp.ti, reinterpret_cast<const int*>(mp.tf)};
+  int off = 0;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int n = mp.stage[a];
+    for (int i = tid; i < n; i += nt) dst[off + i] = src[a][i];
+    off += n;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int o = 0;
+    if (mp.stage[0]) ms->mi = dst + o; o += mp.stage[0];
+    if (mp.stage[1]) ms->mf = reinterpret_cast<const float*>(dst + o); o += mp.stage[1];
+    if (mp.stage[2]) ms->ti = dst + o; o += mp.stage[2];
+    if (mp.stage[3]) ms->tf = reinterpret_cast<const float*>(dst + o);
+  }
+  __syncthreads();
+  return *ms;
+}
+
+template <class D>
+__global__ void __launch_bounds__(512) k_init_envs(const Mdl mp, int n_envs, const uint32_t* __restrict__ init_keys,
                                                    const float* __restrict__ levels, const float* __restrict__ rand,
                                                    float* __restrict__ state, uint32_t* __restrict__ keys,
                                                    float* __restrict__ rec0, uint32_t* __restrict__ act_keys) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int env = blockIdx.x * wpb + warp;
+  const Mdl& m = stage_model<D>(mp, smem, wpb);
   if (env >= n_envs) return;
   Work<D>& w = reinterpret_cast<Work<D>*>(smem)[warp];
   const int* ti = m.ti;
@@ -35,13 +75,14 @@ __global__ void __launch_bounds__(512) k_init_envs(const Mdl m, int n_envs, cons
 
 // n_steps control steps per launch; the environment stays in shared memory between them.
 template <class D>
-__global__ void __launch_bounds__(512) k_rollout(const Mdl m, int n_envs, int n_steps, const float* __restrict__ actions,
+__global__ void __launch_bounds__(512) k_rollout(const Mdl mp, int n_envs, int n_steps, const float* __restrict__ actions,
                                                  const float* __restrict__ rand, float* __restrict__ state,
                                                  uint32_t* __restrict__ keys, float* __restrict__ rec,
                                                  float* __restrict__ rec_next_single, uint32_t* __restrict__ act_keys) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int env = blockIdx.x * wpb + warp;
+  const Mdl& m = stage_model<D>(mp, smem, wpb);
   const int* ti = m.ti;
   if (env >= n_envs) {
     // idle warps of the last CTA still take part in the per-sub-step CTA barriers and votes
@@ -57,12 +98,20 @@ __global__ void __launch_bounds__(512) k_rollout(const Mdl m, int n_envs, int n_
   const size_t NA = ti[TI_ACTION_SIZE];
   apply_overrides(m, w, rand + env * RAND, lane);
   env_load(m, w, state + env * S, keys + env * K, lane);
+#ifdef B2S_PROFILE_STAGES
+  if (lane < B2S_NSTAGE) w.prof[lane] = 0;
+  __syncwarp();
+#endif
   for (int t = 0; t < n_steps; t++) {
     float* cur = rec + ((size_t)t * n_envs + env) * R;
     float* nxt = rec_next_single ? rec_next_single + env * R : rec + ((size_t)(t + 1) * n_envs + env) * R;
     env_step(m, w, actions + ((size_t)t * n_envs + env) * NA, cur, nxt, act_keys ? act_keys + 2 * env : nullptr, lane);
   }
   env_store(m, w, state + env * S, keys + env * K, lane);
+#ifdef B2S_PROFILE_STAGES
+  __syncwarp();
+  if (lane < B2S_NSTAGE) atomicAdd(&g_stage_cycles[lane], (unsigned long long)w.prof[lane]);
+#endif
 }
 
 __global__ void __launch_bounds__(256) k_rewards(const Mdl m, int n_envs, int n_steps, const float* __restrict__ rec,
@@ -139,6 +188,7 @@ struct b200sim_model {
   int variant;
   int warps_per_cta;
   size_t smem_per_env;
+  size_t smem_bytes;   // dynamic shared memory per CTA: workspaces + model view + staged model arrays
   void* dev_blob;
   std::vector<int> ti_host;
 };
@@ -172,16 +222,25 @@ static bool task_fits(const int* ti) {
 static const size_t kSmemBudget = 227 * 1024;
 
 template <class D>
-static int configure(b200sim_model* mo) {
+static int configure(b200sim_model* mo, const size_t* words) {
   mo->smem_per_env = sizeof(Work<D>);
-  const int max_warps = (int)((kSmemBudget - 2048) / sizeof(Work<D>));
+  const size_t fixed = sizeof(Mdl) + 16;
+  const int max_warps = (int)((kSmemBudget - fixed) / sizeof(Work<D>));
   if (max_warps < 1) return fail(B2S_ERR_TOO_LARGE, "workspace does not fit in shared memory");
   int wpb = max_warps > 16 ? 16 : max_warps;  // one CTA per SM: all its warps run in lockstep (shared i-cache fills)
   if (const char* e = getenv("B2S_WPB")) { const int v = atoi(e); if (v >= 1 && v <= max_warps) wpb = v; }  // tuning experiments
   mo->warps_per_cta = wpb;
-  const int bytes = (int)(wpb * sizeof(Work<D>));
-  CUDA_OK(cudaFuncSetAttribute(k_init_envs<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(k_rollout<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  // model arrays staged in shared memory, in priority order mi, mf, ti, tf, while they fit
+  size_t left = (kSmemBudget - fixed - wpb * sizeof(Work<D>)) / 4, staged = 0;
+  const bool no_stage = getenv("B2S_NO_STAGE") != nullptr;  // tuning experiments
+  for (int a = 0; a < 4; a++) {
+    const bool fit = !no_stage && words[a] <= left;
+    mo->mdl.stage[a] = fit ? (int)words[a] : 0;
+    if (fit) { left -= words[a]; staged += words[a]; }
+  }
+  mo->smem_bytes = wpb * sizeof(Work<D>) + fixed + staged * 4;
+  CUDA_OK(cudaFuncSetAttribute(k_init_envs<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mo->smem_bytes));
+  CUDA_OK(cudaFuncSetAttribute(k_rollout<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mo->smem_bytes));
   return B2S_OK;
 }
 
@@ -208,11 +267,12 @@ extern "C" int b200sim_model_create(const void* blob, size_t nbytes, b200sim_mod
   mo->mdl.ti = d + MH_SIZE + ni + nf;
   mo->mdl.tf = (const float*)(d + MH_SIZE + ni + nf + nti);
   mo->mdl.sync_mask = 0xa0;  // measured best on B200: votes inside the solver + the barrier after it (profiles/)
-  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0xff;  // tuning experiments
+  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0x1ff;  // tuning experiments
   int rc;
-  if (fits<DimsHumanoid>(h) && task_fits<DimsHumanoid>(ti)) { mo->variant = 0; rc = configure<DimsHumanoid>(mo); }
-  else if (fits<DimsKbot>(h) && task_fits<DimsKbot>(ti)) { mo->variant = 1; rc = configure<DimsKbot>(mo); }
-  else if (fits<DimsGeneric>(h) && task_fits<DimsGeneric>(ti)) { mo->variant = 2; rc = configure<DimsGeneric>(mo); }
+  const size_t words[4] = {ni, nf, nti, ntf};
+  if (fits<DimsHumanoid>(h) && task_fits<DimsHumanoid>(ti)) { mo->variant = 0; rc = configure<DimsHumanoid>(mo, words); }
+  else if (fits<DimsKbot>(h) && task_fits<DimsKbot>(ti)) { mo->variant = 1; rc = configure<DimsKbot>(mo, words); }
+  else if (fits<DimsGeneric>(h) && task_fits<DimsGeneric>(ti)) { mo->variant = 2; rc = configure<DimsGeneric>(mo, words); }
   else rc = fail(B2S_ERR_TOO_LARGE, "model / task sizes exceed the largest kernel instantiation");
   if (rc != B2S_OK) { cudaFree(mo->dev_blob); delete mo; return rc; }
   *out = mo;
@@ -258,7 +318,7 @@ extern "C" int b200sim_init_envs(const b200sim_model* mo, void* stream, int n_en
   if (!rand && mo->ti_host[TI_RAND_SIZE] > 0) return fail(B2S_ERR_BAD_ARG, "rand is required for this task");
   const int wpb = mo->warps_per_cta;
   const dim3 grid((n_envs + wpb - 1) / wpb), block(wpb * 32);
-  const size_t smem = wpb * mo->smem_per_env;
+  const size_t smem = mo->smem_bytes;
   DISPATCH(mo, (k_init_envs<D><<<grid, block, smem, (cudaStream_t)stream>>>(mo->mdl, n_envs, init_keys, levels, rand, state, keys, rec0, act_keys)));
   CUDA_OK(cudaGetLastError());
   return B2S_OK;
@@ -269,7 +329,7 @@ static int launch_rollout(const b200sim_model* mo, void* stream, int n_envs, int
                           uint32_t* act_keys) {
   const int wpb = mo->warps_per_cta;
   const dim3 grid((n_envs + wpb - 1) / wpb), block(wpb * 32);
-  const size_t smem = wpb * mo->smem_per_env;
+  const size_t smem = mo->smem_bytes;
   DISPATCH(mo, (k_rollout<D><<<grid, block, smem, (cudaStream_t)stream>>>(mo->mdl, n_envs, n_steps, actions, rand, state, keys, rec, rec_next_single, act_keys)));
   CUDA_OK(cudaGetLastError());
   return B2S_OK;

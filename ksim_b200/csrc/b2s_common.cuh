@@ -41,6 +41,22 @@
 #define LANE_PASS 0
 #endif
 
+// Optional per-stage cycle accounting (-DB2S_PROFILE_STAGES; tools/stage_profile.py): lane 0 of every warp adds the
+// clock64() delta of each stage to Work::prof, the kernel sums them into g_stage_cycles.  Off in the product build.
+#if defined(B2S_PROFILE_STAGES) && B2S_DEVICE
+#define B2S_NSTAGE 24
+#define STAGE_BEGIN() long long stage_t0_ = clock64()
+#define STAGE_MARK(w, k) do { const long long t1_ = clock64(); if (lane == 0) (w).prof[k] += (unsigned)(t1_ - stage_t0_); stage_t0_ = t1_; } while (0)
+// nested accounting inside a stage (its own clock): adds to slot k without disturbing the enclosing stage's clock
+#define SUB_BEGIN() long long sub_t0_ = clock64()
+#define SUB_MARK(w, k) do { const long long t1_ = clock64(); if (lane == 0) (w).prof[k] += (unsigned)(t1_ - sub_t0_); sub_t0_ = t1_; } while (0)
+#else
+#define STAGE_BEGIN() ((void)0)
+#define STAGE_MARK(w, k) ((void)0)
+#define SUB_BEGIN() ((void)0)
+#define SUB_MARK(w, k) ((void)0)
+#endif
+
 namespace b2s {
 
 constexpr float MINVAL = 1e-15f;
@@ -90,6 +106,7 @@ struct Mdl {
   const int* ti;
   const float* tf;
   int sync_mask;  // which per-sub-step CTA barriers run (bit 0..5: forward's stages, bit 6: sub-step start)
+  int stage[4];   // words of mi / mf / ti / tf the kernels copy into shared memory (0: read from global memory)
 };
 #define MI(m, name) ((m).mi + (m).h[name])
 #define MF(m, name) ((m).mf + (m).h[name])
@@ -309,6 +326,23 @@ DEVNI float noise_apply(const int* ni, const float* nf, float x, Key key, int i,
     x = mul ? x * r : x + r;
   }
   return x;
+}
+// 1/sqrt(x) for x >= MINVAL: hardware approximation + one Newton step on the device (no slow-path call)
+DEV float inv_sqrt(float x) {
+#if B2S_DEVICE
+  float r = rsqrtf(x);
+  return r * fmaf(-0.5f * x, r * r, 1.5f);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+// a / b without the IEEE slow path on the device (MUFU reciprocal, ~2 ulp; |b| must stay below 2^126)
+DEV float fast_div(float a, float b) {
+#if B2S_DEVICE
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
 }
 DEV float clipf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 

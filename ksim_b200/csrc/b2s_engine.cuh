@@ -272,6 +272,7 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   LANE_FOR(i, nu) w.torque[i] = 0.0f;
   WSYNC();
   for (int step = 0; step < nsub; step++) {
+    STAGE_BEGIN();
     if ((m.sync_mask >> 6) & 1) CTA_SYNC();  // keep the CTA's warps on the same code so they share instruction-cache lines
     const float prct = clipf((float)step - w.latency, 0.0f, 1.0f);
     LANE_FOR(i, na) {
@@ -289,6 +290,7 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
       r = key_split(r, 0);
       event_apply(m, w, ev, rng_event, LANE_PASS);
     }
+    STAGE_MARK(w, 9);
     physics_step(m, w, step == nsub - 1, LANE_PASS);
   }
   LANE_FOR(i, na) w.last_ctrl[i] = w.action[i];
@@ -699,6 +701,7 @@ DEV int env_step(const Mdl& m, Work<D>& w, const float* action_in, float* rec_cu
   const float* ef = m.tf + ti[TI_ENGINE_FOFF];
   const int na = ti[TI_ACTION_SIZE];
   const float aclip = ef[6];
+  STAGE_BEGIN();
   LANE_FOR(i, na) {
     float a = action_in[i];
     if (a != a) a = 0.0f;  // NaN -> 0, then clip (rl.py:998-1001)
@@ -707,7 +710,9 @@ DEV int env_step(const Mdl& m, Work<D>& w, const float* action_in, float* rec_cu
   WSYNC();
   Key rng; rng.k0 = w.keys[0]; rng.k1 = w.keys[1];
   const Key physics_rng = key_split(rng, 1), state_rng = key_split(rng, 2);
+  STAGE_MARK(w, 10);
   engine_step(m, w, physics_rng, LANE_PASS);
+  STAGE_MARK(w, 15);  // double-counts stages 0-9; used as a cross-check only
 
   Key cmd_rng = key_split(state_rng, 0);
   const Key obs_carry_rng = key_split(state_rng, 2), obs_bias_rng = key_split(state_rng, 3);
@@ -753,7 +758,9 @@ DEV int env_step(const Mdl& m, Work<D>& w, const float* action_in, float* rec_cu
   }
   IF_LANE0 { w.keys[0] = next_rng.k0; w.keys[1] = next_rng.k1; }
   WSYNC();
+  STAGE_MARK(w, 11);
   write_pre_block(m, w, rec_next, act_key, LANE_PASS);
+  STAGE_MARK(w, 12);
   return done;
 }
 

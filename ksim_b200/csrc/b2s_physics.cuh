@@ -300,6 +300,9 @@ DEVNI void chol_solve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
 
 enum { FS_MASS = 0, FS_NEWTON = 1, FS_IMPLICIT = 2 };
 
+// bit 8 of sync_mask switches the constraint-space Newton path off (tuning / A-B tests)
+DEV bool dual_enabled(const Mdl& m) { return !((m.sync_mask >> 8) & 1); }
+
 // Builds A (FS_MASS: M; FS_NEWTON: M + J^T diag(D*active) J; FS_IMPLICIT: M + dt*diag(damping)), factors it and
 // solves A x = b.  The three dense factorisations of a physics sub-step all go through here.
 //
@@ -307,10 +310,18 @@ enum { FS_MASS = 0, FS_NEWTON = 1, FS_IMPLICIT = 2 };
 // lane j, which arrives by warp shuffle, so the whole factorisation and the forward substitution run without
 // shared memory or barriers.  Only the backward substitution needs columns of L: the rows are spilled to W once
 // and read back transposed (conflict-free: lanes read consecutive columns of one row).
+//
+// FS_MASS with nz > 0 additionally solves M Z_s = J_s^T for the first nz constraint rows (the dual Newton path's
+// Z = M^-1 J^T), two right-hand sides at a time so their dependent shuffle chains overlap.
 template <class D>
-DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const float* b, LANE_ARG) {
+DEV float jac_entry(const Work<D>& w, int s, int nsparse, int i) {
+  return s < nsparse ? (w.efc_dof[s] == i ? w.efc_sign[s] : 0.0f) : w.Jd[s - nsparse][i];
+}
+
+template <class D>
+DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const float* b, int nz, LANE_ARG) {
   const int nv = DIM(NV, MH_NV);
-#if B2S_DEVICE
+#if B2S_DEVICE && !defined(B2S_COMPACT_CHOL)
   constexpr int N = D::NV;
   constexpr unsigned FULL = 0xffffffffu;
   const int i = lane;
@@ -370,6 +381,27 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
     if (i < k && k < nv) xv = fmaf(-w.W[k][i], xk, xv);
   }
   if (live) x[i] = xv * invd;
+  if (nz > 0) {
+    const int nsparse = w.nsparse;
+    for (int s0 = 0; s0 < nz; s0 += 2) {
+      const bool two = s0 + 1 < nz;
+      float y0 = live ? jac_entry(w, s0, nsparse, i) : 0.0f;
+      float y1 = (live && two) ? jac_entry(w, s0 + 1, nsparse, i) : 0.0f;
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        const float a0 = __shfl_sync(FULL, y0 * invd, k), a1 = __shfl_sync(FULL, y1 * invd, k);
+        if (i > k) { y0 = fmaf(-r[k], a0, y0); y1 = fmaf(-r[k], a1, y1); }
+      }
+      y0 *= invd; y1 *= invd;
+#pragma unroll
+      for (int k = N - 1; k >= 0; k--) {
+        const float wk = (i < k && k < nv) ? w.W[k][i] : 0.0f;
+        const float a0 = __shfl_sync(FULL, y0 * invd, k), a1 = __shfl_sync(FULL, y1 * invd, k);
+        y0 = fmaf(-wk, a0, y0); y1 = fmaf(-wk, a1, y1);
+      }
+      if (live) { w.Z[s0][i] = y0 * invd; if (two) w.Z[s0 + 1][i] = y1 * invd; }
+    }
+  }
   __syncwarp();
 #else
   LANE_FOR(i, nv) {
@@ -389,6 +421,11 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
   WSYNC();
   chol_inplace(w, nv, LANE_PASS);
   chol_solve(w, x, b, nv, LANE_PASS);
+  for (int s = 0; s < nz; s++) {
+    LANE_FOR(i, nv) w.Z[s][i] = jac_entry(w, s, w.nsparse, i);
+    WSYNC();
+    chol_solve(w, w.Z[s], w.Z[s], nv, LANE_PASS);
+  }
 #endif
 }
 
@@ -822,7 +859,9 @@ DEV void acceleration(const Mdl& m, Work<D>& w, LANE_ARG) {
     w.qfrc_smooth[i] = s;
   }
   WSYNC();
-  factor_solve(m, w, FS_MASS, w.qacc_smooth, w.qfrc_smooth, LANE_PASS);
+  // with 1..NDUAL constraint rows the Newton solve runs in constraint space and needs Z = M^-1 J^T (solve())
+  const int ne = w.nefc;
+  factor_solve(m, w, FS_MASS, w.qacc_smooth, w.qfrc_smooth, (ne <= D::NDUAL && dual_enabled(m)) ? ne : 0, LANE_PASS);
 }
 
 // ------------------------------------------------------------------------------------------------- solver
@@ -837,10 +876,9 @@ DEV float row_dot(const Work<D>& w, int r, int nsparse, const float* x, int nv) 
   return s;
 }
 
-// efc_force / active / cost from Jaref; qfrc_constraint = J^T force; returns total cost (gauss + constraint)
+// efc_force / efc_active from efc_Jaref; returns the constraint cost (summed over the warp)
 template <class D>
-DEVNI float solver_update_constraint(const Mdl& m, Work<D>& w, float* gauss_out, LANE_ARG) {
-  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
+DEV float constraint_rows(Work<D>& w, int ne, LANE_ARG) {
   float cost = 0.0f;
   LANE_FOR(r, ne) {
     const float x = w.efc_Jaref[r], Dr = w.efc_D[r];
@@ -856,11 +894,14 @@ DEVNI float solver_update_constraint(const Mdl& m, Work<D>& w, float* gauss_out,
       if (act) cost += 0.5f * Dr * x * x;
     }
   }
-  float gauss = 0.0f;
-  LANE_FOR(i, nv) gauss += (w.s_Ma[i] - w.qfrc_smooth[i]) * (w.s_qacc[i] - w.qacc_smooth[i]);
   cost = wsum(cost);
-  gauss = 0.5f * wsum(gauss);
   WSYNC();
+  return cost;
+}
+
+// qfrc_constraint = J^T efc_force
+template <class D>
+DEV void constraint_force_to_dofs(Work<D>& w, int nv, int ne, int nsparse, LANE_ARG) {
   LANE_FOR(i, nv) {
     float s = 0.0f;
     for (int r = 0; r < nsparse; r++) if (w.efc_dof[r] == i) s += w.efc_sign[r] * w.efc_force[r];
@@ -868,6 +909,17 @@ DEVNI float solver_update_constraint(const Mdl& m, Work<D>& w, float* gauss_out,
     w.qfrc_constraint[i] = s;
   }
   WSYNC();
+}
+
+// efc_force / active / cost from Jaref; qfrc_constraint = J^T force; returns total cost (gauss + constraint)
+template <class D>
+DEVNI float solver_update_constraint(const Mdl& m, Work<D>& w, float* gauss_out, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
+  const float cost = constraint_rows(w, ne, LANE_PASS);
+  float gauss = 0.0f;
+  LANE_FOR(i, nv) gauss += (w.s_Ma[i] - w.qfrc_smooth[i]) * (w.s_qacc[i] - w.qacc_smooth[i]);
+  gauss = 0.5f * wsum(gauss);
+  constraint_force_to_dofs(w, nv, ne, nsparse, LANE_PASS);
   *gauss_out = gauss;
   return gauss + cost;
 }
@@ -878,7 +930,7 @@ DEVNI void solver_update_gradient(const Mdl& m, Work<D>& w, LANE_ARG) {
   const int nv = DIM(NV, MH_NV);
   LANE_FOR(i, nv) w.s_grad[i] = w.s_Ma[i] - w.qfrc_smooth[i] - w.qfrc_constraint[i];
   WSYNC();
-  factor_solve(m, w, FS_NEWTON, w.s_Mgrad, w.s_grad, LANE_PASS);
+  factor_solve(m, w, FS_NEWTON, w.s_Mgrad, w.s_grad, 0, LANE_PASS);
 }
 
 // initialises s_qacc/s_Ma/Jaref from `qacc0`; returns cost
@@ -910,47 +962,125 @@ DEV bool in_bracket(const LSPoint& x, const LSPoint& y) {
   return (x.deriv0 < y.deriv0 && y.deriv0 < 0) || (x.deriv0 > y.deriv0 && y.deriv0 > 0);
 }
 
-// evaluates up to three step sizes in one pass over the constraint rows
+// one constraint row's contribution to the quadratic model of the cost at step size alpha
+struct LSRow { float ja, jv, D, f, rf; int type; };
+
 template <class D>
-DEV void ls_eval3(const Work<D>& w, int ne, const float* alpha, int n, const float* qg, LSPoint* out, LANE_ARG) {
-  float q[3][3];
-#pragma unroll
-  for (int a = 0; a < 3; a++) q[a][0] = q[a][1] = q[a][2] = 0.0f;
-  LANE_FOR(r, ne) {
-    const float ja = w.efc_Jaref[r], jv = w.efc_jv[r], Dr = w.efc_D[r];
-    const int type = w.efc_type[r];
-    const float f = w.efc_floss[r], rf = w.efc_R[r] * f;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      if (a < n) {
-        const float x = ja + alpha[a] * jv;
-        if (type == EFC_FRICTION) {
-          if (x <= -rf) { q[a][0] += f * (-0.5f * rf - ja); q[a][1] += -f * jv; }
-          else if (x >= rf) { q[a][0] += f * (-0.5f * rf + ja); q[a][1] += f * jv; }
-          else { q[a][0] += 0.5f * Dr * ja * ja; q[a][1] += Dr * jv * ja; q[a][2] += 0.5f * Dr * jv * jv; }
-        } else if (x < 0.0f) {
-          q[a][0] += 0.5f * Dr * ja * ja; q[a][1] += Dr * jv * ja; q[a][2] += 0.5f * Dr * jv * jv;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    if (a < n) {
-      const float q0 = wsum(q[a][0]) + qg[0], q1 = wsum(q[a][1]) + qg[1], q2 = wsum(q[a][2]) + qg[2];
-      out[a] = ls_make(alpha[a], q0, q1, q2);
-    }
+DEV LSRow ls_row(const Work<D>& w, int r) {
+  LSRow o;
+  o.ja = w.efc_Jaref[r]; o.jv = w.efc_jv[r]; o.D = w.efc_D[r]; o.type = w.efc_type[r];
+  o.f = w.efc_floss[r]; o.rf = w.efc_R[r] * o.f;
+  return o;
+}
+DEV void ls_accumulate(const LSRow& o, float alpha, float& q0, float& q1, float& q2) {
+  const float x = o.ja + alpha * o.jv;
+  if (o.type == EFC_FRICTION) {
+    if (x <= -o.rf) { q0 += o.f * (-0.5f * o.rf - o.ja); q1 += -o.f * o.jv; }
+    else if (x >= o.rf) { q0 += o.f * (-0.5f * o.rf + o.ja); q1 += o.f * o.jv; }
+    else { q0 += 0.5f * o.D * o.ja * o.ja; q1 += o.D * o.jv * o.ja; q2 += 0.5f * o.D * o.jv * o.jv; }
+  } else if (x < 0.0f) {
+    q0 += 0.5f * o.D * o.ja * o.ja; q1 += o.D * o.jv * o.ja; q2 += 0.5f * o.D * o.jv * o.jv;
   }
 }
 
+// Evaluates three step sizes in one pass over the constraint rows.
+// Device: lanes [8g, 8g+8) evaluate alpha[g] over rows (lane & 7), +8, ...; a 3-step butterfly inside each group of 8
+// sums the three quadratic coefficients for all step sizes at once (9 shuffles instead of 45), and the three
+// resulting points are handed to every lane with 9 more.  `row0` is row (lane & 7), loaded once per line search.
+template <class D>
+DEV void ls_eval3(const Work<D>& w, int ne, const LSRow& row0, const float* alpha, const float* qg, LSPoint* out, LANE_ARG) {
+#if B2S_DEVICE
+  constexpr unsigned FULL = 0xffffffffu;
+  const int g = lane >> 3, sub = lane & 7;
+  const float a = g == 0 ? alpha[0] : (g == 1 ? alpha[1] : alpha[2]);
+  float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f;
+  if (sub < ne) ls_accumulate(row0, a, q0, q1, q2);
+  for (int r = sub + 8; r < ne; r += 8) ls_accumulate(ls_row(w, r), a, q0, q1, q2);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    q0 += __shfl_xor_sync(FULL, q0, o); q1 += __shfl_xor_sync(FULL, q1, o); q2 += __shfl_xor_sync(FULL, q2, o);
+  }
+  const LSPoint mine = ls_make(a, q0 + qg[0], q1 + qg[1], q2 + qg[2]);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    out[k].alpha = alpha[k];
+    out[k].cost = __shfl_sync(FULL, mine.cost, 8 * k);
+    out[k].deriv0 = __shfl_sync(FULL, mine.deriv0, 8 * k);
+    out[k].deriv1 = __shfl_sync(FULL, mine.deriv1, 8 * k);
+  }
+#else
+  (void)row0;
+  for (int k = 0; k < 3; k++) {
+    float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f;
+    for (int r = 0; r < ne; r++) ls_accumulate(ls_row(w, r), alpha[k], q0, q1, q2);
+    out[k] = ls_make(alpha[k], q0 + qg[0], q1 + qg[1], q2 + qg[2]);
+  }
+#endif
+}
+
+// The bracketing line search of the Newton solver over efc_Jaref / efc_jv and the quadratic Gauss term qg
+// (cost(alpha) = qg0 + alpha qg1 + alpha^2 qg2 + sum of the rows); returns the step size.
 // `live` == false (lockstep only): this warp's solve has finished; it only takes part in the CTA votes.
 template <class D>
-DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, bool lockstep, bool live, LANE_ARG) {
+DEV float ls_bracket(const Mdl& m, const Work<D>& w, int nv, int ne, const float* qg, float snorm, bool lockstep, bool live,
+                     LANE_ARG) {
   if (!live) {
     while (CTA_OR(0)) {}
+    return 0.0f;
+  }
+  const float scale = m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1);
+  const float gtol = m.mf[MF_TOLERANCE] * m.mf[MF_LS_TOLERANCE] * snorm * scale;
+#if B2S_DEVICE
+  const LSRow row0 = ls_row(w, (lane & 7) < ne ? (lane & 7) : 0);
+#else
+  const LSRow row0 = ls_row(w, 0);
+#endif
+  LSPoint pts[3];
+  float al[3] = {0.0f, 0.0f, 0.0f};
+  ls_eval3(w, ne, row0, al, qg, pts, LANE_PASS);
+  const LSPoint p0 = pts[0];
+  al[0] = al[1] = al[2] = p0.alpha - fast_div(p0.deriv0, p0.deriv1);
+  ls_eval3(w, ne, row0, al, qg, pts, LANE_PASS);
+  LSPoint lo = pts[0], hi;
+  if (p0.deriv0 < lo.deriv0) { hi = lo; lo = p0; } else { hi = p0; }
+  int swap = 1, it = 0;
+  const int ls_iterations = m.h[MH_LS_ITERATIONS];
+  while (true) {
+    bool done = it >= ls_iterations;
+    done |= !swap;
+    done |= (lo.deriv0 < 0) && (lo.deriv0 > -gtol);
+    done |= (hi.deriv0 > 0) && (hi.deriv0 < gtol);
+    // lockstep: the CTA's warps iterate together (one instruction-cache fill serves all) until none has work left
+    if (lockstep ? !CTA_OR(!done) : done) break;
+    if (done) continue;
+    al[0] = lo.alpha - fast_div(lo.deriv0, lo.deriv1);
+    al[1] = hi.alpha - fast_div(hi.deriv0, hi.deriv1);
+    al[2] = 0.5f * (lo.alpha + hi.alpha);
+    ls_eval3(w, ne, row0, al, qg, pts, LANE_PASS);
+    const LSPoint lo_next = pts[0], hi_next = pts[1], mid = pts[2];
+    const int s1 = in_bracket(lo, lo_next); if (s1) lo = lo_next;
+    const int s2 = in_bracket(lo, mid); if (s2) lo = mid;
+    const int s3 = in_bracket(lo, hi_next); if (s3) lo = hi_next;
+    const int s4 = in_bracket(hi, hi_next); if (s4) hi = hi_next;
+    const int s5 = in_bracket(hi, mid); if (s5) hi = mid;
+    const int s6 = in_bracket(hi, lo_next); if (s6) hi = lo_next;
+    swap = s1 | s2 | s3 | s4 | s5 | s6;
+    it++;
+  }
+  const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+  float alpha = (lo.cost < hi.cost) ? lo.alpha : hi.alpha;
+  if (!improved) alpha = 0.0f;
+  return alpha;
+}
+
+// primal (dof-space) line search: search direction s_search, state s_qacc / s_Ma / efc_Jaref
+template <class D>
+DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, bool lockstep, bool live, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
+  if (!live) {
+    ls_bracket(m, w, nv, ne, nullptr, 0.0f, lockstep, false, LANE_PASS);
     return;
   }
-  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
   float snorm = 0.0f, qg1 = 0.0f, qg2 = 0.0f;
   LANE_FOR(i, nv) {
     float s = 0.0f;
@@ -965,43 +1095,7 @@ DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, bool lockstep, bool l
   snorm = sqrtf(wsum(snorm));
   const float qg[3] = {gauss, wsum(qg1), wsum(qg2)};
   WSYNC();
-  const float scale = m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1);
-  const float gtol = m.mf[MF_TOLERANCE] * m.mf[MF_LS_TOLERANCE] * snorm * scale;
-  LSPoint pts[3];
-  float al[3] = {0.0f, 0.0f, 0.0f};
-  ls_eval3(w, ne, al, 1, qg, pts, LANE_PASS);
-  const LSPoint p0 = pts[0];
-  al[0] = p0.alpha - p0.deriv0 / p0.deriv1;
-  ls_eval3(w, ne, al, 1, qg, pts, LANE_PASS);
-  LSPoint lo = pts[0], hi;
-  if (p0.deriv0 < lo.deriv0) { hi = lo; lo = p0; } else { hi = p0; }
-  int swap = 1, it = 0;
-  const int ls_iterations = m.h[MH_LS_ITERATIONS];
-  while (true) {
-    bool done = it >= ls_iterations;
-    done |= !swap;
-    done |= (lo.deriv0 < 0) && (lo.deriv0 > -gtol);
-    done |= (hi.deriv0 > 0) && (hi.deriv0 < gtol);
-    // lockstep: the CTA's warps iterate together (one instruction-cache fill serves all) until none has work left
-    if (lockstep ? !CTA_OR(!done) : done) break;
-    if (done) continue;
-    al[0] = lo.alpha - lo.deriv0 / lo.deriv1;
-    al[1] = hi.alpha - hi.deriv0 / hi.deriv1;
-    al[2] = 0.5f * (lo.alpha + hi.alpha);
-    ls_eval3(w, ne, al, 3, qg, pts, LANE_PASS);
-    const LSPoint lo_next = pts[0], hi_next = pts[1], mid = pts[2];
-    const int s1 = in_bracket(lo, lo_next); if (s1) lo = lo_next;
-    const int s2 = in_bracket(lo, mid); if (s2) lo = mid;
-    const int s3 = in_bracket(lo, hi_next); if (s3) lo = hi_next;
-    const int s4 = in_bracket(hi, hi_next); if (s4) hi = hi_next;
-    const int s5 = in_bracket(hi, mid); if (s5) hi = mid;
-    const int s6 = in_bracket(hi, lo_next); if (s6) hi = lo_next;
-    swap = s1 | s2 | s3 | s4 | s5 | s6;
-    it++;
-  }
-  const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
-  float alpha = (lo.cost < hi.cost) ? lo.alpha : hi.alpha;
-  if (!improved) alpha = 0.0f;
+  const float alpha = ls_bracket(m, w, nv, ne, qg, snorm, lockstep, true, LANE_PASS);
   LANE_FOR(i, nv) { w.s_qacc[i] += alpha * w.s_search[i]; w.s_Ma[i] += alpha * w.s_mv[i]; }
   LANE_FOR(r, ne) w.efc_Jaref[r] += alpha * w.efc_jv[r];
   WSYNC();
@@ -1009,23 +1103,18 @@ DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, bool lockstep, bool l
 
 // `lockstep` (bit 7 of sync_mask): every warp of the CTA goes through the same sequence of CTA votes -- one per
 // Newton iteration and one per line-search iteration -- so the warps stay on the same code while they iterate.
-// solve_follower() is the vote sequence of a warp that has no environment.
+// solve_follower() is the vote sequence of a warp that has no environment or no constraint rows.
 DEV void solve_follower() {
   while (CTA_OR(0)) {
     while (CTA_OR(0)) {}
   }
 }
 
+// Newton solver in dof space: re-factorises H = M + J^T diag(D active) J every iteration.  Used when the
+// environment has more constraint rows than the constraint-space path holds (ne > NDUAL).
 template <class D>
-DEV void solve(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
-  const int nv = DIM(NV, MH_NV), ne = w.nefc;
-  if (ne == 0) {
-    // no constraint rows: qacc = qacc_smooth, qacc_warmstart keeps its old value (MJX forward())
-    LANE_FOR(i, nv) { w.qacc[i] = w.qacc_smooth[i]; w.qfrc_constraint[i] = 0.0f; }
-    WSYNC();
-    if (lockstep) solve_follower();
-    return;
-  }
+DEV void solve_primal(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV);
   float gauss;
   const float* start = w.qacc_smooth;
   if (!m.h[MH_DISABLE_WARMSTART]) {
@@ -1066,6 +1155,351 @@ DEV void solve(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
   }
   LANE_FOR(i, nv) { w.qacc[i] = w.s_qacc[i]; w.warm[i] = w.s_qacc[i]; }
   WSYNC();
+}
+
+// ------------------------------------------------------------------------ constraint-space Newton (ne <= NDUAL)
+//
+// The same Newton iteration, in the coordinates the iterates actually live in.  With a0 = qacc_smooth, Z = M^-1 J^T
+// (from acceleration()), A = J Z and delta0 = warmstart - a0, every iterate is  qacc = a0 + beta delta0 + Z c  with a
+// scalar beta and an ne-vector c, because the Newton direction is
+//     -H^-1 grad = -delta + Z (f + z - c),   (R_act + A_act,act) z_act = [J delta - A f]_act,  z = 0 off the active set
+// (Woodbury on H = M + J_act^T D_act J_act; f = efc_force, R = 1/D).  So instead of re-factorising the nv x nv Hessian
+// every iteration, one iteration factors the (at most ne x ne) reduced matrix and works on ne-vectors; the line search
+// sees the same efc_Jaref / efc_jv rows and the same quadratic Gauss term as the dof-space solver:
+//     J search = -beta j0 + A d,   search^T M delta = -beta^2 m00 + beta j0.(d - c) + c.(A d),
+//     search^T M search = beta^2 m00 - 2 beta j0.d + d.(A d),      d = f + z - c, j0 = J delta0, m00 = delta0^T M delta0.
+
+template <class D>
+DEV float dual_A(const Work<D>& w, int r, int s) { return s >= r ? w.AS[r][s] : w.AS[s][r]; }
+
+// A (upper triangle of AS), delta0, M delta0, c0 = J a0 - aref, j0 = J delta0; returns m00
+template <class D>
+DEVNI float dual_setup(const Mdl& m, Work<D>& w, bool warmstart, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
+  // rows r <= s with a single-dof row among them: A[r][s] is an entry of Z
+  LANE_FOR(r, ne) {
+    for (int s = r; s < ne; s++) {
+      if (s < nsparse) w.AS[r][s] = w.efc_sign[s] * w.Z[r][w.efc_dof[s]];
+      else if (r < nsparse) w.AS[r][s] = w.efc_sign[r] * w.Z[s][w.efc_dof[r]];
+    }
+  }
+  LANE_FOR(i, nv) w.du_d0[i] = warmstart ? w.warm[i] - w.qacc_smooth[i] : 0.0f;
+  WSYNC();
+  // dense x dense entries: dot products over the dofs
+  for (int r = nsparse; r < ne; r++) {
+    for (int s = r; s < ne; s++) {
+      float p = 0.0f;
+      LANE_FOR(i, nv) p += w.Jd[r - nsparse][i] * w.Z[s][i];
+      p = wsum(p);
+      IF_LANE0 w.AS[r][s] = p;
+    }
+  }
+  float m00 = 0.0f;
+  if (warmstart) {
+    LANE_FOR(i, nv) {
+      float s = 0.0f;
+      for (int j = 0; j < nv; j++) s += w.M[i][j] * w.du_d0[j];
+      w.du_Md0[i] = s;
+      m00 += s * w.du_d0[i];
+    }
+    m00 = wsum(m00);
+  } else {
+    LANE_FOR(i, nv) w.du_Md0[i] = 0.0f;
+  }
+  LANE_FOR(r, nsparse) {
+    const int dof = w.efc_dof[r];
+    w.du_c0[r] = w.efc_sign[r] * w.qacc_smooth[dof] - w.efc_aref[r];
+    w.du_j0[r] = w.efc_sign[r] * w.du_d0[dof];
+  }
+  for (int r = nsparse; r < ne; r++) {
+    float p = 0.0f, q = 0.0f;
+    LANE_FOR(i, nv) { const float j = w.Jd[r - nsparse][i]; p += j * w.qacc_smooth[i]; q += j * w.du_d0[i]; }
+    p = wsum(p); q = wsum(q);
+    IF_LANE0 { w.du_c0[r] = p - w.efc_aref[r]; w.du_j0[r] = q; }
+  }
+  WSYNC();
+  return m00;
+}
+
+struct DualDir { float qg1, qg2, snorm, gradnorm; };
+
+// Newton direction at the current point (efc_force / efc_active / efc_Jaref up to date): fills du_d and efc_jv and
+// returns the line-search coefficients, |search| and |grad| (both in dof space, as the dof-space solver measures them).
+#if B2S_DEVICE
+// Device fast path for ne <= 8 (what the humanoid sees in practice): lane r < ne owns row r, the rows of A and of the
+// reduced system [S | u] sit in registers, and every exchange is a shuffle -- no shared-memory round trips and no
+// loops whose trip count the compiler cannot see (each such iteration would cost a full load latency in order).
+// S z = u is solved by Gauss-Jordan elimination on the rows (S is SPD: no pivoting), which leaves z in place.
+template <class D>
+DEV DualDir dual_direction8(const Mdl& m, Work<D>& w, float beta, float m00, LANE_ARG) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int K = 8;
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
+  const bool live = lane < ne;
+  const int r = live ? lane : 0;
+  float a[K];
+#pragma unroll
+  for (int s = 0; s < K; s++) a[s] = (live && s < ne) ? dual_A(w, r, s) : 0.0f;
+  const float f = live ? w.efc_force[r] : 0.0f, c = live ? w.du_c[r] : 0.0f, j0 = live ? w.du_j0[r] : 0.0f;
+  const bool act = live && w.efc_active[r];
+  const unsigned am = __ballot_sync(FULL, act);
+  // u = J delta - A f (active rows)
+  float u = live ? w.efc_Jaref[r] - w.du_c0[r] : 0.0f;
+#pragma unroll
+  for (int s = 0; s < K; s++) u = fmaf(-a[s], __shfl_sync(FULL, f, s), u);
+  // rows of [S | u]: S = R + A on the active set, identity elsewhere
+  float row[K + 1];
+#pragma unroll
+  for (int s = 0; s < K; s++) {
+    const bool on = act && ((am >> s) & 1u);
+    row[s] = on ? a[s] : 0.0f;
+    if (s == lane) row[s] = act ? a[s] + w.efc_R[r] : 1.0f;
+  }
+  row[K] = act ? u : 0.0f;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (k < ne) {  // warp-uniform
+      const float piv = __shfl_sync(FULL, row[k], k);
+      const float inv = __fdividef(1.0f, fmaxf(piv, MINVAL));
+      const float fac = (lane == k) ? 0.0f : row[k] * inv;
+#pragma unroll
+      for (int j = k + 1; j <= K; j++) row[j] = fmaf(-fac, __shfl_sync(FULL, row[j], k), row[j]);
+      if (lane == k) {
+#pragma unroll
+        for (int j = k + 1; j <= K; j++) row[j] *= inv;
+      }
+    }
+  }
+  const float z = act ? row[K] : 0.0f;
+  const float d = live ? f + z - c : 0.0f;
+  float ad = 0.0f;
+#pragma unroll
+  for (int s = 0; s < K; s++) ad = fmaf(a[s], __shfl_sync(FULL, d, s), ad);
+  if (live) { w.du_d[r] = d; w.efc_jv[r] = ad - beta * j0; }
+  float j0c = j0 * c, j0d = j0 * d, cAd = c * ad, dAd = d * ad;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    j0c += __shfl_xor_sync(FULL, j0c, o); j0d += __shfl_xor_sync(FULL, j0d, o);
+    cAd += __shfl_xor_sync(FULL, cAd, o); dAd += __shfl_xor_sync(FULL, dAd, o);
+  }
+  j0c = __shfl_sync(FULL, j0c, 0); j0d = __shfl_sync(FULL, j0d, 0);
+  cAd = __shfl_sync(FULL, cAd, 0); dAd = __shfl_sync(FULL, dAd, 0);
+  // |search| and |grad| in dof space: search = -beta delta0 + Z d, grad = beta M delta0 + J^T (c - f)
+  const bool dof = lane < nv;
+  const int i = dof ? lane : 0;
+  float sv = dof ? -beta * w.du_d0[i] : 0.0f, gv = dof ? beta * w.du_Md0[i] : 0.0f;
+  const float e = c - f;
+#pragma unroll
+  for (int s = 0; s < K; s++) {
+    const float ds = __shfl_sync(FULL, d, s), es = __shfl_sync(FULL, e, s);
+    if (s < ne && dof) {
+      sv = fmaf(w.Z[s][i], ds, sv);
+      gv = fmaf(jac_entry(w, s, nsparse, i), es, gv);
+    }
+  }
+  const float sn = wsum(sv * sv), gn = wsum(gv * gv);
+  __syncwarp();
+  DualDir o;
+  o.qg1 = -beta * beta * m00 + beta * (j0d - j0c) + cAd;
+  o.qg2 = 0.5f * (beta * beta * m00 - 2.0f * beta * j0d + dAd);
+  o.snorm = sqrtf(sn);
+  o.gradnorm = sqrtf(gn);
+  return o;
+}
+#endif
+
+template <class D>
+DEVNI DualDir dual_direction(const Mdl& m, Work<D>& w, float beta, float m00, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
+#if B2S_DEVICE
+  if (ne <= 8) return dual_direction8(m, w, beta, m00, LANE_PASS);
+#endif
+  // u = J delta - A f on the active rows (into du_d); lower triangle of AS <- active part of A
+  LANE_FOR(r, ne) {
+    const int ar = w.efc_active[r];
+    float u = w.efc_Jaref[r] - w.du_c0[r];
+    for (int s = 0; s < ne; s++) u = fmaf(-dual_A(w, r, s), w.efc_force[s], u);
+    w.du_d[r] = ar ? u : 0.0f;
+    for (int s = 0; s < r; s++) w.AS[r][s] = (ar && w.efc_active[s]) ? w.AS[s][r] : 0.0f;
+  }
+  WSYNC();
+  // Cholesky of S = R_act + A_act,act (identity on inactive rows), column by column; lanes are rows
+  for (int j = 0; j < ne; j++) {
+    LANE_FOR(i, ne) {
+      if (i >= j) {
+        float sj = w.efc_active[j] ? w.AS[j][j] + w.efc_R[j] : 1.0f;
+        float t = w.AS[i][j];
+        for (int k = 0; k < j; k++) {
+          const float ljk = w.AS[j][k];
+          t = fmaf(-w.AS[i][k], ljk, t);
+          sj = fmaf(-ljk, ljk, sj);
+        }
+        sj = fmaxf(sj, MINVAL);
+        const float inv = inv_sqrt(sj);
+        if (i == j) w.du_dinv[j] = inv;
+        else w.AS[i][j] = t * inv;
+      }
+    }
+    WSYNC();
+  }
+  // z = S^-1 u, then d = f + z - c
+#if B2S_DEVICE
+  {
+    constexpr unsigned FULL = 0xffffffffu;
+    const bool live = lane < ne;
+    const int rr = live ? lane : 0;
+    const float dinv = live ? w.du_dinv[rr] : 1.0f;
+    float y = live ? w.du_d[rr] : 0.0f;
+    for (int k = 0; k < ne; k++) {
+      const float yk = __shfl_sync(FULL, y * dinv, k);
+      if (live && lane > k) y = fmaf(-w.AS[rr][k], yk, y);
+    }
+    y *= dinv;
+    for (int k = ne - 1; k >= 0; k--) {
+      const float xk = __shfl_sync(FULL, y * dinv, k);
+      if (lane < k) y = fmaf(-w.AS[k][rr], xk, y);
+    }
+    if (live) w.du_d[rr] = w.efc_force[rr] + y * dinv - w.du_c[rr];
+    __syncwarp();
+  }
+#else
+  for (int k = 0; k < ne; k++) {
+    w.du_d[k] *= w.du_dinv[k];
+    for (int i = k + 1; i < ne; i++) w.du_d[i] -= w.AS[i][k] * w.du_d[k];
+  }
+  for (int k = ne - 1; k >= 0; k--) {
+    w.du_d[k] *= w.du_dinv[k];
+    for (int i = 0; i < k; i++) w.du_d[i] -= w.AS[k][i] * w.du_d[k];
+  }
+  for (int r = 0; r < ne; r++) w.du_d[r] = w.efc_force[r] + w.du_d[r] - w.du_c[r];
+#endif
+  // J search and the scalar products of the line search
+  float j0c = 0.0f, j0d = 0.0f, cAd = 0.0f, dAd = 0.0f;
+  LANE_FOR(r, ne) {
+    float ad = 0.0f;
+    for (int s = 0; s < ne; s++) ad = fmaf(dual_A(w, r, s), w.du_d[s], ad);
+    const float j0 = w.du_j0[r], c = w.du_c[r], d = w.du_d[r];
+    w.efc_jv[r] = ad - beta * j0;
+    j0c += j0 * c; j0d += j0 * d; cAd += c * ad; dAd += d * ad;
+  }
+  // |search| and |grad| in dof space: search = -beta delta0 + Z d, grad = beta M delta0 + J^T (c - f)
+  float sn = 0.0f, gn = 0.0f;
+  LANE_FOR(i, nv) {
+    float sv = -beta * w.du_d0[i], gv = beta * w.du_Md0[i];
+    for (int s = 0; s < ne; s++) sv = fmaf(w.Z[s][i], w.du_d[s], sv);
+    for (int r = 0; r < nsparse; r++) if (w.efc_dof[r] == i) gv += w.efc_sign[r] * (w.du_c[r] - w.efc_force[r]);
+    for (int r = nsparse; r < ne; r++) gv = fmaf(w.Jd[r - nsparse][i], w.du_c[r] - w.efc_force[r], gv);
+    sn += sv * sv; gn += gv * gv;
+  }
+  j0c = wsum(j0c); j0d = wsum(j0d); cAd = wsum(cAd); dAd = wsum(dAd); sn = wsum(sn); gn = wsum(gn);
+  WSYNC();
+  DualDir o;
+  o.qg1 = -beta * beta * m00 + beta * (j0d - j0c) + cAd;
+  o.qg2 = 0.5f * (beta * beta * m00 - 2.0f * beta * j0d + dAd);
+  o.snorm = sqrtf(sn);
+  o.gradnorm = sqrtf(gn);
+  return o;
+}
+
+template <class D>
+DEV void solve_dual(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
+  const bool warmstart = !m.h[MH_DISABLE_WARMSTART];
+  SUB_BEGIN();
+  const float m00 = dual_setup(m, w, warmstart, LANE_PASS);
+  SUB_MARK(w, 16);
+  float beta = 0.0f, gauss = 0.0f;
+  if (warmstart) {
+    LANE_FOR(r, ne) w.efc_Jaref[r] = w.du_c0[r] + w.du_j0[r];
+    WSYNC();
+    const float cw = constraint_rows(w, ne, LANE_PASS) + 0.5f * m00;
+    LANE_FOR(r, ne) w.efc_Jaref[r] = w.du_c0[r];
+    WSYNC();
+    const float cs = constraint_rows(w, ne, LANE_PASS);
+    if (cw < cs) { beta = 1.0f; gauss = 0.5f * m00; }
+  }
+  LANE_FOR(r, ne) { w.efc_Jaref[r] = w.du_c0[r] + beta * w.du_j0[r]; w.du_c[r] = 0.0f; }
+  WSYNC();
+  float cost = constraint_rows(w, ne, LANE_PASS) + gauss;
+  float prev_cost = INFINITY;
+  SUB_MARK(w, 17);
+  DualDir dir = dual_direction(m, w, beta, m00, LANE_PASS);
+  SUB_MARK(w, 18);
+  const int iterations = m.h[MH_ITERATIONS];
+  const float tol = m.mf[MF_TOLERANCE];
+  const float scale = 1.0f / (m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1));
+  int niter = 0;
+  bool finished = false;
+  while (true) {
+    if (!finished && (iterations != 1 || niter > 0)) {
+      const float improvement = (prev_cost - cost) * scale;
+      finished = niter >= iterations;
+      finished |= improvement < tol;
+      finished |= dir.gradnorm * scale < tol;
+    }
+    if (lockstep ? !CTA_OR(!finished) : finished) break;
+    const float qg[3] = {gauss, dir.qg1, dir.qg2};
+    SUB_MARK(w, 19);
+    const float alpha = ls_bracket(m, w, nv, ne, qg, dir.snorm, lockstep, !finished, LANE_PASS);
+    SUB_MARK(w, 20);
+    if (finished) continue;
+    LANE_FOR(r, ne) { w.du_c[r] += alpha * w.du_d[r]; w.efc_Jaref[r] += alpha * w.efc_jv[r]; }
+    WSYNC();
+    gauss = gauss + alpha * dir.qg1 + alpha * alpha * dir.qg2;
+    beta -= alpha * beta;
+    prev_cost = cost;
+    cost = constraint_rows(w, ne, LANE_PASS) + gauss;
+    SUB_MARK(w, 21);
+    dir = dual_direction(m, w, beta, m00, LANE_PASS);
+    SUB_MARK(w, 18);
+    niter++;
+    if (iterations == 1) finished = true;
+  }
+  // Polish: the loop above accepts a step only if it lowers the cost, and in fp32 the cost (O(1e5) with stiff rows)
+  // stops resolving improvements while the iterate is still ~sqrt(eps) away from the minimiser.  `dir` is the Newton
+  // direction at the final point; if the full step leaves the active set unchanged it is the exact minimiser of the
+  // quadratic piece, so it is taken.  This brings the forces to the accuracy of the dof-space solver (tests/).
+  {
+    int changed = 0;
+    LANE_FOR(r, ne) {
+      w.du_c0[r] = w.efc_force[r];               // c0 / j0 / dinv are dead from here on: backups of f, active, c
+      w.du_j0[r] = (float)w.efc_active[r];
+      w.du_dinv[r] = w.du_c[r];
+      w.du_c[r] += w.du_d[r];
+      w.efc_Jaref[r] += w.efc_jv[r];
+    }
+    WSYNC();
+    constraint_rows(w, ne, LANE_PASS);
+    LANE_FOR(r, ne) changed |= (w.efc_active[r] != (int)w.du_j0[r]);
+    changed = wany(changed);
+    if (changed) {
+      LANE_FOR(r, ne) { w.du_c[r] = w.du_dinv[r]; w.efc_force[r] = w.du_c0[r]; w.efc_active[r] = (int)w.du_j0[r]; }
+    } else {
+      beta = 0.0f;
+    }
+    WSYNC();
+  }
+  // back to dof space: qacc = a0 + beta delta0 + Z c, qfrc_constraint = J^T f
+  LANE_FOR(i, nv) {
+    float a = w.qacc_smooth[i] + beta * w.du_d0[i];
+    for (int s = 0; s < ne; s++) a = fmaf(w.Z[s][i], w.du_c[s], a);
+    w.qacc[i] = a; w.warm[i] = a;
+  }
+  constraint_force_to_dofs(w, nv, ne, nsparse, LANE_PASS);
+}
+
+template <class D>
+DEV void solve(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc;
+  if (ne == 0) {
+    // no constraint rows: qacc = qacc_smooth, qacc_warmstart keeps its old value (MJX forward())
+    LANE_FOR(i, nv) { w.qacc[i] = w.qacc_smooth[i]; w.qfrc_constraint[i] = 0.0f; }
+    WSYNC();
+    if (lockstep) solve_follower();
+    return;
+  }
+  if (ne <= D::NDUAL && dual_enabled(m)) solve_dual(m, w, lockstep, LANE_PASS);
+  else solve_primal(m, w, lockstep, LANE_PASS);
 }
 
 // ------------------------------------------------------------------------------------------------ sensors
@@ -1260,26 +1694,35 @@ DEVNI void forward(const Mdl& m, Work<D>& w, bool sensors, bool lockstep, LANE_A
   // `lockstep` (sub-steps of a control step, never the divergent reset path): CTA barriers between stages keep
   // the CTA's warps on the same code, so one instruction-cache fill serves all of them.
 #define B2S_STAGE_SYNC(k) do { if (lockstep && ((m.sync_mask >> (k)) & 1)) CTA_SYNC(); } while (0)
+  STAGE_BEGIN();
   kinematics(m, w, LANE_PASS);
   B2S_STAGE_SYNC(0);
+  STAGE_MARK(w, 0);
   com_pos(m, w, LANE_PASS);
   crb_mass_matrix(m, w, LANE_PASS);
   B2S_STAGE_SYNC(1);
+  STAGE_MARK(w, 1);
   collision(m, w, LANE_PASS);
   com_vel(m, w, LANE_PASS);
   make_constraint(m, w, LANE_PASS);
   B2S_STAGE_SYNC(2);
+  STAGE_MARK(w, 2);
   passive(m, w, LANE_PASS);
   rne(m, w, LANE_PASS);
   if (sensors) sensors_pos_vel(m, w, LANE_PASS);
   actuation(m, w, LANE_PASS);
   B2S_STAGE_SYNC(3);
+  STAGE_MARK(w, 3);
   acceleration(m, w, LANE_PASS);
   B2S_STAGE_SYNC(4);
+  STAGE_MARK(w, 4);
   solve(m, w, lockstep && ((m.sync_mask >> 7) & 1), LANE_PASS);
+  STAGE_MARK(w, 5);
   B2S_STAGE_SYNC(5);
+  STAGE_MARK(w, 6);
 #undef B2S_STAGE_SYNC
   if (sensors) sensors_acc(m, w, LANE_PASS);
+  STAGE_MARK(w, 7);
 }
 
 // the CTA barriers / votes of one lockstep forward(), for a warp that has no environment (tail of the last CTA)
@@ -1296,9 +1739,10 @@ DEV void physics_step(const Mdl& m, Work<D>& w, bool sensors, LANE_ARG) {
   const int nv = DIM(NV, MH_NV), nj = DIM(NJ, MH_NJNT);
   const float dt = m.mf[MF_TIMESTEP];
   forward(m, w, sensors, true, LANE_PASS);
+  STAGE_BEGIN();
   LANE_FOR(i, nv) w.s_grad[i] = w.qfrc_smooth[i] + w.qfrc_constraint[i];
   WSYNC();
-  factor_solve(m, w, FS_IMPLICIT, w.s_Mgrad, w.s_grad, LANE_PASS);
+  factor_solve(m, w, FS_IMPLICIT, w.s_Mgrad, w.s_grad, 0, LANE_PASS);
   LANE_FOR(i, nv) w.qvel[i] += w.s_Mgrad[i] * dt;
   WSYNC();
   const int* jtype = MI(m, MH_JNT_TYPE);
@@ -1322,6 +1766,7 @@ DEV void physics_step(const Mdl& m, Work<D>& w, bool sensors, LANE_ARG) {
   }
   IF_LANE0 w.time += dt;
   WSYNC();
+  STAGE_MARK(w, 8);
 }
 
 }  // namespace b2s

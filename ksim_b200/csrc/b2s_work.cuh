@@ -5,6 +5,10 @@
 
 namespace b2s {
 
+constexpr int dims_min(int a, int b) { return a < b ? a : b; }
+// largest n with n rows of odd stride (n | 1) fitting in `cap` floats
+constexpr int dims_asq(int n, int cap) { return n * (n | 1) <= cap ? n : dims_asq(n - 1, cap); }
+
 // Size traits.  A kernel instantiation serves every model whose sizes are <= the traits' (exact match is
 // fastest because lane loops collapse to a single predicated pass).
 template <int NQ_, int NV_, int NB_, int NJ_, int NU_, int NS_, int NSD_, int NPAIR_, int NCON_, int NDENSE_, int NLIMIT_,
@@ -13,7 +17,8 @@ struct Dims {
   static constexpr bool EXACT = EXACT_;       // model sizes equal the traits: lane loops get compile-time bounds
   static constexpr int NQ = NQ_, NV = NV_, NB = NB_, NJ = NJ_, NU = NU_, NS = NS_, NSD = NSD_;
   static constexpr int NPAIR = NPAIR_, NCON = NCON_, NDENSE = NDENSE_, NLIMIT = NLIMIT_, NFRIC = NFRIC_;
-  static constexpr int NA = 2 * NU_;          // PositionVelocityActuator doubles the action
+  // action size: PositionVelocityActuator doubles it; the exact-fit instantiation serves nu-sized actions only
+  static constexpr int NA = EXACT_ ? NU_ : 2 * NU_;
   static constexpr int NVP = NV_ | 1;         // odd row stride: conflict-free column access
   static constexpr int NSPARSE = NFRIC_ + NLIMIT_;
   static constexpr int NEFC = NFRIC_ + NLIMIT_ + NDENSE_;
@@ -21,7 +26,12 @@ struct Dims {
   static constexpr int ACS = 2 * NU_ + 3;     // PositionActuators state
   static constexpr int CMDS = 24;             // command floats
   static constexpr int OCS = 16;              // observation carry floats
-  static constexpr int NOBS = 32;             // observation plugins (bias keys)
+  static constexpr int NOBS = EXACT_ ? 16 : 32;  // observation plugins (bias keys)
+  // Dual (constraint-space) Newton path: at most NDUAL rows.  Z = M^-1 J^T lives in the storage of
+  // crb/cacc/cfrc/cfrc_ext (28*NB floats, dead during the solve); A = J Z and the factor of the reduced Hessian
+  // share the storage of W.  Rows beyond NDUAL fall back to the primal (dof-space) Newton path.
+  static constexpr int NDUAL = dims_min(dims_min(NEFC, 32), dims_min((28 * NB_) / (NV_ | 1), dims_asq(NV_, NV_ * (NV_ | 1))));
+  static constexpr int NDS = NDUAL | 1;       // odd row stride of AS
 };
 
 // examples/data/scene.mjcf (walking.py): nq 24 nv 23 nbody 17 njnt 18 nu 17 nsite 3 nsensordata 54,
@@ -48,17 +58,26 @@ struct Work {
   float body_mass[D::NB], body_inertia[3][D::NB], body_ipos[3][D::NB];
   // ---- position stage ----
   float xpos[3][D::NB], xquat[4][D::NB], xmat[9][D::NB], xipos[3][D::NB], ximat[9][D::NB];
-  float subtree_com[3][D::NB], cinert[10][D::NB], crb[10][D::NB];
+  float subtree_com[3][D::NB], cinert[10][D::NB];
   float xanchor[3][D::NJ], xaxis[3][D::NJ];
   float cdof[6][D::NV], cdof_dot[6][D::NV];
   float site_xpos[3][D::NS], site_xmat[9][D::NS];
-  float M[D::NV][D::NVP], W[D::NV][D::NVP];  // mass matrix, work matrix (Cholesky factors)
+  float M[D::NV][D::NVP];                     // mass matrix
+  union {
+    float W[D::NV][D::NVP];                   // work matrix (Cholesky factors)
+    // dual Newton path: AS[r][s], s >= r: A = J M^-1 J^T (upper triangle); s < r: factor of the reduced Hessian
+    float AS[D::NDUAL][D::NDS];
+  };
   float Linv_diag[D::NV];                     // 1 / diag of the factor in W
   // ---- contacts ----
   float con_dist[D::NCON], con_pos[3][D::NCON], con_frame[9][D::NCON];
   int con_pair[D::NCON], con_efc[D::NCON];
   // ---- velocity / force stage ----
-  float cvel[6][D::NB], cacc[6][D::NB], cfrc[6][D::NB], cfrc_ext[6][D::NB];
+  float cvel[6][D::NB];
+  union {
+    struct { float crb[10][D::NB], cacc[6][D::NB], cfrc[6][D::NB], cfrc_ext[6][D::NB]; };
+    float Z[D::NDUAL][D::NVP];                // dual Newton path: row s = M^-1 J_s^T (alive from acceleration() to the end of solve())
+  };
   float xfrc[6];                              // Cartesian wrench of the ForcePush event (one body)
   int xfrc_body;
   float qfrc_passive[D::NV], qfrc_bias[D::NV], qfrc_actuator[D::NV], qfrc_smooth[D::NV], qacc_smooth[D::NV];
@@ -71,12 +90,20 @@ struct Work {
   int efc_active[D::NEFC];
   float Jd[D::NDENSE][D::NVP];
   // ---- solver vectors ----
-  float s_qacc[D::NV], s_Ma[D::NV], s_grad[D::NV], s_Mgrad[D::NV], s_search[D::NV], s_mv[D::NV], s_tmp[D::NV];
+  union {
+    struct { float s_qacc[D::NV], s_Ma[D::NV], s_grad[D::NV], s_Mgrad[D::NV], s_search[D::NV], s_mv[D::NV], s_tmp[D::NV]; };
+    // dual Newton path: delta0 = warmstart - qacc_smooth and M delta0 (dof space); per-row c0 = J qacc_smooth - aref,
+    // j0 = J delta0, c (coordinates of qacc - qacc_smooth - beta delta0 in the columns of Z), d (search direction), 1/diag
+    struct { float du_d0[D::NV], du_Md0[D::NV], du_c0[D::NDUAL], du_j0[D::NDUAL], du_c[D::NDUAL], du_d[D::NDUAL], du_dinv[D::NDUAL]; };
+  };
   float sensordata[D::NSD];
   float torque[D::NU], action[D::NA], ctrl_blend[D::NA];
   int drop[D::NA];
   int scratch_i[8];
   float scratch_f[8];
+#if defined(B2S_PROFILE_STAGES) && B2S_DEVICE
+  unsigned prof[B2S_NSTAGE];
+#endif
 };
 
 }  // namespace b2s

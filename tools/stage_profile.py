@@ -1,0 +1,45 @@
+"""Per-stage cycle shares of the rollout kernel (needs a library built with -DB2S_PROFILE_STAGES, see __graft_entry__.build_cuda).
+
+    B2S_EXTRA_NVCC=-DB2S_PROFILE_STAGES python -c "import __graft_entry__ as g; g.build_cuda(force=True)"
+    gpurun -- python tools/stage_profile.py [N] [T]
+"""
+import ctypes
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np
+import torch
+
+from ksim_b200 import binding
+from ksim_b200.engine import B200Engine
+from ksim_b200.examples.walking import RANDOMIZERS, make_spec
+
+NAMES = ["kinematics", "com_pos+crb", "collision+com_vel+constraint", "passive+rne+actuation", "acceleration (M solve, Z)", "solve",
+         "post-solve barrier", "sensors_acc", "implicit solve+integrate", "ctrl/actuators/events/rng", "action load", "terminations/record/reset/commands",
+         "observe", "", "", "(engine_step total)", " solve: dual_setup", " solve: start-point costs", " solve: dual_direction", " solve: convergence check + vote",
+         " solve: line search (incl. votes)", " solve: step update + row costs", "", ""]
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+t = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+spec = make_spec()
+eng = B200Engine(spec, n, randomizers={k: f(spec.model) for k, f in RANDOMIZERS.items()}, seed=0)
+acts = torch.from_numpy((0.3 * np.random.RandomState(2).randn(t, n, eng.NA)).astype(np.float32)).cuda()
+rec = eng.new_record_buffer(t)
+lib = binding.lib()
+for _ in range(3):
+    eng.rollout(acts, rec)
+torch.cuda.synchronize()
+out = (ctypes.c_ulonglong * 24)()
+lib.b200sim_debug_stage_cycles(None, 1)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+eng.rollout(acts, rec)
+e1.record()
+torch.cuda.synchronize()
+lib.b200sim_debug_stage_cycles(out, 0)
+v = np.array(list(out), dtype=np.float64)
+tot = v[:13].sum()
+print(f"rollout {n} x {t}: {e0.elapsed_time(e1):.2f} ms (instrumented build); warp-cycles per env-step: {tot / (n * t):.0f}")
+for name, c in zip(NAMES, v):
+    if c:
+        print(f"{100 * c / tot:6.2f}%  {c / (n * t):10.0f} cyc/env-step  {name}")
