@@ -245,6 +245,31 @@ DEV Key key_split(Key k, int i) {
   Key o; o.k0 = r.a; o.k1 = r.b;
   return o;
 }
+// All children of a key that a warp needs, from ONE threefry evaluation: lane l computes split(k, l) and a shuffle
+// hands child i to every lane (jax.random.split(k, n)[i] is threefry(k, (0, i)) for every n).  Must be called by the
+// whole warp.  The host build evaluates the requested child directly.
+struct KeyFan { Key parent; U2 mine; };
+DEV KeyFan key_fan(Key k, LANE_ARG) {
+  KeyFan f;
+  f.parent = k;
+#if B2S_DEVICE
+  f.mine = threefry2x32(k.k0, k.k1, 0u, (uint32_t)lane);
+#else
+  (void)lane;
+  f.mine.a = f.mine.b = 0u;
+#endif
+  return f;
+}
+DEV Key key_child(const KeyFan& f, int i) {
+#if B2S_DEVICE
+  Key o;
+  o.k0 = __shfl_sync(0xffffffffu, f.mine.a, i);
+  o.k1 = __shfl_sync(0xffffffffu, f.mine.b, i);
+  return o;
+#else
+  return key_split(f.parent, i);
+#endif
+}
 DEV uint32_t key_bits(Key k, int i) {
   const U2 r = threefry2x32(k.k0, k.k1, 0u, (uint32_t)i);
   return r.a ^ r.b;

@@ -120,7 +120,8 @@ DEV void actuators_ctrl(const Mdl& m, Work<D>& w, const float* ctrl_in, Key rng,
   const float* an_f = af + 1; const float* tn_f = an_f + NOISE_NF;
   const float* kp = tn_f + NOISE_NF + 15; const float* kd = kp + nu; const float* clip = kd + nu;
   const float kp_scale = w.act_state[2 * nu], kd_scale = w.act_state[2 * nu + 1], tl_scale = w.act_state[2 * nu + 2];
-  const Key pos_rng = key_split(rng, 0), tor_rng = key_split(rng, 1);
+  const KeyFan fan = key_fan(rng, LANE_PASS);
+  const Key pos_rng = key_child(fan, 0), tor_rng = key_child(fan, 1);
   LANE_FOR(i, nu) {
     const float scaled = ctrl_in[i] * action_scale;
     const float target = noise_apply(an_i, an_f, scaled, pos_rng, i, level) + w.act_state[i];
@@ -265,8 +266,9 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   const int na = ti[TI_ACTION_SIZE], nu = DIM(NU, MH_NU), nsub = ti[TI_NSUB], act_period = ti[TI_ACT_PERIOD];
   const int nevent = ti[TI_N_EVENT];
   const float* ef = m.tf + ti[TI_ENGINE_FOFF];
-  const Key drop_rng = key_split(rng, 0);
-  Key r = key_split(rng, 1);
+  const KeyFan fan0 = key_fan(rng, LANE_PASS);
+  const Key drop_rng = key_child(fan0, 0);
+  Key r = key_child(fan0, 1);
   const float drop_p = ef[2] * w.level;
   LANE_FOR(i, na) w.drop[i] = drop_p > 0.0f ? key_bernoulli(drop_rng, i, drop_p) : 0;
   LANE_FOR(i, nu) w.torque[i] = 0.0f;
@@ -280,14 +282,16 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
       w.ctrl_blend[i] = w.drop[i] ? lc : lc * (1.0f - prct) + w.action[i] * prct;
     }
     WSYNC();
-    const Key rng_update = key_split(r, 1);
-    r = key_split(r, 0);
+    const KeyFan fan = key_fan(r, LANE_PASS);
+    const Key rng_update = key_child(fan, 1);
+    r = key_child(fan, 0);
     if (step % act_period == 0) actuators_ctrl(m, w, w.ctrl_blend, rng_update, LANE_PASS);
     LANE_FOR(i, nu) w.ctrl[i] = w.torque[i];
     WSYNC();
     for (int ev = 0; ev < nevent; ev++) {
-      const Key rng_event = key_split(r, 1);
-      r = key_split(r, 0);
+      const KeyFan fe = key_fan(r, LANE_PASS);
+      const Key rng_event = key_child(fe, 1);
+      r = key_child(fe, 0);
       event_apply(m, w, ev, rng_event, LANE_PASS);
     }
     STAGE_MARK(w, 9);
@@ -373,21 +377,24 @@ DEVNI void engine_reset(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   WSYNC();
   const int nreset = ti[TI_N_RESET];
   for (int i = 0; i < nreset; i++) {
-    const Key reset_rng = key_split(rng, 1);
-    rng = key_split(rng, 0);
+    const KeyFan fr = key_fan(rng, LANE_PASS);
+    const Key reset_rng = key_child(fr, 1);
+    rng = key_child(fr, 0);
     reset_apply(m, w, i, reset_rng, LANE_PASS);
   }
   forward(m, w, true, false, LANE_PASS);
   LANE_FOR(i, nv) { w.qvel[i] = 0.0f; w.qacc[i] = 0.0f; }
   WSYNC();
   actuators_initial_state(m, w, rng, LANE_PASS);
-  Key events_rng = key_split(rng, 0);
-  const Key latency_rng = key_split(rng, 1), zero_rng = key_split(rng, 2);
+  const KeyFan fz = key_fan(rng, LANE_PASS);
+  Key events_rng = key_child(fz, 0);
+  const Key latency_rng = key_child(fz, 1), zero_rng = key_child(fz, 2);
   LANE_FOR(i, ti[TI_ACTION_SIZE]) w.last_ctrl[i] = 0.0f;
   const int nevent = ti[TI_N_EVENT];
   for (int ev = 0; ev < nevent; ev++) {
-    const Key event_rng = key_split(events_rng, 1);
-    events_rng = key_split(events_rng, 0);
+    const KeyFan fe = key_fan(events_rng, LANE_PASS);
+    const Key event_rng = key_child(fe, 1);
+    events_rng = key_child(fe, 0);
     event_initial_state(m, w, ev, event_rng, LANE_PASS);
   }
   IF_LANE0 w.latency = key_uniform(latency_rng, 0, ef[0] * w.level, ef[1] * w.level);
@@ -534,8 +541,9 @@ DEVNI void observe(const Mdl& m, Work<D>& w, Key rng, float* out, LANE_ARG) {
   const int nb = DIM(NB, MH_NBODY);
   (void)nb;
   for (int o = 0; o < nobs; o++) {
-    const Key noise_rng = key_split(rng, 2);
-    rng = key_split(rng, 0);
+    const KeyFan fo = key_fan(rng, LANE_PASS);
+    const Key noise_rng = key_child(fo, 2);
+    rng = key_child(fo, 0);
     const int type = TAB(ti, TI_OBS_TAB, o, TAB_TYPE);
     const int* oi_all = ti + TAB(ti, TI_OBS_TAB, o, TAB_IOFF);
     const float* of_all = m.tf + TAB(ti, TI_OBS_TAB, o, TAB_FOFF);
@@ -664,8 +672,9 @@ template <class D>
 DEV void write_pre_block(const Mdl& m, Work<D>& w, float* rec_next, uint32_t* act_key, LANE_ARG) {
   const int* ti = m.ti;
   Key rng; rng.k0 = w.keys[0]; rng.k1 = w.keys[1];
-  const Key action_rng = key_split(rng, 0);
-  const Key obs_rng = key_split(action_rng, 0), act_rng = key_split(action_rng, 1);
+  const Key action_rng = key_child(key_fan(rng, LANE_PASS), 0);
+  const KeyFan fa = key_fan(action_rng, LANE_PASS);
+  const Key obs_rng = key_child(fa, 0), act_rng = key_child(fa, 1);
   if (act_key) { IF_LANE0 { act_key[0] = act_rng.k0; act_key[1] = act_rng.k1; } }
   observe(m, w, obs_rng, rec_next + ti[TI_R_OBS], LANE_PASS);
   LANE_FOR(i, ti[TI_CMD_SIZE]) rec_next[ti[TI_R_CMD] + i] = w.cmd[i];
@@ -678,12 +687,14 @@ DEV void do_reset(const Mdl& m, Work<D>& w, Key reset_rng, Key cmd_rng, Key obs_
   engine_reset(m, w, reset_rng, LANE_PASS);
   const int ncmd = ti[TI_N_CMD];
   for (int c = 0; c < ncmd; c++) {
-    const Key k = key_split(cmd_rng, 1);
-    cmd_rng = key_split(cmd_rng, 0);
+    const KeyFan fc = key_fan(cmd_rng, LANE_PASS);
+    const Key k = key_child(fc, 1);
+    cmd_rng = key_child(fc, 0);
     IF_LANE0 cmd_initial(m, w, c, k);
   }
   const int nobs = ti[TI_N_OBS];
-  for (int o = 0; o < nobs; o++) obs_carry_initial(m, w, o, key_split(obs_carry_rng, o), LANE_PASS);
+  const KeyFan foc = key_fan(obs_carry_rng, LANE_PASS);
+  for (int o = 0; o < nobs; o++) obs_carry_initial(m, w, o, key_child(foc, o), LANE_PASS);
   LANE_FOR(o, nobs) {
     const Key k = key_split(obs_bias_rng, o);
     w.keys[2 + 2 * o] = k.k0; w.keys[3 + 2 * o] = k.k1;
@@ -714,9 +725,10 @@ DEV int env_step(const Mdl& m, Work<D>& w, const float* action_in, float* rec_cu
   engine_step(m, w, physics_rng, LANE_PASS);
   STAGE_MARK(w, 15);  // double-counts stages 0-9; used as a cross-check only
 
-  Key cmd_rng = key_split(state_rng, 0);
-  const Key obs_carry_rng = key_split(state_rng, 2), obs_bias_rng = key_split(state_rng, 3);
-  const Key reset_rng = key_split(state_rng, 4), next_rng = key_split(state_rng, 5);
+  const KeyFan fs1 = key_fan(state_rng, LANE_PASS);
+  Key cmd_rng = key_child(fs1, 0);
+  const Key obs_carry_rng = key_child(fs1, 2), obs_bias_rng = key_child(fs1, 3);
+  const Key reset_rng = key_child(fs1, 4), next_rng = key_child(fs1, 5);
 
   int done = 0, all_not_fail = 1;
   const int nterm = ti[TI_N_TERM];
@@ -750,8 +762,9 @@ DEV int env_step(const Mdl& m, Work<D>& w, const float* action_in, float* rec_cu
   } else {
     const int ncmd = ti[TI_N_CMD];
     for (int c = 0; c < ncmd; c++) {
-      const Key k = key_split(cmd_rng, 1);
-      cmd_rng = key_split(cmd_rng, 0);
+      const KeyFan fc = key_fan(cmd_rng, LANE_PASS);
+      const Key k = key_child(fc, 1);
+      cmd_rng = key_child(fc, 0);
       IF_LANE0 cmd_update(m, w, c, k);
     }
     WSYNC();

@@ -302,6 +302,8 @@ enum { FS_MASS = 0, FS_NEWTON = 1, FS_IMPLICIT = 2 };
 
 // bit 8 of sync_mask switches the constraint-space Newton path off (tuning / A-B tests)
 DEV bool dual_enabled(const Mdl& m) { return !((m.sync_mask >> 8) & 1); }
+// bit 9: CTA votes per line-search iteration as well (bit 7: per Newton iteration)
+DEV bool ls_votes(const Mdl& m) { return (m.sync_mask >> 9) & 1; }
 
 // Builds A (FS_MASS: M; FS_NEWTON: M + J^T diag(D*active) J; FS_IMPLICIT: M + dt*diag(damping)), factors it and
 // solves A x = b.  The three dense factorisations of a physics sub-step all go through here.
@@ -1024,8 +1026,9 @@ DEV void ls_eval3(const Work<D>& w, int ne, const LSRow& row0, const float* alph
 template <class D>
 DEV float ls_bracket(const Mdl& m, const Work<D>& w, int nv, int ne, const float* qg, float snorm, bool lockstep, bool live,
                      LANE_ARG) {
+  lockstep = lockstep && ls_votes(m);
   if (!live) {
-    while (CTA_OR(0)) {}
+    if (lockstep) while (CTA_OR(0)) {}
     return 0.0f;
   }
   const float scale = m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1);
@@ -1104,9 +1107,10 @@ DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, bool lockstep, bool l
 // `lockstep` (bit 7 of sync_mask): every warp of the CTA goes through the same sequence of CTA votes -- one per
 // Newton iteration and one per line-search iteration -- so the warps stay on the same code while they iterate.
 // solve_follower() is the vote sequence of a warp that has no environment or no constraint rows.
-DEV void solve_follower() {
+DEV void solve_follower(const Mdl& m) {
+  const bool inner = ls_votes(m);
   while (CTA_OR(0)) {
-    while (CTA_OR(0)) {}
+    if (inner) while (CTA_OR(0)) {}
   }
 }
 
@@ -1248,29 +1252,26 @@ DEV DualDir dual_direction8(const Mdl& m, Work<D>& w, float beta, float m00, LAN
 #pragma unroll
   for (int s = 0; s < K; s++) u = fmaf(-a[s], __shfl_sync(FULL, f, s), u);
   // rows of [S | u]: S = R + A on the active set, identity elsewhere
-  float row[K + 1];
+  float row[K];
 #pragma unroll
   for (int s = 0; s < K; s++) {
     const bool on = act && ((am >> s) & 1u);
-    row[s] = on ? a[s] : 0.0f;
-    if (s == lane) row[s] = act ? a[s] + w.efc_R[r] : 1.0f;
+    row[s] = (s == lane) ? (act ? a[s] + w.efc_R[r] : 1.0f) : (on ? a[s] : 0.0f);
   }
-  row[K] = act ? u : 0.0f;
+  float rhs = act ? u : 0.0f;
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    if (k < ne) {  // warp-uniform
+    if (k < ne) {  // warp-uniform; pivots past the last row would be identity rows
       const float piv = __shfl_sync(FULL, row[k], k);
       const float inv = __fdividef(1.0f, fmaxf(piv, MINVAL));
       const float fac = (lane == k) ? 0.0f : row[k] * inv;
+      const float sc = (lane == k) ? inv : 1.0f;
 #pragma unroll
-      for (int j = k + 1; j <= K; j++) row[j] = fmaf(-fac, __shfl_sync(FULL, row[j], k), row[j]);
-      if (lane == k) {
-#pragma unroll
-        for (int j = k + 1; j <= K; j++) row[j] *= inv;
-      }
+      for (int j = k + 1; j < K; j++) row[j] = fmaf(-fac, __shfl_sync(FULL, row[j], k), row[j]) * sc;
+      rhs = fmaf(-fac, __shfl_sync(FULL, rhs, k), rhs) * sc;
     }
   }
-  const float z = act ? row[K] : 0.0f;
+  const float z = act ? rhs : 0.0f;
   const float d = live ? f + z - c : 0.0f;
   float ad = 0.0f;
 #pragma unroll
@@ -1495,7 +1496,7 @@ DEV void solve(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
     // no constraint rows: qacc = qacc_smooth, qacc_warmstart keeps its old value (MJX forward())
     LANE_FOR(i, nv) { w.qacc[i] = w.qacc_smooth[i]; w.qfrc_constraint[i] = 0.0f; }
     WSYNC();
-    if (lockstep) solve_follower();
+    if (lockstep) solve_follower(m);
     return;
   }
   if (ne <= D::NDUAL && dual_enabled(m)) solve_dual(m, w, lockstep, LANE_PASS);
@@ -1729,7 +1730,7 @@ DEVNI void forward(const Mdl& m, Work<D>& w, bool sensors, bool lockstep, LANE_A
 DEV void forward_follower(const Mdl& m) {
 #pragma unroll
   for (int k = 0; k < 5; k++) if ((m.sync_mask >> k) & 1) CTA_SYNC();
-  if ((m.sync_mask >> 7) & 1) solve_follower();
+  if ((m.sync_mask >> 7) & 1) solve_follower(m);
   if ((m.sync_mask >> 5) & 1) CTA_SYNC();
 }
 
