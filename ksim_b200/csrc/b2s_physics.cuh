@@ -58,13 +58,28 @@ DEV Q4 ldgq(const float* p) { Q4 q; q.w = p[0]; q.x = p[1]; q.y = p[2]; q.z = p[
 
 // ------------------------------------------------------------------------------------------ position stage
 
+// Rotates v by the unit quaternion q without forming the matrix: v + 2 w (u x v) + 2 u x (u x v), u = q.xyz
+DEV V3 qrotv(Q4 q, V3 v) {
+  const V3 u = v3(q.x, q.y, q.z);
+  V3 t = cross(u, v);
+  t = t * 2.0f;
+  return v + t * q.w + cross(u, t);
+}
+
+// Forward kinematics in three passes so that only a short compose step sits on the tree's serial path:
+//   A  (lanes = joints, then bodies)  half-angle sin/cos of every hinge; each body's transform RELATIVE to its parent
+//      (body frame followed by its joints' rotations), its joints' anchors / axes in the parent frame;
+//   B  (level by level)               x = parent o local, normalised: one quaternion product + one rotation per level;
+//   C  (lanes = bodies / joints)      rotation matrices, inertial frames, world anchors / axes, sites.
+// Same composition as mj_kinematics (oracle/physics.c), associated differently.
 template <class D>
 DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
-  const int nb = DIM(NB, MH_NBODY);
+  const int nb = DIM(NB, MH_NBODY), nj = DIM(NJ, MH_NJNT);
   const int* parentid = MI(m, MH_BODY_PARENTID);
   const int* jntnum = MI(m, MH_BODY_JNTNUM);
   const int* jntadr = MI(m, MH_BODY_JNTADR);
   const int* jtype = MI(m, MH_JNT_TYPE);
+  const int* jbody = MI(m, MH_JNT_BODYID);
   const int* qposadr = MI(m, MH_JNT_QPOSADR);
   const int* lstart = MI(m, MH_LEVEL_START);
   const int* lbody = MI(m, MH_LEVEL_BODY);
@@ -74,25 +89,23 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
   const float* jnt_pos = MF(m, MH_JNT_POS);
   const float* jnt_axis = MF(m, MH_JNT_AXIS);
   const float* qpos0 = MF(m, MH_QPOS0);
-  IF_LANE0 {
-    ST3(w.xpos, 0, v3(0, 0, 0));
-    Q4 qi; qi.w = 1; qi.x = qi.y = qi.z = 0;
-    STQ(w.xquat, 0, qi);
-    M9 id = q2mat(qi);
-    stm9(w.xmat, 0, id);
-    stm9(w.ximat, 0, id);
-    ST3(w.xipos, 0, v3(0, 0, 0));
+  // ---- A: hinge half-angle sin / cos (scratch: the solver vectors are free here)
+  float* hs = w.s_qacc;
+  float* hc = w.s_Ma;
+  LANE_FOR(jn, nj) {
+    if (jtype[jn] == JNT_HINGE) {
+      const int qa = qposadr[jn];
+      const float half = (w.qpos[qa] - qpos0[qa]) * 0.5f;
+      hs[jn] = sinf(half); hc[jn] = cosf(half);
+    }
   }
   WSYNC();
-  const int nlevel = m.h[MH_NLEVEL];
-  for (int l = 0; l < nlevel; l++) {
-    const int s = lstart[l], e = lstart[l + 1];
-    LANE_FOR(t, e - s) {
-      const int b = lbody[s + t];
-      const int p = parentid[b];
+  // local transforms (into xpos / xquat) and local anchors / axes (into xanchor / xaxis)
+  LANE_FOR(b, nb) {
+    V3 pos = v3(0, 0, 0);
+    Q4 quat; quat.w = 1; quat.x = quat.y = quat.z = 0;
+    if (b > 0) {
       const int jn = jntnum[b], ja = jntadr[b];
-      V3 pos;
-      Q4 quat;
       if (jn == 1 && jtype[ja] == JNT_FREE) {
         const int qa = qposadr[ja];
         Q4 q; q.w = w.qpos[qa + 3]; q.x = w.qpos[qa + 4]; q.y = w.qpos[qa + 5]; q.z = w.qpos[qa + 6];
@@ -103,32 +116,63 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
         ST3(w.xanchor, ja, pos);
         ST3(w.xaxis, ja, ldg3(jnt_axis + 3 * ja));
       } else {
-        M9 pm = ldm9(w.xmat, p);
-        pos = LD3(w.xpos, p) + mulv(pm, ldg3(body_pos + 3 * b));
-        quat = qmul(LDQ(w.xquat, p), ldgq(body_quat + 4 * b));
+        pos = ldg3(body_pos + 3 * b);
+        quat = ldgq(body_quat + 4 * b);
         for (int j = ja; j < ja + jn; j++) {
-          V3 jp = ldg3(jnt_pos + 3 * j), jax = ldg3(jnt_axis + 3 * j);
-          V3 anchor = qrot(quat, jp) + pos;
-          V3 axis = qrot(quat, jax);
+          const V3 jp = ldg3(jnt_pos + 3 * j), jax = ldg3(jnt_axis + 3 * j);
+          const V3 anchor = qrotv(quat, jp) + pos;
           ST3(w.xanchor, j, anchor);
+          const V3 axis = qrotv(quat, jax);
           ST3(w.xaxis, j, axis);
-          const int qa = qposadr[j];
-          Q4 qloc = axis_angle(jax, w.qpos[qa] - qpos0[qa]);
+          Q4 qloc; qloc.w = hc[j]; qloc.x = jax.x * hs[j]; qloc.y = jax.y * hs[j]; qloc.z = jax.z * hs[j];
           quat = qmul(quat, qloc);
-          pos = anchor - qrot(quat, jp);
+          pos = anchor - qrotv(quat, jp);
         }
+      }
+    }
+    ST3(w.xpos, b, pos);
+    STQ(w.xquat, b, quat);
+  }
+  WSYNC();
+  // ---- B: compose down the tree.  Level 1 (children of the world) is already absolute up to normalisation.
+  const int nlevel = m.h[MH_NLEVEL];
+  for (int l = 0; l < nlevel; l++) {
+    const int s = lstart[l], e = lstart[l + 1];
+    LANE_FOR(t, e - s) {
+      const int b = lbody[s + t];
+      const int p = parentid[b];
+      Q4 quat = LDQ(w.xquat, b);
+      V3 pos = LD3(w.xpos, b);
+      if (p > 0) {
+        const Q4 pq = LDQ(w.xquat, p);
+        pos = LD3(w.xpos, p) + qrotv(pq, pos);
+        quat = qmul(pq, quat);
       }
       quat = qnormalize(quat);
       ST3(w.xpos, b, pos);
       STQ(w.xquat, b, quat);
-      M9 xm = q2mat(quat);
-      stm9(w.xmat, b, xm);
-      V3 ip = pos + mulv(xm, LD3(w.body_ipos, b));
-      ST3(w.xipos, b, ip);
-      stm9(w.ximat, b, q2mat(qmul(quat, ldgq(body_iquat + 4 * b))));
     }
     WSYNC();
   }
+  // ---- C: everything that only reads the finished frames
+  LANE_FOR(jn, nj) {
+    const int p = parentid[jbody[jn]];
+    if (p > 0) {
+      const Q4 pq = LDQ(w.xquat, p);
+      const V3 anchor = LD3(w.xpos, p) + qrotv(pq, LD3(w.xanchor, jn)), axis = qrotv(pq, LD3(w.xaxis, jn));
+      ST3(w.xanchor, jn, anchor);  // (ST3 evaluates its argument per component: never pass it an in-place expression)
+      ST3(w.xaxis, jn, axis);
+    }
+  }
+  LANE_FOR(b, nb) {
+    const Q4 quat = LDQ(w.xquat, b);
+    const M9 xm = q2mat(quat);
+    stm9(w.xmat, b, xm);
+    const V3 ip = LD3(w.xpos, b) + mulv(xm, LD3(w.body_ipos, b));
+    ST3(w.xipos, b, ip);
+    stm9(w.ximat, b, q2mat(qmul(quat, ldgq(body_iquat + 4 * b))));
+  }
+  WSYNC();
   const int ns = DIM(NS, MH_NSITE);
   const int* site_body = MI(m, MH_SITE_BODYID);
   const float* site_pos = MF(m, MH_SITE_POS);
@@ -139,7 +183,6 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
     ST3(w.site_xpos, s, p);
     stm9(w.site_xmat, s, q2mat(qmul(LDQ(w.xquat, b), ldgq(site_quat + 4 * s))));
   }
-  (void)nb;
   WSYNC();
 }
 

@@ -73,3 +73,22 @@ extern "C" int emu_rewards(const void* blob, int n, int T, const float* rec, con
 }
 
 extern "C" int emu_sizeof_work(void) { return (int)sizeof(Work<DimsHumanoid>); }
+
+// Debug aid for tests: forward kinematics of one configuration with the base model; xpos[nb][3], xquat[nb][4],
+// xanchor[nj][3], xaxis[nj][3]; rand = one env's override block.
+extern "C" int emu_kinematics(const void* blob, const float* rand, const float* qpos, float* xpos, float* xquat, float* xanchor, float* xaxis) {
+  Mdl m = view(blob);
+  Work<D>* w = new Work<D>();
+  memset(w, 0, sizeof(*w));
+  apply_overrides(m, *w, rand, 0);
+  for (int i = 0; i < m.h[MH_NQ]; i++) w->qpos[i] = qpos[i];
+  kinematics(m, *w, 0);
+  for (int b = 0; b < m.h[MH_NBODY]; b++) {
+    for (int k = 0; k < 3; k++) xpos[3 * b + k] = w->xpos[k][b];
+    for (int k = 0; k < 4; k++) xquat[4 * b + k] = w->xquat[k][b];
+  }
+  for (int j = 0; j < m.h[MH_NJNT]; j++)
+    for (int k = 0; k < 3; k++) { xanchor[3 * j + k] = w->xanchor[k][j]; xaxis[3 * j + k] = w->xaxis[k][j]; }
+  delete w;
+  return 0;
+}
