@@ -44,7 +44,7 @@
 // Optional per-stage cycle accounting (-DB2S_PROFILE_STAGES; tools/stage_profile.py): lane 0 of every warp adds the
 // clock64() delta of each stage to Work::prof, the kernel sums them into g_stage_cycles.  Off in the product build.
 #if defined(B2S_PROFILE_STAGES) && B2S_DEVICE
-#define B2S_NSTAGE 24
+#define B2S_NSTAGE 32
 #define STAGE_BEGIN() long long stage_t0_ = clock64()
 #define STAGE_MARK(w, k) do { const long long t1_ = clock64(); if (lane == 0) (w).prof[k] += (unsigned)(t1_ - stage_t0_); stage_t0_ = t1_; } while (0)
 // nested accounting inside a stage (its own clock): adds to slot k without disturbing the enclosing stage's clock

@@ -89,6 +89,7 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
   const float* jnt_pos = MF(m, MH_JNT_POS);
   const float* jnt_axis = MF(m, MH_JNT_AXIS);
   const float* qpos0 = MF(m, MH_QPOS0);
+  SUB_BEGIN();
   // ---- A: hinge half-angle sin / cos (scratch: the solver vectors are free here)
   float* hs = w.s_qacc;
   float* hc = w.s_Ma;
@@ -96,11 +97,73 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
     if (jtype[jn] == JNT_HINGE) {
       const int qa = qposadr[jn];
       const float half = (w.qpos[qa] - qpos0[qa]) * 0.5f;
-      hs[jn] = sinf(half); hc[jn] = cosf(half);
+      float sn, cs;
+      sincosf(half, &sn, &cs);  // one shared range reduction
+      hs[jn] = sn; hc[jn] = cs;
     }
   }
   WSYNC();
-  // local transforms (into xpos / xquat) and local anchors / axes (into xanchor / xaxis)
+  SUB_MARK(w, 24);
+  // local transforms and local anchors / axes (into xanchor / xaxis); lane = body
+#if B2S_DEVICE
+  {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int b = lane < nb ? lane : 0;
+    const int p = parentid[b];
+    V3 pos = v3(0, 0, 0);
+    Q4 quat; quat.w = 1; quat.x = quat.y = quat.z = 0;
+    if (lane < nb && b > 0) {
+      const int jn = jntnum[b], ja = jntadr[b];
+      if (jn == 1 && jtype[ja] == JNT_FREE) {
+        const int qa = qposadr[ja];
+        Q4 q; q.w = w.qpos[qa + 3]; q.x = w.qpos[qa + 4]; q.y = w.qpos[qa + 5]; q.z = w.qpos[qa + 6];
+        q = qnormalize(q);
+        w.qpos[qa + 3] = q.w; w.qpos[qa + 4] = q.x; w.qpos[qa + 5] = q.y; w.qpos[qa + 6] = q.z;
+        pos = v3(w.qpos[qa], w.qpos[qa + 1], w.qpos[qa + 2]);
+        quat = q;
+        ST3(w.xanchor, ja, pos);
+        const V3 ax0 = ldg3(jnt_axis + 3 * ja);
+        ST3(w.xaxis, ja, ax0);
+      } else {
+        pos = ldg3(body_pos + 3 * b);
+        quat = ldgq(body_quat + 4 * b);
+        for (int j = ja; j < ja + jn; j++) {
+          const V3 jp = ldg3(jnt_pos + 3 * j), jax = ldg3(jnt_axis + 3 * j);
+          const V3 anchor = qrotv(quat, jp) + pos;
+          ST3(w.xanchor, j, anchor);
+          const V3 axis = qrotv(quat, jax);
+          ST3(w.xaxis, j, axis);
+          Q4 qloc; qloc.w = hc[j]; qloc.x = jax.x * hs[j]; qloc.y = jax.y * hs[j]; qloc.z = jax.z * hs[j];
+          quat = qmul(quat, qloc);
+          pos = anchor - qrotv(quat, jp);
+        }
+      }
+    }
+    SUB_MARK(w, 25);
+    // ---- B: compose down the tree in registers.  Every pass rebuilds x = parent o local from the parent's current
+    // frame (fetched by shuffle); after pass k all bodies of depth <= k + 1 are final, so nlevel - 1 passes suffice and
+    // no per-level body lists or shared-memory round trips sit on the serial path.
+    const V3 lpos = pos;
+    const Q4 lquat = quat;
+    quat = qnormalize(quat);
+    const int nlevel = m.h[MH_NLEVEL];
+    for (int l = 1; l < nlevel; l++) {
+      Q4 pq; V3 pp;
+      pq.w = __shfl_sync(FULL, quat.w, p); pq.x = __shfl_sync(FULL, quat.x, p);
+      pq.y = __shfl_sync(FULL, quat.y, p); pq.z = __shfl_sync(FULL, quat.z, p);
+      pp.x = __shfl_sync(FULL, pos.x, p); pp.y = __shfl_sync(FULL, pos.y, p); pp.z = __shfl_sync(FULL, pos.z, p);
+      if (p > 0) {
+        pos = pp + qrotv(pq, lpos);
+        quat = qnormalize(qmul(pq, lquat));
+      }
+    }
+    if (lane < nb) {
+      ST3(w.xpos, b, pos);
+      STQ(w.xquat, b, quat);
+    }
+    __syncwarp();
+  }
+#else
   LANE_FOR(b, nb) {
     V3 pos = v3(0, 0, 0);
     Q4 quat; quat.w = 1; quat.x = quat.y = quat.z = 0;
@@ -114,7 +177,8 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
         pos = v3(w.qpos[qa], w.qpos[qa + 1], w.qpos[qa + 2]);
         quat = q;
         ST3(w.xanchor, ja, pos);
-        ST3(w.xaxis, ja, ldg3(jnt_axis + 3 * ja));
+        const V3 ax0 = ldg3(jnt_axis + 3 * ja);
+        ST3(w.xaxis, ja, ax0);
       } else {
         pos = ldg3(body_pos + 3 * b);
         quat = ldgq(body_quat + 4 * b);
@@ -133,7 +197,6 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
     ST3(w.xpos, b, pos);
     STQ(w.xquat, b, quat);
   }
-  WSYNC();
   // ---- B: compose down the tree.  Level 1 (children of the world) is already absolute up to normalisation.
   const int nlevel = m.h[MH_NLEVEL];
   for (int l = 0; l < nlevel; l++) {
@@ -154,6 +217,8 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
     }
     WSYNC();
   }
+#endif
+  SUB_MARK(w, 26);
   // ---- C: everything that only reads the finished frames
   LANE_FOR(jn, nj) {
     const int p = parentid[jbody[jn]];
@@ -184,6 +249,7 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
     stm9(w.site_xmat, s, q2mat(qmul(LDQ(w.xquat, b), ldgq(site_quat + 4 * s))));
   }
   WSYNC();
+  SUB_MARK(w, 27);
 }
 
 template <class D>

@@ -18,7 +18,8 @@ from ksim_b200.examples.walking import RANDOMIZERS, make_spec
 NAMES = ["kinematics", "com_pos+crb", "collision+com_vel+constraint", "passive+rne+actuation", "acceleration (M solve, Z)", "solve",
          "post-solve barrier", "sensors_acc", "implicit solve+integrate", "ctrl/actuators/events/rng", "action load", "terminations/record/reset/commands",
          "observe", "", "", "(engine_step total)", " solve: dual_setup", " solve: start-point costs", " solve: dual_direction", " solve: convergence check + vote",
-         " solve: line search (incl. votes)", " solve: step update + row costs", "", ""]
+         " solve: line search (incl. votes)", " solve: step update + row costs", "", "",
+         " kin: A0 sin/cos", " kin: A local transforms", " kin: B level compose", " kin: C matrices/anchors/sites", "", "", "", ""]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 t = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 spec = make_spec()
@@ -29,7 +30,7 @@ lib = binding.lib()
 for _ in range(3):
     eng.rollout(acts, rec)
 torch.cuda.synchronize()
-out = (ctypes.c_ulonglong * 24)()
+out = (ctypes.c_ulonglong * 32)()
 lib.b200sim_debug_stage_cycles(None, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
