@@ -157,8 +157,13 @@ DEV V3 mulTv(const M9& m, V3 v) {
 }
 DEV V3 qrot(Q4 q, V3 v) { return mulv(q2mat(q), v); }
 DEVNI Q4 axis_angle(V3 axis, float angle) {
-  float s = sinf(angle * 0.5f);
-  Q4 q; q.w = cosf(angle * 0.5f); q.x = axis.x * s; q.y = axis.y * s; q.z = axis.z * s;
+  float s, c;
+#if B2S_DEVICE
+  sincosf(angle * 0.5f, &s, &c);  // one shared range reduction
+#else
+  s = sinf(angle * 0.5f); c = cosf(angle * 0.5f);
+#endif
+  Q4 q; q.w = c; q.x = axis.x * s; q.y = axis.y * s; q.z = axis.z * s;
   return q;
 }
 // xax.rotate_vector_by_quat (normalises with eps 1e-6); same expression order as the oracle (oracle/physics.c)

@@ -98,7 +98,11 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
       const int qa = qposadr[jn];
       const float half = (w.qpos[qa] - qpos0[qa]) * 0.5f;
       float sn, cs;
+#if B2S_DEVICE
       sincosf(half, &sn, &cs);  // one shared range reduction
+#else
+      sn = sinf(half); cs = cosf(half);
+#endif
       hs[jn] = sn; hc[jn] = cs;
     }
   }
@@ -1085,13 +1089,16 @@ DEV LSRow ls_row(const Work<D>& w, int r) {
 }
 DEV void ls_accumulate(const LSRow& o, float alpha, float& q0, float& q1, float& q2) {
   const float x = o.ja + alpha * o.jv;
-  if (o.type == EFC_FRICTION) {
-    if (x <= -o.rf) { q0 += o.f * (-0.5f * o.rf - o.ja); q1 += -o.f * o.jv; }
-    else if (x >= o.rf) { q0 += o.f * (-0.5f * o.rf + o.ja); q1 += o.f * o.jv; }
-    else { q0 += 0.5f * o.D * o.ja * o.ja; q1 += o.D * o.jv * o.ja; q2 += 0.5f * o.D * o.jv * o.jv; }
-  } else if (x < 0.0f) {
-    q0 += 0.5f * o.D * o.ja * o.ja; q1 += o.D * o.jv * o.ja; q2 += 0.5f * o.D * o.jv * o.jv;
-  }
+  // quadratic zone (limit / contact rows: x < 0; friction rows: |x| < R f), else a friction row's linear zones;
+  // written with selects so the three step sizes of a warp do not diverge
+  const bool fr = o.type == EFC_FRICTION;
+  const bool quad = fr ? (x > -o.rf && x < o.rf) : (x < 0.0f);
+  const float dj = o.D * o.ja;
+  const float sg = (x <= -o.rf) ? -1.0f : 1.0f;  // friction, linear zones: force -sg f
+  const bool lin = fr && !quad;
+  q0 += quad ? 0.5f * dj * o.ja : (lin ? o.f * (-0.5f * o.rf + sg * o.ja) : 0.0f);
+  q1 += quad ? dj * o.jv : (lin ? sg * o.f * o.jv : 0.0f);
+  q2 += quad ? 0.5f * o.D * o.jv * o.jv : 0.0f;
 }
 
 // Evaluates three step sizes in one pass over the constraint rows.
