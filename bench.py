@@ -31,6 +31,16 @@ ROLLOUT = 64
 METRIC = "humanoid env-steps/sec"
 UNIT = "env-steps/s"
 GAMMA, LAM = 0.97, 0.95
+WORKLOAD = "humanoid"  # --workload kbot: BASELINE.json configs[2] (K-Bot, 8192 envs x 100), a secondary measurement
+
+
+def _task():  # noqa: ANN202
+    """(make_spec, RANDOMIZERS) of the selected workload."""
+    if WORKLOAD == "kbot":
+        from ksim_b200.examples import kbot as task
+    else:
+        from ksim_b200.examples import walking as task
+    return task.make_spec, task.RANDOMIZERS
 
 
 def _peaks() -> tuple[float, str]:
@@ -83,10 +93,12 @@ class ClockSampler:
 
 
 def _config(n_gpus: int) -> dict:
-    return {"workload": "humanoid walking (examples/walking.py plugin set) 4096 envs x rollout 64 per GPU: physics+obs+termination+"
+    name = ("K-Bot walking (examples/kbot plugin subset, level 1: actuator noise, latency, drop, force pushes, randomizers)"
+            if WORKLOAD == "kbot" else "humanoid walking (examples/walking.py plugin set)")
+    return {"workload": f"{name} {ENVS_PER_GPU} envs x rollout {ROLLOUT} per GPU: physics+obs+termination+"
                         "reset+reward+GAE", "envs_per_gpu": ENVS_PER_GPU, "rollout": ROLLOUT, "total_envs": ENVS_PER_GPU * n_gpus,
             "physics_substeps_per_env_step": 5, "policy": "synthetic: a_t = 0.3*N(0,1), values = 0", "parallelism": f"env-sharded x{n_gpus}",
-            "l2_note": "per-step inputs+outputs (record buffer 4096x65x608 fp32 = 648 MB) exceed the 126 MB L2"}
+            "l2_note": f"per-step inputs+outputs (record buffer {ENVS_PER_GPU}x{ROLLOUT + 1} records, hundreds of MB) exceed the 126 MB L2"}
 
 
 def run_reference(args: argparse.Namespace) -> None:
@@ -100,10 +112,10 @@ def run_reference(args: argparse.Namespace) -> None:
         return
     import oracle
     from ksim_b200.envinit import make_env_init
-    from ksim_b200.examples.walking import RANDOMIZERS, make_spec
     from ksim_b200.program import build_program
     from oracle import OracleEngine
 
+    make_spec, RANDOMIZERS = _task()
     oracle.build()
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
@@ -112,7 +124,7 @@ def run_reference(args: argparse.Namespace) -> None:
     rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
     n, t = max(cores * 8, 64), 16
     ora = OracleEngine(prog, "f32")
-    init = make_env_init(prog, rz, n, seed=0)
+    init = make_env_init(prog, rz, n, seed=0, level=1.0 if WORKLOAD == "kbot" else 0.0)
     st, keys, rec0, _ = ora.init_envs(init.init_keys, init.levels, init.rand)
     rec = np.zeros((t + 1, n, prog.rec_size), np.float32)
     rec[0] = rec0
@@ -147,10 +159,10 @@ def cpu_baseline_leg() -> dict:
     """Bounded CPU sample (~10-20 s) of the same workload for the `cpu_baseline` object (rank 0, N=1 only)."""
     import oracle
     from ksim_b200.envinit import make_env_init
-    from ksim_b200.examples.walking import RANDOMIZERS, make_spec
     from ksim_b200.program import build_program
     from oracle import OracleEngine
 
+    make_spec, RANDOMIZERS = _task()
     oracle.build()
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
@@ -159,7 +171,7 @@ def cpu_baseline_leg() -> dict:
     rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
     n, t = max(cores * 8, 64), 16
     ora = OracleEngine(prog, "f32")
-    init = make_env_init(prog, rz, n, seed=0)
+    init = make_env_init(prog, rz, n, seed=0, level=1.0 if WORKLOAD == "kbot" else 0.0)
     st, keys, rec0, _ = ora.init_envs(init.init_keys, init.levels, init.rand)
     rec = np.zeros((t + 1, n, prog.rec_size), np.float32)
     rec[0] = rec0
@@ -182,7 +194,11 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="humanoid", choices=["humanoid", "kbot"])
     args = ap.parse_args()
+    global WORKLOAD, ENVS_PER_GPU, ROLLOUT, METRIC, GAMMA, LAM
+    if args.workload == "kbot":
+        WORKLOAD, ENVS_PER_GPU, ROLLOUT, METRIC, GAMMA, LAM = "kbot", 8192, 100, "kbot env-steps/sec", 0.94, 0.94
     if args.impl == "reference":
         run_reference(args)
         return
@@ -191,8 +207,8 @@ def main() -> None:
 
     from ksim_b200 import distributed as D
     from ksim_b200.engine import B200Engine
-    from ksim_b200.examples.walking import RANDOMIZERS, make_spec
 
+    make_spec, RANDOMIZERS = _task()
     rank, local, world = D.init_from_env()
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
@@ -202,7 +218,8 @@ def main() -> None:
     rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
     n, t = ENVS_PER_GPU, ROLLOUT
     lo, _ = D.shard_range(n * world, rank, world)
-    eng = B200Engine(spec, n, device=device, randomizers=rz, seed=0, env_offset=lo, total_envs=n * world)
+    level = 1.0 if WORKLOAD == "kbot" else 0.0  # the K-Bot task pins its curriculum at 1 (train.py:1268-1273)
+    eng = B200Engine(spec, n, device=device, randomizers=rz, seed=0, curriculum_level=level, env_offset=lo, total_envs=n * world)
     na = eng.NA
     # synthetic policy outputs for every step of the run, resident in HBM before timing starts
     gen = torch.Generator(device=device).manual_seed(1 + rank)
@@ -299,7 +316,7 @@ def main() -> None:
                 "d2h_bytes_per_step": int((host_adv.numel() + host_total.numel()) * 4), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "k_rollout<DimsHumanoid>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms,
+                     "kernel": "k_rollout<DimsKbot>" if WORKLOAD == "kbot" else "k_rollout<DimsHumanoid>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms,
                      "algorithmic_bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src,
                      "note": "latency/issue-bound by design (tiny per-env matrices); see DESIGN.md and profiles/"},
         "clocks": clocks,

@@ -67,7 +67,7 @@ constexpr float PI_F = 3.14159265358979323846f;
 enum { JNT_FREE = 0, JNT_HINGE = 3 };
 enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_CAPSULE = 3 };
 enum {
-  SENS_TOUCH = 0, SENS_ACCEL = 1, SENS_VELOCIMETER = 2, SENS_GYRO = 3, SENS_FORCE = 4, SENS_TORQUE = 5,
+  SENS_TOUCH = 0, SENS_ACCEL = 1, SENS_VELOCIMETER = 2, SENS_GYRO = 3, SENS_FORCE = 4, SENS_TORQUE = 5, SENS_MAGNETOMETER = 6,
   SENS_FRAMEPOS = 10, SENS_FRAMEQUAT = 11, SENS_FRAMEXAXIS = 12, SENS_FRAMEYAXIS = 13, SENS_FRAMEZAXIS = 14,
   SENS_FRAMELINVEL = 15, SENS_FRAMEANGVEL = 16, SENS_FRAMELINACC = 17, SENS_FRAMEANGACC = 18
 };

@@ -1663,6 +1663,11 @@ DEV void sensors_pos_vel(const Mdl& m, Work<D>& w, LANE_ARG) {
         const int col = t - SENS_FRAMEXAXIS;
         out[0] = rot.m[col]; out[1] = rot.m[3 + col]; out[2] = rot.m[6 + col];
       }
+    } else if (t == SENS_MAGNETOMETER) {
+      // site frame^T * opt.magnetic; the MJCF compiler only accepts MuJoCo's default field (0, -0.5, 0)
+      const M9 r = ldm9(w.site_xmat, id);
+      const V3 o = mulTv(r, v3(0.0f, -0.5f, 0.0f));
+      out[0] = o.x; out[1] = o.y; out[2] = o.z;
     } else if (t == SENS_VELOCIMETER || t == SENS_GYRO || t == SENS_FRAMELINVEL || t == SENS_FRAMEANGVEL) {
       const bool local = (t == SENS_VELOCIMETER || t == SENS_GYRO);
       object_frame(m, w, local ? OBJ_SITE : ot, id, &body, &pos, &rot);

@@ -48,12 +48,12 @@ class OBJ:
 class SENSOR:
     """Sensor type codes (own numbering; names follow the MJCF element names)."""
 
-    TOUCH, ACCELEROMETER, VELOCIMETER, GYRO, FORCE, TORQUE = 0, 1, 2, 3, 4, 5
+    TOUCH, ACCELEROMETER, VELOCIMETER, GYRO, FORCE, TORQUE, MAGNETOMETER = 0, 1, 2, 3, 4, 5, 6
     FRAMEPOS, FRAMEQUAT, FRAMEXAXIS, FRAMEYAXIS, FRAMEZAXIS = 10, 11, 12, 13, 14
     FRAMELINVEL, FRAMEANGVEL, FRAMELINACC, FRAMEANGACC = 15, 16, 17, 18
     BY_NAME = {
         "touch": (0, 1), "accelerometer": (1, 3), "velocimeter": (2, 3), "gyro": (3, 3),
-        "force": (4, 3), "torque": (5, 3),
+        "force": (4, 3), "torque": (5, 3), "magnetometer": (6, 3),
         "framepos": (10, 3), "framequat": (11, 4), "framexaxis": (12, 3), "frameyaxis": (13, 3),
         "framezaxis": (14, 3), "framelinvel": (15, 3), "frameangvel": (16, 3),
         "framelinacc": (17, 3), "frameangacc": (18, 3),

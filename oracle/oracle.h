@@ -50,7 +50,7 @@ enum { O_GEOM_PLANE = 0, O_GEOM_SPHERE = 2, O_GEOM_CAPSULE = 3 };
 enum { O_EFC_FRICTION = 1, O_EFC_LIMIT = 2, O_EFC_CONTACT = 3 };
 enum {
   O_SENS_TOUCH = 0, O_SENS_ACCEL = 1, O_SENS_VELOCIMETER = 2, O_SENS_GYRO = 3, O_SENS_FORCE = 4,
-  O_SENS_TORQUE = 5, O_SENS_FRAMEPOS = 10, O_SENS_FRAMEQUAT = 11, O_SENS_FRAMEXAXIS = 12,
+  O_SENS_TORQUE = 5, O_SENS_MAGNETOMETER = 6, O_SENS_FRAMEPOS = 10, O_SENS_FRAMEQUAT = 11, O_SENS_FRAMEXAXIS = 12,
   O_SENS_FRAMEYAXIS = 13, O_SENS_FRAMEZAXIS = 14, O_SENS_FRAMELINVEL = 15, O_SENS_FRAMEANGVEL = 16,
   O_SENS_FRAMELINACC = 17, O_SENS_FRAMEANGACC = 18
 };

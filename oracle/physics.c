@@ -874,6 +874,13 @@ static void sensor_pos(const OModel* m, OData* d) {
     REAL* out = d->sensordata + m->sensor_adr[s];
     int t = m->sensor_type[s], ot = m->sensor_objtype[s], id = m->sensor_objid[s];
     int body; const REAL *pos, *rot;
+    if (t == O_SENS_MAGNETOMETER) {
+      /* mj_sensorPos: site_xmat^T * opt.magnetic, MuJoCo's default field (0, -0.5, 0) */
+      const REAL* r = d->site_xmat[id];
+      const REAL mag[3] = {0, (REAL)-0.5, 0};
+      for (int k = 0; k < 3; k++) out[k] = r[k] * mag[0] + r[3 + k] * mag[1] + r[6 + k] * mag[2];
+      continue;
+    }
     if (t < O_SENS_FRAMEPOS || t > O_SENS_FRAMEZAXIS) continue;
     object_frame(m, d, ot, id, &body, &pos, &rot);
     if (t == O_SENS_FRAMEPOS) { for (int k = 0; k < 3; k++) out[k] = pos[k]; }

@@ -38,6 +38,20 @@ def walking_randomizers(walking_spec):  # noqa: ANN001, ANN201
 
 
 @pytest.fixture(scope="session")
+def kbot_spec():  # noqa: ANN201
+    from ksim_b200.examples.kbot import make_spec
+
+    return make_spec()
+
+
+@pytest.fixture(scope="session")
+def kbot_randomizers(kbot_spec):  # noqa: ANN001, ANN201
+    from ksim_b200.examples.kbot import RANDOMIZERS
+
+    return {k: f(kbot_spec.model) for k, f in RANDOMIZERS.items()}
+
+
+@pytest.fixture(scope="session")
 def oracle_built() -> None:
     import oracle
 

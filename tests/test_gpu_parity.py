@@ -244,3 +244,40 @@ def test_edge_cases(ctx) -> None:  # noqa: ANN001
     eng.rollout(torch.zeros((0, 8, eng.NA), device="cuda"))
     with pytest.raises(ValueError):
         eng.step(torch.zeros((7, eng.NA), device="cuda"), rec[0], rec[1])
+
+
+def test_kbot_parity_resynchronised(ctx, kbot_spec, kbot_randomizers) -> None:  # noqa: ANN001
+    """BASELINE config 3's robot through the K-Bot-sized instantiation (variant 1): capsule/plane contacts with
+    pyramidal cones, friction-loss rows, per-joint PD gains with action noise, latency, drop, force pushes, five
+    randomizers.  Same protocol and stated tolerances as the humanoid test (velocities: relative 5e-3 + 3e-2)."""
+    n, steps = 32, 30
+    eng = _engine(kbot_spec, kbot_randomizers, n, level=1.0, seed=5)
+    assert eng.info("VARIANT") == 1
+    ora, st, keys, rec0, _ = _oracle_init(eng)
+    p, m = eng.program, kbot_spec.model
+    np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
+    np.testing.assert_allclose(_np(eng.state), st, rtol=1e-4, atol=5e-5)
+    actions = (0.3 * np.random.RandomState(6).randn(steps, n, eng.NA)).astype(np.float32)
+    rec_o = np.zeros((2, n, eng.R), np.float32)
+    rec_o[0] = rec0
+    cur, nxt = (torch.zeros((n, eng.R), device="cuda") for _ in range(2))
+    q, v, d, sc, te = p["TI_R_QPOS"], p["TI_R_QVEL"], p["TI_R_DONE"], p["TI_R_SUCCESS"], p["TI_R_TERM"]
+    n_bad = 0
+    for s in range(steps):
+        eng.state.copy_(torch.from_numpy(st).cuda())
+        eng.keys.copy_(torch.from_numpy(keys.view(np.int32)).cuda())
+        eng.step(torch.from_numpy(actions[s]).cuda(), cur, nxt)
+        ora.step_ctrl(actions[s], eng.env_init.rand, st, keys, rec_o[0], rec_o[1])
+        g_cur = _np(cur)
+        np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
+        np.testing.assert_array_equal(g_cur[:, d], rec_o[0][:, d])
+        np.testing.assert_array_equal(g_cur[:, sc], rec_o[0][:, sc])
+        np.testing.assert_array_equal(g_cur[:, te : te + 3], rec_o[0][:, te : te + 3])
+        dq = np.abs(g_cur[:, q : q + m.nq] - rec_o[0][:, q : q + m.nq])
+        dv = np.abs(g_cur[:, v : v + m.nv] - rec_o[0][:, v : v + m.nv])
+        bad = (dq > 3e-4).any(axis=1) | (dv > 3e-2 + 5e-3 * np.abs(rec_o[0][:, v : v + m.nv])).any(axis=1)
+        assert dq.max() <= 2e-2 and dv.max() <= 2.0, (s, dq.max(), dv.max())
+        n_bad += int(bad.sum())
+        rec_o[0] = rec_o[1]
+    assert n_bad <= max(1, int(0.003 * n * steps)), f"{n_bad} of {n * steps} env-steps outside the stated tolerance"
+    assert float(eng.state[:, p["TI_S_NONFINITE"]].sum()) == 0.0
