@@ -298,6 +298,7 @@ def main() -> None:
     if nonfinite:
         raise SystemExit(f"{nonfinite} environments produced non-finite states")
     if rank != 0:
+        D.shutdown()
         return
     env_steps = n * t * world
     value = env_steps / (ms * 1e-3)
@@ -324,6 +325,7 @@ def main() -> None:
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg()
     print(json.dumps(out))
+    D.shutdown()
 
 
 if __name__ == "__main__":

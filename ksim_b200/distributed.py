@@ -9,7 +9,7 @@ Backend: ``nccl`` on GPUs, ``gloo`` in the CPU tests.
 
 from __future__ import annotations
 
-__all__ = ["shard_range", "init_from_env", "max_over_ranks", "sum_over_ranks", "global_mean_std"]
+__all__ = ["shard_range", "init_from_env", "shutdown", "max_over_ranks", "sum_over_ranks", "global_mean_std", "allreduce_mean_"]
 
 import os
 
@@ -66,3 +66,44 @@ def global_mean_std(x: torch.Tensor) -> tuple[float, float]:
     mean = acc[0] / acc[2]
     var = torch.clamp(acc[1] / acc[2] - mean * mean, min=0.0)
     return float(mean), float(var.sqrt())
+
+
+def allreduce_mean_(tensors: list[torch.Tensor], bucket_bytes: int = 64 << 20) -> None:
+    """In-place mean over ranks of a list of tensors -- the one collective of the data-parallel PPO step
+    (ksim/task/ppo.py:530-533 computes the gradient of a rank's minibatch; with env-sharded rollouts the ranks'
+    gradients are averaged before the optimizer update).
+
+    Tensors are packed into flat buckets (one ``all_reduce`` each: NVSwitch cost is launch-latency bound, not
+    per-link bound, so few large buckets) and unpacked in place.  No-op in a single-process run.
+    """
+    if not tensors or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    world = dist.get_world_size()
+    bucket: list[torch.Tensor] = []
+    size = 0
+
+    def flush() -> None:
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([t.reshape(-1) for t in bucket])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        off = 0
+        for t in bucket:
+            n = t.numel()
+            t.copy_(flat[off : off + n].view_as(t))
+            off += n
+        bucket, size = [], 0
+
+    for t in tensors:
+        if bucket and (t.dtype != bucket[0].dtype or size + t.numel() * t.element_size() > bucket_bytes):
+            flush()
+        bucket.append(t)
+        size += t.numel() * t.element_size()
+    flush()
+
+
+def shutdown() -> None:
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()

@@ -43,8 +43,12 @@ def _worker(rank: int, world: int, port: int, total_envs: int, out_dir: str) -> 
     work = D.sum_over_ranks(float(hi - lo))
     x = torch.arange(lo, hi, dtype=torch.float32)
     mean, std = D.global_mean_std(x)
+    # gradient averaging (the PPO step's one collective): mixed shapes / dtypes, small bucket to force several flushes
+    grads = [torch.full((5, 3), float(rank + 1)), torch.full((7,), 10.0 * (rank + 1)), torch.full((2, 2), float(rank), dtype=torch.float64)]
+    D.allreduce_mean_(grads, bucket_bytes=64)
     if rank == 0:
         np.save(os.path.join(out_dir, "reduced.npy"), np.array([t, work, mean, std]))
+        np.save(os.path.join(out_dir, "grads.npy"), np.array([float(g.reshape(-1)[0]) for g in grads]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,6 +72,15 @@ def test_two_rank_sharding_matches_single_process(tmp_path) -> None:  # noqa: AN
     assert t == 11.0 and work == total
     assert mean == pytest.approx(np.arange(total).mean()) and std == pytest.approx(np.arange(total).std())
     assert [shard_range(total, r, world) for r in range(world)] == [(0, 7), (7, 13)]
+    np.testing.assert_allclose(np.load(tmp_path / "grads.npy"), [1.5, 15.0, 0.5])
+
+
+def test_allreduce_mean_single_process_is_identity() -> None:
+    from ksim_b200.distributed import allreduce_mean_
+
+    g = [torch.arange(6.0).reshape(2, 3)]
+    allreduce_mean_(g)
+    assert torch.equal(g[0], torch.arange(6.0).reshape(2, 3))
 
 
 def test_shard_range_edge_cases() -> None:
