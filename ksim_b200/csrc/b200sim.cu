@@ -267,7 +267,7 @@ extern "C" int b200sim_model_create(const void* blob, size_t nbytes, b200sim_mod
   mo->mdl.ti = d + MH_SIZE + ni + nf;
   mo->mdl.tf = (const float*)(d + MH_SIZE + ni + nf + nti);
   mo->mdl.sync_mask = 0xff;  // measured best on B200 (profiles/): every stage barrier + one vote per Newton iteration
-  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0x3ff;  // tuning experiments
+  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0x7ff;  // tuning experiments
   int rc;
   const size_t words[4] = {ni, nf, nti, ntf};
   if (fits<DimsHumanoid>(h) && task_fits<DimsHumanoid>(ti)) { mo->variant = 0; rc = configure<DimsHumanoid>(mo, words); }
