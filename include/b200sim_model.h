@@ -13,7 +13,7 @@
 #define B200SIM_MODEL_H
 
 #define B2S_MODEL_MAGIC 0x4232534D /* "B2SM" */
-#define B2S_MODEL_VERSION 3
+#define B2S_MODEL_VERSION 4
 
 #define B2S_MAXNV 32   /* one dof per lane */
 #define B2S_MAXNB 32   /* one body per lane */
@@ -48,6 +48,7 @@
 #define MH_DISABLE_WARMSTART 22
 #define MH_NFRICTION 23 /* dofs with base frictionloss > 0 or a frictionloss override (rows are emitted per env) */
 #define MH_NLIMIT 24    /* limited hinge joints */
+#define MH_NUPPASS 25   /* passes of the leaf-to-root accumulation schedule (MH_UP_START / MH_UP_BODY) */
 /* float scalars live at the start of mf[] */
 #define MF_TIMESTEP 0
 #define MF_GRAVITY 1   /* 3 */
@@ -96,6 +97,11 @@
 #define MH_BODY_DOFMASK 66   /* [nbody] bitmask of dofs that move the body */
 #define MH_DOF_VELPARENT 67  /* [nv] dof whose chain gives the velocity "before" this dof; -2 = none (free translation) */
 #define MH_BODY_LASTDOF 68   /* [nbody] last dof of the body or of its nearest ancestor with dofs; -1 for the world */
+/* Leaf-to-root accumulation schedule: pass p adds bodies MH_UP_BODY[MH_UP_START[p] .. MH_UP_START[p+1]) into their
+ * parents.  Passes go from the deepest level up; within a level, pass r holds each parent's r-th child, so the bodies
+ * of one pass have distinct parents and a pass is one conflict-free lane-parallel phase. */
+#define MH_UP_START 69       /* [nuppass+1] */
+#define MH_UP_BODY 70        /* [nbody-1 minus the children of the world] */
 /* ---- header offsets into mf[] ---- */
 #define MH_BODY_POS 80
 #define MH_BODY_QUAT 81

@@ -52,6 +52,19 @@ def build_model_arrays(model: Model, frictionloss_override: bool = False) -> tup
         level_start[lvl] = level_start[lvl - 1] + int((depth[1:] == lvl).sum())
     assert level_start[-1] == nb - 1
 
+    # leaf-to-root accumulation schedule (composite inertia, subtree force sums): deepest level first, one pass per
+    # sibling rank so that no two bodies of a pass share a parent; children of the world are never accumulated
+    up_start, up_body = [0], []
+    for lvl in range(nlevel, 1, -1):
+        by_parent: dict[int, list[int]] = {}
+        for b in range(1, nb):
+            if depth[b] == lvl:
+                by_parent.setdefault(int(parent[b]), []).append(b)
+        for rank in range(max((len(v) for v in by_parent.values()), default=0)):
+            up_body += [v[rank] for v in by_parent.values() if len(v) > rank]
+            up_start.append(len(up_body))
+    up_start_a, up_body_a = np.array(up_start, dtype=np.int32), np.array(up_body, dtype=np.int32)
+
     dof_parent = a["dof_parentid"]
     body_lastdof = np.full(nb, -1, dtype=np.int32)
     for b in range(1, nb):
@@ -97,6 +110,7 @@ def build_model_arrays(model: Model, frictionloss_override: bool = False) -> tup
         (C.MH_LIMIT_JNT, limit_jnt), (C.MH_PAIR_CONADR, conadr),
         (C.MH_BODY_DOFMASK, body_dofmask.astype(np.uint32).view(np.int32)),
         (C.MH_DOF_VELPARENT, dof_velparent), (C.MH_BODY_LASTDOF, body_lastdof),
+        (C.MH_UP_START, up_start_a), (C.MH_UP_BODY, up_body_a),
     ]
     o = model.opt
     scalars = np.zeros(C.MF_SCALARS, dtype=np.float32)
@@ -150,6 +164,7 @@ def build_model_arrays(model: Model, frictionloss_override: bool = False) -> tup
     header[C.MH_ITERATIONS], header[C.MH_LS_ITERATIONS] = o.iterations, o.ls_iterations
     header[C.MH_DISABLE_REFSAFE], header[C.MH_DISABLE_WARMSTART] = int(o.disable_refsafe), int(o.disable_warmstart)
     header[C.MH_NFRICTION], header[C.MH_NLIMIT] = nfric, limit_jnt.size
+    header[C.MH_NUPPASS] = len(up_start) - 1
     return header, mi, mf
 
 

@@ -256,6 +256,27 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
   SUB_MARK(w, 27);
 }
 
+// Leaf-to-root accumulation of NC per-body components held as arr[c][body]: after the call arr[c][b] is the sum over
+// b's subtree (children of the world excepted -- nothing reads the world's sum).  The schedule (MH_UP_START / MH_UP_BODY)
+// goes up the tree one level and one sibling rank at a time, so a pass touches every parent at most once: ~NC * (bodies
+// in the pass) independent adds per pass instead of one serial loop over each subtree.
+template <int NC, class A>
+DEV void subtree_accumulate(const Mdl& m, A& arr, LANE_ARG) {
+  const int npass = m.h[MH_NUPPASS];
+  const int* ustart = MI(m, MH_UP_START);
+  const int* ubody = MI(m, MH_UP_BODY);
+  const int* parentid = MI(m, MH_BODY_PARENTID);
+  for (int p = 0; p < npass; p++) {
+    const int s = ustart[p], cnt = ustart[p + 1] - s;
+    LANE_FOR(idx, NC * cnt) {
+      const int t = idx / NC, c = idx - t * NC;
+      const int b = ubody[s + t];
+      arr[c][parentid[b]] += arr[c][b];
+    }
+    WSYNC();
+  }
+}
+
 template <class D>
 DEV void com_pos(const Mdl& m, Work<D>& w, LANE_ARG) {
   const int nb = DIM(NB, MH_NBODY), nj = DIM(NJ, MH_NJNT);
@@ -268,13 +289,11 @@ DEV void com_pos(const Mdl& m, Work<D>& w, LANE_ARG) {
     w.cfrc[0][b] = ms * w.xipos[0][b]; w.cfrc[1][b] = ms * w.xipos[1][b]; w.cfrc[2][b] = ms * w.xipos[2][b];
   }
   WSYNC();
+  subtree_accumulate<3>(m, w.cfrc, LANE_PASS);
   LANE_FOR(b, nb) {
-    float sx = 0, sy = 0, sz = 0;
-    const int e = sub_end[b];
-    for (int c = b; c < e; c++) { sx += w.cfrc[0][c]; sy += w.cfrc[1][c]; sz += w.cfrc[2][c]; }
     // nominal body_subtreemass even when body_mass is randomised (ksim/randomization.py:351-355)
     const float sm = fmaxf(subtreemass[b], MINVAL);
-    w.subtree_com[0][b] = sx / sm; w.subtree_com[1][b] = sy / sm; w.subtree_com[2][b] = sz / sm;
+    w.subtree_com[0][b] = w.cfrc[0][b] / sm; w.subtree_com[1][b] = w.cfrc[1][b] / sm; w.subtree_com[2][b] = w.cfrc[2][b] / sm;
   }
   WSYNC();
   LANE_FOR(b, nb) {
@@ -340,13 +359,11 @@ DEV void crb_mass_matrix(const Mdl& m, Work<D>& w, LANE_ARG) {
   const int* dof_parent = MI(m, MH_DOF_PARENTID);
   // composite inertia: sum of cinert over the (contiguous, depth-first) subtree of each body
   LANE_FOR(idx, 10 * nb) {
-    const int k = idx / nb, b = idx - k * nb;
-    float s = 0.0f;
-    const int e = (b == 0) ? 1 : sub_end[b];
-    for (int c = b; c < e; c++) s += w.cinert[k][c];
-    w.crb[k][b] = s;
+    const int b = idx / 10, k = idx - b * 10;
+    w.crb[k][b] = w.cinert[k][b];
   }
   WSYNC();
+  subtree_accumulate<10>(m, w.crb, LANE_PASS);
   LANE_FOR(i, nv) {
     float ci[10];
     const int b = dof_body[i];
@@ -916,13 +933,12 @@ DEV void rne(const Mdl& m, Work<D>& w, LANE_ARG) {
     st6(w.cfrc, b, f);
   }
   WSYNC();
+  subtree_accumulate<6>(m, w.cfrc, LANE_PASS);
   LANE_FOR(i, nv) {
-    const int b = dof_body[i], e = sub_end[b];
+    const int b = dof_body[i];
     float s = 0.0f;
-    for (int c = b; c < e; c++) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) s += w.cdof[k][i] * w.cfrc[k][c];
-    }
+    for (int k = 0; k < 6; k++) s += w.cdof[k][i] * w.cfrc[k][b];
     w.qfrc_bias[i] = s;
   }
   WSYNC();
