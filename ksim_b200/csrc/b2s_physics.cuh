@@ -1469,7 +1469,7 @@ struct DualDir { float qg1, qg2, snorm, gradnorm; };
 // loops whose trip count the compiler cannot see (each such iteration would cost a full load latency in order).
 // S z = u is solved by Gauss-Jordan elimination on the rows (S is SPD: no pivoting), which leaves z in place.
 template <class D>
-DEV DualDir dual_direction8(const Mdl& m, Work<D>& w, float beta, float m00, LANE_ARG) {
+DEV DualDir dual_direction8(const Mdl& m, Work<D>& w, float beta, float m00, bool norms, LANE_ARG) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int K = 8;
   const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
@@ -1519,20 +1519,28 @@ DEV DualDir dual_direction8(const Mdl& m, Work<D>& w, float beta, float m00, LAN
   }
   j0c = __shfl_sync(FULL, j0c, 0); j0d = __shfl_sync(FULL, j0d, 0);
   cAd = __shfl_sync(FULL, cAd, 0); dAd = __shfl_sync(FULL, dAd, 0);
-  // |search| and |grad| in dof space: search = -beta delta0 + Z d, grad = beta M delta0 + J^T (c - f)
-  const bool dof = lane < nv;
-  const int i = dof ? lane : 0;
-  float sv = dof ? -beta * w.du_d0[i] : 0.0f, gv = dof ? beta * w.du_Md0[i] : 0.0f;
+  // |search| and |grad| in dof space: search = -beta delta0 + Z d, grad = beta M delta0 + J^T (c - f).  |search| only
+  // scales the bracketing line search's tolerance and |grad| only feeds `gradient < tolerance`, which fp32 satisfies
+  // solely with an exactly-zero gradient (beta = 0 and c = f on every row): with the exact line search that test is
+  // made directly and the two dof-space sums are skipped.
   const float e = c - f;
+  float sn = 1.0f, gn;
+  if (norms) {
+    const bool dof = lane < nv;
+    const int i = dof ? lane : 0;
+    float sv = dof ? -beta * w.du_d0[i] : 0.0f, gv = dof ? beta * w.du_Md0[i] : 0.0f;
 #pragma unroll
-  for (int s = 0; s < K; s++) {
-    const float ds = __shfl_sync(FULL, d, s), es = __shfl_sync(FULL, e, s);
-    if (s < ne && dof) {
-      sv = fmaf(w.Z[s][i], ds, sv);
-      gv = fmaf(jac_entry(w, s, nsparse, i), es, gv);
+    for (int s = 0; s < K; s++) {
+      const float ds = __shfl_sync(FULL, d, s), es = __shfl_sync(FULL, e, s);
+      if (s < ne && dof) {
+        sv = fmaf(w.Z[s][i], ds, sv);
+        gv = fmaf(jac_entry(w, s, nsparse, i), es, gv);
+      }
     }
+    sn = wsum(sv * sv); gn = wsum(gv * gv);
+  } else {
+    gn = (beta == 0.0f && __all_sync(FULL, e == 0.0f)) ? 0.0f : 1e30f;
   }
-  const float sn = wsum(sv * sv), gn = wsum(gv * gv);
   __syncwarp();
   DualDir o;
   o.qg1 = -beta * beta * m00 + beta * (j0d - j0c) + cAd;
@@ -1547,7 +1555,7 @@ template <class D>
 DEVNI DualDir dual_direction(const Mdl& m, Work<D>& w, float beta, float m00, LANE_ARG) {
   const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
 #if B2S_DEVICE
-  if (ne <= 8) return dual_direction8(m, w, beta, m00, LANE_PASS);
+  if (ne <= 8) return dual_direction8(m, w, beta, m00, !exact_ls_enabled(m), LANE_PASS);
 #endif
   // u = J delta - A f on the active rows (into du_d); lower triangle of AS <- active part of A
   LANE_FOR(r, ne) {
