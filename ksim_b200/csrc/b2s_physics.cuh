@@ -1009,6 +1009,19 @@ DEV float row_dot(const Work<D>& w, int r, int nsparse, const float* x, int nv) 
   return s;
 }
 
+// cost of constraint row r at Jaref = x (same pieces as constraint_rows)
+template <class D>
+DEV float constraint_row_cost(const Work<D>& w, int r, float x) {
+  const float Dr = w.efc_D[r];
+  if (w.efc_type[r] == EFC_FRICTION) {
+    const float f = w.efc_floss[r], rf = w.efc_R[r] * f;
+    if (x <= -rf) return -f * (0.5f * rf + x);
+    if (x >= rf) return -f * (0.5f * rf - x);
+    return 0.5f * Dr * x * x;
+  }
+  return x < 0.0f ? 0.5f * Dr * x * x : 0.0f;
+}
+
 // efc_force / efc_active from efc_Jaref; returns the constraint cost (summed over the warp)
 template <class D>
 DEV float constraint_rows(Work<D>& w, int ne, LANE_ARG) {
@@ -1653,12 +1666,14 @@ DEV void solve_dual(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
   SUB_MARK(w, 16);
   float beta = 0.0f, gauss = 0.0f;
   if (warmstart) {
-    LANE_FOR(r, ne) w.efc_Jaref[r] = w.du_c0[r] + w.du_j0[r];
-    WSYNC();
-    const float cw = constraint_rows(w, ne, LANE_PASS) + 0.5f * m00;
-    LANE_FOR(r, ne) w.efc_Jaref[r] = w.du_c0[r];
-    WSYNC();
-    const float cs = constraint_rows(w, ne, LANE_PASS);
+    // cost at the warm start and at qacc_smooth, both in one pass over the rows
+    float cw = 0.0f, cs = 0.0f;
+    LANE_FOR(r, ne) {
+      cw += constraint_row_cost(w, r, w.du_c0[r] + w.du_j0[r]);
+      cs += constraint_row_cost(w, r, w.du_c0[r]);
+    }
+    cw = wsum(cw) + 0.5f * m00;
+    cs = wsum(cs);
     if (cw < cs) { beta = 1.0f; gauss = 0.5f * m00; }
   }
   LANE_FOR(r, ne) { w.efc_Jaref[r] = w.du_c0[r] + beta * w.du_j0[r]; w.du_c[r] = 0.0f; }
