@@ -31,6 +31,11 @@ DEV void apply_overrides(const Mdl& m, Work<D>& w, const float* rand, LANE_ARG) 
   const float* inertia = MF(m, MH_BODY_INERTIA);
   const float* ipos = MF(m, MH_BODY_IPOS);
   LANE_FOR(i, nv) { w.armature[i] = arm[i]; w.damping[i] = damp[i]; w.frictionloss[i] = fl[i]; }
+  // the mass matrix is only ever written on its ancestor pattern (crb_mass_matrix), which is a property of the model:
+  // zero it once per workspace instead of once per sub-step
+  LANE_FOR(i, nv) {
+    for (int j = 0; j < D::NVP; j++) w.M[i][j] = 0.0f;
+  }
   LANE_FOR(b, nb) {
     w.body_mass[b] = mass[b];
 #pragma unroll

@@ -370,7 +370,7 @@ DEV void crb_mass_matrix(const Mdl& m, Work<D>& w, LANE_ARG) {
 #pragma unroll
     for (int k = 0; k < 10; k++) ci[k] = w.crb[k][b];
     V6 buf = mul_inert_vec(ci, ld6(w.cdof, i));
-    for (int j = 0; j < i; j++) { w.M[i][j] = 0.0f; w.M[j][i] = 0.0f; }
+    // entries outside the (static) ancestor pattern were zeroed once by apply_overrides and are never written
     for (int j = i; j >= 0; j = dof_parent[j]) {
       float s = 0.0f;
 #pragma unroll
