@@ -464,10 +464,31 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
   // back: column j takes L[j][k] from lane j < nv, and every store / substitution below is guarded.
   const int ri = i < N ? i : N - 1;
   float r[N];
-#pragma unroll
-  for (int j = 0; j < N; j++) r[j] = w.M[ri][j];
   float dg = 0.0f;
   if (mode == FS_NEWTON) {
+    const int nsparse = w.nsparse;
+    if (live)
+      for (int rr = 0; rr < nsparse; rr++)
+        if (w.efc_active[rr] && w.efc_dof[rr] == i) dg += w.efc_D[rr];
+  } else if (mode == FS_IMPLICIT) {
+    if (live) dg = m.mf[MF_TIMESTEP] * w.damping[i];
+  }
+  // The diagonal term goes through shared memory: r[i] += dg would be a dynamic register index (the whole row would
+  // move to local memory), and adding it inside the column loop costs three instructions per column.  Lane i bumps
+  // M[i][i], every lane loads its row, lane i puts the old value back.
+  const float diag0 = live ? w.M[ri][ri] : 0.0f;
+  if (mode != FS_MASS) {
+    if (live) w.M[ri][ri] = diag0 + dg;
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < N; j++) r[j] = w.M[ri][j];
+  if (mode != FS_MASS) {
+    __syncwarp();
+    if (live) w.M[ri][ri] = diag0;
+  }
+  if (mode == FS_NEWTON) {
+    // dense constraint rows: J^T D J, accumulated on the register rows (after the load)
     const int ne = w.nefc, nsparse = w.nsparse;
     for (int rr = nsparse; rr < ne; rr++) {
       if (!w.efc_active[rr]) continue;
@@ -476,18 +497,11 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
 #pragma unroll
       for (int j = 0; j < N; j++) r[j] = fmaf(c, J[j], r[j]);
     }
-    if (live)
-      for (int rr = 0; rr < nsparse; rr++)
-        if (w.efc_active[rr] && w.efc_dof[rr] == i) dg += w.efc_D[rr];
-  } else if (mode == FS_IMPLICIT) {
-    if (live) dg = m.mf[MF_TIMESTEP] * w.damping[i];
   }
   float invd = 1.0f;
 #pragma unroll
   for (int j = 0; j < N; j++) {
-    // the diagonal term joins here, on the pivot lane, with a STATIC register index (writing r[i] up front
-    // would be a dynamic index and push the whole row into local memory)
-    float t = r[j] + ((i == j) ? dg : 0.0f);
+    float t = r[j];
 #pragma unroll
     for (int k = 0; k < j; k++) t = fmaf(-r[k], __shfl_sync(FULL, r[k], j), t);
     float sp = __shfl_sync(FULL, t, j);
