@@ -1023,6 +1023,18 @@ DEV float row_dot(const Work<D>& w, int r, int nsparse, const float* x, int nv) 
   return s;
 }
 
+// bit r = efc_active[r] (ne <= 32)
+template <class D>
+DEV unsigned active_mask(const Work<D>& w, int ne, LANE_ARG) {
+#if B2S_DEVICE
+  return __ballot_sync(0xffffffffu, lane < ne && w.efc_active[lane < ne ? lane : 0]);
+#else
+  unsigned mk = 0u;
+  for (int r = 0; r < ne && r < 32; r++) mk |= w.efc_active[r] ? (1u << r) : 0u;
+  return mk;
+#endif
+}
+
 // cost of constraint row r at Jaref = x (same pieces as constraint_rows)
 template <class D>
 DEV float constraint_row_cost(const Work<D>& w, int r, float x) {
@@ -1675,6 +1687,7 @@ template <class D>
 DEV void solve_dual(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
   const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
   const bool warmstart = !m.h[MH_DISABLE_WARMSTART];
+  const bool exact_ls = ne <= 16 && exact_ls_enabled(m);
   SUB_BEGIN();
   const float m00 = dual_setup(m, w, warmstart, LANE_PASS);
   SUB_MARK(w, 16);
@@ -1714,7 +1727,7 @@ DEV void solve_dual(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
     SUB_MARK(w, 19);
     // exact one-pass line search when two breakpoint slots per row fit a warp, else the bracketing iteration
     float alpha;
-    if (ne <= 16 && exact_ls_enabled(m)) alpha = finished ? 0.0f : ls_exact(w, ne, dir.qg1, dir.qg2, LANE_PASS);
+    if (exact_ls) alpha = finished ? 0.0f : ls_exact(w, ne, dir.qg1, dir.qg2, LANE_PASS);
     else alpha = ls_bracket(m, w, nv, ne, qg, dir.snorm, lockstep, !finished, LANE_PASS);
     SUB_MARK(w, 20);
     if (finished) continue;
@@ -1723,12 +1736,18 @@ DEV void solve_dual(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
     gauss = gauss + alpha * dir.qg1 + alpha * alpha * dir.qg2;
     beta -= alpha * beta;
     prev_cost = cost;
+    const unsigned act_before = active_mask(w, ne, LANE_PASS);
     cost = constraint_rows(w, ne, LANE_PASS) + gauss;
     SUB_MARK(w, 21);
     dir = dual_direction(m, w, beta, m00, LANE_PASS);
     SUB_MARK(w, 18);
     niter++;
     if (iterations == 1) finished = true;
+    // A full Newton step (exact line search returned ~1) that left the active set alone has landed on the minimiser
+    // of its quadratic piece, which for this convex cost is the minimum.  The reference would spend one more
+    // iteration confirming it (a step of ~0 and an improvement below tolerance); the polish step below already is that
+    // confirmation, taken along the direction just computed at the new point.
+    if (exact_ls && ne <= 32 && fabsf(alpha - 1.0f) < 1e-3f && act_before == active_mask(w, ne, LANE_PASS)) finished = true;
   }
   // Polish: the loop above accepts a step only if it lowers the cost, and in fp32 the cost (O(1e5) with stiff rows)
   // stops resolving improvements while the iterate is still ~sqrt(eps) away from the minimiser.  `dir` is the Newton
