@@ -432,8 +432,6 @@ enum { FS_MASS = 0, FS_NEWTON = 1, FS_IMPLICIT = 2 };
 
 // bit 8 of sync_mask switches the constraint-space Newton path off (tuning / A-B tests)
 DEV bool dual_enabled(const Mdl& m) { return !((m.sync_mask >> 8) & 1); }
-// bit 9: CTA votes per line-search iteration as well (bit 7: per Newton iteration)
-DEV bool ls_votes(const Mdl& m) { return (m.sync_mask >> 9) & 1; }
 // bit 10 switches the exact one-pass line search off (the bracketing iteration is used everywhere)
 DEV bool exact_ls_enabled(const Mdl& m) { return !((m.sync_mask >> 10) & 1); }
 
@@ -729,6 +727,7 @@ DEV void make_constraint(const Mdl& m, Work<D>& w, LANE_ARG) {
       fill_row(m, w, r, EFC_FRICTION, w.qvel[i], 0.0f, dof_invw[i], dof_solref + 2 * i, dof_solimp + 5 * i, w.frictionloss[i]);
     }
   }
+  IF_LANE0 w.scratch_i[0] = nrow;  // number of friction rows (solve() picks its path on it)
   const int* limit_jnt = MI(m, MH_LIMIT_JNT);
   const int* jqpos = MI(m, MH_JNT_QPOSADR);
   const int* jdof = MI(m, MH_JNT_DOFADR);
@@ -1299,7 +1298,7 @@ DEV float ls_exact(const Work<D>& w, int ne, float qg1, float qg2, LANE_ARG) {
 template <class D>
 DEV float ls_bracket(const Mdl& m, const Work<D>& w, int nv, int ne, const float* qg, float snorm, bool lockstep, bool live,
                      LANE_ARG) {
-  lockstep = lockstep && ls_votes(m);
+  lockstep = false;  // votes per line-search iteration measured slower than per Newton iteration only (profiles/)
   if (!live) {
     if (lockstep) while (CTA_OR(0)) {}
     return 0.0f;
@@ -1381,10 +1380,7 @@ DEV void linesearch(const Mdl& m, Work<D>& w, float gauss, bool lockstep, bool l
 // Newton iteration and one per line-search iteration -- so the warps stay on the same code while they iterate.
 // solve_follower() is the vote sequence of a warp that has no environment or no constraint rows.
 DEV void solve_follower(const Mdl& m) {
-  const bool inner = ls_votes(m);
-  while (CTA_OR(0)) {
-    if (inner) while (CTA_OR(0)) {}
-  }
+  while (CTA_OR(0)) {}
 }
 
 // Newton solver in dof space: re-factorises H = M + J^T diag(D active) J every iteration.  Used when the
@@ -1683,6 +1679,166 @@ DEVNI DualDir dual_direction(const Mdl& m, Work<D>& w, float beta, float m00, LA
   return o;
 }
 
+#if B2S_DEVICE
+// The constraint-space Newton solve for ne <= 8 rows without friction rows (what the humanoid runs), entirely in
+// registers: lane r < ne owns row r -- its row of A, R, D, c0, j0, the iterate (c, Jaref), force and active flag -- and
+// every exchange between rows is a shuffle.  No shared-memory traffic, calls or data-dependent loops inside the Newton
+// loop; the algorithm is solve_dual's (same direction, exact line search, early finish, polish).
+template <class D>
+DEVNI void solve_dual8(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int K = 8;
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
+  const bool warmstart = !m.h[MH_DISABLE_WARMSTART];
+  const float m00 = dual_setup(m, w, warmstart, LANE_PASS);
+  const bool live = lane < ne;
+  const int r = live ? lane : 0;
+  float a[K];
+#pragma unroll
+  for (int s = 0; s < K; s++) a[s] = (live && s < ne) ? dual_A(w, r, s) : 0.0f;
+  const float Rr = live ? w.efc_R[r] : 1.0f, Dr = live ? w.efc_D[r] : 0.0f;
+  const float c0 = live ? w.du_c0[r] : 0.0f, j0 = live ? w.du_j0[r] : 0.0f;
+  // sum over the rows (lanes 0..7), result in every lane
+#define B2S_SUM8(v) do { v += __shfl_xor_sync(FULL, v, 4); v += __shfl_xor_sync(FULL, v, 2); v += __shfl_xor_sync(FULL, v, 1); \
+                         v = __shfl_sync(FULL, v, 0); } while (0)
+  float beta = 0.0f, gauss = 0.0f;
+  if (warmstart) {
+    const float xw = c0 + j0;
+    float cw = (live && xw < 0.0f) ? 0.5f * Dr * xw * xw : 0.0f, cs = (live && c0 < 0.0f) ? 0.5f * Dr * c0 * c0 : 0.0f;
+    B2S_SUM8(cw); B2S_SUM8(cs);
+    if (cw + 0.5f * m00 < cs) { beta = 1.0f; gauss = 0.5f * m00; }
+  }
+  float ja = c0 + beta * j0, c = 0.0f;
+  bool act = live && ja < 0.0f;
+  float f = act ? -Dr * ja : 0.0f;
+  float rc = act ? 0.5f * Dr * ja * ja : 0.0f;
+  B2S_SUM8(rc);
+  float cost = rc + gauss, prev_cost = INFINITY;
+  const int iterations = m.h[MH_ITERATIONS];
+  const float tol = m.mf[MF_TOLERANCE];
+  const float scale = 1.0f / (m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1));
+  int niter = 0;
+  bool finished = false;
+  float d = 0.0f, jv = 0.0f, qg1 = 0.0f, qg2 = 0.0f;
+  bool grad_zero = false;
+  bool dirty = true;  // the point moved since the direction was last computed
+  while (true) {
+    // ---- Newton direction at the current point: d (rows), jv = J search, qg1 / qg2 (Gauss term along the search)
+    if (dirty) {
+      dirty = false;
+      float u = live ? ja - c0 : 0.0f;
+#pragma unroll
+      for (int s = 0; s < K; s++) u = fmaf(-a[s], __shfl_sync(FULL, f, s), u);
+      const unsigned am = __ballot_sync(FULL, act);
+      float row[K];
+#pragma unroll
+      for (int s = 0; s < K; s++) {
+        const bool on = act && ((am >> s) & 1u);
+        row[s] = (s == lane) ? (act ? a[s] + Rr : 1.0f) : (on ? a[s] : 0.0f);
+      }
+      float rhs = act ? u : 0.0f;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        if (k < ne) {  // warp-uniform; pivots past the last row would be identity rows
+          const float piv = __shfl_sync(FULL, row[k], k);
+          const float inv = __fdividef(1.0f, fmaxf(piv, MINVAL));
+          const float fac = (lane == k) ? 0.0f : row[k] * inv;
+          const float sc = (lane == k) ? inv : 1.0f;
+#pragma unroll
+          for (int j = k + 1; j < K; j++) row[j] = fmaf(-fac, __shfl_sync(FULL, row[j], k), row[j]) * sc;
+          rhs = fmaf(-fac, __shfl_sync(FULL, rhs, k), rhs) * sc;
+        }
+      }
+      d = live ? f + (act ? rhs : 0.0f) - c : 0.0f;
+      float ad = 0.0f;
+#pragma unroll
+      for (int s = 0; s < K; s++) ad = fmaf(a[s], __shfl_sync(FULL, d, s), ad);
+      jv = ad - beta * j0;
+      float j0c = j0 * c, j0d = j0 * d, cAd = c * ad, dAd = d * ad;
+      B2S_SUM8(j0c); B2S_SUM8(j0d); B2S_SUM8(cAd); B2S_SUM8(dAd);
+      qg1 = -beta * beta * m00 + beta * (j0d - j0c) + cAd;
+      qg2 = 0.5f * (beta * beta * m00 - 2.0f * beta * j0d + dAd);
+      grad_zero = beta == 0.0f && __all_sync(FULL, c - f == 0.0f);
+    }
+    // ---- convergence (ksim / MJX semantics) and the CTA vote
+    if (!finished && (iterations != 1 || niter > 0)) {
+      const float improvement = (prev_cost - cost) * scale;
+      finished = niter >= iterations;
+      finished |= improvement < tol;
+      finished |= grad_zero;
+    }
+    if (lockstep ? !CTA_OR(!finished) : finished) break;
+    if (finished) continue;
+    // ---- exact line search: root of the piecewise-linear derivative g (ls_exact; one breakpoint per row here)
+    float alpha = 0.0f;
+    {
+      const bool used0 = live && jv != 0.0f;
+      const float ab = used0 ? __fdividef(-ja, jv) : -1.0f;
+      const bool used = used0 && ab > 0.0f;
+      float gb = fmaf(2.0f * qg2, ab, qg1), g0 = qg1;
+#pragma unroll
+      for (int s = 0; s < K; s++) {
+        const float sja = __shfl_sync(FULL, ja, s), sjv = __shfl_sync(FULL, jv, s), sD = __shfl_sync(FULL, Dr, s);
+        const float xb = fmaf(ab, sjv, sja);
+        gb += xb < 0.0f ? sjv * sD * xb : 0.0f;
+        g0 += sja < 0.0f ? sjv * sD * sja : 0.0f;
+      }
+      if (g0 < 0.0f) {
+        const unsigned lo_bits = __reduce_max_sync(FULL, (used && gb <= 0.0f) ? __float_as_uint(ab) : 0u);
+        const unsigned hi_bits = __reduce_min_sync(FULL, (used && gb > 0.0f) ? __float_as_uint(ab) : 0x7f800000u);
+        const float lo = __uint_as_float(lo_bits);
+        const bool open = hi_bits == 0x7f800000u;
+        const float hi = open ? lo + 1.0f : __uint_as_float(hi_bits);
+        const float xm = fmaf(0.5f * (lo + hi), jv, ja);
+        const bool on = live && xm < 0.0f;
+        float G1 = on ? Dr * ja * jv : 0.0f, G2 = on ? Dr * jv * jv : 0.0f;
+        B2S_SUM8(G1); B2S_SUM8(G2);
+        G1 += qg1; G2 += 2.0f * qg2;
+        alpha = G2 > 0.0f ? __fdividef(-G1, G2) : lo;
+        alpha = fmaxf(alpha, lo);
+        if (!open) alpha = fminf(alpha, hi);
+      }
+    }
+    // ---- step, new forces / active set / cost
+    dirty = true;
+    c = fmaf(alpha, d, c);
+    ja = fmaf(alpha, jv, ja);
+    gauss = gauss + alpha * qg1 + alpha * alpha * qg2;
+    beta -= alpha * beta;
+    prev_cost = cost;
+    const unsigned act_before = __ballot_sync(FULL, act);
+    act = live && ja < 0.0f;
+    f = act ? -Dr * ja : 0.0f;
+    rc = act ? 0.5f * Dr * ja * ja : 0.0f;
+    B2S_SUM8(rc);
+    cost = rc + gauss;
+    niter++;
+    if (iterations == 1) finished = true;
+    // a full step that left the active set alone is on the minimiser; the polish below is the confirming iteration
+    if (fabsf(alpha - 1.0f) < 1e-3f && act_before == __ballot_sync(FULL, act)) finished = true;
+  }
+  // ---- polish: one full step along the direction at the final point if it keeps the active set (see solve_dual)
+  {
+    const float c2 = c + d, ja2 = ja + jv;
+    const bool act2 = live && ja2 < 0.0f;
+    if (__ballot_sync(FULL, act2) == __ballot_sync(FULL, act)) {
+      c = c2; ja = ja2; beta = 0.0f;
+      f = act2 ? -Dr * ja2 : 0.0f;
+    }
+  }
+#undef B2S_SUM8
+  if (live) { w.du_c[r] = c; w.efc_force[r] = f; w.efc_active[r] = act ? 1 : 0; w.efc_Jaref[r] = ja; }
+  __syncwarp();
+  // back to dof space: qacc = a0 + beta delta0 + Z c, qfrc_constraint = J^T f
+  LANE_FOR(i, nv) {
+    float acc = w.qacc_smooth[i] + beta * w.du_d0[i];
+    for (int s = 0; s < ne; s++) acc = fmaf(w.Z[s][i], w.du_c[s], acc);
+    w.qacc[i] = acc; w.warm[i] = acc;
+  }
+  constraint_force_to_dofs(w, nv, ne, nsparse, LANE_PASS);
+}
+#endif
+
 template <class D>
 DEV void solve_dual(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
   const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
@@ -1792,8 +1948,14 @@ DEV void solve(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
     if (lockstep) solve_follower(m);
     return;
   }
-  if (ne <= D::NDUAL && dual_enabled(m)) solve_dual(m, w, lockstep, LANE_PASS);
-  else solve_primal(m, w, lockstep, LANE_PASS);
+  if (ne <= D::NDUAL && dual_enabled(m)) {
+#if B2S_DEVICE
+    if (ne <= 8 && w.scratch_i[0] == 0 && exact_ls_enabled(m)) { solve_dual8(m, w, lockstep, LANE_PASS); return; }
+#endif
+    solve_dual(m, w, lockstep, LANE_PASS);
+  } else {
+    solve_primal(m, w, lockstep, LANE_PASS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ sensors
