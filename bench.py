@@ -309,6 +309,13 @@ def main() -> None:
     bytes_per_env_step = 4 * (p.action_size + p.rec_size) + per_launch_env / t
     peak, peak_src = _peaks()
     achieved = n * t * bytes_per_env_step / (kernel_ms * 1e-3) / 1e9
+    # measured DRAM bytes of one launch of this configuration (one ncu capture per round, profiles/r01_traffic.json)
+    traffic = None
+    tpath = ROOT / "profiles" / "r01_traffic.json"
+    if tpath.exists():
+        rec_t = json.loads(tpath.read_text()).get(WORKLOAD)
+        if rec_t and rec_t["envs"] == n and rec_t["rollout"] == t:
+            traffic = rec_t["dram_bytes_read"] + rec_t["dram_bytes_write"]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -316,7 +323,8 @@ def main() -> None:
         "e2e": {"value": env_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_actions.numel() * 4),
                 "d2h_bytes_per_step": int((host_adv.numel() + host_total.numel()) * 4), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": n * t * bytes_per_env_step,
                      "kernel": "k_rollout<DimsKbot>" if WORKLOAD == "kbot" else "k_rollout<DimsHumanoid>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms,
                      "algorithmic_bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src,
                      "note": "latency/issue-bound by design (tiny per-env matrices); see DESIGN.md and profiles/"},
