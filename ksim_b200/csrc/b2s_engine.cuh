@@ -473,32 +473,38 @@ DEV void cmd_update(const Mdl& m, Work<D>& w, int idx, Key rng) {
   const float* cf = m.tf + TAB(ti, TI_CMD_TAB, idx, TAB_FOFF);
   float* st = w.cmd + TAB(ti, TI_CMD_TAB, idx, TAB_OUT_OFF);
   const int dim = TAB(ti, TI_CMD_TAB, idx, TAB_OUT_DIM);
-  const Key ra = key_split(rng, 0), rb = key_split(rng, 1);
+  // the resampled command (key rb) only matters when the switch (key ra) fires -- once in hundreds of steps -- so it is
+  // drawn only then; the values are the same as drawing it always
+  const Key ra = key_split(rng, 0);
   if (type == CMD_LINEAR_VELOCITY) {
     const float sp = scale_get(ci[5], cf + 10, w.level);
     const float ctrl_dt = cf[12], lin_acc = cf[13], ang_acc = cf[14];
-    const int sw = key_bernoulli(ra, 0, sp);
-    float fresh[6];
-    cmd_linvel_initial(ci, cf, w, rb, st, fresh);
-    const float nv = st[0] + clipf(st[4] - st[0], -lin_acc, lin_acc) * ctrl_dt;
-    const float ny = st[1] + clipf(st[5] - st[1], -ang_acc, ang_acc) * ctrl_dt;
-    const float upd[6] = {nv, ny, nv * cosf(ny), nv * sinf(ny), st[4], st[5]};
+    if (key_bernoulli(ra, 0, sp)) {
+      float fresh[6];
+      cmd_linvel_initial(ci, cf, w, key_split(rng, 1), st, fresh);
 #pragma unroll
-    for (int k = 0; k < 6; k++) st[k] = sw ? fresh[k] : upd[k];
+      for (int k = 0; k < 6; k++) st[k] = fresh[k];
+    } else {
+      const float nv = st[0] + clipf(st[4] - st[0], -lin_acc, lin_acc) * ctrl_dt;
+      const float ny = st[1] + clipf(st[5] - st[1], -ang_acc, ang_acc) * ctrl_dt;
+      st[0] = nv; st[1] = ny; st[2] = nv * cosf(ny); st[3] = nv * sinf(ny);
+    }
   } else if (type == CMD_ANGULAR_VELOCITY) {
     const float sp = scale_get(ci[3], cf + 6, w.level);
     const float ctrl_dt = cf[8], ang_acc = cf[9];
-    const int sw = key_bernoulli(ra, 0, sp);
-    float fresh[2];
-    cmd_angvel_initial(ci, cf, w, rb, fresh);
-    const float nv = st[0] + clipf(st[1] - st[0], -ang_acc, ang_acc) * ctrl_dt;
-    st[0] = sw ? fresh[0] : nv;
-    st[1] = sw ? fresh[1] : st[1];
+    if (key_bernoulli(ra, 0, sp)) {
+      float fresh[2];
+      cmd_angvel_initial(ci, cf, w, key_split(rng, 1), fresh);
+      st[0] = fresh[0]; st[1] = fresh[1];
+    } else {
+      st[0] = st[0] + clipf(st[1] - st[0], -ang_acc, ang_acc) * ctrl_dt;
+    }
   } else if (type == CMD_FLOAT_VECTOR) {
-    const int sw = key_bernoulli(ra, 0, cf[2 * dim]);
-    float fresh[16];
-    cmd_floatvec_initial(cf, dim, rb, fresh);
-    if (sw) for (int i = 0; i < dim; i++) st[i] = fresh[i];
+    if (key_bernoulli(ra, 0, cf[2 * dim])) {
+      float fresh[16];
+      cmd_floatvec_initial(cf, dim, key_split(rng, 1), fresh);
+      for (int i = 0; i < dim; i++) st[i] = fresh[i];
+    }
   }
 }
 
