@@ -281,3 +281,34 @@ def test_kbot_parity_resynchronised(ctx, kbot_spec, kbot_randomizers) -> None:  
         rec_o[0] = rec_o[1]
     assert n_bad <= max(1, int(0.003 * n * steps)), f"{n_bad} of {n * steps} env-steps outside the stated tolerance"
     assert float(eng.state[:, p["TI_S_NONFINITE"]].sum()) == 0.0
+
+
+def test_solver_paths_agree_at_full_size(ctx, monkeypatch) -> None:  # noqa: ANN001
+    """The shipped solver (constraint-space Newton, exact line search, register-resident loop) against the
+    reference-shaped one (dof-space Newton with the bracketing line search; B2S_SYNC_MASK bit 8) on the GPU, 4096 envs,
+    one control step from the same states at three points of a rollout: both minimise the same convex cost, so the
+    forces must agree to the stated tolerance on (all but isolated branch-flip) environments."""
+    spec, rz = ctx
+    n = 4096
+    fast = _engine(spec, rz, n, seed=9)
+    monkeypatch.setenv("B2S_SYNC_MASK", "0x1ff")
+    slow = _engine(spec, rz, n, seed=9)
+    monkeypatch.delenv("B2S_SYNC_MASK")
+    p, m = fast.program, spec.model
+    q, v, d = p["TI_R_QPOS"], p["TI_R_QVEL"], p["TI_R_DONE"]
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    cur_f, nxt_f, cur_s, nxt_s = (torch.zeros((n, fast.R), device="cuda") for _ in range(4))
+    n_bad = 0
+    for s in range(12):
+        act = 0.3 * torch.randn((n, fast.NA), generator=gen, device="cuda")
+        slow.state.copy_(fast.state)
+        slow.keys.copy_(fast.keys)
+        fast.step(act, cur_f, nxt_f)
+        slow.step(act, cur_s, nxt_s)
+        assert torch.equal(cur_f[:, d], cur_s[:, d])
+        dq = (cur_f[:, q : q + m.nq] - cur_s[:, q : q + m.nq]).abs()
+        dv = (cur_f[:, v : v + m.nv] - cur_s[:, v : v + m.nv]).abs()
+        bad = (dq > 2e-4).any(dim=1) | (dv > 2e-2 + 5e-3 * cur_s[:, v : v + m.nv].abs()).any(dim=1)
+        assert float(dq.max()) <= 2e-2 and float(dv.max()) <= 2.0, (s, float(dq.max()), float(dv.max()))
+        n_bad += int(bad.sum())
+    assert n_bad <= int(0.003 * n * 12), f"{n_bad} of {n * 12} env-steps outside the stated tolerance"
