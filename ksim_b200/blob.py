@@ -65,6 +65,11 @@ def build_model_arrays(model: Model, frictionloss_override: bool = False) -> tup
             up_start.append(len(up_body))
     up_start_a, up_body_a = np.array(up_start, dtype=np.int32), np.array(up_body, dtype=np.int32)
 
+    dof_act = np.full(nv, -1, dtype=np.int32)
+    for u, jid in enumerate(a["actuator_trnid"]):
+        da = int(a["jnt_dofadr"][int(jid)])
+        dof_act[da] = u if dof_act[da] == -1 else -2
+
     dof_parent = a["dof_parentid"]
     body_lastdof = np.full(nb, -1, dtype=np.int32)
     for b in range(1, nb):
@@ -110,7 +115,7 @@ def build_model_arrays(model: Model, frictionloss_override: bool = False) -> tup
         (C.MH_LIMIT_JNT, limit_jnt), (C.MH_PAIR_CONADR, conadr),
         (C.MH_BODY_DOFMASK, body_dofmask.astype(np.uint32).view(np.int32)),
         (C.MH_DOF_VELPARENT, dof_velparent), (C.MH_BODY_LASTDOF, body_lastdof),
-        (C.MH_UP_START, up_start_a), (C.MH_UP_BODY, up_body_a),
+        (C.MH_UP_START, up_start_a), (C.MH_UP_BODY, up_body_a), (C.MH_DOF_ACT, dof_act),
     ]
     o = model.opt
     scalars = np.zeros(C.MF_SCALARS, dtype=np.float32)

@@ -297,7 +297,17 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
       const KeyFan fe = key_fan(r, LANE_PASS);
       const Key rng_event = key_child(fe, 1);
       r = key_child(fe, 0);
-      event_apply(m, w, ev, rng_event, LANE_PASS);
+      // a push / jump event whose countdown has not expired only counts down: skip the call
+      const int etype = TAB(ti, TI_EVENT_TAB, ev, TAB_TYPE);
+      float* st = w.event + TAB(ti, TI_EVENT_TAB, ev, TAB_OUT_OFF);
+      const float tr = st[0] - m.mf[MF_TIMESTEP];
+      if (etype != EVENT_FORCE_PUSH && tr > 0.0f) {
+        WSYNC();
+        IF_LANE0 st[0] = tr;
+        WSYNC();
+      } else {
+        event_apply(m, w, ev, rng_event, LANE_PASS);
+      }
     }
     STAGE_MARK(w, 9);
     physics_step(m, w, step == nsub - 1, LANE_PASS);

@@ -975,10 +975,15 @@ DEV void actuation(const Mdl& m, Work<D>& w, LANE_ARG) {
     w.actuator_force[u] = f;
   }
   WSYNC();
-  // one motor per hinge at most in the supported subset, but gather generally
+  // MH_DOF_ACT names the one motor of a dof (the usual case); several motors on one dof are gathered
+  const int* dof_act = MI(m, MH_DOF_ACT);
   LANE_FOR(i, nv) {
+    const int ua = dof_act[i];
     float s = 0.0f;
-    for (int u = 0; u < nu; u++) if (jdof[trnid[u]] == i) s += gear[u] * w.actuator_force[u];
+    if (ua >= 0) s = gear[ua] * w.actuator_force[ua];
+    else if (ua == -2) {
+      for (int u = 0; u < nu; u++) if (jdof[trnid[u]] == i) s += gear[u] * w.actuator_force[u];
+    }
     w.qfrc_actuator[i] = s;
   }
   WSYNC();
