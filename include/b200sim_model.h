@@ -13,7 +13,7 @@
 #define B200SIM_MODEL_H
 
 #define B2S_MODEL_MAGIC 0x4232534D /* "B2SM" */
-#define B2S_MODEL_VERSION 5
+#define B2S_MODEL_VERSION 6
 
 #define B2S_MAXNV 32   /* one dof per lane */
 #define B2S_MAXNB 32   /* one body per lane */
@@ -102,6 +102,7 @@
  * of one pass have distinct parents and a pass is one conflict-free lane-parallel phase. */
 #define MH_UP_START 69       /* [nuppass+1] */
 #define MH_UP_BODY 70        /* [nbody-1 minus the children of the world] */
+#define MH_UP_CHILD 72       /* [nuppass][nbody] the child that pass p adds into body b, or -1 (inverse of MH_UP_BODY) */
 #define MH_DOF_ACT 71        /* [nv] the actuator that drives the dof; -1 none; -2 several (the kernel gathers) */
 /* ---- header offsets into mf[] ---- */
 #define MH_BODY_POS 80

@@ -64,6 +64,11 @@ def build_model_arrays(model: Model, frictionloss_override: bool = False) -> tup
             up_body += [v[rank] for v in by_parent.values() if len(v) > rank]
             up_start.append(len(up_body))
     up_start_a, up_body_a = np.array(up_start, dtype=np.int32), np.array(up_body, dtype=np.int32)
+    up_child = np.full((len(up_start) - 1, nb), -1, dtype=np.int32)
+    for pi in range(len(up_start) - 1):
+        for b in up_body[up_start[pi] : up_start[pi + 1]]:
+            assert up_child[pi, parent[b]] == -1
+            up_child[pi, parent[b]] = b
 
     dof_act = np.full(nv, -1, dtype=np.int32)
     for u, jid in enumerate(a["actuator_trnid"]):
@@ -116,6 +121,7 @@ def build_model_arrays(model: Model, frictionloss_override: bool = False) -> tup
         (C.MH_BODY_DOFMASK, body_dofmask.astype(np.uint32).view(np.int32)),
         (C.MH_DOF_VELPARENT, dof_velparent), (C.MH_BODY_LASTDOF, body_lastdof),
         (C.MH_UP_START, up_start_a), (C.MH_UP_BODY, up_body_a), (C.MH_DOF_ACT, dof_act),
+        (C.MH_UP_CHILD, up_child.reshape(-1)),
     ]
     o = model.opt
     scalars = np.zeros(C.MF_SCALARS, dtype=np.float32)

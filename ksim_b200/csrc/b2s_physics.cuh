@@ -263,6 +263,33 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
 template <int NC, class A>
 DEV void subtree_accumulate(const Mdl& m, A& arr, LANE_ARG) {
   const int npass = m.h[MH_NUPPASS];
+#if B2S_DEVICE
+  // lane = body, the NC components in registers; in pass p a parent pulls its (at most one) child of that pass by
+  // shuffle (MH_UP_CHILD): no shared-memory round trip or barrier between the passes
+  {
+    const int nb = m.h[MH_NBODY];
+    const int* uchild = MI(m, MH_UP_CHILD);
+    const int b = lane < nb ? lane : 0;
+    float v[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) v[c] = arr[c][b];
+    for (int p = 0; p < npass; p++) {
+      const int ch = lane < nb ? uchild[p * nb + b] : -1;
+      const int src = ch >= 0 ? ch : 0;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        const float x = __shfl_sync(0xffffffffu, v[c], src);
+        v[c] += ch >= 0 ? x : 0.0f;
+      }
+    }
+    if (lane < nb) {
+#pragma unroll
+      for (int c = 0; c < NC; c++) arr[c][b] = v[c];
+    }
+    __syncwarp();
+    return;
+  }
+#endif
   const int* ustart = MI(m, MH_UP_START);
   const int* ubody = MI(m, MH_UP_BODY);
   const int* parentid = MI(m, MH_BODY_PARENTID);
