@@ -44,7 +44,8 @@ enum {
   B2S_INFO_REW_CARRY_SIZE = 6,
   B2S_INFO_SMEM_PER_ENV = 7,    /* bytes of shared memory one environment (warp) occupies */
   B2S_INFO_WARPS_PER_CTA = 8,
-  B2S_INFO_VARIANT = 9          /* 0 humanoid-sized, 1 kbot-sized, 2 generic */
+  B2S_INFO_VARIANT = 9,         /* 0 humanoid-sized, 1 kbot-sized, 2 generic */
+  B2S_INFO_STAGED_ARRAYS = 10   /* how many of the 4 model / task-program arrays the kernels keep in shared memory */
 };
 
 /* blob: include/b200sim_model.h layout (host memory).  Uploads the model + task program to the current device. */

@@ -20,7 +20,7 @@ EXPORTS = (
 )
 
 INFO = dict(STATE_SIZE=0, REC_SIZE=1, KEY_SIZE=2, RAND_SIZE=3, ACTION_SIZE=4, N_REW_COMP=5, REW_CARRY_SIZE=6,
-            SMEM_PER_ENV=7, WARPS_PER_CTA=8, VARIANT=9)
+            SMEM_PER_ENV=7, WARPS_PER_CTA=8, VARIANT=9, STAGED_ARRAYS=10)
 
 
 class B200SimError(RuntimeError):

@@ -299,6 +299,7 @@ extern "C" int b200sim_model_info(const b200sim_model* mo, int what) {
     case B2S_INFO_SMEM_PER_ENV: return (int)mo->smem_per_env;
     case B2S_INFO_WARPS_PER_CTA: return mo->warps_per_cta;
     case B2S_INFO_VARIANT: return mo->variant;
+    case B2S_INFO_STAGED_ARRAYS: return (mo->mdl.stage[0] > 0) + (mo->mdl.stage[1] > 0) + (mo->mdl.stage[2] > 0) + (mo->mdl.stage[3] > 0);
   }
   return -1;
 }

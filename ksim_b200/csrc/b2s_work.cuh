@@ -22,10 +22,12 @@ struct Dims {
   static constexpr int NVP = NV_ | 1;         // odd row stride: conflict-free column access
   static constexpr int NSPARSE = NFRIC_ + NLIMIT_;
   static constexpr int NEFC = NFRIC_ + NLIMIT_ + NDENSE_;
-  static constexpr int EVS = 16;              // event state floats
+  // task-state budgets: the exact-fit instantiation is sized for the walking task (2 event floats, 8 command floats)
+  // so that the model AND the task program fit in shared memory next to 14 workspaces
+  static constexpr int EVS = EXACT_ ? 4 : 16;  // event state floats
   static constexpr int ACS = 2 * NU_ + 3;     // PositionActuators state
-  static constexpr int CMDS = 24;             // command floats
-  static constexpr int OCS = 16;              // observation carry floats
+  static constexpr int CMDS = EXACT_ ? 8 : 24;  // command floats
+  static constexpr int OCS = 16;              // observation carry floats (two projected-gravity observations: 14)
   static constexpr int NOBS = EXACT_ ? 16 : 32;  // observation plugins (bias keys)
   // Dual (constraint-space) Newton path: at most NDUAL rows.  Z = M^-1 J^T lives in the storage of
   // crb/cacc/cfrc/cfrc_ext (28*NB floats, dead during the solve); A = J Z and the factor of the reduced Hessian
@@ -99,8 +101,7 @@ struct Work {
   float sensordata[D::NSD];
   float torque[D::NU], action[D::NA], ctrl_blend[D::NA];
   int drop[D::NA];
-  int scratch_i[8];
-  float scratch_f[8];
+  int scratch_i[4];                           // [0] friction rows of this sub-step, [1..3] spare
 #if defined(B2S_PROFILE_STAGES) && B2S_DEVICE
   unsigned prof[B2S_NSTAGE];
 #endif
