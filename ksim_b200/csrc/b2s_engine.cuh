@@ -275,7 +275,16 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   const Key drop_rng = key_child(fan0, 0);
   Key r = key_child(fan0, 1);
   const float drop_p = ef[2] * w.level;
-  LANE_FOR(i, na) w.drop[i] = drop_p > 0.0f ? key_bernoulli(drop_rng, i, drop_p) : 0;
+  for (int base = 0; base < na; base += 32) {
+#if B2S_DEVICE
+    const int i = base + lane;
+    const unsigned bits = __ballot_sync(0xffffffffu, i < na && drop_p > 0.0f && key_bernoulli(drop_rng, i, drop_p));
+#else
+    unsigned bits = 0u;
+    for (int i = base; i < na && i < base + 32; i++) bits |= (drop_p > 0.0f && key_bernoulli(drop_rng, i, drop_p)) ? (1u << (i - base)) : 0u;
+#endif
+    IF_LANE0 w.drop_mask[base >> 5] = bits;
+  }
   LANE_FOR(i, nu) w.torque[i] = 0.0f;
   WSYNC();
   for (int step = 0; step < nsub; step++) {
@@ -284,7 +293,7 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
     const float prct = clipf((float)step - w.latency, 0.0f, 1.0f);
     LANE_FOR(i, na) {
       const float lc = w.last_ctrl[i];
-      w.ctrl_blend[i] = w.drop[i] ? lc : lc * (1.0f - prct) + w.action[i] * prct;
+      w.ctrl_blend[i] = ((w.drop_mask[i >> 5] >> (i & 31)) & 1u) ? lc : lc * (1.0f - prct) + w.action[i] * prct;
     }
     WSYNC();
     const KeyFan fan = key_fan(r, LANE_PASS);

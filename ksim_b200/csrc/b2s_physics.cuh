@@ -410,6 +410,7 @@ DEV void crb_mass_matrix(const Mdl& m, Work<D>& w, LANE_ARG) {
   WSYNC();
 }
 
+#if !B2S_DEVICE
 // in-place dense Cholesky of the lower triangle held in W, one phase per column.  The diagonal of W keeps
 // A[j][j] (other lanes read it during the phase); the pivots live in Linv_diag.
 template <class D>
@@ -454,6 +455,7 @@ DEVNI void chol_solve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
   LANE_FOR(i, nv) x[i] = y[i] * w.Linv_diag[i];
   WSYNC();
 }
+#endif
 
 enum { FS_MASS = 0, FS_NEWTON = 1, FS_IMPLICIT = 2 };
 

@@ -70,7 +70,9 @@ struct Work {
     // dual Newton path: AS[r][s], s >= r: A = J M^-1 J^T (upper triangle); s < r: factor of the reduced Hessian
     float AS[D::NDUAL][D::NDS];
   };
-  float Linv_diag[D::NV];                     // 1 / diag of the factor in W
+#if !B2S_DEVICE
+  float Linv_diag[D::NV];                     // 1 / diag of the factor in W (host build's loop Cholesky only)
+#endif
   // ---- contacts ----
   float con_dist[D::NCON], con_pos[3][D::NCON], con_frame[9][D::NCON];
   int con_pair[D::NCON], con_efc[D::NCON];
@@ -100,7 +102,7 @@ struct Work {
   };
   float sensordata[D::NSD];
   float torque[D::NU], action[D::NA], ctrl_blend[D::NA];
-  int drop[D::NA];
+  unsigned drop_mask[(D::NA + 31) / 32];      // per-element action drop of this control step, one bit each
   int scratch_i[4];                           // [0] friction rows of this sub-step, [1..3] spare
 #if defined(B2S_PROFILE_STAGES) && B2S_DEVICE
   unsigned prof[B2S_NSTAGE];

@@ -52,8 +52,8 @@ def test_native_library_is_the_one_running(ctx) -> None:  # noqa: ANN001
 
     eng = _engine(*ctx, 4)
     assert binding.library_path().exists() and eng.info("VARIANT") == 0  # humanoid-sized instantiation
-    # model ints, model floats and the task-program ints all fit in shared memory next to 14 workspaces
-    assert eng.info("WARPS_PER_CTA") == 14 and eng.info("STAGED_ARRAYS") >= 3
+    # the whole model and task program fit in shared memory next to 14 workspaces
+    assert eng.info("WARPS_PER_CTA") == 14 and eng.info("STAGED_ARRAYS") == 4
     maps = open("/proc/self/maps").read()
     assert "libb200sim.so" in maps
 
