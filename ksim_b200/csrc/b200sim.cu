@@ -266,7 +266,7 @@ extern "C" int b200sim_model_create(const void* blob, size_t nbytes, b200sim_mod
   mo->mdl.mf = (const float*)(d + MH_SIZE + ni);
   mo->mdl.ti = d + MH_SIZE + ni + nf;
   mo->mdl.tf = (const float*)(d + MH_SIZE + ni + nf + nti);
-  mo->mdl.sync_mask = 0xff;  // measured best on B200 (profiles/): every stage barrier + one vote per Newton iteration
+  mo->mdl.sync_mask = 0x7f;  // measured best on B200 (profiles/): a CTA barrier after every stage; votes inside the Newton loop (bit 7) are neutral since the solve became short
   if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0x7ff;  // tuning experiments
   int rc;
   const size_t words[4] = {ni, nf, nti, ntf};
