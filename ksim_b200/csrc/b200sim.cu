@@ -55,8 +55,16 @@ __device__ __forceinline__ const Mdl& stage_model(const Mdl& mp, unsigned char* 
   return *ms;
 }
 
+static const size_t kSmemBudget = 227 * 1024;
+// One CTA per SM; its size is what shared memory allows (Work<D> per warp), at most 16 warps.  Telling the compiler
+// lets it use the registers a smaller CTA leaves free (K-Bot: 8 warps -> up to 255 registers per thread).
 template <class D>
-__global__ void __launch_bounds__(512) k_init_envs(const Mdl mp, int n_envs, const uint32_t* __restrict__ init_keys,
+constexpr int max_warps() {
+  return (int)((kSmemBudget - sizeof(Mdl) - 16) / sizeof(Work<D>)) > 16 ? 16 : (int)((kSmemBudget - sizeof(Mdl) - 16) / sizeof(Work<D>));
+}
+
+template <class D>
+__global__ void __launch_bounds__(32 * max_warps<D>()) k_init_envs(const Mdl mp, int n_envs, const uint32_t* __restrict__ init_keys,
                                                    const float* __restrict__ levels, const float* __restrict__ rand,
                                                    float* __restrict__ state, uint32_t* __restrict__ keys,
                                                    float* __restrict__ rec0, uint32_t* __restrict__ act_keys) {
@@ -75,7 +83,7 @@ __global__ void __launch_bounds__(512) k_init_envs(const Mdl mp, int n_envs, con
 
 // n_steps control steps per launch; the environment stays in shared memory between them.
 template <class D>
-__global__ void __launch_bounds__(512) k_rollout(const Mdl mp, int n_envs, int n_steps, const float* __restrict__ actions,
+__global__ void __launch_bounds__(32 * max_warps<D>()) k_rollout(const Mdl mp, int n_envs, int n_steps, const float* __restrict__ actions,
                                                  const float* __restrict__ rand, float* __restrict__ state,
                                                  uint32_t* __restrict__ keys, float* __restrict__ rec,
                                                  float* __restrict__ rec_next_single, uint32_t* __restrict__ act_keys) {
@@ -219,16 +227,14 @@ static bool task_fits(const int* ti) {
          ti[TI_OBS_CARRY_SIZE] <= D::OCS && ti[TI_N_OBS] <= D::NOBS && ti[TI_ACTION_SIZE] <= D::NA;
 }
 
-static const size_t kSmemBudget = 227 * 1024;
-
 template <class D>
 static int configure(b200sim_model* mo, const size_t* words) {
   mo->smem_per_env = sizeof(Work<D>);
   const size_t fixed = sizeof(Mdl) + 16;
-  const int max_warps = (int)((kSmemBudget - fixed) / sizeof(Work<D>));
-  if (max_warps < 1) return fail(B2S_ERR_TOO_LARGE, "workspace does not fit in shared memory");
-  int wpb = max_warps > 16 ? 16 : max_warps;  // one CTA per SM: all its warps run in lockstep (shared i-cache fills)
-  if (const char* e = getenv("B2S_WPB")) { const int v = atoi(e); if (v >= 1 && v <= max_warps) wpb = v; }  // tuning experiments
+  constexpr int mw = max_warps<D>();
+  static_assert(mw >= 1, "workspace does not fit in shared memory");
+  int wpb = mw;  // one CTA per SM: all its warps run in lockstep (shared i-cache fills)
+  if (const char* e = getenv("B2S_WPB")) { const int v = atoi(e); if (v >= 1 && v <= mw) wpb = v; }  // tuning experiments
   mo->warps_per_cta = wpb;
   // model arrays staged in shared memory, in priority order mi, mf, ti, tf, while they fit
   size_t left = (kSmemBudget - fixed - wpb * sizeof(Work<D>)) / 4, staged = 0;

@@ -50,11 +50,13 @@
 // nested accounting inside a stage (its own clock): adds to slot k without disturbing the enclosing stage's clock
 #define SUB_BEGIN() long long sub_t0_ = clock64()
 #define SUB_MARK(w, k) do { const long long t1_ = clock64(); if (lane == 0) (w).prof[k] += (unsigned)(t1_ - sub_t0_); sub_t0_ = t1_; } while (0)
+#define PROF_COUNT(w, k) do { if (lane == 0) (w).prof[k] += 1u; } while (0)
 #else
 #define STAGE_BEGIN() ((void)0)
 #define STAGE_MARK(w, k) ((void)0)
 #define SUB_BEGIN() ((void)0)
 #define SUB_MARK(w, k) ((void)0)
+#define PROF_COUNT(w, k) ((void)0)
 #endif
 
 namespace b2s {

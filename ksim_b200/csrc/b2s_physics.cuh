@@ -457,12 +457,27 @@ DEVNI void chol_solve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
 }
 #endif
 
-enum { FS_MASS = 0, FS_NEWTON = 1, FS_IMPLICIT = 2 };
+// FS_NEWTON_DIAG: FS_NEWTON with the single-dof rows' diagonal term already summed per dof in w.s_mv (newton_dof());
+// it also leaves 1/diag(L) behind (device: w.s_tmp, host: Linv_diag) so that fs_resolve() can reuse the factor.
+enum { FS_MASS = 0, FS_NEWTON = 1, FS_IMPLICIT = 2, FS_NEWTON_DIAG = 3 };
 
 // bit 8 of sync_mask switches the constraint-space Newton path off (tuning / A-B tests)
 DEV bool dual_enabled(const Mdl& m) { return !((m.sync_mask >> 8) & 1); }
 // bit 10 switches the exact one-pass line search off (the bracketing iteration is used everywhere)
 DEV bool exact_ls_enabled(const Mdl& m) { return !((m.sync_mask >> 10) & 1); }
+// true: the constraint-space (dual) Newton path handles this sub-step's rows, and acceleration() must provide
+// Z = M^-1 J^T.  The register-resident solve (ne <= 8, no friction rows) always wins; the shared-memory dual path is
+// only kept for A/B tests (bit 9) and for the vote-synchronised mode (bit 7), which newton_dof() does not take part in.
+template <class D>
+DEV bool dual_path(const Mdl& m, const Work<D>& w, int ne) {
+  if (!(ne <= D::NDUAL && ((m.sync_mask >> 8) & 1) == 0)) return false;
+#if B2S_DEVICE
+  if (ne <= 8 && w.scratch_i[0] == 0 && ((m.sync_mask >> 10) & 1) == 0) return true;
+#endif
+  return ((m.sync_mask >> 9) & 1) || ((m.sync_mask >> 7) & 1);
+}
+// bit 9 switches the factor-reusing dof-space Newton path (newton_dof) off: the reference-shaped solve_primal runs instead
+DEV bool newton_dof_enabled(const Mdl& m) { return !((m.sync_mask >> 9) & 1); }
 
 // Builds A (FS_MASS: M; FS_NEWTON: M + J^T diag(D*active) J; FS_IMPLICIT: M + dt*diag(damping)), factors it and
 // solves A x = b.  The three dense factorisations of a physics sub-step all go through here.
@@ -497,6 +512,8 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
     if (live)
       for (int rr = 0; rr < nsparse; rr++)
         if (w.efc_active[rr] && w.efc_dof[rr] == i) dg += w.efc_D[rr];
+  } else if (mode == FS_NEWTON_DIAG) {
+    if (live) dg = w.s_mv[i];
   } else if (mode == FS_IMPLICIT) {
     if (live) dg = m.mf[MF_TIMESTEP] * w.damping[i];
   }
@@ -514,7 +531,7 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
     __syncwarp();
     if (live) w.M[ri][ri] = diag0;
   }
-  if (mode == FS_NEWTON) {
+  if (mode == FS_NEWTON || mode == FS_NEWTON_DIAG) {
     // dense constraint rows: J^T D J, accumulated on the register rows (after the load)
     const int ne = w.nefc, nsparse = w.nsparse;
     for (int rr = nsparse; rr < ne; rr++) {
@@ -540,6 +557,7 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
     if (i == j) invd = idj;
   }
   float y = live ? b[i] : 0.0f;
+  if (mode == FS_NEWTON_DIAG && live) w.s_tmp[i] = invd;
 #pragma unroll
   for (int k = 0; k < N; k++) {
     const float yk = __shfl_sync(FULL, y * invd, k);
@@ -582,12 +600,13 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
   LANE_FOR(i, nv) {
     for (int j = 0; j <= i; j++) w.W[i][j] = w.M[i][j];
     float dg = 0.0f;
-    if (mode == FS_NEWTON) {
+    if (mode == FS_NEWTON || mode == FS_NEWTON_DIAG) {
       const int ne = w.nefc, nsparse = w.nsparse;
       for (int j = 0; j <= i; j++)
         for (int rr = nsparse; rr < ne; rr++)
           if (w.efc_active[rr]) w.W[i][j] += w.efc_D[rr] * w.Jd[rr - nsparse][i] * w.Jd[rr - nsparse][j];
-      for (int rr = 0; rr < nsparse; rr++) if (w.efc_active[rr] && w.efc_dof[rr] == i) dg += w.efc_D[rr];
+      if (mode == FS_NEWTON_DIAG) dg = w.s_mv[i];
+      else for (int rr = 0; rr < nsparse; rr++) if (w.efc_active[rr] && w.efc_dof[rr] == i) dg += w.efc_D[rr];
     } else if (mode == FS_IMPLICIT) {
       dg = m.mf[MF_TIMESTEP] * w.damping[i];
     }
@@ -601,6 +620,40 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
     WSYNC();
     chol_solve(w, w.Z[s], w.Z[s], nv, LANE_PASS);
   }
+#endif
+}
+
+// Solves A x = b again with the factor the last factor_solve(FS_NEWTON_DIAG) left behind (strict lower triangle in W,
+// 1/diag in s_tmp / Linv_diag): substitutions only.  x and b may alias; b must not be s_tmp.
+template <class D>
+DEVNI void fs_resolve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
+#if B2S_DEVICE && !defined(B2S_COMPACT_CHOL)
+  constexpr int N = D::NV;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int i = lane;
+  const bool live = i < nv;
+  const int ri = i < N ? i : N - 1;
+  float r[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) r[j] = j < ri ? w.W[ri][j] : 0.0f;
+  const float invd = live ? w.s_tmp[i] : 1.0f;
+  float y = live ? b[i] : 0.0f;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const float yk = __shfl_sync(FULL, y * invd, k);
+    if (i > k) y = fmaf(-r[k], yk, y);
+  }
+  y *= invd;
+  float xv = y;
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) {
+    const float xk = __shfl_sync(FULL, xv * invd, k);
+    if (i < k && k < nv) xv = fmaf(-w.W[k][i], xk, xv);
+  }
+  if (live) x[i] = xv * invd;
+  __syncwarp();
+#else
+  chol_solve(w, x, b, nv, LANE_PASS);
 #endif
 }
 
@@ -1041,7 +1094,7 @@ DEV void acceleration(const Mdl& m, Work<D>& w, LANE_ARG) {
   WSYNC();
   // with 1..NDUAL constraint rows the Newton solve runs in constraint space and needs Z = M^-1 J^T (solve())
   const int ne = w.nefc;
-  factor_solve(m, w, FS_MASS, w.qacc_smooth, w.qfrc_smooth, (ne <= D::NDUAL && dual_enabled(m)) ? ne : 0, LANE_PASS);
+  factor_solve(m, w, FS_MASS, w.qacc_smooth, w.qfrc_smooth, dual_path(m, w, ne) ? ne : 0, LANE_PASS);
 }
 
 // ------------------------------------------------------------------------------------------------- solver
@@ -1461,6 +1514,206 @@ DEV void solve_primal(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
     if (iterations == 1) finished = true;
   }
   LANE_FOR(i, nv) { w.qacc[i] = w.s_qacc[i]; w.warm[i] = w.s_qacc[i]; }
+  WSYNC();
+}
+
+// ------------------------------------------------------------------- dof-space Newton with factor reuse (any ne)
+//
+// The same Newton iteration as solve_primal, organised around what changes between iterations.  With D fixed, the
+// Hessian H = M + J^T diag(D active) J depends on the iterate only through the ACTIVE SET, so it is rebuilt and
+// refactorised only when a row switched piece; otherwise the factor in W is reused (substitutions only).  The iterate is
+// kept as delta = qacc - qacc_smooth with M delta alongside, so grad = M delta - J^T f and the Gauss term is
+// 0.5 delta^T M delta (no M qacc products); single-dof rows (friction loss, limits) enter H's diagonal and J^T f by
+// per-dof scatter instead of per-lane loops over all rows; the line search is exact (ls_newton).  A full step that
+// keeps the active set has landed on the minimiser of its quadratic piece, which for the convex cost is the minimum.
+// This is the path of every model whose rows do not fit the register-resident constraint-space solve (the K-Bot:
+// 20 friction rows + limits + up to 32 pyramid rows).
+
+// out[i] = sum of val(r) over the single-dof rows r of dof i.  Friction rows [0, nfric) sit on distinct dofs and so
+// do limit rows [nfric, nsparse): two conflict-free passes.
+template <class D, class F>
+DEV void sparse_scatter(Work<D>& w, float* out, int nv, F val, LANE_ARG) {
+  const int nfric = w.scratch_i[0], nlim = w.nsparse - nfric;
+  LANE_FOR(i, nv) out[i] = 0.0f;
+  WSYNC();
+  LANE_FOR(r, nfric) out[w.efc_dof[r]] += val(r);
+  WSYNC();
+  LANE_FOR(k, nlim) out[w.efc_dof[nfric + k]] += val(nfric + k);
+  WSYNC();
+}
+
+// qfrc_constraint = J^T efc_force (scatter for the single-dof rows, lanes over dofs for the dense ones)
+template <class D>
+DEV void constraint_force_scatter(Work<D>& w, int nv, int ne, int nsparse, LANE_ARG) {
+  sparse_scatter(w, w.qfrc_constraint, nv, [&](int r) { return w.efc_sign[r] * w.efc_force[r]; }, LANE_PASS);
+  LANE_FOR(i, nv) {
+    float s = w.qfrc_constraint[i];
+    for (int r = nsparse; r < ne; r++) s = fmaf(w.Jd[r - nsparse][i], w.efc_force[r], s);
+    w.qfrc_constraint[i] = s;
+  }
+  WSYNC();
+}
+
+// constraint_rows() that also reports whether any row switched piece: *hess_changed when an active flag flipped (the
+// Hessian changes), *piece_changed also when a friction row jumped between its two linear zones (same Hessian, other
+// gradient: a full step across such a jump has not landed on a minimiser)
+template <class D>
+DEV float constraint_rows_track(Work<D>& w, int ne, int* hess_changed, int* piece_changed, LANE_ARG) {
+  float cost = 0.0f;
+  int ch = 0, cp = 0;
+  LANE_FOR(r, ne) {
+    const float x = w.efc_Jaref[r], Dr = w.efc_D[r];
+    const int was = w.efc_active[r];
+    int act;
+    if (w.efc_type[r] == EFC_FRICTION) {
+      const float f = w.efc_floss[r], rf = w.efc_R[r] * f, fwas = w.efc_force[r];
+      if (x <= -rf) { w.efc_force[r] = f; act = 0; cost += -f * (0.5f * rf + x); cp |= (fwas != f); }
+      else if (x >= rf) { w.efc_force[r] = -f; act = 0; cost += -f * (0.5f * rf - x); cp |= (fwas != -f); }
+      else { w.efc_force[r] = -Dr * x; act = 1; cost += 0.5f * Dr * x * x; }
+    } else {
+      act = x < 0.0f;
+      w.efc_force[r] = act ? -Dr * x : 0.0f;
+      if (act) cost += 0.5f * Dr * x * x;
+    }
+    w.efc_active[r] = act;
+    ch |= (act != was);
+  }
+  cost = wsum(cost);
+  *hess_changed = wany(ch);
+  *piece_changed = wany(ch | cp);
+  WSYNC();
+  return cost;
+}
+
+// EXACT line search for any number of rows.  g(alpha) = d cost / d alpha is continuous, piecewise linear and
+// non-decreasing (see ls_exact); its root is found by Newton's iteration on g with the slope of the piece the iterate
+// is in -- from a point inside the root's piece one step lands exactly on the root -- safeguarded by the bracket
+// [lo, hi] of the sign changes seen so far (an iterate leaving it is replaced by the secant point).  Every evaluation is
+// one pass with the rows spread over all 32 lanes and two warp sums.  The returned step never overshoots the root's
+// piece: if the iteration cap is hit, the last point with g <= 0 is returned, which is a descent step of a convex cost.
+template <class D>
+DEV float ls_newton(const Work<D>& w, int ne, float qg1, float qg2, LANE_ARG) {
+  float lo = 0.0f, hi = INFINITY, glo = 0.0f, ghi = 0.0f;
+  float a = 0.0f;
+  for (int it = 0; it < 12; it++) {
+    float g = 0.0f, h = 0.0f;
+    LANE_FOR(r, ne) {
+      const LSRow o = ls_row(w, r);
+      const float x = fmaf(a, o.jv, o.ja);
+      const bool fr = o.type == EFC_FRICTION;
+      const bool quad = fr ? (x > -o.rf && x < o.rf) : (x < 0.0f);
+      const float dj = o.D * o.jv;
+      g += quad ? dj * x : (fr ? (x <= -o.rf ? -o.f : o.f) * o.jv : 0.0f);
+      h += quad ? dj * o.jv : 0.0f;
+    }
+    g = wsum(g) + fmaf(2.0f * qg2, a, qg1);
+    h = wsum(h) + 2.0f * qg2;
+    if (it == 0) {
+      if (!(g < 0.0f)) return 0.0f;  // not a descent direction (round-off at convergence)
+      glo = g;
+    } else if (g <= 0.0f) { lo = a; glo = g; }
+    else { hi = a; ghi = g; }
+    float an = h > 0.0f ? a - fast_div(g, h) : (hi < INFINITY ? 0.5f * (lo + hi) : 2.0f * a + 1.0f);
+    // converged: the Newton step of this piece no longer moves the iterate (the root's piece has been reached)
+    if (fabsf(an - a) <= 1e-6f * fmaxf(fabsf(a), 1e-6f)) return a;
+    if (!(an > lo) || !(an < hi)) {
+      if (!(hi < INFINITY)) { an = 2.0f * a + 1.0f; }
+      else {
+        an = lo + (hi - lo) * fast_div(glo, glo - ghi);
+        if (!(an > lo) || !(an < hi)) an = 0.5f * (lo + hi);
+      }
+    }
+    a = an;
+  }
+  // iteration cap: a is the Newton point of the last piece; keep it only if it is inside the bracket's descent side
+  return lo > 0.0f ? lo : a;
+}
+
+template <class D>
+DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
+  const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
+  const bool warmstart = !m.h[MH_DISABLE_WARMSTART];
+  // ---- start point: costs at qacc_smooth and at the warm start in one pass over the rows
+  float gw = 0.0f;
+  LANE_FOR(i, nv) w.s_search[i] = warmstart ? w.warm[i] - w.qacc_smooth[i] : 0.0f;
+  WSYNC();
+  LANE_FOR(i, nv) {
+    float s = 0.0f;
+    for (int j = 0; j < nv; j++) s = fmaf(w.M[i][j], w.s_search[j], s);
+    w.s_mv[i] = s;
+    gw += w.s_search[i] * s;
+  }
+  gw = 0.5f * wsum(gw);
+  float cs = 0.0f, cw = 0.0f;
+  LANE_FOR(r, ne) {
+    const float js = row_dot(w, r, nsparse, w.qacc_smooth, nv) - w.efc_aref[r];
+    const float jd = row_dot(w, r, nsparse, w.s_search, nv);
+    cs += constraint_row_cost(w, r, js);
+    cw += constraint_row_cost(w, r, js + jd);
+    w.efc_Jaref[r] = js;
+    w.efc_jv[r] = jd;
+    w.efc_active[r] = -1;  // unknown piece: the first constraint_rows_track() reports a change
+  }
+  cs = wsum(cs);
+  cw = wsum(cw) + gw;
+  const bool use_warm = warmstart && cw < cs;
+  float gauss = use_warm ? gw : 0.0f;
+  // iterate: s_qacc = delta = qacc - qacc_smooth, s_Ma = M delta
+  LANE_FOR(i, nv) { w.s_qacc[i] = use_warm ? w.s_search[i] : 0.0f; w.s_Ma[i] = use_warm ? w.s_mv[i] : 0.0f; }
+  if (use_warm) { LANE_FOR(r, ne) w.efc_Jaref[r] += w.efc_jv[r]; }
+  WSYNC();
+  int changed, moved;
+  float cost = constraint_rows_track(w, ne, &changed, &moved, LANE_PASS) + gauss;
+  constraint_force_scatter(w, nv, ne, nsparse, LANE_PASS);
+  float prev_cost = INFINITY;
+  const int iterations = m.h[MH_ITERATIONS];
+  const float tol = m.mf[MF_TOLERANCE];
+  const float scale = 1.0f / (m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1));
+  bool need_factor = true;
+  // The exact line search and the factor reuse make an iteration cheap, and a cold start (after a reset) with many
+  // contact rows can need more than the reference's cap to settle its active set: up to 2x `iterations` are allowed, so
+  // that what is returned is the converged minimum rather than wherever the cap happened to stop the reference.
+  for (int niter = 0; niter < 2 * iterations; niter++) {
+    float gn = 0.0f;
+    LANE_FOR(i, nv) { const float g = w.s_Ma[i] - w.qfrc_constraint[i]; w.s_grad[i] = g; gn += g * g; }
+    gn = sqrtf(wsum(gn));
+    WSYNC();
+    if (iterations != 1 || niter > 0) {
+      if ((prev_cost - cost) * scale < tol || gn * scale < tol) break;
+    }
+    if (need_factor) {
+      sparse_scatter(w, w.s_mv, nv, [&](int r) { return w.efc_active[r] ? w.efc_D[r] : 0.0f; }, LANE_PASS);
+      factor_solve(m, w, FS_NEWTON_DIAG, w.s_Mgrad, w.s_grad, 0, LANE_PASS);
+    } else {
+      fs_resolve(w, w.s_Mgrad, w.s_grad, nv, LANE_PASS);
+    }
+    LANE_FOR(i, nv) w.s_search[i] = -w.s_Mgrad[i];
+    WSYNC();
+    float qg1 = 0.0f, qg2 = 0.0f;
+    LANE_FOR(i, nv) {
+      float s = 0.0f;
+      for (int j = 0; j < nv; j++) s = fmaf(w.M[i][j], w.s_search[j], s);
+      w.s_mv[i] = s;
+      qg1 += w.s_search[i] * w.s_Ma[i];
+      qg2 += w.s_search[i] * s;
+    }
+    LANE_FOR(r, ne) w.efc_jv[r] = row_dot(w, r, nsparse, w.s_search, nv);
+    qg1 = wsum(qg1);
+    qg2 = 0.5f * wsum(qg2);
+    WSYNC();
+    const float alpha = ls_newton(w, ne, qg1, qg2, LANE_PASS);
+    if (alpha == 0.0f) break;
+    LANE_FOR(i, nv) { w.s_qacc[i] = fmaf(alpha, w.s_search[i], w.s_qacc[i]); w.s_Ma[i] = fmaf(alpha, w.s_mv[i], w.s_Ma[i]); }
+    LANE_FOR(r, ne) w.efc_Jaref[r] = fmaf(alpha, w.efc_jv[r], w.efc_Jaref[r]);
+    WSYNC();
+    gauss += alpha * qg1 + alpha * alpha * qg2;
+    prev_cost = cost;
+    cost = constraint_rows_track(w, ne, &changed, &moved, LANE_PASS) + gauss;
+    constraint_force_scatter(w, nv, ne, nsparse, LANE_PASS);
+    need_factor = changed != 0;
+    if (!moved && fabsf(alpha - 1.0f) < 1e-3f) break;
+  }
+  LANE_FOR(i, nv) { const float a = w.qacc_smooth[i] + w.s_qacc[i]; w.qacc[i] = a; w.warm[i] = a; }
   WSYNC();
 }
 
@@ -1980,15 +2233,29 @@ DEV void solve(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
     LANE_FOR(i, nv) { w.qacc[i] = w.qacc_smooth[i]; w.qfrc_constraint[i] = 0.0f; }
     WSYNC();
     if (lockstep) solve_follower(m);
+    PROF_COUNT(w, 28);
     return;
   }
-  if (ne <= D::NDUAL && dual_enabled(m)) {
+  // profile build: slots 28..31 count solves by path (none / register dual / shared dual / primal); 13, 14, 22 hold
+  // the cycles of the primal, shared-memory dual and register dual paths
+  SUB_BEGIN();
+  if (dual_path(m, w, ne)) {
 #if B2S_DEVICE
-    if (ne <= 8 && w.scratch_i[0] == 0 && exact_ls_enabled(m)) { solve_dual8(m, w, lockstep, LANE_PASS); return; }
+    if (ne <= 8 && w.scratch_i[0] == 0 && exact_ls_enabled(m)) {
+      solve_dual8(m, w, lockstep, LANE_PASS);
+      SUB_MARK(w, 22);
+      PROF_COUNT(w, 29);
+      return;
+    }
 #endif
     solve_dual(m, w, lockstep, LANE_PASS);
+    SUB_MARK(w, 14);
+    PROF_COUNT(w, 30);
   } else {
-    solve_primal(m, w, lockstep, LANE_PASS);
+    if (!lockstep && newton_dof_enabled(m)) newton_dof(m, w, LANE_PASS);
+    else solve_primal(m, w, lockstep, LANE_PASS);
+    SUB_MARK(w, 13);
+    PROF_COUNT(w, 31);
   }
 }
 

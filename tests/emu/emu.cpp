@@ -6,6 +6,7 @@
 // fallback of any product path, and says nothing about races (those are checked on the GPU with
 // compute-sanitizer); only tests/test_emu_vs_oracle.py builds and loads it.
 #define B2S_EMU 1
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../ksim_b200/csrc/b2s_engine.cuh"
@@ -23,6 +24,7 @@ static Mdl view(const void* blob) {
   m.ti = h + MH_SIZE + h[MH_NI] + h[MH_NF];
   m.tf = (const float*)(h + MH_SIZE + h[MH_NI] + h[MH_NF] + h[MH_NTI]);
   m.sync_mask = 0xff;  // barriers / votes are no-ops on the host; the lockstep code paths still run
+  if (const char* e = getenv("B2S_EMU_SYNC_MASK")) m.sync_mask = (int)strtol(e, nullptr, 0);  // e.g. 0x7f: the product default
   return m;
 }
 

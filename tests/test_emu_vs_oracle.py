@@ -25,6 +25,14 @@ def emu() -> ctypes.CDLL:
     return ctypes.CDLL(str(out))
 
 
+@pytest.fixture(params=["0xff", "0x7f"], ids=["votes-dual-primal", "product-default"])
+def sync_mask(request, monkeypatch) -> str:  # noqa: ANN001
+    """0xff: vote-synchronised mode (shared-memory constraint-space path / reference-shaped dof-space path);
+    0x7f: the product default (factor-reusing dof-space Newton, newton_dof, for everything the host build solves)."""
+    monkeypatch.setenv("B2S_EMU_SYNC_MASK", request.param)
+    return request.param
+
+
 def _p(a: np.ndarray) -> ctypes.c_void_p:
     return ctypes.c_void_p(a.ctypes.data)
 
@@ -56,7 +64,7 @@ def _run(emu, prog, rz, n, t, level, seed=0, state_rtol=0.0):  # noqa: ANN001, A
     return prog, rec_e, rec_o, st_e, st_o, ora, blob, init
 
 
-def test_walking_single_step_parity(emu, oracle_built, walking_program, walking_randomizers) -> None:  # noqa: ANN001
+def test_walking_single_step_parity(emu, sync_mask, oracle_built, walking_program, walking_randomizers) -> None:  # noqa: ANN001
     prog, rec_e, rec_o, st_e, st_o, *_ = _run(emu, walking_program, walking_randomizers, n=16, t=12, level=0.0)
     m = prog.spec.model
     q, v, d = prog["TI_R_QPOS"], prog["TI_R_QVEL"], prog["TI_R_DONE"]
@@ -67,7 +75,7 @@ def test_walking_single_step_parity(emu, oracle_built, walking_program, walking_
     np.testing.assert_array_equal(rec_e[:12, :, tm : tm + 3], rec_o[:12, :, tm : tm + 3])
 
 
-def test_walking_with_noise_and_resets(emu, oracle_built, walking_program, walking_randomizers) -> None:  # noqa: ANN001
+def test_walking_with_noise_and_resets(emu, sync_mask, oracle_built, walking_program, walking_randomizers) -> None:  # noqa: ANN001
     """Curriculum level 1: every RandomVariable is live (noise.py:86,102,118); long enough for falls and resets."""
     prog, rec_e, rec_o, st_e, st_o, *_ = _run(emu, walking_program, walking_randomizers, n=12, t=60, level=1.0, seed=3)
     d, tm = prog["TI_R_DONE"], prog["TI_R_TIME"]
@@ -96,7 +104,7 @@ def test_rewards_parity(emu, oracle_built, walking_program, walking_randomizers)
     assert np.abs(comps_o).sum(axis=(1, 2)).min() >= 0 and np.isfinite(total_o).all()
 
 
-def test_tripod_with_events_and_latency(emu, oracle_built) -> None:  # noqa: ANN001
+def test_tripod_with_events_and_latency(emu, sync_mask, oracle_built) -> None:  # noqa: ANN001
     from ksim_b200 import events, terminations
     from ksim_b200.program import build_program
     from tests.helpers import tripod_spec
@@ -119,7 +127,7 @@ def test_tripod_with_events_and_latency(emu, oracle_built) -> None:  # noqa: ANN
     np.testing.assert_allclose(rec_e[:50, :, q : q + 10], rec_o[:50, :, q : q + 10], rtol=0, atol=5e-4)
 
 
-def test_kbot_single_step_parity(emu, oracle_built, kbot_spec, kbot_randomizers) -> None:  # noqa: ANN001
+def test_kbot_single_step_parity(emu, sync_mask, oracle_built, kbot_spec, kbot_randomizers) -> None:  # noqa: ANN001
     """K-Bot (examples/kbot plugin subset, level 1): capsule feet with pyramidal friction cones, 20 friction-loss rows
     (always more than 8 constraint rows: the general constraint-space path and, past NDUAL rows, the dof-space one),
     explicit inertials, per-joint actuator gains / noise, latency, action drop, force pushes, all randomizers."""
