@@ -163,7 +163,9 @@
 #define OBS_FEET_TORQUE 19
 #define OBS_TIMESTEP 20
 #define OBS_CONTACT 21
-#define OBS_FEET_POSITION 22
+#define OBS_FEET_POSITION 22     /* examples/kbot/train.py:653-689: feet relative to the base, in the base's yaw frame */
+#define OBS_BASE_HEIGHT 23       /* examples/kbot/train.py:693-697: xpos[1][2] */
+#define OBS_COM_DISTANCE 24      /* examples/kbot/train.py:500-649: |hull centroid of the contact points - subtree_com[2]| */
 
 /* ---- terminations (ksim/terminations.py) ---- */
 #define TERM_NOT_UPRIGHT 1
@@ -173,11 +175,13 @@
 #define TERM_BAD_VELOCITY 5
 #define TERM_FAR_FROM_ORIGIN 6
 #define TERM_EPISODE_LENGTH 7
+#define TERM_TERRAIN_BAD_Z 8     /* examples/kbot/train.py:779-813: base z - lowest foot z < unhealthy_z */
 
 /* ---- commands (ksim/commands.py) ---- */
 #define CMD_LINEAR_VELOCITY 1
 #define CMD_ANGULAR_VELOCITY 2
 #define CMD_FLOAT_VECTOR 3
+#define CMD_UNIFIED 4            /* examples/kbot/train.py:701-775: [vx vy wz bh rx ry arms[10]], 6-way mode switch */
 
 /* ---- rewards (ksim/rewards.py) ---- */
 #define REW_STAY_ALIVE 1
@@ -195,6 +199,18 @@
 #define REW_BASE_HEIGHT_RANGE 13
 #define REW_OFF_AXIS_VELOCITY 14
 #define REW_SMALL_JOINT_VELOCITY 15
+/* the K-Bot task's own rewards (examples/kbot/train.py:128-496) */
+#define REW_KBOT_SINGLE_FOOT_CONTACT 16
+#define REW_KBOT_NO_CONTACT 17
+#define REW_KBOT_FEET_AIRTIME 18
+#define REW_KBOT_ARM_POSITION 19
+#define REW_KBOT_LINVEL_TRACKING 20
+#define REW_KBOT_ANGVEL_TRACKING 21
+#define REW_KBOT_XY_ORIENTATION 22
+#define REW_KBOT_TERRAIN_BASE_HEIGHT 23
+#define REW_KBOT_FEET_ORIENTATION 24
+#define REW_KBOT_COM_DISTANCE 25
+#define REW_KBOT_BASE_ACCELERATION 26
 
 /* ---- per-env model override fields (ksim/randomization.py) ---- */
 #define RAND_DOF_FRICTIONLOSS 1

@@ -60,11 +60,18 @@ static const size_t kSmemBudget = 227 * 1024;
 // lets it use the registers a smaller CTA leaves free (K-Bot: 8 warps -> up to 255 registers per thread).
 template <class D>
 constexpr int max_warps() {
+
   return (int)((kSmemBudget - sizeof(Mdl) - 16) / sizeof(Work<D>)) > 16 ? 16 : (int)((kSmemBudget - sizeof(Mdl) - 16) / sizeof(Work<D>));
 }
 
+// Launch bound per instantiation (measured, gpurun_out/variants1.txt): the K-Bot kernel gains 20 % from the registers its
+// 8-warp CTA leaves free (256 threads -> up to 255 registers); the humanoid kernel (14 warps) is 3 % faster when held
+// to 128 registers (bound 512) than with the 144 its 448 threads would allow.
 template <class D>
-__global__ void __launch_bounds__(32 * max_warps<D>()) k_init_envs(const Mdl mp, int n_envs, const uint32_t* __restrict__ init_keys,
+constexpr int launch_threads() { return D::EXACT ? 512 : 32 * max_warps<D>(); }
+
+template <class D>
+__global__ void __launch_bounds__(launch_threads<D>()) k_init_envs(const Mdl mp, int n_envs, const uint32_t* __restrict__ init_keys,
                                                    const float* __restrict__ levels, const float* __restrict__ rand,
                                                    float* __restrict__ state, uint32_t* __restrict__ keys,
                                                    float* __restrict__ rec0, uint32_t* __restrict__ act_keys) {
@@ -83,7 +90,7 @@ __global__ void __launch_bounds__(32 * max_warps<D>()) k_init_envs(const Mdl mp,
 
 // n_steps control steps per launch; the environment stays in shared memory between them.
 template <class D>
-__global__ void __launch_bounds__(32 * max_warps<D>()) k_rollout(const Mdl mp, int n_envs, int n_steps, const float* __restrict__ actions,
+__global__ void __launch_bounds__(launch_threads<D>()) k_rollout(const Mdl mp, int n_envs, int n_steps, const float* __restrict__ actions,
                                                  const float* __restrict__ rand, float* __restrict__ state,
                                                  uint32_t* __restrict__ keys, float* __restrict__ rec,
                                                  float* __restrict__ rec_next_single, uint32_t* __restrict__ act_keys) {

@@ -194,6 +194,18 @@ DEVNI Q4 euler_to_quat(float roll, float pitch, float yaw) {
   return q;
 }
 
+// xax.quat_to_euler(wxyz) -> (roll, pitch, yaw), normalising with eps 1e-6; same expressions as the oracle (oracle/engine.c)
+DEVNI V3 quat_to_euler(Q4 q) {
+  const float n = sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z) + 1e-6f;
+  const float w = q.w / n, x = q.x / n, y = q.y / n, z = q.z / n;
+  const float roll = atan2f(2.0f * (w * x + y * z), 1.0f - 2.0f * (x * x + y * y));
+  const float sinp = 2.0f * (w * y - z * x);
+  const float pitch = fabsf(sinp) >= 1.0f ? (sinp > 0 ? 1.57079632679489661923f : -1.57079632679489661923f) : asinf(sinp);
+  const float yaw = atan2f(2.0f * (w * z + x * y), 1.0f - 2.0f * (y * y + z * z));
+  return v3(roll, pitch, yaw);
+}
+DEV float qdot(Q4 a, Q4 b) { return a.w * b.w + a.x * b.x + a.y * b.y + a.z * b.z; }
+
 // spatial 6-vectors are [rotational(3), translational(3)]; inertia is the 10-vector MuJoCo uses for cinert
 DEV V6 mul_inert_vec(const float* i, const V6& v) {
   V6 r;

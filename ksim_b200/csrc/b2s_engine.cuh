@@ -162,13 +162,14 @@ DEV void actuators_initial_state(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
 
 // ------------------------------------------------------------------------------------------------- events
 
-// jax.random.randint(key, (), 0, 3) (see oracle/engine.c)
-DEV uint32_t randint3(Key k) {
+// jax.random.randint(key, (), 0, span) (see oracle/engine.c)
+DEV uint32_t key_randint(Key k, uint32_t span) {
   const Key ra = key_split(k, 0), rb = key_split(k, 1);
   const uint32_t hi = key_bits(ra, 0), lo = key_bits(rb, 0);
-  const uint32_t span = 3u, mult = ((65536u % span) * (65536u % span)) % span;
+  const uint32_t mult = ((65536u % span) * (65536u % span)) % span;
   return ((hi % span) * mult + (lo % span)) % span;
 }
+DEV uint32_t randint3(Key k) { return key_randint(k, 3u); }
 
 template <class D>
 DEVNI void event_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
@@ -469,6 +470,30 @@ DEV void cmd_floatvec_initial(const float* cf, int dim, Key rng, float* out) {
   for (int i = 0; i < dim; i++) out[i] = zero ? 0.0f : key_uniform(rng, i, cf[2 * i], cf[2 * i + 1]);
 }
 
+// UnifiedCommand.initial_command (examples/kbot/train.py:714-756); floats: 6 x [lo, hi], arms lo[10], arms hi[10], switch_prob
+DEVNI void cmd_unified_initial(const float* cf, Key rng, float* out) {
+  float v[6], arms[10];
+#pragma unroll
+  for (int k = 0; k < 6; k++) v[k] = key_uniform(key_split(rng, 1 + k), 0, cf[2 * k], cf[2 * k + 1]);
+  const Key rh = key_split(rng, 7);
+#pragma unroll
+  for (int k = 0; k < 10; k++) {
+    const float a = key_uniform(rh, k, cf[12 + k], cf[22 + k]);
+    arms[k] = key_bernoulli(rh, k, 0.5f) ? a : 0.0f;
+  }
+  const uint32_t mode = key_randint(key_split(rng, 0), 6u);
+#pragma unroll
+  for (int k = 0; k < 16; k++) out[k] = 0.0f;
+  if (mode == 0u || mode == 3u) out[0] = v[0];
+  if (mode == 1u || mode == 3u) out[1] = v[1];
+  if (mode == 2u || mode == 3u) out[2] = v[2];
+  if (mode == 4u) { out[3] = v[3]; out[4] = v[4]; out[5] = v[5]; }
+  if (mode == 3u || mode == 4u) {
+#pragma unroll
+    for (int k = 0; k < 10; k++) out[6 + k] = arms[k];
+  }
+}
+
 // lane 0 only
 template <class D>
 DEV void cmd_initial(const Mdl& m, Work<D>& w, int idx, Key rng) {
@@ -481,6 +506,7 @@ DEV void cmd_initial(const Mdl& m, Work<D>& w, int idx, Key rng) {
   if (type == CMD_LINEAR_VELOCITY) cmd_linvel_initial(ci, cf, w, rng, nullptr, st);
   else if (type == CMD_ANGULAR_VELOCITY) cmd_angvel_initial(ci, cf, w, rng, st);
   else if (type == CMD_FLOAT_VECTOR) cmd_floatvec_initial(cf, dim, rng, st);
+  else if (type == CMD_UNIFIED) cmd_unified_initial(cf, rng, st);
 }
 
 // lane 0 only
@@ -524,6 +550,8 @@ DEV void cmd_update(const Mdl& m, Work<D>& w, int idx, Key rng) {
       cmd_floatvec_initial(cf, dim, key_split(rng, 1), fresh);
       for (int i = 0; i < dim; i++) st[i] = fresh[i];
     }
+  } else if (type == CMD_UNIFIED) {
+    if (key_bernoulli(ra, 0, cf[32])) cmd_unified_initial(cf, key_split(rng, 1), st);
   }
 }
 
@@ -561,6 +589,58 @@ DEV void obs_carry_initial(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG)
       for (int k = 0; k < 3; k++) c[4 + k] = key_uniform(brng, k, -of[5], of[5]);
     }
   }
+}
+
+// COMDistanceObservation (examples/kbot/train.py:500-649): monotone-chain hull of the contact points' xy (points of
+// contacts whose geom1 is not the floor are (0,0)), area centroid of the hull polygon (vertex mean when the area
+// vanishes), distance to subtree_com[2].  A few dozen operations on <= NCON points, once per control step; serial.
+template <class D>
+DEVNI float com_distance(const Mdl& m, const Work<D>& w) {
+  constexpr int NC = D::NCON;
+  const int n = DIM(NCON, MH_NCON);
+  const int* pg1 = MI(m, MH_PAIR_GEOM1);
+  float px[NC], py[NC];
+  for (int c = 0; c < n; c++) {
+    const bool floor = pg1[w.con_pair[c]] == 0;
+    px[c] = floor ? w.con_pos[0][c] : 0.0f;
+    py[c] = floor ? w.con_pos[1][c] : 0.0f;
+  }
+  for (int i = 1; i < n; i++) {  // stable insertion sort == lexsort by x then y
+    const float x = px[i], y = py[i];
+    int j = i - 1;
+    while (j >= 0 && (px[j] > x || (px[j] == x && py[j] > y))) { px[j + 1] = px[j]; py[j + 1] = py[j]; j--; }
+    px[j + 1] = x; py[j + 1] = y;
+  }
+  float hx[2 * NC], hy[2 * NC];
+  int np = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    int stack[NC], ptr = 0;
+    for (int t = 0; t < n; t++) {
+      const int idx = pass == 0 ? t : n - 1 - t;
+      while (ptr >= 2) {
+        const int a = stack[ptr - 2], b = stack[ptr - 1];
+        const float cr = (px[b] - px[a]) * (py[idx] - py[a]) - (py[b] - py[a]) * (px[idx] - px[a]);
+        if (cr <= 0.0f) ptr--; else break;
+      }
+      stack[ptr++] = idx;
+    }
+    for (int t = 0; t < ptr - 1; t++) { hx[np] = px[stack[t]]; hy[np] = py[stack[t]]; np++; }
+  }
+  float area = 0.0f, sx = 0.0f, sy = 0.0f, mx = 0.0f, my = 0.0f;
+  for (int i = 0; i < np; i++) {
+    const int j = i + 1 < np ? i + 1 : 0;
+    const float cr = hx[i] * hy[j] - hx[j] * hy[i];
+    area += cr;
+    sx += (hx[i] + hx[j]) * cr;
+    sy += (hy[i] + hy[j]) * cr;
+    mx += hx[i]; my += hy[i];
+  }
+  area *= 0.5f;
+  const float cnt = np > 0 ? (float)np : 1.0f;
+  const bool flat = fabsf(area) < 1e-12f;
+  const float cx = flat ? mx / cnt : sx / (6.0f * area), cy = flat ? my / cnt : sy / (6.0f * area);
+  const float dx = cx - w.subtree_com[0][2], dy = cy - w.subtree_com[1][2];
+  return sqrtf(dx * dx + dy * dy);
 }
 
 // get_observation: writes the obs block of a record (global memory)
@@ -632,6 +712,17 @@ DEVNI void observe(const Mdl& m, Work<D>& w, Key rng, float* out, LANE_ARG) {
         case OBS_FEET_FORCE: x = w.cfrc_ext[k % 3][oi[k / 3]]; break;
         case OBS_FEET_TORQUE: x = w.cfrc_ext[3 + k % 3][oi[k / 3]]; break;
         case OBS_TIMESTEP: x = w.time; break;
+        case OBS_FEET_POSITION: {
+          // examples/kbot/train.py:672-689; ints [base, left, right]
+          Q4 bqx; bqx.w = w.xquat[0][oi[0]]; bqx.x = w.xquat[1][oi[0]]; bqx.y = w.xquat[2][oi[0]]; bqx.z = w.xquat[3][oi[0]];
+          const Q4 yawq = euler_to_quat(0.0f, 0.0f, quat_to_euler(bqx).z);
+          const int fb = oi[1 + k / 3];
+          const V3 rel = v3(w.xpos[0][fb] - w.xpos[0][oi[0]], w.xpos[1][fb] - w.xpos[1][oi[0]], w.xpos[2][fb] - w.xpos[2][oi[0]]);
+          const V3 r = rot_vec_quat(rel, yawq, true);
+          x = k % 3 == 0 ? r.x : (k % 3 == 1 ? r.y : r.z);
+        } break;
+        case OBS_BASE_HEIGHT: x = w.xpos[2][1]; break;
+        case OBS_COM_DISTANCE: x = oi[0] ? com_distance(m, w) : -1.0f; break;
         default: x = 0.0f; break;
       }
       v[k] = x;
@@ -686,6 +777,10 @@ DEV int termination(const Mdl& m, const Work<D>& w, int idx) {
     case TERM_FAR_FROM_ORIGIN: {
       const float n = sqrtf(w.qpos[0] * w.qpos[0] + w.qpos[1] * w.qpos[1] + w.qpos[2] * w.qpos[2]);
       return n > xf[0] ? xi[0] : 0;
+    }
+    case TERM_TERRAIN_BAD_Z: {
+      const float height = w.xpos[2][xi[0]] - fminf(w.xpos[2][xi[1]], w.xpos[2][xi[2]]);
+      return height < xf[0] ? -1 : 0;
     }
     case TERM_EPISODE_LENGTH: {
       const int v = w.time > xf[0] ? xi[0] : 0;

@@ -471,6 +471,7 @@ DEV bool exact_ls_enabled(const Mdl& m) { return !((m.sync_mask >> 10) & 1); }
 template <class D>
 DEV bool dual_path(const Mdl& m, const Work<D>& w, int ne) {
   if (!(ne <= D::NDUAL && ((m.sync_mask >> 8) & 1) == 0)) return false;
+  if (D::NEFC <= D::NDUAL) return true;  // every row count of this model fits (humanoid): newton_dof is compiled out
 #if B2S_DEVICE
   if (ne <= 8 && w.scratch_i[0] == 0 && ((m.sync_mask >> 10) & 1) == 0) return true;
 #endif
@@ -2252,8 +2253,12 @@ DEV void solve(const Mdl& m, Work<D>& w, bool lockstep, LANE_ARG) {
     SUB_MARK(w, 14);
     PROF_COUNT(w, 30);
   } else {
-    if (!lockstep && newton_dof_enabled(m)) newton_dof(m, w, LANE_PASS);
-    else solve_primal(m, w, lockstep, LANE_PASS);
+    if constexpr (D::NEFC > D::NDUAL) {
+      if (!lockstep && newton_dof_enabled(m)) newton_dof(m, w, LANE_PASS);
+      else solve_primal(m, w, lockstep, LANE_PASS);
+    } else {
+      solve_primal(m, w, lockstep, LANE_PASS);
+    }
     SUB_MARK(w, 13);
     PROF_COUNT(w, 31);
   }

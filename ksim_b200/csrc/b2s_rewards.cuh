@@ -211,6 +211,134 @@ DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, floa
           OUT(0, s) = acc / (float)(nq - 7);
         }
         break;
+      // ---- the K-Bot task's own rewards (examples/kbot/train.py:128-496; same structure as oracle/engine.c)
+#define UCMD(s, k) REC(s, CM + ucmd + (k))
+#define ZERO_CMD(s) (sqrtf(UCMD(s, 0) * UCMD(s, 0) + UCMD(s, 1) * UCMD(s, 1) + UCMD(s, 2) * UCMD(s, 2)) < 1e-3f)
+      case REW_KBOT_SINGLE_FOOT_CONTACT: {
+        const int ucmd = xi[2];
+        IF_LANE0 {
+          for (int s = 0; s < T; s++) {
+            const bool l = REC(s, OB + xi[0]) > 0.1f, r_ = REC(s, OB + xi[1]) > 0.1f, zero = ZERO_CMD(s);
+            float tm = (l != r_) ? 0.0f : cr[0] + xf[0];
+            if (zero) tm = xf[1];
+            cr[0] = tm;
+            OUT(0, s) = zero ? 1.0f : (tm < xf[1] ? 1.0f : 0.0f);
+          }
+        }
+      } break;
+      case REW_KBOT_NO_CONTACT: {
+        const int ucmd = xi[2];
+        LANE_FOR(s, T) {
+          const bool l = REC(s, OB + xi[0]) > 0.1f, r_ = REC(s, OB + xi[1]) > 0.1f;
+          OUT(0, s) = ZERO_CMD(s) ? 0.0f : ((l || r_) ? 0.0f : 1.0f);
+        }
+      } break;
+      case REW_KBOT_FEET_AIRTIME: {
+        const int ucmd = xi[2];
+        IF_LANE0 {
+          for (int s = 0; s < T; s++) {
+            const bool dn = REC(s, DN) != 0.0f;
+            float rew = 0.0f;
+            for (int f = 0; f < 2; f++) {
+              const bool contact = REC(s, OB + xi[f]) > 0.1f;
+              const bool prev_contact = cr[2 + f] == 0.0f;
+              const bool first = contact && !prev_contact && !dn;
+              rew += (cr[f] - xf[1]) * (first ? 1.0f : 0.0f);
+              cr[f] = (contact || dn) ? 0.0f : cr[f] + xf[0];
+              cr[2 + f] = contact ? 0.0f : 1.0f;
+            }
+            OUT(0, s) = ZERO_CMD(s) ? 0.0f : rew;
+          }
+        }
+      } break;
+      case REW_KBOT_ARM_POSITION: {
+        const int ucmd = xi[0];
+        LANE_FOR(s, T) {
+          float err = 0.0f;
+          for (int k = 0; k < 10; k++) {
+            const float dlt = REC(s, QP + xi[1 + k]) - (UCMD(s, 6 + k) + xf[1 + k]);
+            err += dlt * dlt;
+          }
+          OUT(0, s) = expf(-err / xf[0]);
+        }
+      } break;
+      case REW_KBOT_LINVEL_TRACKING: {
+        const int ucmd = xi[0], XQ = ti[TI_R_XQUAT];
+        LANE_FOR(s, T) {
+          Q4 bq; bq.w = REC(s, XQ + 4); bq.x = REC(s, XQ + 5); bq.y = REC(s, XQ + 6); bq.z = REC(s, XQ + 7);
+          const Q4 zq = euler_to_quat(0.0f, 0.0f, quat_to_euler(bq).z);
+          const V3 g = rot_vec_quat(v3(UCMD(s, 0), UCMD(s, 1), 0.0f), zq, false);
+          const float ex = REC(s, QV) - g.x, ey = REC(s, QV + 1) - g.y;
+          const float ve = sqrtf(ex * ex + ey * ey);
+          OUT(0, s) = expf(-(ZERO_CMD(s) ? ve : ve * ve) / xf[0]);
+        }
+      } break;
+      case REW_KBOT_ANGVEL_TRACKING: {
+        const int ucmd = xi[0];
+        LANE_FOR(s, T) OUT(0, s) = expf(-fabsf(REC(s, QV + 5) - UCMD(s, 2)) / xf[0]);
+      } break;
+      case REW_KBOT_XY_ORIENTATION: {
+        const int ucmd = xi[0], XQ = ti[TI_R_XQUAT];
+        LANE_FOR(s, T) {
+          Q4 bq; bq.w = REC(s, XQ + 4); bq.x = REC(s, XQ + 5); bq.y = REC(s, XQ + 6); bq.z = REC(s, XQ + 7);
+          const V3 e = quat_to_euler(bq);
+          const float dt_ = qdot(euler_to_quat(UCMD(s, 4), UCMD(s, 5), 0.0f), euler_to_quat(e.x, e.y, 0.0f));
+          OUT(0, s) = expf(-(1.0f - dt_ * dt_) / (ZERO_CMD(s) ? xf[1] : xf[0]));
+        }
+      } break;
+      case REW_KBOT_TERRAIN_BASE_HEIGHT: {
+        const int ucmd = xi[0], XP = ti[TI_R_XPOS];
+        LANE_FOR(s, T) {
+          const float lf = REC(s, XP + 3 * xi[2] + 2) - xf[2], rf_ = REC(s, XP + 3 * xi[3] + 2) - xf[2];
+          const float cur = REC(s, XP + 3 * xi[1] + 2) - fminf(lf, rf_);
+          OUT(0, s) = expf(-fabsf(cur - (UCMD(s, 3) + xf[1])) / xf[0]);
+        }
+      } break;
+      case REW_KBOT_FEET_ORIENTATION: {
+        // `is_rotating` is one flag per trajectory: the norm of the yaw-rate command column over time (train.py:464)
+        const int ucmd = xi[0], XQ = ti[TI_R_XQUAT];
+        float n2 = 0.0f;
+        LANE_FOR(s, T) n2 += UCMD(s, 2) * UCMD(s, 2);
+        const bool rotating = sqrtf(wsum(n2)) > 1e-3f;
+        const float hp = 1.57079632679489661923f, pi = 3.14159265358979323846f;
+        LANE_FOR(s, T) {
+          Q4 bq; bq.w = REC(s, XQ + 4); bq.x = REC(s, XQ + 5); bq.y = REC(s, XQ + 6); bq.z = REC(s, XQ + 7);
+          const float yaw = quat_to_euler(bq).z;
+          float err = 0.0f;
+          for (int f = 0; f < 2; f++) {
+            const int fo = XQ + 4 * xi[1 + f];
+            Q4 fq; fq.w = REC(s, fo); fq.x = REC(s, fo + 1); fq.y = REC(s, fo + 2); fq.z = REC(s, fo + 3);
+            const float roll = f == 0 ? -hp : hp;
+            float dt_;
+            if (rotating) {
+              const V3 fe = quat_to_euler(fq);
+              dt_ = qdot(euler_to_quat(roll, 0.0f, 0.0f), euler_to_quat(fe.x, fe.y, 0.0f));
+            } else {
+              dt_ = qdot(euler_to_quat(roll, 0.0f, yaw - pi), fq);
+            }
+            err += 1.0f - dt_ * dt_;
+          }
+          OUT(0, s) = expf(-err / xf[0]);
+        }
+      } break;
+      case REW_KBOT_COM_DISTANCE: {
+        const int ucmd = xi[0];
+        LANE_FOR(s, T) {
+          const float dist = REC(s, OB + xi[1]);
+          OUT(0, s) = (dist >= 0.0f && ZERO_CMD(s)) ? expf(-dist / xf[0]) : 0.0f;
+        }
+      } break;
+      case REW_KBOT_BASE_ACCELERATION:
+        LANE_FOR(s, T) {
+          const int prev = s > 0 ? s - 1 : 0;
+          const bool dn = REC(prev, DN) != 0.0f;
+          float err = 0.0f;
+          for (int k = 0; k < 6; k++) err += (dn || s == 0) ? 0.0f : fabsf(REC(s, QV + k) - REC(prev, QV + k));
+          OUT(0, s) = expf(-err / xf[0]);
+        }
+        break;
+#undef UCMD
+#undef ZERO_CMD
       default:
         for (int c = 0; c < ncomp; c++) { LANE_FOR(s, T) OUT(c, s) = 0.0f; }
         break;

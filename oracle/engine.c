@@ -32,6 +32,7 @@
 #define LOG logf
 #define ATAN2 atan2f
 #define ACOS acosf
+#define ASIN asinf
 #define RINT rintf
 #else
 #define SQRT sqrt
@@ -42,6 +43,7 @@
 #define LOG log
 #define ATAN2 atan2
 #define ACOS acos
+#define ASIN asin
 #define RINT rint
 #endif
 
@@ -534,6 +536,89 @@ static void engine_reset(const Task* t, Env* e, Key rng) {
 
 /* ------------------------------------------------------------------------------------------ commands */
 
+/* xax.quat_to_euler(wxyz) -> [roll, pitch, yaw], normalising with eps 1e-6 [restated from memory, like o_euler_to_quat] */
+static void quat_to_euler(REAL* rpy, const REAL* q) {
+  REAL n = SQRT(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]) + (REAL)1e-6;
+  REAL w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
+  rpy[0] = ATAN2((REAL)2 * (w * x + y * z), (REAL)1 - (REAL)2 * (x * x + y * y));
+  REAL sinp = (REAL)2 * (w * y - z * x);
+  rpy[1] = FABS(sinp) >= (REAL)1 ? (sinp > 0 ? PI_R / 2 : -PI_R / 2) : ASIN(sinp);
+  rpy[2] = ATAN2((REAL)2 * (w * z + x * y), (REAL)1 - (REAL)2 * (y * y + z * z));
+}
+
+/* jax.random.randint(key, (), 0, span): two 32-bit draws from split(key) and modular arithmetic */
+static uint32_t key_randint(Key k, uint32_t span) {
+  Key ra = key_split(k, 0), rb = key_split(k, 1);
+  uint32_t hi = key_bits(ra, 0), lo = key_bits(rb, 0);
+  uint32_t mult = (uint32_t)((65536u % span) * (65536u % span)) % span;
+  return ((hi % span) * mult + (lo % span)) % span;
+}
+
+/* UnifiedCommand.initial_command (examples/kbot/train.py:714-756).  floats: 6 x [lo, hi] (vx vy wz bh rx ry),
+ * arms lo[10], arms hi[10], switch_prob.  The arm draw and its 50 % mask share one key (train.py:725-728). */
+static void cmd_unified_initial(const REAL* cf, Key rng, REAL* out) {
+  REAL v[6], arms[10];
+  for (int k = 0; k < 6; k++) v[k] = key_uniform(key_split(rng, 1 + k), 0, cf[2 * k], cf[2 * k + 1]);
+  Key rh = key_split(rng, 7);
+  for (int k = 0; k < 10; k++) {
+    REAL a = key_uniform(rh, k, cf[12 + k], cf[22 + k]);
+    arms[k] = key_bernoulli(rh, k, (REAL)0.5) ? a : 0;
+  }
+  uint32_t mode = key_randint(key_split(rng, 0), 6u);
+  for (int k = 0; k < 16; k++) out[k] = 0;
+  switch (mode) {
+    case 0: out[0] = v[0]; break;
+    case 1: out[1] = v[1]; break;
+    case 2: out[2] = v[2]; break;
+    case 3: out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; for (int k = 0; k < 10; k++) out[6 + k] = arms[k]; break;
+    case 4: out[3] = v[3]; out[4] = v[4]; out[5] = v[5]; for (int k = 0; k < 10; k++) out[6 + k] = arms[k]; break;
+    default: break;
+  }
+}
+
+/* COMDistanceObservation (examples/kbot/train.py:500-649): Andrew's monotone chain over the n contact points
+ * (pts[i] = contact i's xy, or (0,0) when its geom1 is not the floor), area centroid of the hull polygon (mean of its
+ * vertices when the area vanishes), distance to `com`. */
+static REAL hull_cross(const REAL* a, const REAL* b, const REAL* c) {
+  return (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]);
+}
+static REAL com_distance(const REAL (*pts)[2], int n, const REAL* com) {
+  int order[O_MAXCON];
+  for (int i = 0; i < n; i++) order[i] = i;
+  for (int i = 1; i < n; i++) {  /* stable insertion sort == lexsort by x then y */
+    int o = order[i], j = i - 1;
+    while (j >= 0 && (pts[order[j]][0] > pts[o][0] || (pts[order[j]][0] == pts[o][0] && pts[order[j]][1] > pts[o][1]))) {
+      order[j + 1] = order[j]; j--;
+    }
+    order[j + 1] = o;
+  }
+  REAL poly[2 * O_MAXCON][2];
+  int np_ = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    int stack[O_MAXCON], ptr = 0;
+    for (int t = 0; t < n; t++) {
+      int idx = pass == 0 ? t : n - 1 - t;
+      while (ptr >= 2 && hull_cross(pts[order[stack[ptr - 2]]], pts[order[stack[ptr - 1]]], pts[order[idx]]) <= 0) ptr--;
+      stack[ptr++] = idx;
+    }
+    for (int t = 0; t < ptr - 1; t++) { poly[np_][0] = pts[order[stack[t]]][0]; poly[np_][1] = pts[order[stack[t]]][1]; np_++; }
+  }
+  REAL area = 0, sx = 0, sy = 0, mx = 0, my = 0;
+  for (int i = 0; i < np_; i++) {
+    int j = i + 1 < np_ ? i + 1 : 0;
+    REAL cr = poly[i][0] * poly[j][1] - poly[j][0] * poly[i][1];
+    area += cr;
+    sx += (poly[i][0] + poly[j][0]) * cr;
+    sy += (poly[i][1] + poly[j][1]) * cr;
+    mx += poly[i][0]; my += poly[i][1];
+  }
+  area *= (REAL)0.5;
+  REAL cnt = np_ > 0 ? (REAL)np_ : (REAL)1;
+  REAL cx = FABS(area) < (REAL)1e-12 ? mx / cnt : sx / ((REAL)6 * area);
+  REAL cy = FABS(area) < (REAL)1e-12 ? my / cnt : sy / ((REAL)6 * area);
+  return SQRT((cx - com[0]) * (cx - com[0]) + (cy - com[1]) * (cy - com[1]));
+}
+
 static void cmd_linvel_initial(const int* ci, const REAL* cf, const Env* e, Key rng, const REAL* prev, REAL* out) {
   /* commands.py:295-342; value order: vel, yaw, xvel, yvel, target_vel, target_yaw */
   REAL lvl = e->level;
@@ -580,7 +665,7 @@ static void cmd_initial(const Task* t, Env* e, int idx, Key rng) {
     /* commands.py:112-121: bernoulli and uniform draw share the key; floats [lo,hi]*n, switch_prob, zero_prob */
     int zero = key_bernoulli(rng, 0, cf[2 * dim + 1]);
     for (int i = 0; i < dim; i++) st[i] = zero ? 0 : key_uniform(rng, i, cf[2 * i], cf[2 * i + 1]);
-  }
+  } else if (type == CMD_UNIFIED) cmd_unified_initial(cf, rng, st);
 }
 
 static void cmd_update(const Task* t, Env* e, int idx, Key rng) {
@@ -617,6 +702,12 @@ static void cmd_update(const Task* t, Env* e, int idx, Key rng) {
     int sw = key_bernoulli(ra, 0, cf[2 * dim]);
     cmd_initial(t, e, idx, rb);
     if (!sw) for (int i = 0; i < dim; i++) st[i] = prev[i];
+  } else if (type == CMD_UNIFIED) {
+    /* train.py:758-775 */
+    REAL fresh[16];
+    int sw = key_bernoulli(ra, 0, cf[32]);
+    cmd_unified_initial(cf, rb, fresh);
+    if (sw) for (int i = 0; i < 16; i++) st[i] = fresh[i];
   }
 }
 
@@ -706,6 +797,30 @@ static void observe(const Task* t, Env* e, Key rng, REAL* out) {
       case OBS_FEET_FORCE: for (int s = 0; s < 2; s++) for (int k = 0; k < 3; k++) v[3 * s + k] = d->cfrc_ext[oi[s]][k]; break;
       case OBS_FEET_TORQUE: for (int s = 0; s < 2; s++) for (int k = 0; k < 3; k++) v[3 * s + k] = d->cfrc_ext[oi[s]][3 + k]; break;
       case OBS_TIMESTEP: v[0] = d->time; break;
+      case OBS_FEET_POSITION: {
+        /* train.py:672-689; ints [base, left, right] */
+        REAL rpy[3], yawq[4], e0[3] = {0, 0, 0};
+        quat_to_euler(rpy, d->xquat[oi[0]]);
+        e0[2] = rpy[2];
+        o_euler_to_quat(yawq, e0);
+        for (int f = 0; f < 2; f++) {
+          REAL rel[3];
+          for (int k = 0; k < 3; k++) rel[k] = d->xpos[oi[1 + f]][k] - d->xpos[oi[0]][k];
+          o_rot_vec_quat(v + 3 * f, rel, yawq, 1);
+        }
+      } break;
+      case OBS_BASE_HEIGHT: v[0] = d->xpos[1][2]; break;
+      case OBS_COM_DISTANCE: {
+        /* train.py:627-649; ints [enough distinct geom2 values (static: MJX keeps every candidate contact)] */
+        if (!oi[0]) { v[0] = -1; break; }
+        REAL pts[O_MAXCON][2];
+        for (int c = 0; c < d->ncon; c++) {
+          int floor = d->contact[c].geom1 == 0;
+          pts[c][0] = floor ? d->contact[c].pos[0] : 0;
+          pts[c][1] = floor ? d->contact[c].pos[1] : 0;
+        }
+        v[0] = com_distance((const REAL (*)[2])pts, d->ncon, d->subtree_com[2]);
+      } break;
       default: for (int k = 0; k < dim; k++) v[k] = 0; break;
     }
     if (noff >= 0) {
@@ -757,6 +872,12 @@ static int termination(const Task* t, const Env* e, int idx) {
     case TERM_FAR_FROM_ORIGIN: {
       REAL n = SQRT(d->qpos[0] * d->qpos[0] + d->qpos[1] * d->qpos[1] + d->qpos[2] * d->qpos[2]);
       return n > xf[0] ? xi[0] : 0;
+    }
+    case TERM_TERRAIN_BAD_Z: {
+      /* train.py:807-813; ints [base, left, right] */
+      REAL lf = d->xpos[xi[1]][2], rf_ = d->xpos[xi[2]][2];
+      REAL height = d->xpos[xi[0]][2] - (lf < rf_ ? lf : rf_);
+      return height < xf[0] ? -1 : 0;
     }
     case TERM_EPISODE_LENGTH: {
       int v = d->time > xf[0] ? xi[0] : 0;
@@ -1101,6 +1222,151 @@ static void env_rewards(const Task* t, const REAL* rec, size_t tstride, int T, R
           out[0][s] = acc / (REAL)(nq - 7);
         }
         break;
+      /* ---- the K-Bot task's own rewards (examples/kbot/train.py:128-496).  ZERO_CMD(s): |cmd[:3]| < 1e-3.
+       * Foot contact: touch-sensor observation > 0.1.  Observations / commands are pre-step, qpos / qvel / xpos /
+       * xquat post-step (types.py:51-54). */
+#define UCMD(s, k) REC(s, CM + ucmd + (k))
+#define ZERO_CMD(s) (SQRT(UCMD(s, 0) * UCMD(s, 0) + UCMD(s, 1) * UCMD(s, 1) + UCMD(s, 2) * UCMD(s, 2)) < (REAL)1e-3)
+      case REW_KBOT_SINGLE_FOOT_CONTACT: {
+        /* train.py:128-156; ints [left obs, right obs, cmd]; floats [ctrl_dt, grace]; carry [time since single contact] */
+        int ucmd = xi[2];
+        for (int s = 0; s < T; s++) {
+          int l = REC(s, OB + xi[0]) > (REAL)0.1, r_ = REC(s, OB + xi[1]) > (REAL)0.1, zero = ZERO_CMD(s);
+          REAL tm = (l != r_) ? 0 : cr[0] + xf[0];
+          if (zero) tm = xf[1];
+          cr[0] = tm;
+          out[0][s] = zero ? 1 : (tm < xf[1] ? 1 : 0);
+        }
+      } break;
+      case REW_KBOT_NO_CONTACT: {
+        /* train.py:159-167 */
+        int ucmd = xi[2];
+        for (int s = 0; s < T; s++) {
+          int l = REC(s, OB + xi[0]) > (REAL)0.1, r_ = REC(s, OB + xi[1]) > (REAL)0.1;
+          out[0][s] = ZERO_CMD(s) ? 0 : ((l || r_) ? 0 : 1);
+        }
+      } break;
+      case REW_KBOT_FEET_AIRTIME: {
+        /* train.py:170-218; carry [airtime l, airtime r, NOT prev contact l, r] (initial carry: airtime 0, contact True) */
+        int ucmd = xi[2];
+        for (int s = 0; s < T; s++) {
+          int dn = REC(s, DN) != 0;
+          REAL rew = 0;
+          for (int f = 0; f < 2; f++) {
+            int contact = REC(s, OB + xi[f]) > (REAL)0.1;
+            int prev_contact = cr[2 + f] == 0;
+            int first = contact && !prev_contact && !dn;
+            rew += (cr[f] - xf[1]) * (first ? 1 : 0);       /* airtime of the previous step */
+            cr[f] = (contact || dn) ? 0 : cr[f] + xf[0];
+            cr[2 + f] = contact ? 0 : 1;
+          }
+          out[0][s] = ZERO_CMD(s) ? 0 : rew;
+        }
+      } break;
+      case REW_KBOT_ARM_POSITION: {
+        /* train.py:221-270; ints [cmd, 10 qpos indices]; floats [error_scale, 10 biases] */
+        int ucmd = xi[0];
+        for (int s = 0; s < T; s++) {
+          REAL err = 0;
+          for (int k = 0; k < 10; k++) {
+            REAL dlt = REC(s, QP + xi[1 + k]) - (UCMD(s, 6 + k) + xf[1 + k]);
+            err += dlt * dlt;
+          }
+          out[0][s] = EXP(-err / xf[0]);
+        }
+      } break;
+      case REW_KBOT_LINVEL_TRACKING: {
+        /* train.py:273-299 */
+        int ucmd = xi[0], XQ = ti[TI_R_XQUAT];
+        for (int s = 0; s < T; s++) {
+          REAL rpy[3], zq[4], cmdv[3] = {UCMD(s, 0), UCMD(s, 1), 0}, g[3];
+          quat_to_euler(rpy, &REC(s, XQ + 4));
+          rpy[0] = rpy[1] = 0;
+          o_euler_to_quat(zq, rpy);
+          o_rot_vec_quat(g, cmdv, zq, 0);
+          REAL ex = REC(s, QV) - g[0], ey = REC(s, QV + 1) - g[1];
+          REAL ve = SQRT(ex * ex + ey * ey);
+          out[0][s] = EXP(-(ZERO_CMD(s) ? ve : ve * ve) / xf[0]);
+        }
+      } break;
+      case REW_KBOT_ANGVEL_TRACKING: {
+        /* train.py:302-313 */
+        int ucmd = xi[0];
+        for (int s = 0; s < T; s++) out[0][s] = EXP(-FABS(REC(s, QV + 5) - UCMD(s, 2)) / xf[0]);
+      } break;
+      case REW_KBOT_XY_ORIENTATION: {
+        /* train.py:316-343; floats [error_scale, error_scale_zero_cmd] */
+        int ucmd = xi[0], XQ = ti[TI_R_XQUAT];
+        for (int s = 0; s < T; s++) {
+          REAL rpy[3], q[4], ce[3] = {UCMD(s, 4), UCMD(s, 5), 0}, qc[4];
+          quat_to_euler(rpy, &REC(s, XQ + 4));
+          rpy[2] = 0;
+          o_euler_to_quat(q, rpy);
+          o_euler_to_quat(qc, ce);
+          REAL dt_ = qc[0] * q[0] + qc[1] * q[1] + qc[2] * q[2] + qc[3] * q[3];
+          out[0][s] = EXP(-((REAL)1 - dt_ * dt_) / (ZERO_CMD(s) ? xf[1] : xf[0]));
+        }
+      } break;
+      case REW_KBOT_TERRAIN_BASE_HEIGHT: {
+        /* train.py:346-401; ints [cmd, base, left, right]; floats [error_scale, standard_height, foot_origin_height] */
+        int ucmd = xi[0], XP = ti[TI_R_XPOS];
+        for (int s = 0; s < T; s++) {
+          REAL lf = REC(s, XP + 3 * xi[2] + 2) - xf[2], rf_ = REC(s, XP + 3 * xi[3] + 2) - xf[2];
+          REAL cur = REC(s, XP + 3 * xi[1] + 2) - (lf < rf_ ? lf : rf_);
+          out[0][s] = EXP(-FABS(cur - (UCMD(s, 3) + xf[1])) / xf[0]);
+        }
+      } break;
+      case REW_KBOT_FEET_ORIENTATION: {
+        /* train.py:404-467; ints [cmd, left, right]; `is_rotating` is ONE flag per trajectory: the reference takes the
+         * norm of the (T,) yaw-rate command column over axis -1, i.e. over time (train.py:464) */
+        int ucmd = xi[0], XQ = ti[TI_R_XQUAT];
+        REAL n2 = 0;
+        for (int s = 0; s < T; s++) n2 += UCMD(s, 2) * UCMD(s, 2);
+        int rotating = SQRT(n2) > (REAL)1e-3;
+        for (int s = 0; s < T; s++) {
+          REAL rpy[3];
+          quat_to_euler(rpy, &REC(s, XQ + 4));
+          REAL yaw = rpy[2], err = 0;
+          for (int f = 0; f < 2; f++) {
+            REAL se[3] = {f == 0 ? -PI_R / 2 : PI_R / 2, 0, yaw - PI_R}, sq[4];
+            const REAL* fq = &REC(s, XQ + 4 * xi[1 + f]);
+            if (rotating) {
+              REAL fe[3], fq2[4];
+              quat_to_euler(fe, fq);
+              fe[2] = 0; se[2] = 0;
+              o_euler_to_quat(fq2, fe);
+              o_euler_to_quat(sq, se);
+              REAL dt_ = sq[0] * fq2[0] + sq[1] * fq2[1] + sq[2] * fq2[2] + sq[3] * fq2[3];
+              err += (REAL)1 - dt_ * dt_;
+            } else {
+              o_euler_to_quat(sq, se);
+              REAL dt_ = sq[0] * fq[0] + sq[1] * fq[1] + sq[2] * fq[2] + sq[3] * fq[3];
+              err += (REAL)1 - dt_ * dt_;
+            }
+          }
+          out[0][s] = EXP(-err / xf[0]);
+        }
+      } break;
+      case REW_KBOT_COM_DISTANCE: {
+        /* train.py:470-484; ints [cmd, com_distance obs] */
+        int ucmd = xi[0];
+        for (int s = 0; s < T; s++) {
+          REAL dist = REC(s, OB + xi[1]);
+          out[0][s] = (dist >= 0 && ZERO_CMD(s)) ? EXP(-dist / xf[0]) : 0;
+        }
+      } break;
+      case REW_KBOT_BASE_ACCELERATION: {
+        /* train.py:487-497: edge-padded difference of qvel[:6], zeroed after a done */
+        for (int s = 0; s < T; s++) {
+          int prev = s > 0 ? s - 1 : 0;
+          int dn = REC(prev, DN) != 0;
+          REAL err = 0;
+          for (int k = 0; k < 6; k++) err += (dn || s == 0) ? 0 : FABS(REC(s, QV + k) - REC(prev, QV + k));
+          out[0][s] = EXP(-err / xf[0]);
+        }
+      } break;
+#undef UCMD
+#undef ZERO_CMD
       default: for (int c = 0; c < ncomp; c++) for (int s = 0; s < T; s++) out[c][s] = 0; break;
     }
     for (int c = 0; c < ncomp; c++) for (int s = 0; s < T; s++) out[c][s] *= scale;
@@ -1188,4 +1454,13 @@ int o_test_termination(const int* ti, const REAL* tf, int idx, const REAL* qpos,
   int v = termination(&t, e, idx);
   free(e);
   return v;
+}
+
+/* exported for tests: UnifiedCommand.initial_command for one key; COMDistanceObservation's geometry for one point set */
+void o_test_cmd_unified(const REAL* cf, const uint32_t* key, REAL* out) {
+  Key k = {key[0], key[1]};
+  cmd_unified_initial(cf, k, out);
+}
+REAL o_test_com_distance(const REAL* pts, int n, const REAL* com) {
+  return com_distance((const REAL (*)[2])pts, n < O_MAXCON ? n : O_MAXCON, com);
 }

@@ -249,40 +249,101 @@ def test_edge_cases(ctx) -> None:  # noqa: ANN001
 
 
 def test_kbot_parity_resynchronised(ctx, kbot_spec, kbot_randomizers) -> None:  # noqa: ANN001
-    """BASELINE config 3's robot through the K-Bot-sized instantiation (variant 1): capsule/plane contacts with
-    pyramidal cones, friction-loss rows, per-joint PD gains with action noise, latency, drop, force pushes, five
-    randomizers.  Same protocol and stated tolerances as the humanoid test (velocities: relative 5e-3 + 3e-2)."""
+    """BASELINE config 3's task (examples/kbot/train.py incl. its own plugins) through the K-Bot-sized instantiation
+    (variant 1): capsule/plane contacts with pyramidal cones, friction-loss rows, per-joint PD gains with action noise,
+    latency, drop, force pushes, five randomizers.  Resynchronised single-step protocol, stated tolerances
+    qpos 3e-4, qvel 3e-2 + 5e-3 |v|; keys, done / success / termination codes bit-exact.
+
+    Two references.  (a) The f32 oracle at the reference's solver caps (8 Newton x 8 line-search iterations).  With 40-70
+    constraint rows that iteration often stops at its cap before converging, so its output there is an unconverged
+    iterate; the CUDA solver (exact line search, factor reuse, up to 16 cheap iterations) converges further and differs
+    from it in those env-steps.  They are COUNTED (<= 3 %), and hard-bounded (qpos 2e-2, qvel 2.0).  (b) The f64 oracle run
+    to convergence (60 x 240 iterations) from the same state: the minimum both iterations approximate.  Against it the
+    CUDA path must be inside the tolerance on all but isolated (<= 0.3 %) env-steps -- measured: CUDA 1 of 960, the
+    reference-shaped f32 iteration 11 of 960 (tools/emu_accuracy.py)."""
+    from ksim_b200.examples.kbot import KbotConfig, make_spec
+    from ksim_b200.program import build_program
+    from oracle import OracleEngine
+
     n, steps = 32, 30
     eng = _engine(kbot_spec, kbot_randomizers, n, level=1.0, seed=5)
     assert eng.info("VARIANT") == 1
     ora, st, keys, rec0, _ = _oracle_init(eng)
+    conv = OracleEngine(build_program(make_spec(KbotConfig(iterations=60, ls_iterations=240))), "f64")
     p, m = eng.program, kbot_spec.model
     np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
-    np.testing.assert_allclose(_np(eng.state), st, rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(_np(eng.state), st, rtol=1e-3, atol=5e-5)
     actions = (0.3 * np.random.RandomState(6).randn(steps, n, eng.NA)).astype(np.float32)
     rec_o = np.zeros((2, n, eng.R), np.float32)
     rec_o[0] = rec0
+    rec_c = np.zeros((2, n, eng.R), np.float64)
     cur, nxt = (torch.zeros((n, eng.R), device="cuda") for _ in range(2))
     q, v, d, sc, te = p["TI_R_QPOS"], p["TI_R_QVEL"], p["TI_R_DONE"], p["TI_R_SUCCESS"], p["TI_R_TERM"]
-    n_bad = 0
+    rand64 = eng.env_init.rand.astype(np.float64)
+    n_bad = n_bad_conv = 0
     for s in range(steps):
         eng.state.copy_(torch.from_numpy(st).cuda())
         eng.keys.copy_(torch.from_numpy(keys.view(np.int32)).cuda())
         eng.step(torch.from_numpy(actions[s]).cuda(), cur, nxt)
+        st_c, keys_c = st.astype(np.float64), keys.copy()
+        conv.step_ctrl(actions[s].astype(np.float64), rand64, st_c, keys_c, rec_c[0], rec_c[1])
         ora.step_ctrl(actions[s], eng.env_init.rand, st, keys, rec_o[0], rec_o[1])
         g_cur = _np(cur)
         np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
         np.testing.assert_array_equal(g_cur[:, d], rec_o[0][:, d])
         np.testing.assert_array_equal(g_cur[:, sc], rec_o[0][:, sc])
         np.testing.assert_array_equal(g_cur[:, te : te + 3], rec_o[0][:, te : te + 3])
-        dq = np.abs(g_cur[:, q : q + m.nq] - rec_o[0][:, q : q + m.nq])
-        dv = np.abs(g_cur[:, v : v + m.nv] - rec_o[0][:, v : v + m.nv])
-        bad = (dq > 3e-4).any(axis=1) | (dv > 3e-2 + 5e-3 * np.abs(rec_o[0][:, v : v + m.nv])).any(axis=1)
-        assert dq.max() <= 2e-2 and dv.max() <= 2.0, (s, dq.max(), dv.max())
-        n_bad += int(bad.sum())
+        for ref, which in ((rec_o[0], "caps"), (rec_c[0], "converged")):
+            dq = np.abs(g_cur[:, q : q + m.nq] - ref[:, q : q + m.nq])
+            dv = np.abs(g_cur[:, v : v + m.nv] - ref[:, v : v + m.nv])
+            bad = (dq > 3e-4).any(axis=1) | (dv > 3e-2 + 5e-3 * np.abs(ref[:, v : v + m.nv])).any(axis=1)
+            assert dq.max() <= 2e-2 and dv.max() <= 2.0, (s, which, dq.max(), dv.max())
+            if which == "caps":
+                n_bad += int(bad.sum())
+            else:
+                n_bad_conv += int(bad.sum())
         rec_o[0] = rec_o[1]
-    assert n_bad <= max(1, int(0.003 * n * steps)), f"{n_bad} of {n * steps} env-steps outside the stated tolerance"
+    assert n_bad_conv <= max(1, int(0.003 * n * steps)), f"{n_bad_conv} of {n * steps} env-steps away from the converged solution"
+    assert n_bad <= int(0.03 * n * steps), f"{n_bad} of {n * steps} env-steps away from the reference-capped iteration"
     assert float(eng.state[:, p["TI_S_NONFINITE"]].sum()) == 0.0
+
+
+def test_kbot_task_plugins_on_gpu(ctx, kbot_spec, kbot_randomizers) -> None:  # noqa: ANN001
+    """The K-Bot task's own plugins through the C-ABI: unified command (bit-exact: RNG only), feet position / base height /
+    COM distance observations, TerrainBadZ codes (bit-exact), and the eleven rewards + carries over two consecutive rollouts
+    evaluated on the ORACLE's records (the reward kernel alone is under test)."""
+    n, t = 64, 25
+    eng = _engine(kbot_spec, kbot_randomizers, n, level=1.0, seed=11)
+    ora, st, keys, rec0, _ = _oracle_init(eng)
+    p = eng.program
+    actions = (0.4 * np.random.RandomState(12).randn(2 * t, n, eng.NA)).astype(np.float32)
+    rec_o = np.zeros((2 * t + 1, n, eng.R), np.float32)
+    rec_o[0] = rec0
+    cur, nxt = (torch.zeros((n, eng.R), device="cuda") for _ in range(2))
+    ob, cm, te = p["TI_R_OBS"], p["TI_R_CMD"], p["TI_R_TERM"]
+    for s in range(2 * t):
+        eng.state.copy_(torch.from_numpy(st).cuda())
+        eng.keys.copy_(torch.from_numpy(keys.view(np.int32)).cuda())
+        eng.step(torch.from_numpy(actions[s]).cuda(), cur, nxt)
+        ora.step_ctrl(actions[s], eng.env_init.rand, st, keys, rec_o[s], rec_o[s + 1])
+        g_cur, g_nxt = _np(cur), _np(nxt)
+        np.testing.assert_array_equal(g_nxt[:, cm : cm + 16], rec_o[s + 1][:, cm : cm + 16])
+        np.testing.assert_array_equal(g_cur[:, te : te + 3], rec_o[s][:, te : te + 3])
+        for name in ("feet_position", "base_height", "com_distance"):
+            o, dim, _ = p.obs_slices[name]
+            np.testing.assert_allclose(g_nxt[:, ob + o : ob + o + dim], rec_o[s + 1][:, ob + o : ob + o + dim], rtol=2e-3, atol=2e-3, err_msg=name)
+    assert len({tuple(r) for r in (rec_o[:, :, cm : cm + 6] != 0).reshape(-1, 6).tolist()}) >= 5
+    c = p["TI_REW_CARRY_SIZE"]
+    carry_o = np.zeros((n, c), np.float32)
+    eng.reward_carry.zero_()
+    for chunk in range(2):
+        r = np.ascontiguousarray(rec_o[chunk * t : (chunk + 1) * t])
+        total_o, comps_o = ora.rewards(r, eng.env_init.levels, carry_o)
+        total_g, comps_g = eng.rewards(torch.from_numpy(r).cuda(), t)
+        np.testing.assert_allclose(_np(comps_g), comps_o, rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(_np(total_g), total_o, rtol=2e-4, atol=1e-4)
+        np.testing.assert_allclose(_np(eng.reward_carry), carry_o, atol=1e-6)
+    assert np.abs(comps_o).sum(axis=(1, 2)).min() > 0
 
 
 def test_solver_paths_agree_at_full_size(ctx, monkeypatch) -> None:  # noqa: ANN001
