@@ -41,12 +41,38 @@ DEV void apply_overrides(const Mdl& m, Work<D>& w, const float* rand, LANE_ARG) 
 #pragma unroll
     for (int k = 0; k < 3; k++) { w.body_inertia[k][b] = inertia[3 * b + k]; w.body_ipos[k][b] = ipos[3 * b + k]; }
   }
+  const int* pgeom[2] = {MI(m, MH_PAIR_GEOM1), MI(m, MH_PAIR_GEOM2)};
+  if constexpr (!D::EXACT) {
+    const float* gpos = MF(m, MH_GEOM_POS);
+    const float* gsize = MF(m, MH_GEOM_SIZE);
+    LANE_FOR(p, DIM(NPAIR, MH_NPAIR)) {
+#pragma unroll
+      for (int sd = 0; sd < 2; sd++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) { w.pair_gpos[sd][k][p] = gpos[3 * pgeom[sd][p] + k]; w.pair_gsize[sd][k][p] = gsize[3 * pgeom[sd][p] + k]; }
+    }
+  }
   WSYNC();
   const int* ti = m.ti;
   const int n = ti[TI_N_RAND];
   int off = 0;
   for (int r = 0; r < n; r++) {
     const int code = TAB(ti, TI_RAND_TAB, r, TAB_AUX0), cnt = TAB(ti, TI_RAND_TAB, r, TAB_AUX1);
+    if (code == RAND_GEOM_SIZE || code == RAND_GEOM_POS) {
+      if constexpr (!D::EXACT) {
+        LANE_FOR(p, DIM(NPAIR, MH_NPAIR)) {
+#pragma unroll
+          for (int sd = 0; sd < 2; sd++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const float v = rand[off + 3 * pgeom[sd][p] + k];
+              if (code == RAND_GEOM_SIZE) w.pair_gsize[sd][k][p] = v; else w.pair_gpos[sd][k][p] = v;
+            }
+        }
+      }
+      off += cnt;
+      continue;
+    }
     LANE_FOR(k, cnt) {
       const float v = rand[off + k];
       switch (code) {

@@ -698,15 +698,25 @@ DEV void collision(const Mdl& m, Work<D>& w, LANE_ARG) {
     const int g1 = pg1[p], g2 = pg2[p];
     const int t1 = gtype[g1], t2 = gtype[g2];
     const int b1 = gbody[g1], b2 = gbody[g2];
-    V3 p1 = LD3(w.xpos, b1) + mulv(ldm9(w.xmat, b1), ldg3(gpos + 3 * g1));
-    V3 p2 = LD3(w.xpos, b2) + mulv(ldm9(w.xmat, b2), ldg3(gpos + 3 * g2));
+    // geom_pos / geom_size: per-env copies where the instantiation carries them (CollisionBodyRandomizer)
+    V3 gp1, gp2, gs1, gs2;
+    if constexpr (D::EXACT) {
+      gp1 = ldg3(gpos + 3 * g1); gp2 = ldg3(gpos + 3 * g2); gs1 = ldg3(gsize + 3 * g1); gs2 = ldg3(gsize + 3 * g2);
+    } else {
+      gp1 = v3(w.pair_gpos[0][0][p], w.pair_gpos[0][1][p], w.pair_gpos[0][2][p]);
+      gp2 = v3(w.pair_gpos[1][0][p], w.pair_gpos[1][1][p], w.pair_gpos[1][2][p]);
+      gs1 = v3(w.pair_gsize[0][0][p], w.pair_gsize[0][1][p], w.pair_gsize[0][2][p]);
+      gs2 = v3(w.pair_gsize[1][0][p], w.pair_gsize[1][1][p], w.pair_gsize[1][2][p]);
+    }
+    V3 p1 = LD3(w.xpos, b1) + mulv(ldm9(w.xmat, b1), gp1);
+    V3 p2 = LD3(w.xpos, b2) + mulv(ldm9(w.xmat, b2), gp2);
     M9 m1 = q2mat(qmul(LDQ(w.xquat, b1), ldgq(gquat + 4 * g1)));
     M9 m2 = q2mat(qmul(LDQ(w.xquat, b2), ldgq(gquat + 4 * g2)));
     const int c0 = conadr[p];
     float frame[9];
     if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) {
       V3 n = v3(m1.m[2], m1.m[5], m1.m[8]);
-      const float r = gsize[3 * g2];
+      const float r = gs2.x;
       const float dist = dot(p2 - p1, n) - r;
       V3 pos = p2 - n * (r + 0.5f * dist);
       make_frame(n, frame);
@@ -714,7 +724,7 @@ DEV void collision(const Mdl& m, Work<D>& w, LANE_ARG) {
     } else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) {
       V3 n = v3(m1.m[2], m1.m[5], m1.m[8]);
       V3 axis = v3(m2.m[2], m2.m[5], m2.m[8]);
-      const float r = gsize[3 * g2], half = gsize[3 * g2 + 1];
+      const float r = gs2.x, half = gs2.y;
       make_frame(n, frame);
       // tangent aligned with the capsule axis projected on the plane, when well defined (oracle/physics.c)
       const float dpa = dot(axis, n);
@@ -737,7 +747,7 @@ DEV void collision(const Mdl& m, Work<D>& w, LANE_ARG) {
       V3 dv = p2 - p1;
       const float len = sqrtf(dot(dv, dv));
       V3 n = len < MINVAL ? v3(1, 0, 0) : dv * (1.0f / len);
-      const float r1 = gsize[3 * g1], r2 = gsize[3 * g2];
+      const float r1 = gs1.x, r2 = gs2.x;
       const float dist = len - r1 - r2;
       V3 pos = p1 + n * (r1 + 0.5f * dist);
       make_frame(n, frame);
@@ -1635,6 +1645,9 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
   const int nv = DIM(NV, MH_NV), ne = w.nefc, nsparse = w.nsparse;
   const bool warmstart = !m.h[MH_DISABLE_WARMSTART];
   // ---- start point: costs at qacc_smooth and at the warm start in one pass over the rows
+  // (profile build: slots 16..21 = setup / gradient / refactorisation / substitution-only solve / direction + line search /
+  //  step + rows; slot 22 counts iterations, slot 23 refactorisations)
+  SUB_BEGIN();
   float gw = 0.0f;
   LANE_FOR(i, nv) w.s_search[i] = warmstart ? w.warm[i] - w.qacc_smooth[i] : 0.0f;
   WSYNC();
@@ -1667,6 +1680,7 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
   float cost = constraint_rows_track(w, ne, &changed, &moved, LANE_PASS) + gauss;
   constraint_force_scatter(w, nv, ne, nsparse, LANE_PASS);
   float prev_cost = INFINITY;
+  SUB_MARK(w, 16);
   const int iterations = m.h[MH_ITERATIONS];
   const float tol = m.mf[MF_TOLERANCE];
   const float scale = 1.0f / (m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1));
@@ -1679,14 +1693,19 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
     LANE_FOR(i, nv) { const float g = w.s_Ma[i] - w.qfrc_constraint[i]; w.s_grad[i] = g; gn += g * g; }
     gn = sqrtf(wsum(gn));
     WSYNC();
+    SUB_MARK(w, 17);
     if (iterations != 1 || niter > 0) {
       if ((prev_cost - cost) * scale < tol || gn * scale < tol) break;
     }
+    PROF_COUNT(w, 22);
     if (need_factor) {
       sparse_scatter(w, w.s_mv, nv, [&](int r) { return w.efc_active[r] ? w.efc_D[r] : 0.0f; }, LANE_PASS);
       factor_solve(m, w, FS_NEWTON_DIAG, w.s_Mgrad, w.s_grad, 0, LANE_PASS);
+      SUB_MARK(w, 18);
+      PROF_COUNT(w, 23);
     } else {
       fs_resolve(w, w.s_Mgrad, w.s_grad, nv, LANE_PASS);
+      SUB_MARK(w, 19);
     }
     LANE_FOR(i, nv) w.s_search[i] = -w.s_Mgrad[i];
     WSYNC();
@@ -1703,6 +1722,7 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
     qg2 = 0.5f * wsum(qg2);
     WSYNC();
     const float alpha = ls_newton(w, ne, qg1, qg2, LANE_PASS);
+    SUB_MARK(w, 20);
     if (alpha == 0.0f) break;
     LANE_FOR(i, nv) { w.s_qacc[i] = fmaf(alpha, w.s_search[i], w.s_qacc[i]); w.s_Ma[i] = fmaf(alpha, w.s_mv[i], w.s_Ma[i]); }
     LANE_FOR(r, ne) w.efc_Jaref[r] = fmaf(alpha, w.efc_jv[r], w.efc_Jaref[r]);
@@ -1712,6 +1732,7 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
     cost = constraint_rows_track(w, ne, &changed, &moved, LANE_PASS) + gauss;
     constraint_force_scatter(w, nv, ne, nsparse, LANE_PASS);
     need_factor = changed != 0;
+    SUB_MARK(w, 21);
     if (!moved && fabsf(alpha - 1.0f) < 1e-3f) break;
   }
   LANE_FOR(i, nv) { const float a = w.qacc_smooth[i] + w.s_qacc[i]; w.qacc[i] = a; w.warm[i] = a; }

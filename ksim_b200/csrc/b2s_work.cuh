@@ -58,6 +58,9 @@ struct Work {
   // ---- per-env model overrides (ksim/randomization.py); filled from the base model then the rand block ----
   float armature[D::NV], damping[D::NV], frictionloss[D::NV];
   float body_mass[D::NB], body_inertia[3][D::NB], body_ipos[3][D::NB];
+  // geom_pos / geom_size of the two geoms of every contact pair (CollisionBodyRandomizer, randomization.py:380-442);
+  // the exact-fit instantiation has no room to spare and reads the shared model instead (its task has no such override)
+  float pair_gpos[D::EXACT ? 1 : 2][3][D::NPAIR], pair_gsize[D::EXACT ? 1 : 2][3][D::NPAIR];
   // ---- position stage ----
   float xpos[3][D::NB], xquat[4][D::NB], xmat[9][D::NB], xipos[3][D::NB], ximat[9][D::NB];
   float subtree_com[3][D::NB], cinert[10][D::NB];

@@ -16,7 +16,7 @@ import numpy as np
 
 from ksim_b200 import rng as R
 from ksim_b200.program import TaskProgram
-from ksim_b200.randomization import PhysicsRandomizer
+from ksim_b200.randomization import PhysicsRandomizer, pair_friction_unaffected
 
 
 @dataclass
@@ -57,6 +57,11 @@ def make_env_init(program: TaskProgram, randomizers: Mapping[str, PhysicsRandomi
             if k in randomizations:
                 raise ValueError(f"Found duplicate randomization keys: {k}")
         randomizations.update(out)
+    if "geom_friction" in randomizations:
+        # contact pairs carry their own (compile-time mixed) friction: only a no-op override is supported (FloorFrictionRandomizer)
+        if not pair_friction_unaffected(model, randomizations["geom_friction"]):
+            raise NotImplementedError("per-env geom_friction that changes a contact pair's friction is not supported by the CUDA engine")
+        del randomizations["geom_friction"]
     if set(randomizations) != set(program.rand_slices):
         raise ValueError(f"randomizers produce {sorted(randomizations)}, the program expects {sorted(program.rand_slices)}")
     rand = np.zeros((num_envs, program.rand_size), dtype=np.float32)

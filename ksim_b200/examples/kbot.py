@@ -14,9 +14,9 @@ list (train.py:1144-1151), all twenty observations with their noise (train.py:11
 
 What differs, and why:
 * the floor is a plain plane (the reference takes its scene from the un-vendored ``mujoco_scenes`` package);
-* ``FloorFrictionRandomizer`` is omitted: the foot capsules have ``priority=1`` over the floor's 0, so MuJoCo takes the
-  capsule's friction for the pair and the floor's value never enters the contact model (robot.mjcf:23-25);
-* ``CollisionBodyRandomizer`` (per-env capsule size / position) is not supported by the engine yet.
+* ``FloorFrictionRandomizer`` is accepted and checked to be a no-op: the foot capsules have ``priority=1`` over the floor's
+  0, so MuJoCo takes the capsule's friction for the pair and the floor's value never enters the contact model
+  (robot.mjcf:23-25; ``randomization.pair_friction_unaffected``).
 
 ``make_spec(core_only=True)`` keeps the earlier reduced task (core ksim commands / rewards / ``BadZTermination``) that
 the round-1 measurements were taken with.
@@ -373,8 +373,13 @@ RANDOMIZERS = {
     "static_friction": lambda m: randomization.StaticFrictionRandomizer(),
     "armature": lambda m: randomization.ArmatureRandomizer(),
     "joint_damping": lambda m: randomization.JointDampingRandomizer(scale_lower=0.5, scale_upper=2.5),
+    "floor_friction": lambda m: randomization.FloorFrictionRandomizer.from_geom_name(model=m, floor_geom_name="floor", scale_lower=0.5,
+                                                                                     scale_upper=1.5),
     "all_body_COM": lambda m: randomization.AllBodiesCOMRandomizer(scale=0.05),
     "all_body_inertia": lambda m: randomization.AllBodiesInertiaRandomizer(scale=0.15),
+    "collision_body": lambda m: randomization.CollisionBodyRandomizer.from_geom_names(
+        model=m, geom_names=[f"{side}FootBushing_GPF_1517_12_collision_capsule_{k}" for side in "LR" for k in (0, 1)],
+        radius_scale=0.01, length_scale=0.03, position_jitter_x=0.020, position_jitter_y=0.005, position_jitter_z=0.005),
 }
 
 
@@ -453,7 +458,8 @@ def _spec(model: Model, metadata: Metadata, eng: EngineConfig, obs: dict, cmds: 
                                                                duration_range=(0.1, 0.5), interval_range=(0.0, 6.0)),
         },
         observations=obs, commands=cmds, rewards=rews, terminations=terms,
-        randomized_fields=("dof_frictionloss", "dof_armature", "dof_damping", "body_ipos", "body_mass", "body_inertia"),
+        randomized_fields=("dof_frictionloss", "dof_armature", "dof_damping", "body_ipos", "body_mass", "body_inertia", "geom_size",
+                           "geom_pos"),
     )
 
 

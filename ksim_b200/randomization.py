@@ -12,7 +12,8 @@ from __future__ import annotations
 __all__ = [
     "PhysicsRandomizer", "StaticFrictionRandomizer", "ArmatureRandomizer", "MassAdditionRandomizer",
     "MassMultiplicationRandomizer", "AllBodiesMassMultiplicationRandomizer", "JointDampingRandomizer",
-    "COMRandomizer", "AllBodiesCOMRandomizer", "AllBodiesInertiaRandomizer", "FIELD_CODES",
+    "COMRandomizer", "AllBodiesCOMRandomizer", "AllBodiesInertiaRandomizer", "FloorFrictionRandomizer",
+    "CollisionBodyRandomizer", "FIELD_CODES", "pair_friction_unaffected",
 ]
 
 from abc import ABC, abstractmethod
@@ -32,6 +33,8 @@ FIELD_CODES = {
     "body_mass": C.RAND_BODY_MASS,
     "body_inertia": C.RAND_BODY_INERTIA,
     "body_ipos": C.RAND_BODY_IPOS,
+    "geom_size": C.RAND_GEOM_SIZE,
+    "geom_pos": C.RAND_GEOM_POS,
 }
 
 _F32 = np.float32
@@ -177,3 +180,75 @@ class AllBodiesInertiaRandomizer(PhysicsRandomizer):
         mass = model.body_mass.astype(_F32)[None] * mass_scaling
         inertia = model.body_inertia.astype(_F32)[None] * mass_scaling[:, :, None] * pert
         return {"body_mass": mass.astype(_F32), "body_inertia": inertia.astype(_F32)}
+
+
+@attrs.define(frozen=True, kw_only=True)
+class FloorFrictionRandomizer(PhysicsRandomizer):
+    """randomization.py:75-104: scales nothing, *sets* the floor geom's sliding friction to U(lower, upper).
+
+    The engine's contact pairs carry their own friction, mixed from the two geoms at model-compile time by MuJoCo's rule
+    (higher ``priority`` wins, else the maximum).  ``make_env_init`` therefore accepts this randomizer only when the rule
+    makes it a no-op for every pair of the model (``pair_friction_unaffected``) -- the K-Bot's foot capsules have
+    ``priority=1`` over the floor's 0 (robot.mjcf:23-25) -- and raises otherwise."""
+
+    floor_geom_id: int = attrs.field()
+    scale_lower: float = attrs.field(default=0.4)
+    scale_upper: float = attrs.field(default=1.0)
+
+    def __call__(self, model: Model, rng: np.ndarray) -> dict[str, np.ndarray]:
+        fr = np.broadcast_to(model.arrays["geom_friction"].astype(_F32)[None], (rng.shape[0], model.ngeom, 3)).copy()
+        fr[:, self.floor_geom_id, 0] = _u(rng, 1, self.scale_lower, self.scale_upper)[:, 0]
+        return {"geom_friction": fr}
+
+    @classmethod
+    def from_geom_name(cls, model: Model, floor_geom_name: str, scale_lower: float = 0.4, scale_upper: float = 1.0) -> "FloorFrictionRandomizer":
+        return cls(floor_geom_id=model.id("geom", floor_geom_name), scale_lower=scale_lower, scale_upper=scale_upper)
+
+
+def pair_friction_unaffected(model: Model, geom_friction: np.ndarray) -> bool:
+    """True when per-env ``geom_friction`` (E, ngeom, 3) cannot change any contact pair's friction: every changed geom
+    only meets geoms of strictly higher priority."""
+    base = model.arrays["geom_friction"].astype(_F32)
+    changed = np.nonzero((geom_friction != base[None]).any(axis=(0, 2)))[0]
+    prio = model.arrays["geom_priority"]
+    for g1, g2 in zip(model.arrays["pair_geom1"], model.arrays["pair_geom2"]):
+        for a, b in ((g1, g2), (g2, g1)):
+            if a in changed and not prio[b] > prio[a]:
+                return False
+    return True
+
+
+@attrs.define(frozen=True, kw_only=True)
+class CollisionBodyRandomizer(PhysicsRandomizer):
+    """randomization.py:380-487: per-env capsule radius / half-length scaling and position jitter of the listed geoms."""
+
+    geom_ids: tuple[int, ...] = attrs.field()
+    radius_scale: float = attrs.field(default=0.05)
+    length_scale: float = attrs.field(default=0.05)
+    position_jitter_x: float = attrs.field(default=0.001)
+    position_jitter_y: float = attrs.field(default=0.001)
+    position_jitter_z: float = attrs.field(default=0.001)
+
+    def __call__(self, model: Model, rng: np.ndarray) -> dict[str, np.ndarray]:
+        e, n = rng.shape[0], len(self.geom_ids)
+        pair = R.split(rng, 2); rng, radius_rng = pair[:, 0], pair[:, 1]
+        pair = R.split(rng, 2); rng, length_rng = pair[:, 0], pair[:, 1]
+        pos_rng = R.split(rng, 2)[:, 1]
+        rs = _u(radius_rng, n, 1.0 - self.radius_scale, 1.0 + self.radius_scale)
+        ls = _u(length_rng, n, 1.0 - self.length_scale, 1.0 + self.length_scale)
+        jit = np.array([self.position_jitter_x, self.position_jitter_y, self.position_jitter_z], dtype=_F32)
+        off = _u(pos_rng, 3 * n, np.tile(-jit, n), np.tile(jit, n)).reshape(e, n, 3)
+        size = np.broadcast_to(model.arrays["geom_size"].astype(_F32)[None], (e, model.ngeom, 3)).copy()
+        pos = np.broadcast_to(model.arrays["geom_pos"].astype(_F32)[None], (e, model.ngeom, 3)).copy()
+        for i, g in enumerate(self.geom_ids):
+            size[:, g, 0] = size[:, g, 0] * rs[:, i]
+            size[:, g, 1] = size[:, g, 1] * ls[:, i]
+            pos[:, g] = pos[:, g] + off[:, i]
+        return {"geom_size": size, "geom_pos": pos}
+
+    @classmethod
+    def from_geom_names(cls, model: Model, geom_names: list[str] | tuple[str, ...], radius_scale: float = 0.05,
+                        length_scale: float = 0.05, position_jitter_x: float = 0.001, position_jitter_y: float = 0.001,
+                        position_jitter_z: float = 0.001) -> "CollisionBodyRandomizer":
+        return cls(geom_ids=tuple(model.id("geom", n) for n in geom_names), radius_scale=radius_scale, length_scale=length_scale,
+                   position_jitter_x=position_jitter_x, position_jitter_y=position_jitter_y, position_jitter_z=position_jitter_z)

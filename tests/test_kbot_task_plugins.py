@@ -316,3 +316,37 @@ def test_warp_code_matches_oracle_on_the_task_plugins(oracle_built, kbot_program
     np.testing.assert_allclose(comps_e, comps_o, rtol=2e-4, atol=2e-5)
     np.testing.assert_allclose(total_e, total_o, rtol=2e-4, atol=1e-4)
     np.testing.assert_allclose(carry_e, carry_o, atol=1e-6)
+
+
+def test_collision_body_and_floor_friction_randomizers(kbot_spec, kbot_randomizers, kbot_program) -> None:  # noqa: ANN001
+    """randomization.py:75-104, 380-442: value ranges, untouched geoms, key discipline (three successive splits), and the
+    floor-friction override being accepted only as the no-op it is for this model."""
+    from ksim_b200 import randomization
+    from ksim_b200.envinit import make_env_init
+
+    m = kbot_spec.model
+    cb = kbot_randomizers["collision_body"]
+    keys = R.split(R.prng_key(3), 50)
+    out = cb(m, keys)
+    size0, pos0 = m.arrays["geom_size"].astype(np.float32), m.arrays["geom_pos"].astype(np.float32)
+    others = [g for g in range(m.ngeom) if g not in cb.geom_ids]
+    np.testing.assert_array_equal(out["geom_size"][:, others], np.broadcast_to(size0[others], (50, len(others), 3)))
+    np.testing.assert_array_equal(out["geom_pos"][:, others], np.broadcast_to(pos0[others], (50, len(others), 3)))
+    g = list(cb.geom_ids)
+    rs, ls = out["geom_size"][:, g, 0] / size0[g, 0], out["geom_size"][:, g, 1] / size0[g, 1]
+    assert (np.abs(rs - 1) <= 0.01 + 1e-6).all() and (np.abs(ls - 1) <= 0.03 + 1e-6).all() and rs.std() > 1e-3 and ls.std() > 1e-3
+    np.testing.assert_array_equal(out["geom_size"][:, g, 2], np.broadcast_to(size0[g, 2], (50, 4)))
+    d = out["geom_pos"][:, g] - pos0[g]
+    assert (np.abs(d) <= np.array([0.020, 0.005, 0.005]) + 1e-6).all() and (d.std(axis=(0, 1)) > 1e-4).all()
+    # key discipline of the first draw: rng, radius_rng = split(rng); uniform(radius_rng, (4,), .99, 1.01)
+    want = R.uniform(R.split(keys[7], 2)[1], 4, 0.99, 1.01) * size0[g, 0]
+    np.testing.assert_array_equal(out["geom_size"][7, g, 0], want.astype(np.float32))
+    # the program carries both fields; the floor-friction override is dropped as a checked no-op
+    assert {"geom_size", "geom_pos"} <= set(kbot_program.rand_slices) and "geom_friction" not in kbot_program.rand_slices
+    init = make_env_init(kbot_program, kbot_randomizers, 4, seed=0, level=1.0)
+    o, c = kbot_program.rand_slices["geom_size"]
+    assert (init.rand[:, o : o + c].reshape(4, m.ngeom, 3)[:, g, 0] != size0[g, 0]).any()
+    ff = randomization.FloorFrictionRandomizer(floor_geom_id=int(cb.geom_ids[0]), scale_lower=0.5, scale_upper=1.5)  # a foot capsule
+    assert not randomization.pair_friction_unaffected(m, ff(m, keys)["geom_friction"])
+    with pytest.raises(NotImplementedError):
+        make_env_init(kbot_program, {**kbot_randomizers, "floor_friction": ff}, 4, seed=0, level=1.0)

@@ -16,8 +16,9 @@ from ksim_b200.engine import B200Engine
 
 NAMES = ["kinematics", "com_pos+crb", "collision+com_vel+constraint", "passive+rne+actuation", "acceleration (M solve, Z)", "solve",
          "post-solve barrier", "sensors_acc", "implicit solve+integrate", "ctrl/actuators/events/rng", "action load", "terminations/record/reset/commands",
-         "observe", " solve path: primal (dof space)", " solve path: dual (shared memory)", "(engine_step total)", " solve: dual_setup", " solve: start-point costs", " solve: dual_direction", " solve: convergence check + vote",
-         " solve: line search (incl. votes)", " solve: step update + row costs", " solve path: dual8 (registers)", "",
+         "observe", " solve path: primal (dof space)", " solve path: dual (shared memory)", "(engine_step total)", " solve: setup (dual_setup | newton_dof start point)", " solve: start-point costs | newton_dof gradient", " solve: dual_direction | newton_dof refactorisation",
+         " solve: convergence check + vote | newton_dof substitution-only solve", " solve: line search (newton_dof: + direction, jv)", " solve: step update + row costs",
+         " solve path: dual8 (registers) cycles | newton_dof ITERATION COUNT", " newton_dof REFACTORISATION COUNT",
          " kin: A0 sin/cos", " kin: A local transforms", " kin: B level compose", " kin: C matrices/anchors/sites", "", "", "", ""]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 t = int(sys.argv[2]) if len(sys.argv) > 2 else 16
