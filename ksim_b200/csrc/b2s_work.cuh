@@ -48,8 +48,16 @@ using DimsGeneric = Dims<33, 32, 32, 32, 32, 8, 96, 8, 16, 64, 32, 32, false>;
 // model dimension: compile-time when the traits match the model exactly
 #define DIM(X, H) (D::EXACT ? (int)D::X : m.h[H])
 
+// geom_pos / geom_size of the two geoms of every contact pair, per environment (CollisionBodyRandomizer,
+// randomization.py:380-442).  The exact-fit instantiation has no shared memory to spare (its workspaces, the model and the
+// task program fill the SM) and its task has no such override: it reads the shared model instead and carries nothing.
+template <class D, bool EXACT>
+struct PairGeom { float pair_gpos[2][3][D::NPAIR], pair_gsize[2][3][D::NPAIR]; };
 template <class D>
-struct Work {
+struct PairGeom<D, true> {};
+
+template <class D>
+struct Work : PairGeom<D, D::EXACT> {
   // ---- persistent per-env state (mirrors the HBM state block) ----
   float qpos[D::NQ], qvel[D::NV], qacc[D::NV], warm[D::NV], ctrl[D::NU];
   float last_ctrl[D::NA], zero_off[D::NU], event[D::EVS], act_state[D::ACS], cmd[D::CMDS], obs_carry[D::OCS];
@@ -58,9 +66,6 @@ struct Work {
   // ---- per-env model overrides (ksim/randomization.py); filled from the base model then the rand block ----
   float armature[D::NV], damping[D::NV], frictionloss[D::NV];
   float body_mass[D::NB], body_inertia[3][D::NB], body_ipos[3][D::NB];
-  // geom_pos / geom_size of the two geoms of every contact pair (CollisionBodyRandomizer, randomization.py:380-442);
-  // the exact-fit instantiation has no room to spare and reads the shared model instead (its task has no such override)
-  float pair_gpos[D::EXACT ? 1 : 2][3][D::NPAIR], pair_gsize[D::EXACT ? 1 : 2][3][D::NPAIR];
   // ---- position stage ----
   float xpos[3][D::NB], xquat[4][D::NB], xmat[9][D::NB], xipos[3][D::NB], ximat[9][D::NB];
   float subtree_com[3][D::NB], cinert[10][D::NB];

@@ -75,6 +75,8 @@ extern "C" int emu_rewards(const void* blob, int n, int T, const float* rec, con
 }
 
 extern "C" int emu_sizeof_work(void) { return (int)sizeof(Work<DimsHumanoid>); }
+extern "C" int emu_sizeof_work_kbot(void) { return (int)sizeof(Work<DimsKbot>); }
+extern "C" int emu_sizeof_mdl(void) { return (int)sizeof(Mdl); }
 
 // Debug aid for tests: forward kinematics of one configuration with the base model; xpos[nb][3], xquat[nb][4],
 // xanchor[nj][3], xaxis[nj][3]; rand = one env's override block.

@@ -150,3 +150,17 @@ def test_kbot_single_step_parity(emu, sync_mask, oracle_built, kbot_spec, kbot_r
     np.testing.assert_array_equal(rec_e[:25, :, d], rec_o[:25, :, d])
     np.testing.assert_array_equal(rec_e[:25, :, tm : tm + 3], rec_o[:25, :, tm : tm + 3])
     assert np.isfinite(rec_o[:25]).all() and rec_o[:25, :, q + 2].min() > 0.3, "the robot should still be standing"
+
+
+def test_humanoid_model_and_task_program_fit_next_to_14_workspaces(emu, walking_program) -> None:  # noqa: ANN001
+    """The exact-fit budget the humanoid kernel's speed depends on (configure() in ksim_b200/csrc/b200sim.cu):
+    14 per-env workspaces + the model view + all four model / task-program arrays within 227 KB of shared memory.  The
+    device structs have the same layout as the host build's except for the host-only Linv_diag array."""
+    prog = walking_program
+    m = prog.spec.model
+    blob = np.frombuffer(pack_blob(m, prog.ti, prog.tf), dtype=np.int32)
+    words = int(blob.size) - C.MH_SIZE
+    work_device = emu.emu_sizeof_work() - 4 * m.nv   # Linv_diag[NV] exists in the host build only
+    need = 14 * work_device + emu.emu_sizeof_mdl() + 16 + 4 * words
+    assert need <= 227 * 1024, (need, 227 * 1024, work_device)
+    assert (227 * 1024 - emu.emu_sizeof_mdl() - 16) // (emu.emu_sizeof_work_kbot() - 4 * 26) >= 8   # K-Bot: 8 envs per SM
