@@ -82,6 +82,13 @@ int b200sim_gae(void* stream, int batch, int n_steps, const float* values, const
 int b200sim_extract_flags(const b200sim_model* model, void* stream, int n_envs, int n_steps, const float* rec,
                           uint8_t* dones, uint8_t* successes);
 
+/* TrajectoryDatasetWriter.write (ksim/dataset.py:59-103) for every env at once: out[N][sample_size] fp32, one flattened
+ * trajectory sample per env, fields in the order of the table.  fields[n_fields][4] int32 in DEVICE memory:
+ * {source, offset, dim, out_offset}; source 0 = record (float offset inside a record, emits [T][dim]), 1 = reward total
+ * (emits [T]), 2 = reward component number `offset` (emits [T]).  rec[T][N][R]; total[N][T]; comps[K][N][T]. */
+int b200sim_dataset_pack(void* stream, int n_envs, int n_steps, int rec_size, const float* rec, const float* total,
+                         const float* comps, const int32_t* fields, int n_fields, int sample_size, float* out);
+
 #ifdef __cplusplus
 }
 #endif

