@@ -148,7 +148,7 @@ def run_reference(args: argparse.Namespace) -> None:
     dt = (time.perf_counter() - t0) / args.steps
     value = n * t / dt
     sample = f"{n} envs x {t} control steps per step (same plugin set), f32 C oracle, OpenMP over envs"
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": _config(args.gpus),
@@ -189,7 +189,20 @@ def cpu_baseline_leg() -> dict:
             "sample": f"{reps} x ({n} envs x {t} control steps), f32 C oracle of the same path, OpenMP over envs, ~10 s"}
 
 
+_JSON_FD = 1
+
+
+def _emit(line: str) -> None:
+    """The ONE stdout line of the contract.  Everything else a library prints to fd 1 (NCCL announces its version there when
+    the first communicator is built) has been routed to stderr by main()."""
+    os.write(_JSON_FD, (line + "\n").encode())
+
+
 def main() -> None:
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -355,7 +368,7 @@ def main() -> None:
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg()
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     D.shutdown()
 
 

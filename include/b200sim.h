@@ -82,6 +82,18 @@ int b200sim_gae(void* stream, int batch, int n_steps, const float* values, const
 int b200sim_extract_flags(const b200sim_model* model, void* stream, int n_envs, int n_steps, const float* rec,
                           uint8_t* dones, uint8_t* successes);
 
+/* Per-iteration reductions over the (N, T) trajectory that the curricula and the logged metrics consume
+ * (Trajectory.episode_length types.py:72-76; get_termination_metrics / get_reward_metrics rl.py:1544-1573;
+ * curriculum.py:125,187,262).  per_env[N][B2S_METRICS_FIXED + 8 + 1 + K] scratch/out:
+ *   [0] episode_length, [1] deaths = sum(done), [2] max |qpos[:3]|, [3] steps with any termination,
+ *   [4..12) sum of each termination component's codes (up to 8), [12] sum of the total reward, [13..13+K) component sums.
+ * out[4 + 8 + 1 + K]: [0] mean episode length, [1] mean deaths (mean_terminations), [2] max distance from the origin,
+ *   [3] num_terminations (clipped to >= 1), [4..12) prct/<termination> = code sum / num_terminations,
+ *   [12] mean total reward per (env, step), [13..) mean of each reward component.  Deterministic (fixed reduction order). */
+#define B2S_METRICS_FIXED 13
+int b200sim_metrics(const b200sim_model* model, void* stream, int n_envs, int n_steps, const float* rec, const float* total,
+                    const float* comps, float* per_env, float* out);
+
 /* TrajectoryDatasetWriter.write (ksim/dataset.py:59-103) for every env at once: out[N][sample_size] fp32, one flattened
  * trajectory sample per env, fields in the order of the table.  fields[n_fields][4] int32 in DEVICE memory:
  * {source, offset, dim, out_offset}; source 0 = record (float offset inside a record, emits [T][dim]), 1 = reward total

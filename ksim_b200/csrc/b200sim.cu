@@ -196,6 +196,76 @@ __global__ void __launch_bounds__(1024) k_gae_normalize(size_t n, float* __restr
   for (size_t i = tid; i < n; i += 1024) adv[i] = (adv[i] - mean) / sd;
 }
 
+// Trajectory metrics, stage 1: one warp per environment, lanes over time steps (warp-shuffle reductions).
+__global__ void __launch_bounds__(256) k_metrics_env(int n_envs, int n_steps, int R, int off_done, int off_time, int off_qpos,
+                                                     int off_term, int n_term, int n_comp, const float* __restrict__ rec,
+                                                     const float* __restrict__ total, const float* __restrict__ comps,
+                                                     float* __restrict__ per_env) {
+  const int lane = threadIdx.x & 31;
+  const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (env >= n_envs) return;
+  const int W = B2S_METRICS_FIXED + n_comp;
+  float tsum = 0.0f, dm = 0.0f, deaths = 0.0f, maxd = 0.0f, anyt = 0.0f, rsum = 0.0f;
+  float ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = lane; t < n_steps; t += 32) {
+    const float* r = rec + ((size_t)t * n_envs + env) * R;
+    const bool done = r[off_done] != 0.0f;
+    const bool mask = done || t == n_steps - 1;   // done.at[..., -1].set(True)
+    tsum += mask ? r[off_time] : 0.0f;
+    dm += mask ? 1.0f : 0.0f;
+    deaths += done ? 1.0f : 0.0f;
+    maxd = fmaxf(maxd, sqrtf(r[off_qpos] * r[off_qpos] + r[off_qpos + 1] * r[off_qpos + 1] + r[off_qpos + 2] * r[off_qpos + 2]));
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < n_term) { const float c = r[off_term + k]; ts[k] += c; any |= c != 0.0f; }
+    anyt += any ? 1.0f : 0.0f;
+    rsum += total[(size_t)env * n_steps + t];
+  }
+  tsum = wsum(tsum); dm = wsum(dm); deaths = wsum(deaths); maxd = wmax(maxd); anyt = wsum(anyt); rsum = wsum(rsum);
+#pragma unroll
+  for (int k = 0; k < 8; k++) ts[k] = wsum(ts[k]);
+  float* o = per_env + (size_t)env * W;
+  if (lane == 0) {
+    o[0] = tsum / dm; o[1] = deaths; o[2] = maxd; o[3] = anyt; o[12] = rsum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[4 + k] = ts[k];
+  }
+  for (int c = 0; c < n_comp; c++) {
+    float cs = 0.0f;
+    const float* row = comps + ((size_t)c * n_envs + env) * n_steps;
+    for (int t = lane; t < n_steps; t += 32) cs += row[t];
+    cs = wsum(cs);
+    if (lane == 0) o[B2S_METRICS_FIXED + c] = cs;
+  }
+}
+
+// stage 2: one CTA, fixed order, fp64 accumulators -> out[]
+__global__ void __launch_bounds__(256) k_metrics_reduce(int n_envs, int n_steps, int n_comp, const float* __restrict__ per_env,
+                                                        float* __restrict__ out) {
+  __shared__ double red[256];
+  const int W = B2S_METRICS_FIXED + n_comp, tid = threadIdx.x;
+  for (int j = 0; j < W; j++) {
+    double a = 0.0;
+    for (int e = tid; e < n_envs; e += 256) { const double v = per_env[(size_t)e * W + j]; a = j == 2 ? (v > a ? v : a) : a + v; }
+    red[tid] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o) red[tid] = j == 2 ? (red[tid + o] > red[tid] ? red[tid + o] : red[tid]) : red[tid] + red[tid + o];
+      __syncthreads();
+    }
+    if (tid == 0) out[j] = (float)red[0];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float n = (float)n_envs, nt = (float)n_envs * (float)n_steps;
+    out[0] /= n; out[1] /= n;
+    const float num = fmaxf(out[3], 1.0f);
+    out[3] = num;
+    for (int k = 0; k < 8; k++) out[4 + k] /= num;
+    for (int j = 12; j < W; j++) out[j] /= nt;
+  }
+}
+
 // TrajectoryDatasetWriter.write (ksim/dataset.py:59-103): one CTA per environment gathers its T records (and its reward
 // rows) into one flattened sample; writes are contiguous, record reads contiguous along each field.
 __global__ void __launch_bounds__(256) k_dataset_pack(int n_envs, int n_steps, int R, const float* __restrict__ rec,
@@ -435,6 +505,23 @@ extern "C" int b200sim_dataset_pack(void* stream, int n_envs, int n_steps, int r
   if (!rec || !fields || !out) return fail(B2S_ERR_BAD_ARG, "null argument");
   k_dataset_pack<<<n_envs, 256, 0, (cudaStream_t)stream>>>(n_envs, n_steps, rec_size, rec, total, comps, fields, n_fields,
                                                           sample_size, out);
+  CUDA_OK(cudaGetLastError());
+  return B2S_OK;
+}
+
+extern "C" int b200sim_metrics(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* rec, const float* total,
+                               const float* comps, float* per_env, float* out) {
+  if (!mo || n_envs < 0 || n_steps < 0) return fail(B2S_ERR_BAD_ARG, "bad argument");
+  if (n_envs == 0 || n_steps == 0) return B2S_OK;
+  if (!rec || !total || !per_env || !out) return fail(B2S_ERR_BAD_ARG, "null argument");
+  const int* ti = mo->ti_host.data();
+  const int n_term = ti[TI_N_TERM], n_comp = ti[TI_N_REW_COMP];
+  if (n_term > 8) return fail(B2S_ERR_UNSUPPORTED, "more than 8 termination components");
+  if (n_comp > 0 && !comps) return fail(B2S_ERR_BAD_ARG, "comps is required for this task");
+  k_metrics_env<<<(unsigned)(((size_t)n_envs * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      n_envs, n_steps, ti[TI_REC_SIZE], ti[TI_R_DONE], ti[TI_R_TIME], ti[TI_R_QPOS], ti[TI_R_TERM], n_term, n_comp, rec, total, comps, per_env);
+  CUDA_OK(cudaGetLastError());
+  k_metrics_reduce<<<1, 256, 0, (cudaStream_t)stream>>>(n_envs, n_steps, n_comp, per_env, out);
   CUDA_OK(cudaGetLastError());
   return B2S_OK;
 }

@@ -245,6 +245,28 @@ class B200Engine:
         self.launches += 1
         return total, comps
 
+    def metrics(self, rec: torch.Tensor, total: torch.Tensor, comps: torch.Tensor, n_steps: int | None = None) -> dict[str, torch.Tensor]:
+        """The per-iteration trajectory reductions the curricula and the logger consume: ``Trajectory.episode_length``
+        (types.py:72-76), ``get_termination_metrics`` / ``get_reward_metrics`` (rl.py:1544-1573), the inputs of
+        ``EpisodeLengthCurriculum`` / ``DistanceFromOriginCurriculum`` / ``StepWhenSaturated`` (curriculum.py:125,187,262).
+        Returns 0-d / 1-d device tensors; ``episode_length`` and ``deaths`` are per environment."""
+        t = int(rec.shape[0]) if n_steps is None else int(n_steps)
+        n, k = self.num_envs, self.program["TI_N_REW_COMP"]
+        width = 13 + k
+        per_env = torch.empty((n, width), dtype=torch.float32, device=self.device)
+        out = torch.empty((width,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            binding.check(self.lib.b200sim_metrics(self._handle, self._stream(), n, t, _ptr(rec), _ptr(total), _ptr(comps),
+                                                   _ptr(per_env), _ptr(out)), "b200sim_metrics")
+        self.launches += 2
+        res = {"episode_length": per_env[:, 0], "deaths": per_env[:, 1], "mean_episode_length": out[0], "mean_terminations": out[1],
+               "max_distance_from_origin": out[2], "num_terminations": out[3], "reward/_total": out[12]}
+        for i, name in enumerate(self.program.termination_names):
+            res[f"prct/{name}"] = out[4 + i]
+        for i, name in enumerate(self.program.reward_components):
+            res[f"reward/{name}"] = out[13 + i]
+        return res
+
     def flags(self, rec: torch.Tensor, n_steps: int) -> tuple[torch.Tensor, torch.Tensor]:
         n = self.num_envs
         dones = torch.empty((n, n_steps), dtype=torch.uint8, device=self.device)

@@ -58,3 +58,40 @@ def test_pack_and_write_match_numpy(tmp_path, walking_spec, walking_randomizers)
     o = sum(int(np.prod(s)) for s in meta["shapes"][:i])
     qpos = data[3, o : o + int(np.prod(meta["shapes"][i]))].reshape(meta["shapes"][i])
     np.testing.assert_array_equal(qpos, eng.view(rec[:t]).qpos[:, 3].cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_trajectory_metrics_match_the_reference_formulas(walking_spec, walking_randomizers) -> None:  # noqa: ANN001
+    """Trajectory.episode_length (types.py:72-76), get_termination_metrics / get_reward_metrics (rl.py:1544-1573) and the
+    curriculum inputs (curriculum.py:125,187,262) restated in numpy over the same records."""
+    import torch
+
+    from ksim_b200.engine import B200Engine
+
+    n, t = 200, 48
+    eng = B200Engine(walking_spec, n, randomizers=walking_randomizers, seed=5, curriculum_level=1.0)
+    rec = eng.rollout(0.5 * torch.randn((t, n, eng.NA), device="cuda"))
+    total, comps = eng.rewards(rec, t)
+    got = {k: v.cpu().numpy() for k, v in eng.metrics(rec[:t], total, comps).items()}
+    tv = eng.view(rec[:t])
+    done = tv.done.cpu().numpy().T                      # (N, T)
+    timestep = tv.timestep.cpu().numpy().T
+    qpos = tv.qpos.cpu().numpy().transpose(1, 0, 2)
+    p = eng.program
+    terms = rec[:t, :, p["TI_R_TERM"] : p["TI_R_TERM"] + len(p.termination_names)].cpu().numpy().transpose(1, 0, 2)
+    assert done.sum() > 0
+    mask = done.copy(); mask[:, -1] = True
+    ep = np.where(mask, timestep, 0.0).sum(-1) / mask.sum(-1)
+    np.testing.assert_allclose(got["episode_length"], ep, rtol=1e-5)
+    np.testing.assert_allclose(got["mean_episode_length"], ep.mean(), rtol=1e-5)
+    np.testing.assert_allclose(got["deaths"], done.sum(-1))
+    np.testing.assert_allclose(got["mean_terminations"], done.sum(-1).mean(), rtol=1e-6)
+    np.testing.assert_allclose(got["max_distance_from_origin"], np.linalg.norm(qpos[..., :3], axis=-1).max(), rtol=1e-6)
+    num = max((terms != 0).any(-1).sum(), 1)
+    assert got["num_terminations"] == num
+    for i, name in enumerate(p.termination_names):
+        np.testing.assert_allclose(got[f"prct/{name}"], terms[..., i].sum() / num, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(got["reward/_total"], total.cpu().numpy().mean(), rtol=1e-4, atol=1e-6)
+    cm = comps.cpu().numpy()
+    for i, name in enumerate(p.reward_components):
+        np.testing.assert_allclose(got[f"reward/{name}"], cm[i].mean(), rtol=1e-4, atol=1e-6)
