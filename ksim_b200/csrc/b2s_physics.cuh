@@ -1688,7 +1688,11 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
   // The exact line search and the factor reuse make an iteration cheap, and a cold start (after a reset) with many
   // contact rows can need more than the reference's cap to settle its active set: up to 2x `iterations` are allowed, so
   // that what is returned is the converged minimum rather than wherever the cap happened to stop the reference.
-  for (int niter = 0; niter < 2 * iterations; niter++) {
+#ifndef B2S_NDOF_ITER_NUM
+#define B2S_NDOF_ITER_NUM 2   // iteration cap = B2S_NDOF_ITER_NUM / B2S_NDOF_ITER_DEN x the model's `iterations`
+#define B2S_NDOF_ITER_DEN 1
+#endif
+  for (int niter = 0; niter < (B2S_NDOF_ITER_NUM * iterations) / B2S_NDOF_ITER_DEN; niter++) {
     float gn = 0.0f;
     LANE_FOR(i, nv) { const float g = w.s_Ma[i] - w.qfrc_constraint[i]; w.s_grad[i] = g; gn += g * g; }
     gn = sqrtf(wsum(gn));

@@ -3,8 +3,9 @@
 // The device code in ksim_b200/csrc/*.cuh is written as lane-parallel phases (LANE_FOR / WSYNC).  Compiled
 // with B2S_EMU those phases become plain loops, which lets GPU-less machines run the *same source* against
 // the CPU oracle to catch logic errors before spending GPU time.  It is never imported by ksim_b200, is not a
-// fallback of any product path, and says nothing about races (those are checked on the GPU with
-// compute-sanitizer); only tests/test_emu_vs_oracle.py builds and loads it.
+// fallback of any product path, and says nothing about races (on the GPU those are covered by the bit-identical
+// repeat / shard / step-vs-rollout checks of tests/test_gpu_parity.py::test_*full_size_properties; compute-sanitizer is
+// not available on the GPU pool); only tests/ and tools/emu_accuracy.py build and load it.
 #define B2S_EMU 1
 #include <stdlib.h>
 #include <string.h>

@@ -354,6 +354,42 @@ def test_kbot_task_plugins_on_gpu(ctx, kbot_spec, kbot_randomizers) -> None:  # 
     assert np.abs(comps_o).sum(axis=(1, 2)).min() > 0
 
 
+def test_kbot_full_size_properties(kbot_spec, kbot_randomizers) -> None:  # noqa: ANN001
+    """BASELINE config 3 (8192 envs x 100 steps, level 1) through size-independent properties.  Bit-identical repeats,
+    shard invariance and step-by-step == fused launches double as the race check of the K-Bot path (the sanitizer's
+    racecheck is not available on this pool): a shared-memory race in the scatter / factor-reuse code would show up as
+    run-to-run differences."""
+    n, t = 8192, 100
+    actions = torch.from_numpy((0.3 * np.random.RandomState(8).randn(t, n, 20)).astype(np.float32)).cuda()
+    eng = _engine(kbot_spec, kbot_randomizers, n, level=1.0, seed=9)
+    rec = eng.rollout(actions)
+    view = eng.view(rec[:t])
+    assert torch.isfinite(rec).all() and float(eng.state[:, eng.program["TI_S_NONFINITE"]].sum()) == 0
+    assert float((view.qpos[..., 3:7].norm(dim=-1) - 1).abs().max()) < 1e-5
+    done = view.done
+    assert 0.0005 < float(done.float().mean()) < 0.2
+    nxt = view.timestep[1:][done[:-1]]
+    assert torch.allclose(nxt, torch.full_like(nxt, 0.02), atol=1e-6)
+    p = eng.program
+    cm = rec[:, :, p["TI_R_CMD"] : p["TI_R_CMD"] + 16]
+    assert len({tuple(r) for r in (cm[::10, ::16, :6] != 0).reshape(-1, 6).cpu().tolist()}) == 6   # all six command modes
+    total, comps = eng.rewards(rec, t)
+    assert torch.isfinite(total).all() and bool((comps.abs().sum(dim=(1, 2)) > 0).all())
+    eng2 = _engine(kbot_spec, kbot_randomizers, n, level=1.0, seed=9)
+    rec2 = eng2.rollout(actions)
+    assert torch.equal(rec, rec2) and torch.equal(eng.state, eng2.state) and torch.equal(eng.keys, eng2.keys)
+    del rec2, eng2
+    hi = _engine(kbot_spec, kbot_randomizers, n // 2, level=1.0, seed=9, env_offset=n // 2, total_envs=n)
+    rec_hi = hi.rollout(actions[:, n // 2 :].contiguous())
+    assert torch.equal(rec_hi, rec[:, n // 2 :])
+    del rec_hi, hi
+    eng3 = _engine(kbot_spec, kbot_randomizers, 200, level=1.0, seed=9, env_offset=0, total_envs=n)
+    rec3 = eng3.new_record_buffer(6)
+    for s in range(6):
+        eng3.step(actions[s, :200].contiguous(), rec3[s], rec3[s + 1])
+    assert torch.equal(rec3[:6], rec[:6, :200])
+
+
 def test_solver_paths_agree_at_full_size(ctx, monkeypatch) -> None:  # noqa: ANN001
     """The shipped solver (constraint-space Newton, exact line search, register-resident loop) against the
     reference-shaped one (dof-space Newton with the bracketing line search; B2S_SYNC_MASK bit 8) on the GPU, 4096 envs,
