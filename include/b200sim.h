@@ -20,6 +20,9 @@
  *   b200sim_rollout     RLTask._single_unroll's scan over T of the above with given actions (rl.py:1604-1665)
  *   b200sim_rewards     get_rewards vmapped over envs (ksim/task/rl.py:189-245, 1663; ksim/rewards.py)
  *   b200sim_gae         compute_ppo_inputs (ksim/task/ppo.py:54-121)
+ *   b200sim_ppo_loss    compute_ppo_loss + the mean over (B, T) of the summed terms, and that mean's gradient with respect to
+ *                       the new policy's log-probs / values / entropy (ksim/task/ppo.py:149-246, 471-488; the backward
+ *                       pass jax.grad derives from it at ppo.py:521-534)
  */
 #ifndef B200SIM_H
 #define B200SIM_H
@@ -77,6 +80,24 @@ int b200sim_rewards(const b200sim_model* model, void* stream, int n_envs, int n_
 int b200sim_gae(void* stream, int batch, int n_steps, const float* values, const float* rewards,
                 const uint8_t* dones, const uint8_t* successes, float gamma, float lam, int flags, float* adv,
                 float* targets, float* returns);
+
+/* PPO loss, forward and backward in one pass (the loss half).  Device arrays, fp32:
+ *   logp_on / logp_off / entropy [B][T][A] (entropy may be NULL: no entropy term, ppo.py:236-238);
+ *   values_on / values_off / adv / targets [B][T]  (adv, targets: b200sim_gae's outputs, constants of the loss, ppo.py:121).
+ * Terms per (b, t) (ppo.py:205-244): policy = -min(r A, clip(r, 1 +- clip_param) A), r = exp(clip(sum_a(logp_off - logp_on),
+ * +-log_clip_value)); value = value_loss_coef * 0.5 * (clipped or plain squared error; flags & PPO_CLIPPED_VALUE_LOSS);
+ * kl = kl_coef * kl_scale * sum_a(logp_on - logp_off) (kl_scale: the adaptive-KL factor of ppo.py:471-473);
+ * entropy = -entropy_coef * sum_a entropy.
+ * Outputs: losses[PPO_N_TERMS][B][T]; out[1 + PPO_N_TERMS] = mean over (B, T) of the summed terms, then of each term
+ * (deterministic: fixed grid, fp64 partial sums in `scratch`, PPO_SCRATCH_BYTES of device memory);
+ * d_logp[B][T] = d mean / d logp_off[b][t][a] (the same for every a); d_values[B][T] = d mean / d values_off;
+ * d mean / d entropy[b][t][a] is the constant -entropy_coef / (B T) and is not materialised.
+ * Any of losses, d_logp, d_values may be NULL (not wanted). */
+int b200sim_ppo_loss(void* stream, int batch, int n_steps, int n_act, const float* logp_on, const float* logp_off,
+                     const float* values_on, const float* values_off, const float* adv, const float* targets,
+                     const float* entropy, float clip_param, float value_loss_coef, float entropy_coef, float kl_coef,
+                     float log_clip_value, float kl_scale, int flags, float* losses, float* out, float* d_logp,
+                     float* d_values, void* scratch);
 
 /* done / success flags of a record buffer as bytes: out[N][T] from rec[T][N][R] (feeds b200sim_gae). */
 int b200sim_extract_flags(const b200sim_model* model, void* stream, int n_envs, int n_steps, const float* rec,

@@ -226,6 +226,12 @@
 #define GAE_NORMALIZE_ADVANTAGES 1
 #define GAE_MONTE_CARLO_RETURNS 2
 
+/* ---- PPO loss flags / layout (ksim/task/ppo.py:149-246) ---- */
+#define PPO_CLIPPED_VALUE_LOSS 1
+#define PPO_N_TERMS 4            /* losses[PPO_N_TERMS][B][T]: policy, value, kl (already x kl_scale), entropy */
+#define PPO_MAX_ACTIONS 128      /* widest log-prob row the kernel stages */
+#define PPO_SCRATCH_BYTES 40960  /* caller-owned device scratch: per-CTA partial sums (<= 1024 CTAs x 5 doubles) */
+
 /* ---- error codes ---- */
 #define B2S_OK 0
 #define B2S_ERR_BAD_ARG 1

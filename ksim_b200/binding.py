@@ -17,7 +17,7 @@ _LIB: ctypes.CDLL | None = None
 EXPORTS = (
     "b200sim_model_create", "b200sim_model_destroy", "b200sim_model_info", "b200sim_last_error", "b200sim_init_envs",
     "b200sim_step_ctrl", "b200sim_rollout", "b200sim_rewards", "b200sim_gae", "b200sim_extract_flags", "b200sim_dataset_pack",
-    "b200sim_metrics",
+    "b200sim_metrics", "b200sim_ppo_loss",
 )
 
 INFO = dict(STATE_SIZE=0, REC_SIZE=1, KEY_SIZE=2, RAND_SIZE=3, ACTION_SIZE=4, N_REW_COMP=5, REW_CARRY_SIZE=6,
@@ -67,6 +67,8 @@ def lib() -> ctypes.CDLL:
         cdll.b200sim_dataset_pack.restype = ci
         cdll.b200sim_metrics.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
         cdll.b200sim_metrics.restype = ci
+        cdll.b200sim_ppo_loss.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp, vp, vp]
+        cdll.b200sim_ppo_loss.restype = ci
         _LIB = cdll
     return _LIB
 

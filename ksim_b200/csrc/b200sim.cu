@@ -83,8 +83,11 @@ __global__ void __launch_bounds__(launch_threads<D>()) k_init_envs(const Mdl mp,
   Work<D>& w = reinterpret_cast<Work<D>*>(smem)[warp];
   const int* ti = m.ti;
   const size_t S = ti[TI_STATE_SIZE], R = ti[TI_REC_SIZE], K = ti[TI_KEY_SIZE], RAND = ti[TI_RAND_SIZE];
+  DBG_STOP(m, 1);
   apply_overrides(m, w, rand + env * RAND, lane);
+  DBG_STOP(m, 2);
   env_init(m, w, init_keys + (size_t)env * 10, levels[env], rec0 + env * R, act_keys ? act_keys + 2 * env : nullptr, lane);
+  DBG_STOP(m, 3);
   env_store(m, w, state + env * S, keys + env * K, lane);
 }
 
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(launch_threads<D>()) k_rollout(const Mdl mp, i
     // idle warps of the last CTA still take part in the per-sub-step CTA barriers and votes
     const int nsub = ti[TI_NSUB];
     for (int i = 0; i < n_steps * nsub; i++) {
-      if ((m.sync_mask >> 6) & 1) __syncthreads();
+      if ((m.sync_mask >> 6) & 1) CTA_SYNC();
       forward_follower(m);
     }
     return;
@@ -194,6 +197,95 @@ __global__ void __launch_bounds__(1024) k_gae_normalize(size_t n, float* __restr
   float sd = sqrtf((float)(red[0] / (double)n));
   if (sd < 1e-6f) sd = 1e-6f;
   for (size_t i = tid; i < n; i += 1024) adv[i] = (adv[i] - mean) / sd;
+}
+
+// compute_ppo_loss (ksim/task/ppo.py:149-246), the mean of the summed terms (ppo.py:484-486) and that mean's gradient, fused.
+// HBM-bound: per (b, t) it reads 2A (+A with entropy) + 4 floats and writes up to 6.  A CTA walks tiles of PPO_TILE
+// elements: the A-wide rows of the [B][T][A] arrays are streamed with coalesced loads (consecutive threads, consecutive
+// floats) into shared memory as log-ratio terms (odd row stride: conflict-free), then thread r reduces row r in index
+// order (the oracle's order).  Partial sums are fp64 per CTA; k_ppo_reduce adds them in CTA order (deterministic).
+constexpr int PPO_TILE = 128;
+__global__ void __launch_bounds__(PPO_TILE) k_ppo_loss(size_t n, int A, const float* __restrict__ logp_on,
+                                                       const float* __restrict__ logp_off, const float* __restrict__ values_on,
+                                                       const float* __restrict__ values_off, const float* __restrict__ adv,
+                                                       const float* __restrict__ targets, const float* __restrict__ entropy,
+                                                       float clip_param, float value_loss_coef, float entropy_coef, float kl_coef,
+                                                       float log_clip_value, float kl_scale, int flags, float* __restrict__ losses,
+                                                       float* __restrict__ d_logp, float* __restrict__ d_values,
+                                                       double* __restrict__ partial) {
+  extern __shared__ __align__(16) float ppo_sh[];
+  __shared__ double red[PPO_TILE];
+  const int tid = threadIdx.x, AP = A | 1;
+  float* sd = ppo_sh;
+  float* se = ppo_sh + PPO_TILE * AP;
+  const float inv_n = 1.0f / (float)n;
+  double acc[1 + PPO_N_TERMS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (size_t e0 = (size_t)blockIdx.x * PPO_TILE; e0 < n; e0 += (size_t)gridDim.x * PPO_TILE) {
+    const int cnt = (int)(n - e0 < (size_t)PPO_TILE ? n - e0 : (size_t)PPO_TILE);
+    const size_t f0 = e0 * A;
+    const int nf = cnt * A;
+    for (int f = tid; f < nf; f += PPO_TILE) {
+      const int r = f / A, c = f - r * A;
+      sd[r * AP + c] = __fsub_rn(logp_off[f0 + f], logp_on[f0 + f]);
+      if (entropy) se[r * AP + c] = entropy[f0 + f];
+    }
+    __syncthreads();
+    if (tid < cnt) {
+      const size_t e = e0 + tid;
+      float lr = 0.0f, es = 0.0f;
+      for (int a = 0; a < A; a++) lr = __fadd_rn(lr, sd[tid * AP + a]);
+      if (entropy) for (int a = 0; a < A; a++) es = __fadd_rn(es, se[tid * AP + a]);
+      const float ad = adv[e], vt = targets[e], von = values_on[e], voff = values_off[e];
+      // policy term (ppo.py:205-210); clip gradients follow lax.clamp (1 strictly inside), min / max ties split evenly
+      const float lrc = fminf(fmaxf(lr, -log_clip_value), log_clip_value);
+      const float ratio = expf(lrc);
+      const float lo = 1.0f - clip_param, hi = 1.0f + clip_param;
+      const float rcl = fminf(fmaxf(ratio, lo), hi);
+      const float s1 = __fmul_rn(ratio, ad), s2 = __fmul_rn(rcl, ad);
+      const float pol = -fminf(s1, s2);
+      const float dr_dlr = (lr > -log_clip_value && lr < log_clip_value) ? ratio : 0.0f;
+      const float g1 = -ad, g2 = (ratio > lo && ratio < hi) ? -ad : 0.0f;
+      const float dpol = (s1 < s2 ? g1 : (s2 < s1 ? g2 : 0.5f * (g1 + g2))) * dr_dlr;
+      // value term (ppo.py:212-222, clipped_value_loss :124-135)
+      float val, dval;
+      const float err = __fsub_rn(voff, vt);
+      if (flags & PPO_CLIPPED_VALUE_LOSS) {
+        const float d = __fsub_rn(voff, von);
+        const float cerr = __fsub_rn(__fadd_rn(von, fminf(fmaxf(d, -clip_param), clip_param)), vt);
+        const float e2 = __fmul_rn(err, err), c2 = __fmul_rn(cerr, cerr);
+        const float gc = (d > -clip_param && d < clip_param) ? cerr : 0.0f;
+        val = __fmul_rn(__fmul_rn(0.5f, fmaxf(e2, c2)), value_loss_coef);
+        dval = value_loss_coef * (e2 > c2 ? err : (c2 > e2 ? gc : 0.5f * (err + gc)));
+      } else {
+        val = __fmul_rn(__fmul_rn(0.5f, __fmul_rn(err, err)), value_loss_coef);
+        dval = value_loss_coef * err;
+      }
+      // kl and entropy terms (ppo.py:224-238, 471-473)
+      const float kl = __fmul_rn(__fmul_rn(-lr, kl_coef), kl_scale);
+      const float ent = entropy ? __fmul_rn(-es, entropy_coef) : 0.0f;
+      if (losses) { losses[e] = pol; losses[n + e] = val; losses[2 * n + e] = kl; losses[3 * n + e] = ent; }
+      if (d_logp) d_logp[e] = (dpol - kl_coef * kl_scale) * inv_n;
+      if (d_values) d_values[e] = dval * inv_n;
+      acc[0] += (double)__fadd_rn(__fadd_rn(__fadd_rn(pol, val), kl), ent);
+      acc[1] += (double)pol; acc[2] += (double)val; acc[3] += (double)kl; acc[4] += (double)ent;
+    }
+    __syncthreads();
+  }
+  for (int k = 0; k < 1 + PPO_N_TERMS; k++) {
+    red[tid] = acc[k];
+    __syncthreads();
+    for (int o = PPO_TILE / 2; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+    if (tid == 0) partial[(size_t)blockIdx.x * (1 + PPO_N_TERMS) + k] = red[0];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(32) k_ppo_reduce(int n_blocks, size_t n, const double* __restrict__ partial, float* __restrict__ out) {
+  const int k = threadIdx.x;
+  if (k >= 1 + PPO_N_TERMS) return;
+  double s = 0.0;
+  for (int b = 0; b < n_blocks; b++) s += partial[(size_t)b * (1 + PPO_N_TERMS) + k];
+  out[k] = (float)(s / (double)n);
 }
 
 // Trajectory metrics, stage 1: one warp per environment, lanes over time steps (warp-shuffle reductions).
@@ -372,11 +464,17 @@ extern "C" int b200sim_model_create(const void* blob, size_t nbytes, b200sim_mod
   mo->mdl.ti = d + MH_SIZE + ni + nf;
   mo->mdl.tf = (const float*)(d + MH_SIZE + ni + nf + nti);
   mo->mdl.sync_mask = 0x7f;  // measured best on B200 (profiles/): a CTA barrier after every stage; votes inside the Newton loop (bit 7) are neutral since the solve became short
+#ifdef B2S_DEBUG_STOP
+  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0xff07ff;  // + DBG_STOP point
+#else
   if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0x7ff;  // tuning experiments
+#endif
   int rc;
   const size_t words[4] = {ni, nf, nti, ntf};
-  if (fits<DimsHumanoid>(h) && task_fits<DimsHumanoid>(ti)) { mo->variant = 0; rc = configure<DimsHumanoid>(mo, words); }
-  else if (fits<DimsKbot>(h) && task_fits<DimsKbot>(ti)) { mo->variant = 1; rc = configure<DimsKbot>(mo, words); }
+  int vmin = 0;  // B2S_MIN_VARIANT: tests run a small model through a larger instantiation than the first that fits
+  if (const char* e = getenv("B2S_MIN_VARIANT")) vmin = atoi(e);
+  if (vmin <= 0 && fits<DimsHumanoid>(h) && task_fits<DimsHumanoid>(ti)) { mo->variant = 0; rc = configure<DimsHumanoid>(mo, words); }
+  else if (vmin <= 1 && fits<DimsKbot>(h) && task_fits<DimsKbot>(ti)) { mo->variant = 1; rc = configure<DimsKbot>(mo, words); }
   else if (fits<DimsGeneric>(h) && task_fits<DimsGeneric>(ti)) { mo->variant = 2; rc = configure<DimsGeneric>(mo, words); }
   else rc = fail(B2S_ERR_TOO_LARGE, "model / task sizes exceed the largest kernel instantiation");
   if (rc != B2S_OK) { cudaFree(mo->dev_blob); delete mo; return rc; }
@@ -495,6 +593,32 @@ extern "C" int b200sim_gae(void* stream, int batch, int n_steps, const float* va
     k_gae_normalize<<<1, 1024, 0, (cudaStream_t)stream>>>((size_t)batch * n_steps, adv);
     CUDA_OK(cudaGetLastError());
   }
+  return B2S_OK;
+}
+
+extern "C" int b200sim_ppo_loss(void* stream, int batch, int n_steps, int n_act, const float* logp_on, const float* logp_off,
+                                const float* values_on, const float* values_off, const float* adv, const float* targets,
+                                const float* entropy, float clip_param, float value_loss_coef, float entropy_coef, float kl_coef,
+                                float log_clip_value, float kl_scale, int flags, float* losses, float* out, float* d_logp,
+                                float* d_values, void* scratch) {
+  if (batch < 0 || n_steps < 0) return fail(B2S_ERR_BAD_ARG, "bad argument");
+  if (n_act < 1 || n_act > PPO_MAX_ACTIONS) return fail(B2S_ERR_UNSUPPORTED, "n_act outside [1, PPO_MAX_ACTIONS]");
+  if (batch == 0 || n_steps == 0) return B2S_OK;
+  if (!logp_on || !logp_off || !values_on || !values_off || !adv || !targets || !out || !scratch)
+    return fail(B2S_ERR_BAD_ARG, "null argument");
+  const size_t n = (size_t)batch * n_steps;
+  const size_t tiles = (n + PPO_TILE - 1) / PPO_TILE;
+  const int n_blocks = (int)(tiles < 1024 ? tiles : 1024);  // a function of n only: the reduction order is reproducible
+  static_assert(1024 * (1 + PPO_N_TERMS) * sizeof(double) <= PPO_SCRATCH_BYTES, "scratch too small");
+  const size_t smem = (size_t)(entropy ? 2 : 1) * PPO_TILE * (n_act | 1) * sizeof(float);
+  if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k_ppo_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_ppo_loss<<<n_blocks, PPO_TILE, smem, (cudaStream_t)stream>>>(n, n_act, logp_on, logp_off, values_on, values_off, adv, targets,
+                                                                 entropy, clip_param, value_loss_coef, entropy_coef, kl_coef,
+                                                                 log_clip_value, kl_scale, flags, losses, d_logp, d_values,
+                                                                 (double*)scratch);
+  CUDA_OK(cudaGetLastError());
+  k_ppo_reduce<<<1, 32, 0, (cudaStream_t)stream>>>(n_blocks, n, (const double*)scratch, out);
+  CUDA_OK(cudaGetLastError());
   return B2S_OK;
 }
 

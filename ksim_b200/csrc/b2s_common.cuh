@@ -23,7 +23,13 @@
 #define DEVNI __device__ __noinline__
 #define LANE_FOR(i, n) for (int i = lane; i < (n); i += 32)
 #define WSYNC() __syncwarp()
+// Stage barriers keep a CTA's warps on the same code (shared instruction-cache fills); they carry no data dependence.
+// B2S_BAR_GROUP = g > 0 (tuning experiments) synchronises groups of g consecutive warps on named barriers instead.
+#if defined(B2S_BAR_GROUP) && B2S_BAR_GROUP > 0
+#define CTA_SYNC() asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x >> 5) / B2S_BAR_GROUP + 1), "r"(B2S_BAR_GROUP * 32) : "memory")
+#else
 #define CTA_SYNC() __syncthreads()
+#endif
 #define CTA_OR(p) __syncthreads_or(p)
 #define IF_LANE0 if (lane == 0)
 #define LANE_ARG const int lane
@@ -43,6 +49,13 @@
 
 // Optional per-stage cycle accounting (-DB2S_PROFILE_STAGES; tools/stage_profile.py): lane 0 of every warp adds the
 // clock64() delta of each stage to Work::prof, the kernel sums them into g_stage_cycles.  Off in the product build.
+// -DB2S_DEBUG_STOP (fault bisection; compute-sanitizer is closed on the pool): threads exit at stop point k when bits
+// 16..23 of B2S_SYNC_MASK equal k.  Run with B2S_WPB=1 so that no CTA barrier waits for the exited warp.
+#if defined(B2S_DEBUG_STOP) && B2S_DEVICE
+#define DBG_STOP(m, k) do { if ((((m).sync_mask >> 16) & 0xff) == (k)) asm volatile("exit;"); } while (0)
+#else
+#define DBG_STOP(m, k) do { } while (0)
+#endif
 #if defined(B2S_PROFILE_STAGES) && B2S_DEVICE
 #define B2S_NSTAGE 32
 #define STAGE_BEGIN() long long stage_t0_ = clock64()

@@ -433,7 +433,9 @@ DEVNI void engine_reset(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
     rng = key_child(fr, 0);
     reset_apply(m, w, i, reset_rng, LANE_PASS);
   }
+  DBG_STOP(m, 10);
   forward(m, w, true, false, LANE_PASS);
+  DBG_STOP(m, 11);
   LANE_FOR(i, nv) { w.qvel[i] = 0.0f; w.qacc[i] = 0.0f; }
   WSYNC();
   actuators_initial_state(m, w, rng, LANE_PASS);
@@ -836,6 +838,7 @@ template <class D>
 DEV void do_reset(const Mdl& m, Work<D>& w, Key reset_rng, Key cmd_rng, Key obs_carry_rng, Key obs_bias_rng, LANE_ARG) {
   const int* ti = m.ti;
   engine_reset(m, w, reset_rng, LANE_PASS);
+  DBG_STOP(m, 6);
   const int ncmd = ti[TI_N_CMD];
   for (int c = 0; c < ncmd; c++) {
     const KeyFan fc = key_fan(cmd_rng, LANE_PASS);
@@ -941,7 +944,9 @@ DEV void env_init(const Mdl& m, Work<D>& w, const uint32_t* ik, float level, flo
   WSYNC();
   Key kr, kc, ko, kb;
   kr.k0 = ik[0]; kr.k1 = ik[1]; kc.k0 = ik[2]; kc.k1 = ik[3]; ko.k0 = ik[4]; ko.k1 = ik[5]; kb.k0 = ik[6]; kb.k1 = ik[7];
+  DBG_STOP(m, 4);
   do_reset(m, w, kr, kc, ko, kb, LANE_PASS);
+  DBG_STOP(m, 5);
   IF_LANE0 { w.keys[0] = ik[8]; w.keys[1] = ik[9]; }
   WSYNC();
   write_pre_block(m, w, rec0, act_key, LANE_PASS);

@@ -505,9 +505,16 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
   const bool live = i < nv;
   // Rows / columns >= nv (and the duplicate row idle lanes load) only ever feed entries that are never read
   // back: column j takes L[j][k] from lane j < nv, and every store / substitution below is guarded.
-  const int ri = i < N ? i : N - 1;
+  int ri = i < N ? i : N - 1;
+  // ptxas 12.9 miscompiles the NV = 32 instantiation of this function: it hoists the row address &w.M[lane] into a
+  // register the callers are supposed to set, one call site passes something else in it, and the 32 row loads below were
+  // merged into 64 / 128-bit ones although a row of the odd stride NVP is only 4-byte aligned ("misaligned address", found
+  // by the generic-instantiation GPU test).  An opaque row index keeps the address arithmetic inside the function and
+  // volatile keeps the loads scalar; the measured instantiations (NV = 23, 26) are left as they were.
+  if constexpr (N % 4 == 0) asm volatile("mov.b32 %0, %0;" : "+r"(ri));
   float r[N];
   float dg = 0.0f;
+  DBG_STOP(m, 40);
   if (mode == FS_NEWTON) {
     const int nsparse = w.nsparse;
     if (live)
@@ -526,8 +533,15 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
     if (live) w.M[ri][ri] = diag0 + dg;
     __syncwarp();
   }
+  if constexpr (N % 4 == 0) {
+    const volatile float* row = w.M[ri];
 #pragma unroll
-  for (int j = 0; j < N; j++) r[j] = w.M[ri][j];
+    for (int j = 0; j < N; j++) r[j] = row[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = w.M[ri][j];
+  }
+  DBG_STOP(m, 41);
   if (mode != FS_MASS) {
     __syncwarp();
     if (live) w.M[ri][ri] = diag0;
@@ -557,6 +571,7 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
     r[j] = t * idj;  // lane j: sqrt(pivot); lanes below: L[i][j]
     if (i == j) invd = idj;
   }
+  DBG_STOP(m, 42);
   float y = live ? b[i] : 0.0f;
   if (mode == FS_NEWTON_DIAG && live) w.s_tmp[i] = invd;
 #pragma unroll
@@ -565,16 +580,20 @@ DEVNI void factor_solve(const Mdl& m, Work<D>& w, int mode, float* x, const floa
     if (i > k) y = fmaf(-r[k], yk, y);
   }
   y *= invd;
+  DBG_STOP(m, 43);
 #pragma unroll
   for (int j = 0; j < N; j++) if (live && j < i) w.W[i][j] = r[j];
   __syncwarp();
+  DBG_STOP(m, 44);
   float xv = y;
 #pragma unroll
   for (int k = N - 1; k >= 0; k--) {
     const float xk = __shfl_sync(FULL, xv * invd, k);
     if (i < k && k < nv) xv = fmaf(-w.W[k][i], xk, xv);
   }
+  DBG_STOP(m, 45);
   if (live) x[i] = xv * invd;
+  DBG_STOP(m, 46);
   if (nz > 0) {
     const int nsparse = w.nsparse;
     for (int s0 = 0; s0 < nz; s0 += 2) {
@@ -633,7 +652,8 @@ DEVNI void fs_resolve(Work<D>& w, float* x, const float* b, int nv, LANE_ARG) {
   constexpr unsigned FULL = 0xffffffffu;
   const int i = lane;
   const bool live = i < nv;
-  const int ri = i < N ? i : N - 1;
+  int ri = i < N ? i : N - 1;
+  if constexpr (N % 4 == 0) asm volatile("mov.b32 %0, %0;" : "+r"(ri));  // same precaution as in factor_solve
   float r[N];
 #pragma unroll
   for (int j = 0; j < N; j++) r[j] = j < ri ? w.W[ri][j] : 0.0f;
@@ -2487,29 +2507,41 @@ DEVNI void forward(const Mdl& m, Work<D>& w, bool sensors, bool lockstep, LANE_A
   // the CTA's warps on the same code, so one instruction-cache fill serves all of them.
 #define B2S_STAGE_SYNC(k) do { if (lockstep && ((m.sync_mask >> (k)) & 1)) CTA_SYNC(); } while (0)
   STAGE_BEGIN();
+  DBG_STOP(m, 20);
   kinematics(m, w, LANE_PASS);
+  DBG_STOP(m, 21);
   B2S_STAGE_SYNC(0);
   STAGE_MARK(w, 0);
   com_pos(m, w, LANE_PASS);
+  DBG_STOP(m, 22);
   crb_mass_matrix(m, w, LANE_PASS);
+  DBG_STOP(m, 23);
   B2S_STAGE_SYNC(1);
   STAGE_MARK(w, 1);
   collision(m, w, LANE_PASS);
+  DBG_STOP(m, 24);
   com_vel(m, w, LANE_PASS);
+  DBG_STOP(m, 25);
   make_constraint(m, w, LANE_PASS);
+  DBG_STOP(m, 26);
   B2S_STAGE_SYNC(2);
   STAGE_MARK(w, 2);
   passive(m, w, LANE_PASS);
+  DBG_STOP(m, 27);
   rne(m, w, LANE_PASS);
+  DBG_STOP(m, 28);
   if (sensors) sensors_pos_vel(m, w, LANE_PASS);
   actuation(m, w, LANE_PASS);
+  DBG_STOP(m, 29);
   B2S_STAGE_SYNC(3);
   STAGE_MARK(w, 3);
   acceleration(m, w, LANE_PASS);
+  DBG_STOP(m, 30);
   B2S_STAGE_SYNC(4);
   STAGE_MARK(w, 4);
   solve(m, w, lockstep && ((m.sync_mask >> 7) & 1), LANE_PASS);
   STAGE_MARK(w, 5);
+  DBG_STOP(m, 31);
   B2S_STAGE_SYNC(5);
   STAGE_MARK(w, 6);
 #undef B2S_STAGE_SYNC

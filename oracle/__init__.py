@@ -164,7 +164,7 @@ class OracleEngine:
         self.tf = np.ascontiguousarray(program.tf.astype(self.real))
         self.S, self.R, self.K = program.state_size, program.rec_size, program.key_size
         self.RAND, self.NA = program.rand_size, program.action_size
-        for fn in (self.lib.o_init_envs, self.lib.o_step_ctrl, self.lib.o_rewards, self.lib.o_gae):
+        for fn in (self.lib.o_init_envs, self.lib.o_step_ctrl, self.lib.o_rewards, self.lib.o_gae, self.lib.o_ppo_loss):
             fn.restype = ctypes.c_int
 
     @staticmethod
@@ -234,3 +234,23 @@ class OracleEngine:
         if rc != 0:
             raise RuntimeError(f"o_gae -> {rc}")
         return adv, tgt, ret
+
+    def ppo_loss(self, logp_on: np.ndarray, logp_off: np.ndarray, values_on: np.ndarray, values_off: np.ndarray, adv: np.ndarray,
+                 targets: np.ndarray, entropy: np.ndarray | None, clip_param: float, value_loss_coef: float, entropy_coef: float,
+                 kl_coef: float, log_clip_value: float, kl_scale: float, flags: int,
+                 ) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """o_ppo_loss: (losses[4][B][T], out[5], d_logp[B][T], d_values[B][T])."""
+        b, t, a = logp_on.shape
+        arrs = [np.ascontiguousarray(x, dtype=self.real) for x in (logp_on, logp_off, values_on, values_off, adv, targets)]
+        ent = None if entropy is None else np.ascontiguousarray(entropy, dtype=self.real)
+        losses = np.zeros((4, b, t), dtype=self.real)
+        out = np.zeros(5, dtype=self.real)
+        d_logp, d_values = (np.zeros((b, t), dtype=self.real) for _ in range(2))
+        real_c = ctypes.c_float if self.precision == "f32" else ctypes.c_double
+        rc = self.lib.o_ppo_loss(ctypes.c_int(b), ctypes.c_int(t), ctypes.c_int(a), *(self._p(x) for x in arrs),
+                                 None if ent is None else self._p(ent), real_c(clip_param), real_c(value_loss_coef),
+                                 real_c(entropy_coef), real_c(kl_coef), real_c(log_clip_value), real_c(kl_scale),
+                                 ctypes.c_int(flags), self._p(losses), self._p(out), self._p(d_logp), self._p(d_values))
+        if rc != 0:
+            raise RuntimeError(f"o_ppo_loss -> {rc}")
+        return losses, out, d_logp, d_values

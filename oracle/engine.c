@@ -1434,6 +1434,62 @@ int o_gae(int B, int T, const REAL* values, const REAL* rewards, const uint8_t* 
   return B2S_OK;
 }
 
+/* ------------------------------------------------------------------------------------------ PPO loss */
+
+/* compute_ppo_loss (ppo.py:149-246; clipped_value_loss :124-135), the mean over (B, T) of the summed terms
+ * (_get_ppo_loss_and_metrics ppo.py:471-486, incl. the kl_scale factor) and the gradient of that mean with respect to the
+ * new policy's log-probs / values -- what jax.grad derives at ppo.py:521-534; ppo_inputs are constants (stop_gradient,
+ * ppo.py:121).  Gradient conventions at the measure-zero kinks: clip passes 1 strictly inside its range (lax.clamp),
+ * min / max ties split evenly (lax.min / lax.max).  logp_* / entropy [B][T][A]; the rest [B][T]; entropy may be NULL.
+ * losses[4][B][T] (policy, value, kl, entropy); out[5] = mean total, mean of each term; d_logp[B][T] is the gradient for
+ * every logp_off[b][t][a]; d_values[B][T]. */
+int o_ppo_loss(int B, int T, int A, const REAL* logp_on, const REAL* logp_off, const REAL* values_on, const REAL* values_off,
+               const REAL* adv, const REAL* targets, const REAL* entropy, REAL clip_param, REAL value_loss_coef,
+               REAL entropy_coef, REAL kl_coef, REAL log_clip_value, REAL kl_scale, int flags, REAL* losses, REAL* out,
+               REAL* d_logp, REAL* d_values) {
+  const size_t n = (size_t)B * T;
+  double acc[5] = {0, 0, 0, 0, 0};
+  const REAL inv_n = (REAL)1 / (REAL)n;
+  for (size_t e = 0; e < n; e++) {
+    REAL lr = 0, es = 0;
+    for (int a = 0; a < A; a++) lr += logp_off[e * A + a] - logp_on[e * A + a];
+    if (entropy) for (int a = 0; a < A; a++) es += entropy[e * A + a];
+    const REAL ad = adv[e], vt = targets[e], von = values_on[e], voff = values_off[e];
+    REAL lrc = lr < -log_clip_value ? -log_clip_value : (lr > log_clip_value ? log_clip_value : lr);
+    const REAL ratio = EXP(lrc);
+    const REAL lo = (REAL)1 - clip_param, hi = (REAL)1 + clip_param;
+    const REAL rcl = ratio < lo ? lo : (ratio > hi ? hi : ratio);
+    const REAL s1 = ratio * ad, s2 = rcl * ad;
+    const REAL pol = -(s1 < s2 ? s1 : s2);
+    const REAL dr_dlr = (lr > -log_clip_value && lr < log_clip_value) ? ratio : (REAL)0;
+    const REAL g1 = -ad, g2 = (ratio > lo && ratio < hi) ? -ad : (REAL)0;
+    const REAL dpol = (s1 < s2 ? g1 : (s2 < s1 ? g2 : (REAL)0.5 * (g1 + g2))) * dr_dlr;
+    REAL val, dval;
+    const REAL err = voff - vt;
+    if (flags & PPO_CLIPPED_VALUE_LOSS) {
+      const REAL d = voff - von;
+      const REAL dc = d < -clip_param ? -clip_param : (d > clip_param ? clip_param : d);
+      const REAL cerr = (von + dc) - vt;
+      const REAL e2 = err * err, c2 = cerr * cerr;
+      const REAL gc = (d > -clip_param && d < clip_param) ? cerr : (REAL)0;
+      val = (REAL)0.5 * (e2 > c2 ? e2 : c2) * value_loss_coef;
+      dval = value_loss_coef * (e2 > c2 ? err : (c2 > e2 ? gc : (REAL)0.5 * (err + gc)));
+    } else {
+      val = (REAL)0.5 * (err * err) * value_loss_coef;
+      dval = value_loss_coef * err;
+    }
+    const REAL kl = (-lr * kl_coef) * kl_scale;
+    const REAL ent = entropy ? -es * entropy_coef : (REAL)0;
+    if (losses) { losses[e] = pol; losses[n + e] = val; losses[2 * n + e] = kl; losses[3 * n + e] = ent; }
+    if (d_logp) d_logp[e] = (dpol - kl_coef * kl_scale) * inv_n;
+    if (d_values) d_values[e] = dval * inv_n;
+    acc[0] += (double)(((pol + val) + kl) + ent);
+    acc[1] += (double)pol; acc[2] += (double)val; acc[3] += (double)kl; acc[4] += (double)ent;
+  }
+  for (int k = 0; k < 5; k++) out[k] = n ? (REAL)(acc[k] / (double)n) : (REAL)0;
+  return B2S_OK;
+}
+
 /* ------------------------------------------------------------------------------------------ test hooks */
 
 /* evaluates termination `idx` of the task program on a hand-built state (tests/test_golden_terminations.py);

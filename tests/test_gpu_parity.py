@@ -390,6 +390,52 @@ def test_kbot_full_size_properties(kbot_spec, kbot_randomizers) -> None:  # noqa
     assert torch.equal(rec3[:6], rec[:6, :200])
 
 
+def test_generic_instantiation_tripod_with_events(monkeypatch) -> None:  # noqa: ANN001
+    """The third kernel instantiation (DimsGeneric, run-time sizes) on a small free-floating tripod: TorqueActuators, the
+    three velocity-impulse events (linear / angular push, jump), latency, action drop, zero offsets, FloatVectorCommand,
+    MinimumHeight / NotUpright / EpisodeLength (success) terminations -- resynchronised against the f32 oracle, flags and
+    keys bit-exact."""
+    from ksim_b200 import events, terminations
+    from tests.helpers import tripod_spec
+
+    spec = tripod_spec(
+        events={"push": events.LinearPushEvent(linvel=1.0, interval_range=(0.05, 0.2)),
+                "spin": events.AngularPushEvent(angvel=1.0, interval_range=(0.05, 0.2)),
+                "jump": events.JumpEvent(jump_height_range=(0.05, 0.1), interval_range=(0.1, 0.3))},
+        terminations={"low": terminations.MinimumHeightTermination(min_height=0.2),
+                      "tilt": terminations.NotUprightTermination(max_radians=1.0),
+                      "len": terminations.EpisodeLengthTermination(max_length_sec=0.5)},
+        action_latency_range=(0.004, 0.012), drop_action_prob=0.2, zero_offset_std=0.02, zero_offset_mag=0.02)
+    n, steps = 40, 50
+    monkeypatch.setenv("B2S_MIN_VARIANT", "2")  # the tripod would fit the K-Bot-sized instantiation
+    eng = _engine(spec, {}, n, level=1.0, seed=9)
+    assert eng.info("VARIANT") == 2
+    ora, st, keys, rec0, _ = _oracle_init(eng)
+    p = eng.program
+    np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
+    np.testing.assert_allclose(_np(eng.state), st, rtol=1e-4, atol=2e-5)
+    actions = (0.3 * np.random.RandomState(10).randn(steps, n, eng.NA)).astype(np.float32)
+    rec_o = np.zeros((2, n, eng.R), np.float32)
+    rec_o[0] = rec0
+    cur, nxt = (torch.zeros((n, eng.R), device="cuda") for _ in range(2))
+    q, d, sc, ev = p["TI_R_QPOS"], p["TI_R_DONE"], p["TI_R_SUCCESS"], p["TI_R_EVENT"]
+    n_done = n_succ = 0
+    for s in range(steps):
+        eng.state.copy_(torch.from_numpy(st).cuda())
+        eng.keys.copy_(torch.from_numpy(keys.view(np.int32)).cuda())
+        eng.step(torch.from_numpy(actions[s]).cuda(), cur, nxt)
+        ora.step_ctrl(actions[s], eng.env_init.rand, st, keys, rec_o[0], rec_o[1])
+        g_cur = _np(cur)
+        np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
+        np.testing.assert_array_equal(g_cur[:, d], rec_o[0][:, d])
+        np.testing.assert_array_equal(g_cur[:, sc], rec_o[0][:, sc])
+        np.testing.assert_allclose(g_cur[:, q : q + 10], rec_o[0][:, q : q + 10], rtol=0, atol=5e-4)
+        np.testing.assert_allclose(g_cur[:, ev : ev + p["TI_EVENT_SIZE"]], rec_o[0][:, ev : ev + p["TI_EVENT_SIZE"]], rtol=1e-5, atol=1e-6)
+        n_done += int(rec_o[0][:, d].sum()); n_succ += int(rec_o[0][:, sc].sum())
+        rec_o[0] = rec_o[1]
+    assert n_succ > 0 and n_done >= n_succ
+
+
 def test_solver_paths_agree_at_full_size(ctx, monkeypatch) -> None:  # noqa: ANN001
     """The shipped solver (constraint-space Newton, exact line search, register-resident loop) against the
     reference-shaped one (dof-space Newton with the bracketing line search; B2S_SYNC_MASK bit 8) on the GPU, 4096 envs,
@@ -419,3 +465,87 @@ def test_solver_paths_agree_at_full_size(ctx, monkeypatch) -> None:  # noqa: ANN
         assert float(dq.max()) <= 2e-2 and float(dv.max()) <= 2.0, (s, float(dq.max()), float(dv.max()))
         n_bad += int(bad.sum())
     assert n_bad <= int(0.003 * n * 12), f"{n_bad} of {n * 12} env-steps outside the stated tolerance"
+
+
+@pytest.mark.parametrize("b,t,a", [(1, 1, 1), (7, 3, 17), (512, 24, 17), (300, 100, 20), (4096, 64, 17), (5, 9, 128)])
+@pytest.mark.parametrize("clipped,with_entropy", [(True, True), (False, False)])
+def test_ppo_loss_parity(ctx, b, t, a, clipped, with_entropy) -> None:  # noqa: ANN001
+    """b200sim_ppo_loss against the f32 C oracle: per-element terms and gradients to 2e-6 relative (same fp32 operation
+    order; device expf is within 2 ulp of libm's), the means to 1e-6 (fp64 accumulation on both sides)."""
+    from ksim_b200 import codes as C, ppo
+    from oracle import OracleEngine
+    from tests.test_ppo_loss import HYPER, make_case
+
+    eng = _engine(*ctx, 4)
+    ora = OracleEngine(eng.program, "f32")
+    case = [x.astype(np.float32) for x in make_case(b, t, a, seed=b + t + a)]
+    if not with_entropy:
+        case[6] = None
+    lp_on, lp_off, v_on, v_off, adv, tgt, ent = case
+    o_losses, o_out, o_dlp, o_dv = ora.ppo_loss(*case, kl_scale=1.7, flags=C.PPO_CLIPPED_VALUE_LOSS if clipped else 0, **HYPER)
+    tv = lambda x: None if x is None else torch.from_numpy(x).cuda()  # noqa: E731
+    cfg = ppo.PPOLossConfig(use_clipped_value_loss=clipped, **HYPER)
+    losses, out, d_lp, d_v = ppo.ppo_loss_and_grads(ppo.PPOInputs(tv(adv), tv(tgt)), ppo.PPOVariables(tv(lp_on), tv(v_on)),
+                                                    ppo.PPOVariables(tv(lp_off), tv(v_off), tv(ent)), cfg, kl_scale=1.7)
+    np.testing.assert_allclose(_np(losses), o_losses, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(_np(out), o_out, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(_np(d_lp), o_dlp, rtol=2e-6, atol=1e-12)
+    np.testing.assert_allclose(_np(d_v), o_dv, rtol=2e-6, atol=1e-12)
+    # the kl term involves no transcendental: bit-exact
+    np.testing.assert_array_equal(_np(losses)[2], o_losses[2])
+    # deterministic reduction: a second launch gives the same bits
+    _, out2, _, _ = ppo.ppo_loss_and_grads(ppo.PPOInputs(tv(adv), tv(tgt)), ppo.PPOVariables(tv(lp_on), tv(v_on)),
+                                           ppo.PPOVariables(tv(lp_off), tv(v_off), tv(ent)), cfg, kl_scale=1.7)
+    assert torch.equal(out, out2)
+
+
+def test_ppo_loss_autograd_matches_torch_reference(ctx) -> None:  # noqa: ANN001
+    """PPOLossFunction (kernel forward + analytic backward) against a plain torch fp32 statement of the reference's
+    expressions differentiated by autograd, through a small network so that the gradients reach parameters; and the
+    reference-named compute_ppo_loss dict."""
+    from ksim_b200 import ppo
+    from tests.test_ppo_loss import HYPER, make_case, torch_ppo_loss
+
+    b, t, a = 64, 24, 17
+    lp_on, lp_off, v_on, v_off, adv, tgt, ent = (torch.from_numpy(x.astype(np.float32)).cuda() for x in make_case(b, t, a, seed=3))
+    grads = []
+    for use_kernel in (True, False):
+        torch.manual_seed(0)
+        scale = torch.nn.Parameter(torch.ones(a, device="cuda"))
+        shift = torch.nn.Parameter(torch.zeros(1, device="cuda"))
+        n_lp, n_v, n_ent = lp_off * scale, v_off + shift, ent * scale
+        if use_kernel:
+            loss, terms = ppo.ppo_loss(ppo.PPOInputs(adv, tgt), ppo.PPOVariables(lp_on, v_on), ppo.PPOVariables(n_lp, n_v, n_ent),
+                                       ppo.PPOLossConfig(**HYPER), kl_scale=1.3)
+            assert set(terms) == {"policy", "value", "kl", "entropy"}
+        else:
+            _, loss = torch_ppo_loss(lp_on, n_lp, v_on, n_v, adv, tgt, n_ent, kl_scale=1.3, clipped=True, **HYPER)
+        loss.backward()
+        grads.append((loss.item(), scale.grad.clone(), shift.grad.clone()))
+    assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[1][0]) + 1e-7
+    torch.testing.assert_close(grads[0][1], grads[1][1], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(grads[0][2], grads[1][2], rtol=1e-4, atol=1e-6)
+    d = ppo.compute_ppo_loss(ppo.PPOInputs(adv, tgt), ppo.PPOVariables(lp_on, v_on), ppo.PPOVariables(lp_off, v_off, None),
+                             use_clipped_value_loss=True, **HYPER)
+    want, _ = torch_ppo_loss(lp_on, lp_off, v_on, v_off, adv, tgt, None, kl_scale=1.0, clipped=True, **HYPER)
+    assert set(d) == {"policy", "value", "kl"}
+    for k in d:
+        torch.testing.assert_close(d[k], want[k], rtol=1e-5, atol=1e-6)
+
+
+def test_ppo_loss_edge_cases(ctx) -> None:  # noqa: ANN001
+    import ctypes
+
+    from ksim_b200 import binding, codes as C, ppo
+
+    lib = binding.lib()
+    assert lib.b200sim_ppo_loss(None, 0, 5, 3, *([None] * 7), *([ctypes.c_float(0.1)] * 6), 0, *([None] * 5)) == C.B2S_OK
+    assert lib.b200sim_ppo_loss(None, 2, 5, 3, *([None] * 7), *([ctypes.c_float(0.1)] * 6), 0, *([None] * 5)) == C.B2S_ERR_BAD_ARG
+    assert lib.b200sim_ppo_loss(None, 2, 5, C.PPO_MAX_ACTIONS + 1, *([None] * 7), *([ctypes.c_float(0.1)] * 6), 0, *([None] * 5)) == C.B2S_ERR_UNSUPPORTED
+    z3, z2 = torch.zeros(2, 3, 4, device="cuda"), torch.zeros(2, 3, device="cuda")
+    _, out, d_lp, d_v = ppo.ppo_loss_and_grads(ppo.PPOInputs(z2, z2), ppo.PPOVariables(z3, z2), ppo.PPOVariables(z3, z2))
+    assert float(out.abs().sum()) == 0.0 and float(d_v.abs().sum()) == 0.0
+    # identical policies: ratio 1, the policy gradient is -A / n - kl_coef / n
+    adv = torch.randn(2, 3, device="cuda")
+    _, _, d_lp, _ = ppo.ppo_loss_and_grads(ppo.PPOInputs(adv, z2), ppo.PPOVariables(z3, z2), ppo.PPOVariables(z3, z2))
+    torch.testing.assert_close(d_lp, (-adv - 1e-3) / 6.0, rtol=1e-6, atol=1e-9)
