@@ -230,7 +230,8 @@
 #define PPO_CLIPPED_VALUE_LOSS 1
 #define PPO_N_TERMS 4            /* losses[PPO_N_TERMS][B][T]: policy, value, kl (already x kl_scale), entropy */
 #define PPO_MAX_ACTIONS 128      /* widest log-prob row the kernel stages */
-#define PPO_SCRATCH_BYTES 40960  /* caller-owned device scratch: per-CTA partial sums (<= 1024 CTAs x 5 doubles) */
+#define PPO_MAX_CTAS 2368        /* grid cap: 16 resident CTAs (the 2048-thread limit) on each of 148 SMs */
+#define PPO_SCRATCH_BYTES 94720  /* caller-owned device scratch: per-CTA partial sums (<= PPO_MAX_CTAS x 5 doubles) */
 
 /* ---- error codes ---- */
 #define B2S_OK 0

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(PPO_TILE) k_ppo_loss(size_t n, int A, const fl
                                                        float clip_param, float value_loss_coef, float entropy_coef, float kl_coef,
                                                        float log_clip_value, float kl_scale, int flags, float* __restrict__ losses,
                                                        float* __restrict__ d_logp, float* __restrict__ d_values,
-                                                       double* __restrict__ partial) {
+                                                       double* __restrict__ partial, int vec_ok) {
   extern __shared__ __align__(16) float ppo_sh[];
   __shared__ double red[PPO_TILE];
   const int tid = threadIdx.x, AP = A | 1;
@@ -224,7 +224,25 @@ __global__ void __launch_bounds__(PPO_TILE) k_ppo_loss(size_t n, int A, const fl
     const int cnt = (int)(n - e0 < (size_t)PPO_TILE ? n - e0 : (size_t)PPO_TILE);
     const size_t f0 = e0 * A;
     const int nf = cnt * A;
-    for (int f = tid; f < nf; f += PPO_TILE) {
+    // a full tile starts on a 16-byte boundary (128 A floats per tile) and holds a multiple of 4 floats: 128-bit loads
+    const int nf4 = vec_ok ? (nf >> 2) : 0;
+#pragma unroll 4
+    for (int v = tid; v < nf4; v += PPO_TILE) {
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(logp_off + f0) + v);
+      const float4 y = __ldcs(reinterpret_cast<const float4*>(logp_on + f0) + v);
+      float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (entropy) z = __ldcs(reinterpret_cast<const float4*>(entropy + f0) + v);
+      int r = (4 * v) / A, c = 4 * v - r * A;
+      const float dx[4] = {__fsub_rn(x.x, y.x), __fsub_rn(x.y, y.y), __fsub_rn(x.z, y.z), __fsub_rn(x.w, y.w)};
+      const float ze[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        sd[r * AP + c] = dx[k];
+        if (entropy) se[r * AP + c] = ze[k];
+        if (++c == A) { c = 0; r++; }
+      }
+    }
+    for (int f = 4 * nf4 + tid; f < nf; f += PPO_TILE) {
       const int r = f / A, c = f - r * A;
       sd[r * AP + c] = __fsub_rn(logp_off[f0 + f], logp_on[f0 + f]);
       if (entropy) se[r * AP + c] = entropy[f0 + f];
@@ -280,12 +298,14 @@ __global__ void __launch_bounds__(PPO_TILE) k_ppo_loss(size_t n, int A, const fl
   }
 }
 
-__global__ void __launch_bounds__(32) k_ppo_reduce(int n_blocks, size_t n, const double* __restrict__ partial, float* __restrict__ out) {
-  const int k = threadIdx.x;
-  if (k >= 1 + PPO_N_TERMS) return;
+// one warp per term: lane l adds partials l, l + 32, ... in order, then a fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(32 * (1 + PPO_N_TERMS)) k_ppo_reduce(int n_blocks, size_t n, const double* __restrict__ partial,
+                                                                       float* __restrict__ out) {
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double s = 0.0;
-  for (int b = 0; b < n_blocks; b++) s += partial[(size_t)b * (1 + PPO_N_TERMS) + k];
-  out[k] = (float)(s / (double)n);
+  for (int b = lane; b < n_blocks; b += 32) s += partial[(size_t)b * (1 + PPO_N_TERMS) + k];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) out[k] = (float)(s / (double)n);
 }
 
 // Trajectory metrics, stage 1: one warp per environment, lanes over time steps (warp-shuffle reductions).
@@ -608,16 +628,25 @@ extern "C" int b200sim_ppo_loss(void* stream, int batch, int n_steps, int n_act,
     return fail(B2S_ERR_BAD_ARG, "null argument");
   const size_t n = (size_t)batch * n_steps;
   const size_t tiles = (n + PPO_TILE - 1) / PPO_TILE;
-  const int n_blocks = (int)(tiles < 1024 ? tiles : 1024);  // a function of n only: the reduction order is reproducible
-  static_assert(1024 * (1 + PPO_N_TERMS) * sizeof(double) <= PPO_SCRATCH_BYTES, "scratch too small");
+  static_assert(PPO_MAX_CTAS * (1 + PPO_N_TERMS) * sizeof(double) <= PPO_SCRATCH_BYTES, "scratch too small");
+  const int vec_ok = ((((uintptr_t)logp_on | (uintptr_t)logp_off | (uintptr_t)entropy) & 15) == 0) ? 1 : 0;
   const size_t smem = (size_t)(entropy ? 2 : 1) * PPO_TILE * (n_act | 1) * sizeof(float);
   if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k_ppo_loss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // one wave of resident CTAs, each striding over the tiles (no tail wave): the grid, and with it the order of the
+  // reduction, is a function of (n, n_act, entropy, device model) only -- reproducible run to run
+  int dev = 0, sms = 0, per_sm = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppo_loss, PPO_TILE, smem));
+  size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+  if (resident > PPO_MAX_CTAS) resident = PPO_MAX_CTAS;
+  const int n_blocks = (int)(tiles < resident ? tiles : resident);
   k_ppo_loss<<<n_blocks, PPO_TILE, smem, (cudaStream_t)stream>>>(n, n_act, logp_on, logp_off, values_on, values_off, adv, targets,
                                                                  entropy, clip_param, value_loss_coef, entropy_coef, kl_coef,
                                                                  log_clip_value, kl_scale, flags, losses, d_logp, d_values,
-                                                                 (double*)scratch);
+                                                                 (double*)scratch, vec_ok);
   CUDA_OK(cudaGetLastError());
-  k_ppo_reduce<<<1, 32, 0, (cudaStream_t)stream>>>(n_blocks, n, (const double*)scratch, out);
+  k_ppo_reduce<<<1, 32 * (1 + PPO_N_TERMS), 0, (cudaStream_t)stream>>>(n_blocks, n, (const double*)scratch, out);
   CUDA_OK(cudaGetLastError());
   return B2S_OK;
 }

@@ -84,10 +84,10 @@ def ppo_loss_and_grads(ppo_inputs: PPOInputs, on_policy_variables: PPOVariables,
     adv = _chk(ppo_inputs.advantages_bt, (b, t), dev, "advantages_bt")
     tgt = _chk(ppo_inputs.value_targets_bt, (b, t), dev, "value_targets_bt")
     ent = None if off_policy_variables.entropy is None else _chk(off_policy_variables.entropy, (b, t, a), dev, "entropy")
-    losses = torch.zeros((C.PPO_N_TERMS, b, t), dtype=torch.float32, device=dev) if want_losses else None
+    losses = torch.empty((C.PPO_N_TERMS, b, t), dtype=torch.float32, device=dev) if want_losses else None  # every element is written
     out = torch.zeros(1 + C.PPO_N_TERMS, dtype=torch.float32, device=dev)
-    d_logp = torch.zeros((b, t), dtype=torch.float32, device=dev) if want_grads else None
-    d_values = torch.zeros((b, t), dtype=torch.float32, device=dev) if want_grads else None
+    d_logp = torch.empty((b, t), dtype=torch.float32, device=dev) if want_grads else None
+    d_values = torch.empty((b, t), dtype=torch.float32, device=dev) if want_grads else None
     scratch = torch.empty(C.PPO_SCRATCH_BYTES, dtype=torch.uint8, device=dev)
     flags = C.PPO_CLIPPED_VALUE_LOSS if config.use_clipped_value_loss else 0
     cf = ctypes.c_float
