@@ -70,6 +70,16 @@ constexpr int max_warps() {
 template <class D>
 constexpr int launch_threads() { return D::EXACT ? 512 : 32 * max_warps<D>(); }
 
+// -DB2S_POISON_SMEM (debug): a workspace starts as whatever the previous kernel left in shared memory; filling a byte range
+// of it with 0xFF (NaN floats, -1 ints) makes a read of a field nobody wrote visible in the outputs (tools/debug_poison.py)
+#ifdef B2S_POISON_SMEM
+#define POISON_WORK(mp, w) do { unsigned* pw_ = reinterpret_cast<unsigned*>(&(w)); \
+    for (int i_ = (mp).poison_lo / 4 + lane; i_ < (mp).poison_hi / 4 && i_ < (int)(sizeof(w) / 4); i_ += 32) pw_[i_] = 0xffffffffu; \
+    __syncwarp(); } while (0)
+#else
+#define POISON_WORK(mp, w) do { } while (0)
+#endif
+
 template <class D>
 __global__ void __launch_bounds__(launch_threads<D>()) k_init_envs(const Mdl mp, int n_envs, const uint32_t* __restrict__ init_keys,
                                                    const float* __restrict__ levels, const float* __restrict__ rand,
@@ -81,6 +91,7 @@ __global__ void __launch_bounds__(launch_threads<D>()) k_init_envs(const Mdl mp,
   const Mdl& m = stage_model<D>(mp, smem, wpb);
   if (env >= n_envs) return;
   Work<D>& w = reinterpret_cast<Work<D>*>(smem)[warp];
+  POISON_WORK(mp, w);
   const int* ti = m.ti;
   const size_t S = ti[TI_STATE_SIZE], R = ti[TI_REC_SIZE], K = ti[TI_KEY_SIZE], RAND = ti[TI_RAND_SIZE];
   DBG_STOP(m, 1);
@@ -112,6 +123,7 @@ __global__ void __launch_bounds__(launch_threads<D>()) k_rollout(const Mdl mp, i
     return;
   }
   Work<D>& w = reinterpret_cast<Work<D>*>(smem)[warp];
+  POISON_WORK(mp, w);
   const size_t S = ti[TI_STATE_SIZE], R = ti[TI_REC_SIZE], K = ti[TI_KEY_SIZE], RAND = ti[TI_RAND_SIZE];
   const size_t NA = ti[TI_ACTION_SIZE];
   apply_overrides(m, w, rand + env * RAND, lane);
@@ -484,6 +496,10 @@ extern "C" int b200sim_model_create(const void* blob, size_t nbytes, b200sim_mod
   mo->mdl.ti = d + MH_SIZE + ni + nf;
   mo->mdl.tf = (const float*)(d + MH_SIZE + ni + nf + nti);
   mo->mdl.sync_mask = 0x7f;  // measured best on B200 (profiles/): a CTA barrier after every stage; votes inside the Newton loop (bit 7) are neutral since the solve became short
+#ifdef B2S_POISON_SMEM
+  mo->mdl.poison_lo = getenv("B2S_POISON_LO") ? atoi(getenv("B2S_POISON_LO")) : 0;
+  mo->mdl.poison_hi = getenv("B2S_POISON_HI") ? atoi(getenv("B2S_POISON_HI")) : 0;
+#endif
 #ifdef B2S_DEBUG_STOP
   if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0xff07ff;  // + DBG_STOP point
 #else

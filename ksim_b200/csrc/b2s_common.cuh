@@ -122,6 +122,9 @@ struct Mdl {
   const float* tf;
   int sync_mask;  // which per-sub-step CTA barriers run (bit 0..5: forward's stages, bit 6: sub-step start)
   int stage[4];   // words of mi / mf / ti / tf the kernels copy into shared memory (0: read from global memory)
+#ifdef B2S_POISON_SMEM
+  int poison_lo, poison_hi;  // debug build: bytes [lo, hi) of every workspace start as 0xFF (tools/debug_poison.py)
+#endif
 };
 #define MI(m, name) ((m).mi + (m).h[name])
 #define MF(m, name) ((m).mf + (m).h[name])

@@ -32,8 +32,10 @@ DEV void apply_overrides(const Mdl& m, Work<D>& w, const float* rand, LANE_ARG) 
   const float* ipos = MF(m, MH_BODY_IPOS);
   LANE_FOR(i, nv) { w.armature[i] = arm[i]; w.damping[i] = damp[i]; w.frictionloss[i] = fl[i]; }
   // the mass matrix is only ever written on its ancestor pattern (crb_mass_matrix), which is a property of the model:
-  // zero it once per workspace instead of once per sub-step
-  LANE_FOR(i, nv) {
+  // zero it once per workspace instead of once per sub-step.  ALL D::NV rows, not only the model's nv: the register-resident
+  // factor_solve loads one row per lane, and a stale NaN / Inf in a row beyond nv reaches the live lanes through the
+  // unguarded 0 * x products of its Z substitutions (found with tools/debug_poison.py in the larger instantiations)
+  LANE_FOR(i, D::NV) {
     for (int j = 0; j < D::NVP; j++) w.M[i][j] = 0.0f;
   }
   LANE_FOR(b, nb) {

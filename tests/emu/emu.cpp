@@ -16,6 +16,10 @@
 using namespace b2s;
 typedef DimsGeneric D;
 
+// the workspace starts as whatever the previous kernel left in shared memory: B2S_EMU_POISON=1 fills it with 0xFF bytes
+// (NaN floats, -1 ints) so that a read of a field nobody wrote shows up in the parity tests
+static int poison_byte() { const char* e = getenv("B2S_EMU_POISON"); return (e && atoi(e)) ? 0xFF : 0; }
+
 static Mdl view(const void* blob) {
   Mdl m;
   const int* h = (const int*)blob;
@@ -37,7 +41,7 @@ extern "C" int emu_init_envs(const void* blob, int n, const uint32_t* init_keys,
 #pragma omp parallel for schedule(static)
   for (int e = 0; e < n; e++) {
     Work<D>* w = new Work<D>();
-    memset(w, 0, sizeof(*w));
+    memset(w, poison_byte(), sizeof(*w));
     apply_overrides(m, *w, rand + e * RAND, 0);
     env_init(m, *w, init_keys + (size_t)e * 10, levels[e], rec0 + e * R, act_keys ? act_keys + 2 * e : nullptr, 0);
     env_store(m, *w, state + e * S, keys + e * K, 0);
@@ -54,7 +58,7 @@ extern "C" int emu_step_ctrl(const void* blob, int n, const float* action, const
 #pragma omp parallel for schedule(static)
   for (int e = 0; e < n; e++) {
     Work<D>* w = new Work<D>();
-    memset(w, 0, sizeof(*w));
+    memset(w, poison_byte(), sizeof(*w));
     apply_overrides(m, *w, rand + e * RAND, 0);
     env_load(m, *w, state + e * S, keys + e * K, 0);
     env_step(m, *w, action + e * NA, rec_cur + e * R, rec_next + e * R, act_keys ? act_keys + 2 * e : nullptr, 0);
@@ -84,7 +88,7 @@ extern "C" int emu_sizeof_mdl(void) { return (int)sizeof(Mdl); }
 extern "C" int emu_kinematics(const void* blob, const float* rand, const float* qpos, float* xpos, float* xquat, float* xanchor, float* xaxis) {
   Mdl m = view(blob);
   Work<D>* w = new Work<D>();
-  memset(w, 0, sizeof(*w));
+  memset(w, poison_byte(), sizeof(*w));
   apply_overrides(m, *w, rand, 0);
   for (int i = 0; i < m.h[MH_NQ]; i++) w->qpos[i] = qpos[i];
   kinematics(m, *w, 0);

@@ -436,6 +436,46 @@ def test_generic_instantiation_tripod_with_events(monkeypatch) -> None:  # noqa:
     assert n_succ > 0 and n_done >= n_succ
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+def test_humanoid_through_the_larger_instantiations(ctx, monkeypatch, variant) -> None:  # noqa: ANN001
+    """The humanoid task pushed through the K-Bot-sized (1) and the generic (2) kernel instantiations (B2S_MIN_VARIANT):
+    run-time loop bounds, the shared-memory constraint-space / dof-space solver paths and per-pair geom storage instead of
+    the exact-fit code.  Same resynchronised protocol and tolerances as test_single_step_parity_resynchronised."""
+    spec, rz = ctx
+    monkeypatch.setenv("B2S_MIN_VARIANT", str(variant))
+    n, steps, seed, level = 40, 40, 3, 1.0
+    eng = _engine(spec, rz, n, level=level, seed=seed)
+    assert eng.info("VARIANT") == variant
+    ora, st, keys, rec0, _ = _oracle_init(eng)
+    np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
+    np.testing.assert_allclose(_np(eng.state), st, rtol=1e-4, atol=2e-5)
+    p, m = eng.program, spec.model
+    actions = (0.3 * np.random.RandomState(seed + 1).randn(steps, n, eng.NA)).astype(np.float32)
+    rec_o = np.zeros((2, n, eng.R), np.float32)
+    rec_o[0] = rec0
+    cur, nxt = (torch.zeros((n, eng.R), device="cuda") for _ in range(2))
+    q, v, d, sc, te = p["TI_R_QPOS"], p["TI_R_QVEL"], p["TI_R_DONE"], p["TI_R_SUCCESS"], p["TI_R_TERM"]
+    n_bad = n_done = 0
+    for s in range(steps):
+        eng.state.copy_(torch.from_numpy(st).cuda())
+        eng.keys.copy_(torch.from_numpy(keys.view(np.int32)).cuda())
+        eng.step(torch.from_numpy(actions[s]).cuda(), cur, nxt)
+        ora.step_ctrl(actions[s], eng.env_init.rand, st, keys, rec_o[0], rec_o[1])
+        g_cur = _np(cur)
+        np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
+        np.testing.assert_array_equal(g_cur[:, d], rec_o[0][:, d])
+        np.testing.assert_array_equal(g_cur[:, sc], rec_o[0][:, sc])
+        np.testing.assert_array_equal(g_cur[:, te : te + 3], rec_o[0][:, te : te + 3])
+        dq = np.abs(g_cur[:, q : q + m.nq] - rec_o[0][:, q : q + m.nq])
+        dv = np.abs(g_cur[:, v : v + m.nv] - rec_o[0][:, v : v + m.nv])
+        assert dq.max() <= 2e-2 and dv.max() <= 2.0, (s, dq.max(), dv.max())
+        n_bad += int(((dq > 2e-4).any(axis=1) | (dv > 2e-2 + 5e-3 * np.abs(rec_o[0][:, v : v + m.nv])).any(axis=1)).sum())
+        n_done += int(rec_o[0][:, d].sum())
+        rec_o[0] = rec_o[1]
+    assert n_bad <= max(1, int(0.003 * n * steps)), f"{n_bad} of {n * steps} env-steps outside the stated tolerance"
+    assert n_done > 0
+
+
 def test_solver_paths_agree_at_full_size(ctx, monkeypatch) -> None:  # noqa: ANN001
     """The shipped solver (constraint-space Newton, exact line search, register-resident loop) against the
     reference-shaped one (dof-space Newton with the bracketing line search; B2S_SYNC_MASK bit 8) on the GPU, 4096 envs,
