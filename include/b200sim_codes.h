@@ -200,6 +200,17 @@
 #define REW_OFF_AXIS_VELOCITY 14
 #define REW_SMALL_JOINT_VELOCITY 15
 /* the K-Bot task's own rewards (examples/kbot/train.py:128-496) */
+/* more of ksim/rewards.py (not used by the two example tasks): ints / floats listed with each class in ksim_b200/rewards.py */
+#define REW_SMALL_JOINT_ACCELERATION 27
+#define REW_SMALL_JOINT_JERK 28
+#define REW_AVOID_LIMITS 29
+#define REW_TORQUE 30
+#define REW_ENERGY 31
+#define REW_JOINT_DEVIATION 32
+#define REW_FLAT_BODY 33
+#define REW_NO_ROLL 34
+#define REW_LINK_ACCELERATION 35
+#define REW_LINK_JERK 36
 #define REW_KBOT_SINGLE_FOOT_CONTACT 16
 #define REW_KBOT_NO_CONTACT 17
 #define REW_KBOT_FEET_AIRTIME 18

@@ -211,6 +211,108 @@ DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, floa
           OUT(0, s) = acc / (float)(nq - 7);
         }
         break;
+      // ---- more of ksim/rewards.py (same structure as oracle/engine.c) ----
+      case REW_SMALL_JOINT_ACCELERATION: case REW_SMALL_JOINT_JERK: {
+        // rewards.py:479-508: edge-padded differences of qpos[7:] with done masking; no mask on the first steps
+        const int order = type == REW_SMALL_JOINT_ACCELERATION ? 2 : 3;
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int k = 7; k < nq; k++) {
+#define QPAD(p) REC(((p) - order) > 0 ? ((p) - order) : 0, QP + k)
+#define DPAD(p) (REC(((p) - order) > 0 ? ((p) - order) : 0, DN) != 0.0f)
+#define VEL(i) (DPAD(i) ? 0.0f : QPAD((i) + 1) - QPAD(i))
+#define ACC(i) (DPAD((i) + 1) ? 0.0f : VEL((i) + 1) - VEL(i))
+#define JRK(i) (DPAD((i) + 2) ? 0.0f : ACC((i) + 1) - ACC(i))
+            const float v = order == 2 ? ACC(s) : JRK(s);
+            acc += exp_kernel(v, xf[0]);
+#undef QPAD
+#undef VEL
+#undef ACC
+#undef JRK
+          }
+          OUT(0, s) = acc / (float)(nq - 7);
+        }
+      } break;
+      case REW_LINK_ACCELERATION: case REW_LINK_JERK: {
+        // rewards.py:809-841: body speeds from edge-padded position differences, second / third difference
+        const int order = type == REW_LINK_ACCELERATION ? 2 : 3;
+        const int XP = ti[TI_R_XPOS], nb = xi[1];
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int b = 1; b < nb; b++) {
+#define TPAD(p) (((p) - order) > 0 ? ((p) - order) : 0)
+#define PDIF(i, c) (REC(TPAD((i) + 1), XP + 3 * b + (c)) - REC(TPAD(i), XP + 3 * b + (c)))
+#define VEL(i) (DPAD(i) ? 0.0f : sqrtf(PDIF(i, 0) * PDIF(i, 0) + PDIF(i, 1) * PDIF(i, 1) + PDIF(i, 2) * PDIF(i, 2)))
+#define ACC(i) (DPAD((i) + 1) ? 0.0f : VEL((i) + 1) - VEL(i))
+#define JRK(i) (DPAD((i) + 2) ? 0.0f : ACC((i) + 1) - ACC(i))
+            const float v = order == 2 ? ACC(s) : JRK(s);
+            acc += norm_fn(v, xi[0]);
+#undef TPAD
+#undef PDIF
+#undef VEL
+#undef ACC
+#undef JRK
+#undef DPAD
+          }
+          OUT(0, s) = acc / (float)(nb - 1);
+        }
+      } break;
+      case REW_AVOID_LIMITS: {
+        const int n = xi[0];
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int k = 0; k < n; k++) {
+            const float q = REC(s, QP + 7 + k), a = q - xf[k], b = q - xf[n + k];
+            acc += -(a < 0.0f ? a : 0.0f) + (b > 0.0f ? b : 0.0f);
+          }
+          OUT(0, s) = acc / (float)n;
+        }
+      } break;
+      case REW_TORQUE: case REW_ENERGY: {
+        const int n = xi[0], CT = ti[TI_R_CTRL];
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int k = 0; k < n; k++) {
+            float c = REC(s, CT + k) / xf[k];
+            if (type == REW_ENERGY) c = c * REC(s, QV + 6 + k);
+            acc += fabsf(c);
+          }
+          OUT(0, s) = acc / (float)n;
+        }
+      } break;
+      case REW_JOINT_DEVIATION: {
+        const int n = xi[1];
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int k = 0; k < n; k++) {
+            float d = REC(s, QP + 7 + xi[3 + k]) - xf[k];
+            if (xi[2]) d *= xf[n + k];
+            acc += norm_fn(d, xi[0]);
+          }
+          OUT(0, s) = acc;
+        }
+      } break;
+      case REW_FLAT_BODY: {
+        const int n = xi[0], XQ = ti[TI_R_XQUAT];
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          const V3 pl = v3(xf[0], xf[1], xf[2]);
+          for (int k = 0; k < n; k++) {
+            const int o = XQ + 4 * xi[1 + k];
+            Q4 q; q.w = REC(s, o); q.x = REC(s, o + 1); q.y = REC(s, o + 2); q.z = REC(s, o + 3);
+            acc += dot(rot_vec_quat(pl, q, true), pl);
+          }
+          OUT(0, s) = acc / (float)n;
+        }
+      } break;
+      case REW_NO_ROLL:
+        LANE_FOR(s, T) {
+          Q4 q; q.w = REC(s, QP + 3); q.x = REC(s, QP + 4); q.y = REC(s, QP + 5); q.z = REC(s, QP + 6);
+          const V3 zb = rot_vec_quat(v3(0, 0, 1), q, true);
+          OUT(0, s) = exp_kernel_pen(REC(s, QV + 3), xf[0], xf[2], xf[3]);
+          OUT(1, s) = exp_kernel_pen(-atan2f(zb.y, zb.z), xf[1], xf[4], xf[5]);
+        }
+        break;
       // ---- the K-Bot task's own rewards (examples/kbot/train.py:128-496; same structure as oracle/engine.c)
 #define UCMD(s, k) REC(s, CM + ucmd + (k))
 #define ZERO_CMD(s) (sqrtf(UCMD(s, 0) * UCMD(s, 0) + UCMD(s, 1) * UCMD(s, 1) + UCMD(s, 2) * UCMD(s, 2)) < 1e-3f)

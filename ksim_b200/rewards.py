@@ -12,8 +12,9 @@ __all__ = [
     "Reward", "StatefulReward", "StayAliveReward", "UprightReward", "LinearVelocityReward", "AngularVelocityReward",
     "FeetAirTimeReward", "SparseTargetHeightReward", "ForcePenalty", "MotionlessAtRestPenalty",
     "ActionVelocityPenalty", "ActionAccelerationPenalty", "ActionJerkPenalty", "BaseHeightReward",
-    "BaseHeightRangeReward", "OffAxisVelocityReward", "SmallJointVelocityReward", "exp_kernel",
-    "exp_kernel_with_penalty",
+    "BaseHeightRangeReward", "OffAxisVelocityReward", "SmallJointVelocityReward", "SmallJointAccelerationReward",
+    "SmallJointJerkReward", "AvoidLimitsPenalty", "TorquePenalty", "EnergyPenalty", "JointDeviationPenalty", "FlatBodyReward",
+    "NoRollReward", "LinkAccelerationPenalty", "LinkJerkPenalty", "exp_kernel", "exp_kernel_with_penalty",
 ]
 
 import math
@@ -37,6 +38,8 @@ def exp_kernel_with_penalty(x: float, scale: float, sq_scale: float, abs_scale: 
 
 
 class EncodeContext(Protocol):
+    model: object  # ksim_b200.mjcf.Model
+
     def obs_offset(self, name: str) -> int: ...
     def obs_shape(self, name: str) -> tuple[int, ...]: ...
     def cmd_offset(self, name: str, field: str | None = None) -> int: ...
@@ -170,6 +173,167 @@ class SmallJointVelocityReward(Reward):
 
     def encode(self, ctx: EncodeContext) -> Encoded:
         return C.REW_SMALL_JOINT_VELOCITY, [], [float(self.kernel_scale)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class SmallJointAccelerationReward(Reward):
+    """ksim/rewards.py:479-491."""
+
+    kernel_scale: float = attrs.field(default=0.25)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_SMALL_JOINT_ACCELERATION, [], [float(self.kernel_scale)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class SmallJointJerkReward(Reward):
+    """ksim/rewards.py:495-508."""
+
+    kernel_scale: float = attrs.field(default=0.25)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_SMALL_JOINT_JERK, [], [float(self.kernel_scale)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class AvoidLimitsPenalty(Reward):
+    """ksim/rewards.py:522-554; ``joint_limits`` is ``((lo, hi), ...)`` for the joints after the free joint (+-inf: unlimited)."""
+
+    joint_limits: tuple[tuple[float, float], ...] = attrs.field()
+
+    @joint_limits.validator
+    def _check(self, _attr: object, value: tuple[tuple[float, float], ...]) -> None:
+        if any(len(r) != 2 or r[0] > r[1] for r in value):
+            raise ValueError(f"Joint range must be sorted (n_joints, 2), got {value}")
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        n = len(self.joint_limits)
+        if n != ctx.model.nq - 7:
+            raise ValueError(f"AvoidLimitsPenalty has {n} joint ranges, the model has {ctx.model.nq - 7} joints after the free joint")
+        return (C.REW_AVOID_LIMITS, [n], [float(r[0]) for r in self.joint_limits] + [float(r[1]) for r in self.joint_limits], [""], 0)
+
+    @classmethod
+    def create(cls, model: object, factor: float = 0.05, scale: float | Scale = 1.0) -> "AvoidLimitsPenalty":
+        lims = []
+        for j in range(1, model.njnt):
+            lo, hi = (float(v) for v in model.jnt_range[j])
+            diff = (hi - lo) * factor
+            lims.append((lo - diff, hi + diff) if model.jnt_limited[j] else (-math.inf, math.inf))
+        return cls(joint_limits=tuple(lims), scale=scale)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class TorquePenalty(Reward):
+    """ksim/rewards.py:557-582."""
+
+    ctrl_scales: tuple[float, ...] = attrs.field()
+    _code = C.REW_TORQUE
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        if len(self.ctrl_scales) != ctx.model.nu:
+            raise ValueError(f"{len(self.ctrl_scales)} ctrl scales for {ctx.model.nu} actuators")
+        return self._code, [len(self.ctrl_scales)], [float(v) for v in self.ctrl_scales], [""], 0
+
+    @classmethod
+    def create(cls, model: object, scale: float | Scale = 1.0) -> "TorquePenalty":
+        rng = model.actuator_ctrlrange
+        return cls(ctrl_scales=tuple(float((hi - lo) / 2.0) for lo, hi in rng), scale=scale)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class EnergyPenalty(TorquePenalty):
+    """ksim/rewards.py:586-593: |ctrl / scale * qvel[6:]| (one actuator per joint dof, in dof order)."""
+
+    _code = C.REW_ENERGY
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        if ctx.model.nu != ctx.model.nv - 6:
+            raise ValueError("EnergyPenalty multiplies ctrl and qvel[6:] element-wise: needs one actuator per joint dof")
+        return super().encode(ctx)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class JointDeviationPenalty(Reward):
+    """ksim/rewards.py:596-662; ``joint_indices`` count from the first joint after the free joint."""
+
+    norm: str = attrs.field(default="l2")
+    joint_indices: tuple[int, ...] = attrs.field()
+    joint_targets: tuple[float, ...] = attrs.field()
+    joint_weights: tuple[float, ...] | None = attrs.field(default=None)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        n = len(self.joint_indices)
+        if len(self.joint_targets) != n or (self.joint_weights is not None and len(self.joint_weights) != n):
+            raise ValueError("joint indices, targets and weights must have the same length")
+        if any(i < 0 or i >= ctx.model.nq - 7 for i in self.joint_indices):
+            raise ValueError(f"joint index outside [0, {ctx.model.nq - 7})")
+        w = [1.0] * n if self.joint_weights is None else [float(v) for v in self.joint_weights]
+        return (C.REW_JOINT_DEVIATION, [_norm_flag(self.norm), n, int(self.joint_weights is not None), *self.joint_indices],
+                [float(v) for v in self.joint_targets] + w, [""], 0)
+
+    @classmethod
+    def create(cls, physics_model: object, joint_names: tuple[str, ...], joint_targets: tuple[float, ...],
+               scale: float | Scale = 1.0, joint_weights: tuple[float, ...] | None = None) -> "JointDeviationPenalty":
+        if len(joint_names) != len(joint_targets):
+            raise ValueError(f"Joint names and targets must match, got {len(joint_names)} and {len(joint_targets)}")
+        idx = tuple(int(physics_model.jnt_qposadr[physics_model.id("joint", n)]) - 7 for n in joint_names)
+        return cls(joint_indices=idx, joint_targets=tuple(float(v) for v in joint_targets),
+                   joint_weights=None if joint_weights is None else tuple(float(v) for v in joint_weights), scale=scale)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class FlatBodyReward(Reward):
+    """ksim/rewards.py:666-700 (``norm`` is accepted and, as in the reference, unused)."""
+
+    body_indices: tuple[int, ...] = attrs.field()
+    plane: tuple[float, float, float] = attrs.field(default=(0.0, 0.0, 1.0))
+    norm: str = attrs.field(default="l2")
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        if not self.body_indices or any(b < 0 or b >= ctx.model.nbody for b in self.body_indices):
+            raise ValueError("FlatBodyReward needs body indices inside the model")
+        return C.REW_FLAT_BODY, [len(self.body_indices), *self.body_indices], [float(v) for v in self.plane], [""], 0
+
+    @classmethod
+    def create(cls, physics_model: object, body_names: tuple[str, ...], plane: tuple[float, float, float] = (0.0, 0.0, 1.0),
+               norm: str = "l2", scale: float | Scale = 1.0) -> "FlatBodyReward":
+        return cls(body_indices=tuple(physics_model.id("body", n) for n in body_names), plane=plane, norm=norm, scale=scale)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class NoRollReward(Reward):
+    """ksim/rewards.py:781-805."""
+
+    angvel_scale: float = attrs.field(default=0.25)
+    roll_scale: float = attrs.field(default=0.25)
+    angvel_sq_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    angvel_abs_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    roll_sq_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    roll_abs_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        floats = [self.angvel_scale, self.roll_scale, self.angvel_sq_scale, self.angvel_abs_scale, self.roll_sq_scale, self.roll_abs_scale]
+        return C.REW_NO_ROLL, [], [float(f) for f in floats], ["angvel", "pose"], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class LinkAccelerationPenalty(Reward):
+    """ksim/rewards.py:809-822."""
+
+    norm: str = attrs.field(default="l2")
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_LINK_ACCELERATION, [_norm_flag(self.norm), int(ctx.model.nbody)], [], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class LinkJerkPenalty(Reward):
+    """ksim/rewards.py:826-841."""
+
+    norm: str = attrs.field(default="l2")
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        return C.REW_LINK_JERK, [_norm_flag(self.norm), int(ctx.model.nbody)], [], [""], 0
 
 
 @attrs.define(frozen=True, kw_only=True)

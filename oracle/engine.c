@@ -1194,6 +1194,11 @@ static void env_rewards(const Task* t, const REAL* rec, size_t tstride, int T, R
           REAL pen = acc / (REAL)na;
           out[0][s] = s >= order ? pen : 0;
         }
+#undef APAD
+#undef DPAD
+#undef VEL
+#undef ACC
+#undef JRK
       } break;
       case REW_BASE_HEIGHT: for (int s = 0; s < T; s++) out[0][s] = exp_kernel(REC(s, QP + 2) - xf[0], xf[1]); break;
       case REW_BASE_HEIGHT_RANGE:
@@ -1222,6 +1227,114 @@ static void env_rewards(const Task* t, const REAL* rec, size_t tstride, int T, R
             acc += exp_kernel(v, xf[0]);
           }
           out[0][s] = acc / (REAL)(nq - 7);
+        }
+        break;
+      case REW_SMALL_JOINT_ACCELERATION: case REW_SMALL_JOINT_JERK: {
+        /* rewards.py:479-508: edge-padded second / third differences of qpos[7:] with done masking, exp kernel, mean over
+         * joints; unlike the action penalties the first `order` steps are NOT masked out.  floats [kernel_scale] */
+        int order = type == REW_SMALL_JOINT_ACCELERATION ? 2 : 3;
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int k = 7; k < nq; k++) {
+#define QPAD(p) REC(((p) - order) > 0 ? ((p) - order) : 0, QP + k)
+#define DPAD(p) (REC(((p) - order) > 0 ? ((p) - order) : 0, DN) != 0)
+#define VEL(i) (DPAD(i) ? (REAL)0 : QPAD((i) + 1) - QPAD(i))
+#define ACC(i) (DPAD((i) + 1) ? (REAL)0 : VEL((i) + 1) - VEL(i))
+#define JRK(i) (DPAD((i) + 2) ? (REAL)0 : ACC((i) + 1) - ACC(i))
+            REAL v = order == 2 ? ACC(s) : JRK(s);
+            acc += exp_kernel(v, xf[0]);
+#undef QPAD
+#undef VEL
+#undef ACC
+#undef JRK
+          }
+          out[0][s] = acc / (REAL)(nq - 7);
+        }
+      } break;
+      case REW_LINK_ACCELERATION: case REW_LINK_JERK: {
+        /* rewards.py:809-841: speed of every body but the world (norm of the edge-padded position difference), second /
+         * third difference with done masking, get_norm, mean over bodies.  ints [l2, nbody] */
+        int order = type == REW_LINK_ACCELERATION ? 2 : 3;
+        int XP = ti[TI_R_XPOS], nb = xi[1];
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int b = 1; b < nb; b++) {
+#define TPAD(p) (((p) - order) > 0 ? ((p) - order) : 0)
+#define PDIF(i, c) (REC(TPAD((i) + 1), XP + 3 * b + (c)) - REC(TPAD(i), XP + 3 * b + (c)))
+#define VEL(i) (DPAD(i) ? (REAL)0 : SQRT(PDIF(i, 0) * PDIF(i, 0) + PDIF(i, 1) * PDIF(i, 1) + PDIF(i, 2) * PDIF(i, 2)))
+#define ACC(i) (DPAD((i) + 1) ? (REAL)0 : VEL((i) + 1) - VEL(i))
+#define JRK(i) (DPAD((i) + 2) ? (REAL)0 : ACC((i) + 1) - ACC(i))
+            REAL v = order == 2 ? ACC(s) : JRK(s);
+            acc += norm_fn(v, xi[0]);
+#undef TPAD
+#undef PDIF
+#undef VEL
+#undef ACC
+#undef JRK
+#undef DPAD
+          }
+          out[0][s] = acc / (REAL)(nb - 1);
+        }
+      } break;
+      case REW_AVOID_LIMITS: {
+        /* rewards.py:522-554; ints [n]; floats lo[n], hi[n] (+-inf for unlimited joints) */
+        int n = xi[0];
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int k = 0; k < n; k++) {
+            REAL q = REC(s, QP + 7 + k), a = q - xf[k], b = q - xf[n + k];
+            acc += -(a < 0 ? a : (REAL)0) + (b > 0 ? b : (REAL)0);
+          }
+          out[0][s] = acc / (REAL)n;
+        }
+      } break;
+      case REW_TORQUE: case REW_ENERGY: {
+        /* rewards.py:557-593; ints [nu]; floats ctrl_scales[nu] */
+        int n = xi[0], CT = ti[TI_R_CTRL];
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int k = 0; k < n; k++) {
+            REAL c = REC(s, CT + k) / xf[k];
+            if (type == REW_ENERGY) c = c * REC(s, QV + 6 + k);
+            acc += FABS(c);
+          }
+          out[0][s] = acc / (REAL)n;
+        }
+      } break;
+      case REW_JOINT_DEVIATION: {
+        /* rewards.py:596-662; ints [l2, n, has_weights, idx[n]]; floats targets[n], weights[n] */
+        int n = xi[1];
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int k = 0; k < n; k++) {
+            REAL d = REC(s, QP + 7 + xi[3 + k]) - xf[k];
+            if (xi[2]) d *= xf[n + k];
+            acc += norm_fn(d, xi[0]);
+          }
+          out[0][s] = acc;
+        }
+      } break;
+      case REW_FLAT_BODY: {
+        /* rewards.py:666-700; ints [n, body[n]]; floats plane[3] */
+        int n = xi[0], XQ = ti[TI_R_XQUAT];
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int k = 0; k < n; k++) {
+            REAL q[4], u[3], pl[3] = {xf[0], xf[1], xf[2]};
+            for (int c = 0; c < 4; c++) q[c] = REC(s, XQ + 4 * xi[1 + k] + c);
+            o_rot_vec_quat(u, pl, q, 1);
+            acc += u[0] * pl[0] + u[1] * pl[1] + u[2] * pl[2];
+          }
+          out[0][s] = acc / (REAL)n;
+        }
+      } break;
+      case REW_NO_ROLL:
+        /* rewards.py:781-805; floats [angvel_scale, roll_scale, angvel_sq, angvel_abs, roll_sq, roll_abs] */
+        for (int s = 0; s < T; s++) {
+          REAL q[4] = {REC(s, QP + 3), REC(s, QP + 4), REC(s, QP + 5), REC(s, QP + 6)}, z[3] = {0, 0, 1}, zb[3];
+          o_rot_vec_quat(zb, z, q, 1);
+          out[0][s] = exp_kernel_pen(REC(s, QV + 3), xf[0], xf[2], xf[3]);
+          out[1][s] = exp_kernel_pen(-ATAN2(zb[1], zb[2]), xf[1], xf[4], xf[5]);
         }
         break;
       /* ---- the K-Bot task's own rewards (examples/kbot/train.py:128-496).  ZERO_CMD(s): |cmd[:3]| < 1e-3.
