@@ -267,6 +267,13 @@ class B200Engine:
             res[f"reward/{name}"] = out[13 + i]
         return res
 
+    def set_curriculum_level(self, level: float) -> None:
+        """The level the next rollout runs at.  The reference passes ``curriculum_state.level`` to every ``step_engine`` call
+        of an iteration (rl.py:1615-1634); here it travels in each environment's state block, so the once-per-iteration update
+        (``ksim_b200.curriculum``) is written into that column and into the per-env levels the rewards pass scales with."""
+        self.state[:, self.program["TI_S_LEVEL"]].fill_(float(level))
+        self.levels.fill_(float(level))
+
     def flags(self, rec: torch.Tensor, n_steps: int) -> tuple[torch.Tensor, torch.Tensor]:
         n = self.num_envs
         dones = torch.empty((n, n_steps), dtype=torch.uint8, device=self.device)

@@ -616,3 +616,38 @@ def test_more_rewards_on_gpu(ctx) -> None:  # noqa: ANN001
         np.testing.assert_allclose(_np(comps)[i], o_comps[i], rtol=1e-5, atol=1e-6, err_msg=name)
         assert np.abs(o_comps[i]).max() > 0, name
     np.testing.assert_allclose(_np(total), o_total, rtol=1e-5, atol=1e-5)
+
+
+def test_curriculum_loop_on_gpu(ctx) -> None:  # noqa: ANN001
+    """Three training iterations' worth of rollout -> rewards -> metrics -> curriculum -> set_curriculum_level: the level the
+    curriculum returns is the one the next rollout records (pre-step block) and runs its noise / events / scales at, and the
+    trajectory reductions the curricula read agree with a numpy statement of Trajectory.episode_length (types.py:72-76),
+    done.sum(-1).mean() and the largest |qpos[:3]|."""
+    from ksim_b200 import curriculum as cur
+
+    spec, rz = ctx
+    n, t = 64, 32
+    eng = _engine(spec, rz, n, level=0.0, seed=21)
+    c = cur.StepWhenSaturated(num_levels=4, increase_threshold=5.0, decrease_threshold=9.0, min_level_steps=0, min_level=0.25)
+    state = c.get_initial_state()
+    eng.set_curriculum_level(float(state.level))
+    p = eng.program
+    seen = []
+    for it in range(3):
+        actions = torch.from_numpy((0.3 * np.random.RandomState(30 + it).randn(t, n, eng.NA)).astype(np.float32)).cuda()
+        rec = eng.rollout(actions)
+        total, comps = eng.rewards(rec, t)
+        m = eng.metrics(rec, total, comps, t)
+        r = _np(rec)[:t]
+        np.testing.assert_array_equal(r[:, :, p["TI_R_LEVEL"]], np.float32(state.level))
+        done = r[:, :, p["TI_R_DONE"]] != 0
+        np.testing.assert_allclose(float(m["mean_terminations"]), done.sum(axis=0).mean(), rtol=1e-6)
+        dist = np.linalg.norm(r[:, :, p["TI_R_QPOS"] : p["TI_R_QPOS"] + 3], axis=-1).max()
+        np.testing.assert_allclose(float(m["max_distance_from_origin"]), dist, rtol=1e-6)
+        mask = done.copy(); mask[-1] = True
+        ep = (r[:, :, p["TI_R_TIME"]] * mask).sum(axis=0) / mask.sum(axis=0)
+        np.testing.assert_allclose(float(m["mean_episode_length"]), ep.mean(), rtol=1e-5)
+        seen.append(float(state.level))
+        state = c(m, it, state)
+        eng.set_curriculum_level(float(state.level))
+    assert seen == [0.25, 0.5, 0.75]   # fewer than 5 deaths per env in 32 steps: the level rises by 1 / num_levels each time
