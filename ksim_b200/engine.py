@@ -273,6 +273,10 @@ class B200Engine:
         (``ksim_b200.curriculum``) is written into that column and into the per-env levels the rewards pass scales with."""
         self.state[:, self.program["TI_S_LEVEL"]].fill_(float(level))
         self.levels.fill_(float(level))
+        # the pre-step block of the next rollout's first step was written at the end of the last one: its recorded level is
+        # patched here; its observation noise was drawn at the old level (the fused step evaluates the observation of step
+        # t + 1 at the end of step t), a one-step lag at the iteration boundary that the reference does not have
+        self.first_rec[:, self.program["TI_R_LEVEL"]].fill_(float(level))
 
     def flags(self, rec: torch.Tensor, n_steps: int) -> tuple[torch.Tensor, torch.Tensor]:
         n = self.num_envs
