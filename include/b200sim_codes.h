@@ -211,6 +211,10 @@
 #define REW_NO_ROLL 34
 #define REW_LINK_ACCELERATION 35
 #define REW_LINK_JERK 36
+#define REW_FEET_SLIP 37
+#define REW_REACHABILITY 38
+#define REW_SYMMETRY 39
+#define REW_PAIRWISE_SYMMETRY 40
 #define REW_KBOT_SINGLE_FOOT_CONTACT 16
 #define REW_KBOT_NO_CONTACT 17
 #define REW_KBOT_FEET_AIRTIME 18

@@ -313,6 +313,73 @@ DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, floa
           OUT(1, s) = exp_kernel_pen(-atan2f(zb.y, zb.z), xf[1], xf[4], xf[5]);
         }
         break;
+      case REW_FEET_SLIP: {
+        const int co = xi[0], rows = xi[1], nf = xi[2], vo = xi[3];
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int f = 0; f < nf; f++) {
+            bool contact = false;
+            for (int c = 0; c < rows; c++) contact |= REC(s, OB + co + c * nf + f) > 0.5f;
+            float n2 = 0.0f;
+            for (int k = 0; k < 6; k++) { const float v = REC(s, OB + vo + 6 * f + k); n2 += v * v; }
+            if (contact) acc += sqrtf(n2);
+          }
+          OUT(0, s) = acc;
+        }
+      } break;
+      case REW_REACHABILITY: {
+        const int n = xi[1];
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int k = 0; k < n; k++) {
+            float ex = fabsf(REC(s, AC + k) - REC(s, QP + 7 + k)) - xf[k];
+            if (ex < 0.0f) ex = 0.0f;
+            acc += xi[0] ? ex * ex : ex;
+          }
+          OUT(0, s) = acc;
+        }
+      } break;
+      case REW_SYMMETRY: {
+        // stateful (rewards.py:844-897): one carry update per rollout from the time mean, then the per-step product;
+        // the carry is kept relative to the targets so that it starts and resets at 0 like every other carry
+        const int n = xi[0];
+        for (int k = 0; k < n; k++) {
+          float mean = 0.0f;
+          LANE_FOR(s, T) mean += REC(s, QP + 7 + xi[1 + k]) - xf[1 + k];
+          mean = wsum(mean) / (float)T;
+          WSYNC();
+          IF_LANE0 cr[k] = (cr[k] + xf[1 + k]) * (1.0f - xf[0]) + mean * xf[0] - xf[1 + k];
+        }
+        WSYNC();
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int k = 0; k < n; k++) acc += (REC(s, QP + 7 + xi[1 + k]) - xf[1 + k]) * -(cr[k] + xf[1 + k]);
+          OUT(0, s) = acc;
+        }
+      } break;
+      case REW_PAIRWISE_SYMMETRY: {
+        float m0 = 0.0f, m1 = 0.0f;
+        LANE_FOR(s, T) {
+          const float l = REC(s, QP + 7 + xi[0]) - xf[0];
+          float r_ = REC(s, QP + 7 + xi[1]) - xf[1];
+          if (xi[2]) r_ = -r_;
+          m0 += l; m1 += r_;
+        }
+        m0 = wsum(m0) / (float)T; m1 = wsum(m1) / (float)T;
+        WSYNC();
+        IF_LANE0 {
+          cr[0] = (cr[0] + xf[0]) * (1.0f - xf[2]) + m0 * xf[2] - xf[0];
+          cr[1] = (cr[1] + xf[1]) * (1.0f - xf[2]) + m1 * xf[2] - xf[1];
+        }
+        WSYNC();
+        LANE_FOR(s, T) {
+          const float l = REC(s, QP + 7 + xi[0]) - xf[0];
+          float r_ = REC(s, QP + 7 + xi[1]) - xf[1];
+          if (xi[2]) r_ = -r_;
+          OUT(0, s) = exp_kernel_pen(l - r_, xf[3], xf[4], xf[5]);
+          OUT(1, s) = l * -(cr[0] + xf[0]) + r_ * -(cr[1] + xf[1]);
+        }
+      } break;
       // ---- the K-Bot task's own rewards (examples/kbot/train.py:128-496; same structure as oracle/engine.c)
 #define UCMD(s, k) REC(s, CM + ucmd + (k))
 #define ZERO_CMD(s) (sqrtf(UCMD(s, 0) * UCMD(s, 0) + UCMD(s, 1) * UCMD(s, 1) + UCMD(s, 2) * UCMD(s, 2)) < 1e-3f)

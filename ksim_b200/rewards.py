@@ -14,7 +14,8 @@ __all__ = [
     "ActionVelocityPenalty", "ActionAccelerationPenalty", "ActionJerkPenalty", "BaseHeightReward",
     "BaseHeightRangeReward", "OffAxisVelocityReward", "SmallJointVelocityReward", "SmallJointAccelerationReward",
     "SmallJointJerkReward", "AvoidLimitsPenalty", "TorquePenalty", "EnergyPenalty", "JointDeviationPenalty", "FlatBodyReward",
-    "NoRollReward", "LinkAccelerationPenalty", "LinkJerkPenalty", "exp_kernel", "exp_kernel_with_penalty",
+    "NoRollReward", "LinkAccelerationPenalty", "LinkJerkPenalty", "FeetSlipPenalty", "ReachabilityPenalty", "SymmetryReward",
+    "PairwiseSymmetryReward", "exp_kernel", "exp_kernel_with_penalty",
 ]
 
 import math
@@ -427,3 +428,83 @@ class ForcePenalty(Reward):
             raise ValueError(f"force observation {self.force_obs} must be (rows, dim), got {shape}")
         ints = [ctx.obs_offset(self.force_obs), shape[0], shape[1]]
         return C.REW_FORCE_PENALTY, ints, [float(self.ctrl_dt), float(self.expected_weight), float(self.bias)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class FeetSlipPenalty(Reward):
+    """ksim/rewards.py:1089-1106: speed of the feet that are in contact; ``contact_obs`` is ``(rows, n_feet)``,
+    ``velocity_obs`` ``(n_feet, 6)`` (e.g. ``BodyVelocityObservation`` of the foot bodies)."""
+
+    contact_obs: str = attrs.field()
+    velocity_obs: str = attrs.field()
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        cs, vs = ctx.obs_shape(self.contact_obs), ctx.obs_shape(self.velocity_obs)
+        if len(cs) != 2 or len(vs) != 2 or vs[1] != 6 or vs[0] != cs[1]:
+            raise ValueError(f"FeetSlipPenalty needs contact (rows, n) and velocity (n, 6) observations, got {cs} and {vs}")
+        return C.REW_FEET_SLIP, [ctx.obs_offset(self.contact_obs), cs[0], cs[1], ctx.obs_offset(self.velocity_obs)], [], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class ReachabilityPenalty(Reward):
+    """ksim/rewards.py:970-989: |action - qpos[7:]| beyond the per-joint envelope ``delta_max_j``."""
+
+    delta_max_j: tuple[float, ...] = attrs.field()
+    squared: bool = attrs.field(default=True)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        n = len(self.delta_max_j)
+        if n != ctx.model.nq - 7 or n != ctx.model.nu:
+            raise ValueError("ReachabilityPenalty compares action and qpos[7:] element-wise: delta_max_j needs one entry per joint")
+        return C.REW_REACHABILITY, [int(self.squared), n], [float(v) for v in self.delta_max_j], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class SymmetryReward(StatefulReward):
+    """ksim/rewards.py:844-897 (carry: an EMA over rollouts of the mean joint offsets, initially the targets)."""
+
+    joint_indices: tuple[int, ...] = attrs.field()
+    joint_targets: tuple[float, ...] = attrs.field()
+    alpha: float = attrs.field(default=0.1)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        n = len(self.joint_indices)
+        if n == 0 or len(self.joint_targets) != n or any(i < 0 or i >= ctx.model.nq - 7 for i in self.joint_indices):
+            raise ValueError("SymmetryReward needs matching joint indices / targets inside the model")
+        return C.REW_SYMMETRY, [n, *self.joint_indices], [float(self.alpha)] + [float(v) for v in self.joint_targets], [""], n
+
+    @classmethod
+    def create(cls, physics_model: object, joint_names: tuple[str, ...], joint_targets: tuple[float, ...], alpha: float = 0.1,
+               scale: float | Scale = 1.0) -> "SymmetryReward":
+        if len(joint_names) != len(joint_targets):
+            raise ValueError(f"Joint names and targets must match, got {len(joint_names)} and {len(joint_targets)}")
+        idx = tuple(int(physics_model.jnt_qposadr[physics_model.id("joint", n)]) - 7 for n in joint_names)
+        return cls(joint_indices=idx, joint_targets=tuple(float(v) for v in joint_targets), alpha=alpha, scale=scale)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class PairwiseSymmetryReward(StatefulReward):
+    """ksim/rewards.py:901-966."""
+
+    left_joint_index: int = attrs.field()
+    right_joint_index: int = attrs.field()
+    left_zero: float = attrs.field(default=0.0)
+    right_zero: float = attrs.field(default=0.0)
+    flipped: bool = attrs.field(default=False)
+    alpha: float = attrs.field(default=0.1)
+    kernel_scale: float = attrs.field(default=0.25)
+    sq_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    abs_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        if any(i < 0 or i >= ctx.model.nq - 7 for i in (self.left_joint_index, self.right_joint_index)):
+            raise ValueError("PairwiseSymmetryReward joint index outside the model")
+        floats = [self.left_zero, self.right_zero, self.alpha, self.kernel_scale, self.sq_scale, self.abs_scale]
+        return (C.REW_PAIRWISE_SYMMETRY, [self.left_joint_index, self.right_joint_index, int(self.flipped)],
+                [float(f) for f in floats], ["lr", "self"], 2)
+
+    @classmethod
+    def create(cls, physics_model: object, left_joint_name: str, right_joint_name: str, **kw: object) -> "PairwiseSymmetryReward":
+        adr = physics_model.jnt_qposadr
+        return cls(left_joint_index=int(adr[physics_model.id("joint", left_joint_name)]) - 7,
+                   right_joint_index=int(adr[physics_model.id("joint", right_joint_name)]) - 7, **kw)

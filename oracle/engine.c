@@ -1337,6 +1337,68 @@ static void env_rewards(const Task* t, const REAL* rec, size_t tstride, int T, R
           out[1][s] = exp_kernel_pen(-ATAN2(zb[1], zb[2]), xf[1], xf[4], xf[5]);
         }
         break;
+      case REW_FEET_SLIP: {
+        /* rewards.py:1089-1106; ints [contact_off, contact_rows, n_feet, velocity_off]; contact obs [rows][n], velocity obs [n][6] */
+        int co = xi[0], rows = xi[1], nf = xi[2], vo = xi[3];
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int f = 0; f < nf; f++) {
+            int contact = 0;
+            for (int c = 0; c < rows; c++) contact |= REC(s, OB + co + c * nf + f) > (REAL)0.5;
+            REAL n2 = 0;
+            for (int k = 0; k < 6; k++) { REAL v = REC(s, OB + vo + 6 * f + k); n2 += v * v; }
+            if (contact) acc += SQRT(n2);
+          }
+          out[0][s] = acc;
+        }
+      } break;
+      case REW_REACHABILITY: {
+        /* rewards.py:970-989; ints [squared, n]; floats delta_max[n] */
+        int n = xi[1];
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int k = 0; k < n; k++) {
+            REAL ex = FABS(REC(s, AC + k) - REC(s, QP + 7 + k)) - xf[k];
+            if (ex < 0) ex = 0;
+            acc += xi[0] ? ex * ex : ex;
+          }
+          out[0][s] = acc;
+        }
+      } break;
+      case REW_SYMMETRY: {
+        /* rewards.py:844-897 (stateful); ints [n, idx[n]]; floats [alpha, targets[n]]; carry[n] holds reward_carry - targets
+         * (the reference's initial carry is the targets; every carry here starts and resets at 0) */
+        int n = xi[0];
+        for (int k = 0; k < n; k++) {
+          REAL mean = 0;
+          for (int s = 0; s < T; s++) mean += REC(s, QP + 7 + xi[1 + k]) - xf[1 + k];
+          mean /= (REAL)T;
+          cr[k] = (cr[k] + xf[1 + k]) * ((REAL)1 - xf[0]) + mean * xf[0] - xf[1 + k];
+        }
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int k = 0; k < n; k++) acc += (REC(s, QP + 7 + xi[1 + k]) - xf[1 + k]) * -(cr[k] + xf[1 + k]);
+          out[0][s] = acc;
+        }
+      } break;
+      case REW_PAIRWISE_SYMMETRY: {
+        /* rewards.py:901-966 (stateful); ints [left, right, flipped]; floats [left_zero, right_zero, alpha, kernel, sq, abs];
+         * carry[2] holds reward_carry - (left_zero, right_zero) */
+        REAL zero[2] = {xf[0], xf[1]};
+        REAL mean[2] = {0, 0};
+        for (int s = 0; s < T; s++) {
+          REAL l = REC(s, QP + 7 + xi[0]) - xf[0], r_ = REC(s, QP + 7 + xi[1]) - xf[1];
+          if (xi[2]) r_ = -r_;
+          mean[0] += l; mean[1] += r_;
+        }
+        for (int k = 0; k < 2; k++) cr[k] = (cr[k] + zero[k]) * ((REAL)1 - xf[2]) + (mean[k] / (REAL)T) * xf[2] - zero[k];
+        for (int s = 0; s < T; s++) {
+          REAL l = REC(s, QP + 7 + xi[0]) - xf[0], r_ = REC(s, QP + 7 + xi[1]) - xf[1];
+          if (xi[2]) r_ = -r_;
+          out[0][s] = exp_kernel_pen(l - r_, xf[3], xf[4], xf[5]);
+          out[1][s] = l * -(cr[0] + zero[0]) + r_ * -(cr[1] + zero[1]);
+        }
+      } break;
       /* ---- the K-Bot task's own rewards (examples/kbot/train.py:128-496).  ZERO_CMD(s): |cmd[:3]| < 1e-3.
        * Foot contact: touch-sensor observation > 0.1.  Observations / commands are pre-step, qpos / qvel / xpos /
        * xquat post-step (types.py:51-54). */

@@ -592,30 +592,32 @@ def test_ppo_loss_edge_cases(ctx) -> None:  # noqa: ANN001
 
 
 def test_more_rewards_on_gpu(ctx) -> None:  # noqa: ANN001
-    """The ksim/rewards.py plugins beyond the example tasks' lists (tests/test_more_rewards.py) through k_rewards: a noisy
-    humanoid rollout with resets on the GPU, its records scored by the GPU and by the f32 oracle (rtol 1e-5)."""
-    import dataclasses
-
+    """The ksim/rewards.py plugins beyond the example tasks' lists (tests/test_more_rewards.py) through k_rewards: two
+    consecutive noisy humanoid rollouts with resets on the GPU, their records scored by the GPU and by the f32 oracle
+    (rtol 1e-5), the stateful carries crossing the boundary between them."""
     from oracle import OracleEngine
-    from tests.test_more_rewards import extra_rewards
+    from tests.test_more_rewards import extra_spec
 
     spec, rz = ctx
-    spec = dataclasses.replace(spec, rewards=extra_rewards(spec.model))
-    n, t = 96, 64
+    spec = extra_spec(spec)
+    n, t = 96, 48
     eng = _engine(spec, rz, n, level=1.0, seed=11)
     assert eng.info("VARIANT") == 0
-    actions = torch.from_numpy((0.4 * np.random.RandomState(12).randn(t, n, eng.NA)).astype(np.float32)).cuda()
-    rec = eng.rollout(actions)
-    total, comps = eng.rewards(rec, t)
-    rec_np = _np(rec)[:t]
-    assert (rec_np[:, :, eng.program["TI_R_DONE"]] != 0).sum() > 0
     ora = OracleEngine(eng.program, "f32")
-    o_total, o_comps = ora.rewards(rec_np, _np(eng.levels), np.zeros((n, max(eng.program["TI_REW_CARRY_SIZE"], 1)), np.float32))
-    assert len(eng.program.reward_components) == 12
-    for i, name in enumerate(eng.program.reward_components):
-        np.testing.assert_allclose(_np(comps)[i], o_comps[i], rtol=1e-5, atol=1e-6, err_msg=name)
-        assert np.abs(o_comps[i]).max() > 0, name
-    np.testing.assert_allclose(_np(total), o_total, rtol=1e-5, atol=1e-5)
+    o_carry = np.zeros((n, eng.program["TI_REW_CARRY_SIZE"]), np.float32)
+    assert len(eng.program.reward_components) == 18
+    for it in range(2):
+        actions = torch.from_numpy((0.4 * np.random.RandomState(12 + it).randn(t, n, eng.NA)).astype(np.float32)).cuda()
+        rec = eng.rollout(actions)
+        total, comps = eng.rewards(rec, t)
+        rec_np = _np(rec)[:t]
+        assert (rec_np[:, :, eng.program["TI_R_DONE"]] != 0).sum() > 0
+        o_total, o_comps = ora.rewards(rec_np, _np(eng.levels), o_carry)
+        for i, name in enumerate(eng.program.reward_components):
+            np.testing.assert_allclose(_np(comps)[i], o_comps[i], rtol=1e-5, atol=2e-6, err_msg=name)
+            assert np.abs(o_comps[i]).max() > 0, name
+        np.testing.assert_allclose(_np(total), o_total, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(_np(eng.reward_carry), o_carry, rtol=1e-5, atol=1e-6)
 
 
 def test_curriculum_loop_on_gpu(ctx) -> None:  # noqa: ANN001

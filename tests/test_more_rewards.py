@@ -28,14 +28,31 @@ def extra_rewards(model):  # noqa: ANN001, ANN201
         "no_roll": R.NoRollReward(scale=0.7, roll_scale=0.3),
         "link_acc": R.LinkAccelerationPenalty(scale=3.0),
         "link_jerk": R.LinkJerkPenalty(norm="l1", scale=4.0),
+        "slip": R.FeetSlipPenalty(contact_obs="feet_contact", velocity_obs="feet_velocity", scale=0.2),
+        "reach": R.ReachabilityPenalty(delta_max_j=tuple(0.05 + 0.01 * k for k in range(model.nu)), scale=0.6),
+        "reach_l1": R.ReachabilityPenalty(delta_max_j=tuple(0.1 for _ in range(model.nu)), squared=False, scale=0.4),
+        "symmetry": R.SymmetryReward.create(model, ("hip_y_left", "hip_y_right", "knee_left"), (0.1, -0.1, 0.25), alpha=0.3, scale=0.9),
+        "pair": R.PairwiseSymmetryReward.create(model, "shoulder1_left", "shoulder1_right", left_zero=0.05, right_zero=-0.1,
+                                                flipped=True, alpha=0.2, scale=1.1),
     }
+
+
+def extra_spec(walking_spec):  # noqa: ANN001, ANN201
+    """The walking task with the extra rewards; one unused observation makes room for the feet velocities (16 observation
+    plugins: the humanoid-sized kernel instantiation still serves it)."""
+    from ksim_b200 import observation
+
+    model = walking_spec.model
+    obs = {k: v for k, v in walking_spec.observations.items() if k != "center_of_mass_velocity"}
+    obs["feet_velocity"] = observation.BodyVelocityObservation.create(physics_model=model, body_names=("foot_left", "foot_right"))
+    return dataclasses.replace(walking_spec, observations=obs, rewards=extra_rewards(model))
 
 
 @pytest.fixture(scope="module")
 def extra_program(walking_spec):  # noqa: ANN001, ANN201
     from ksim_b200.program import build_program
 
-    return build_program(dataclasses.replace(walking_spec, rewards=extra_rewards(walking_spec.model)))
+    return build_program(extra_spec(walking_spec))
 
 
 def _exp_kernel(x, scale):  # noqa: ANN001, ANN202
@@ -61,8 +78,10 @@ def _diffs(x, done, order):  # noqa: ANN001, ANN202
     return xz, dz
 
 
-def numpy_rewards(prog, rec, model):  # noqa: ANN001, ANN201
-    """{component name: (N, T)} from records rec[T][N][R], reference expression by expression (unscaled, unsigned)."""
+def numpy_rewards(prog, rec, model, carry):  # noqa: ANN001, ANN201
+    """{component name: (N, T)} from records rec[T][N][R], reference expression by expression (unscaled, unsigned).
+    carry: {reward name: (N, dim)} of the stateful rewards, updated in place (reset to the initial carry where done[-1],
+    rl.py:205-213)."""
     q0, v0, xp, xq, ct, dn = (prog[k] for k in ("TI_R_QPOS", "TI_R_QVEL", "TI_R_XPOS", "TI_R_XQUAT", "TI_R_CTRL", "TI_R_DONE"))
     t, n, _ = rec.shape
     nb = model.nbody
@@ -105,6 +124,32 @@ def numpy_rewards(prog, rec, model):  # noqa: ANN001, ANN201
             acc = np.where(dz[1:, :, 0], 0.0, vel[1:] - vel[:-1])
             val = acc if order == 2 else np.where(dz[2:, :, 0], 0.0, acc[1:] - acc[:-1])
             res[name] = (np.square(val) if rw[name].norm == "l2" else np.abs(val)).mean(axis=-1)
+        ob, ac = prog["TI_R_OBS"], prog["TI_R_ACTION"]
+        co, _, cshape = prog.obs_slices["feet_contact"]
+        vo, _, vshape = prog.obs_slices["feet_velocity"]
+        contact = (r[:, ob + co : ob + co + int(np.prod(cshape))].reshape((t,) + cshape) > 0.5).any(axis=-2)
+        vel6 = r[:, ob + vo : ob + vo + int(np.prod(vshape))].reshape((t,) + vshape)
+        res["slip"] = np.where(contact, np.linalg.norm(vel6, axis=-1), 0.0).sum(axis=-1)
+        action = r[:, ac : ac + model.nu]
+        for name in ("reach", "reach_l1"):
+            excess = np.maximum(0.0, np.abs(action - qpos[:, 7:]) - np.array(rw[name].delta_max_j))
+            res[name] = (excess**2 if rw[name].squared else excess).sum(axis=-1)
+        sy = rw["symmetry"]
+        c = np.array(sy.joint_targets) if done[-1] else carry["symmetry"][e]
+        qs = qpos[:, np.array(sy.joint_indices) + 7] - np.array(sy.joint_targets)
+        c = c * (1.0 - sy.alpha) + qs.mean(axis=-2) * sy.alpha
+        res["symmetry"] = (qs * -c[None, :]).sum(axis=-1)
+        carry["symmetry"][e] = c
+        pw = rw["pair"]
+        c = np.array([pw.left_zero, pw.right_zero]) if done[-1] else carry["pair"][e]
+        ql, qr = qpos[:, pw.left_joint_index + 7] - pw.left_zero, qpos[:, pw.right_joint_index + 7] - pw.right_zero
+        if pw.flipped:
+            qr = -qr
+        res["pair/lr"] = _exp_kernel_pen(ql - qr, pw.kernel_scale, pw.sq_scale, pw.abs_scale)
+        qp = np.stack([ql, qr], axis=-1)
+        c = c * (1.0 - pw.alpha) + qp.mean(axis=-2) * pw.alpha
+        res["pair/self"] = (qp * -c[None, :]).sum(axis=-1)
+        carry["pair"][e] = c
         for k, v in res.items():
             out.setdefault(k, np.zeros((n, t)))[e] = v
     return out
@@ -125,34 +170,49 @@ def test_oracle_matches_numpy_restatement(oracle_built, extra_program, walking_r
     ora.rollout(actions, init.rand, st, keys, rec)
     done = rec[:t, :, prog["TI_R_DONE"]] != 0
     assert done.sum() >= 3 and done[0].sum() == 0, "the case must exercise the done masking away from step 0"
-    total, comps = ora.rewards(rec[:t], init.levels, np.zeros((n, max(prog["TI_REW_CARRY_SIZE"], 1))))
-    want = numpy_rewards(prog, rec[:t], prog.spec.model)
+    # two consecutive reward passes over the two halves of the rollout: the stateful carries cross a boundary, and the
+    # environments whose first half ends on a done step start the second half from the initial carry
+    rw_all = prog.spec.rewards
+    np_carry = {"symmetry": np.tile(np.array(rw_all["symmetry"].joint_targets), (n, 1)),
+                "pair": np.tile(np.array([rw_all["pair"].left_zero, rw_all["pair"].right_zero]), (n, 1))}
+    o_carry = np.zeros((n, prog["TI_REW_CARRY_SIZE"]))
+    assert prog["TI_REW_CARRY_SIZE"] == 3 + 2
+    h = t // 2
+    done[h - 1, :3] = True
+    rec[h - 1, :3, prog["TI_R_DONE"]] = 1.0   # force the reset-of-carry branch for three environments
     names = prog.reward_components
-    assert set(names) == set(want), (names, sorted(want))
-    signed_sum = np.zeros((n, t))
-    for i, name in enumerate(names):
-        rw = prog.spec.rewards[name.split("/")[0]]
-        sign = -1.0 if rw.is_penalty else 1.0
-        scale = float(rw.scale.scale)
-        # parameters are stored as fp32 (1e-6); the 1e-6 eps of xax's quaternion normalisation enters the two rotation
-        # formulas (polynomial in the oracle, cross products here) differently (2e-5, as in tests/test_kbot_task_plugins.py)
-        rot = name in ("flat", "no_roll/pose")
-        np.testing.assert_allclose(comps[i], want[name] * scale * sign, rtol=2e-5 if rot else 1e-6, atol=2e-5 if rot else 1e-9, err_msg=name)
-        assert np.abs(comps[i]).max() > 0, name
-        signed_sum += comps[i]
-    np.testing.assert_allclose(total, signed_sum, rtol=1e-9, atol=1e-9)
+    for seg in (slice(0, h), slice(h, t)):
+        total, comps = ora.rewards(np.ascontiguousarray(rec[seg]), init.levels, o_carry)
+        want = numpy_rewards(prog, rec[seg], prog.spec.model, np_carry)
+        assert set(names) == set(want), (names, sorted(want))
+        signed_sum = np.zeros((n, h))
+        for i, name in enumerate(names):
+            rw = rw_all[name.split("/")[0]]
+            sign = -1.0 if rw.is_penalty else 1.0
+            scale = float(rw.scale.scale)
+            # parameters are stored as fp32 (1e-6); the 1e-6 eps of xax's quaternion normalisation enters the two rotation
+            # formulas (polynomial in the oracle, cross products here) differently (2e-5, as in tests/test_kbot_task_plugins.py)
+            rot = name in ("flat", "no_roll/pose")
+            np.testing.assert_allclose(comps[i], want[name] * scale * sign, rtol=2e-5 if rot else 1e-6, atol=2e-5 if rot else 1e-8, err_msg=name)
+            assert np.abs(comps[i]).max() > 0, name
+            signed_sum += comps[i]
+        np.testing.assert_allclose(total, signed_sum, rtol=1e-9, atol=1e-9)
 
 
 def test_emu_matches_oracle(emu, oracle_built, extra_program, walking_randomizers) -> None:  # noqa: ANN001, F811
     prog, rec_e, rec_o, _, _, ora, blob, init = _run(emu, extra_program, walking_randomizers, n=6, t=40, level=1.0, seed=5)
     n, t = 6, 40
     k, c = prog["TI_N_REW_COMP"], max(prog["TI_REW_CARRY_SIZE"], 1)
-    total_o, comps_o = ora.rewards(rec_o[:t], init.levels, np.zeros((n, c), np.float32))
-    total_e, comps_e, carry_e = np.zeros((n, t), np.float32), np.zeros((k, n, t), np.float32), np.zeros((n, c), np.float32)
-    rec_in = np.ascontiguousarray(rec_o[:t])
-    emu.emu_rewards(_p(blob), n, t, _p(rec_in), _p(init.levels), _p(carry_e), _p(total_e), _p(comps_e))
-    np.testing.assert_allclose(comps_e, comps_o, rtol=1e-5, atol=1e-5)
-    np.testing.assert_allclose(total_e, total_o, rtol=1e-5, atol=1e-4)
+    carry_o, carry_e = np.zeros((n, c), np.float32), np.zeros((n, c), np.float32)
+    for seg in (slice(0, t // 2), slice(t // 2, t)):   # two passes: the stateful carries cross a boundary
+        h = t // 2
+        rec_in = np.ascontiguousarray(rec_o[seg])
+        total_o, comps_o = ora.rewards(rec_in, init.levels, carry_o)
+        total_e, comps_e = np.zeros((n, h), np.float32), np.zeros((k, n, h), np.float32)
+        emu.emu_rewards(_p(blob), n, h, _p(rec_in), _p(init.levels), _p(carry_e), _p(total_e), _p(comps_e))
+        np.testing.assert_allclose(comps_e, comps_o, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(total_e, total_o, rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(carry_e, carry_o, rtol=1e-5, atol=1e-6)
 
 
 def test_encode_rejects_mismatched_sizes(walking_spec) -> None:  # noqa: ANN001
