@@ -129,8 +129,9 @@ class PPOLossFunction(torch.autograd.Function):
         ctx.has_entropy = entropy is not None
         ctx.d_entropy = -config.entropy_coef / float(values.numel())
         ctx.entropy_shape = None if entropy is None else tuple(entropy.shape)
-        ctx.mark_non_differentiable(out[1:])
-        return out[0], out[1:]
+        terms = out[1:]
+        ctx.mark_non_differentiable(terms)
+        return out[0], terms
 
     @staticmethod
     def backward(ctx, g_loss, _g_terms):  # noqa: ANN001, ANN205
