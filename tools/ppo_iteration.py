@@ -72,7 +72,9 @@ def mixture_log_prob(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, log
 
 
 def mixture_sample(mean: torch.Tensor, std: torch.Tensor, logw: torch.Tensor) -> torch.Tensor:
-    k = torch.distributions.Categorical(logits=logw).sample()[..., None]
+    # Gumbel-max instead of torch.distributions.Categorical: no host-side argument validation, so the step can be captured
+    u = torch.rand_like(logw).clamp_(1e-20, 1.0)
+    k = torch.argmax(logw - torch.log(-torch.log(u)), dim=-1, keepdim=True)
     return torch.gather(mean, -1, k)[..., 0] + torch.gather(std, -1, k)[..., 0] * torch.randn_like(k[..., 0], dtype=mean.dtype)
 
 
@@ -84,6 +86,8 @@ def main() -> None:
     ap.add_argument("--passes", type=int, default=4)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--graph", action="store_true", help="capture one PPO update (replay, GAE, loss, backward, AdamW) in a CUDA graph "
+                    "and replay it per minibatch (single-process runs)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -122,78 +126,148 @@ def main() -> None:
     actor = Recurrent(43, nj * 3 * NUM_MIXTURES, nn.GELU).to(dev)
     critic = Recurrent(340, 1, nn.ELU).to(dev)
     params = list(actor.parameters()) + list(critic.parameters())
-    opt = torch.optim.AdamW(params, lr=3e-4, weight_decay=1e-5)
+    use_graph = args.graph and world == 1
+    opt = torch.optim.AdamW(params, lr=3e-4, weight_decay=1e-5, capturable=use_graph)
     cfg = ppo.PPOLossConfig()
     a_carry = torch.zeros((DEPTH, n, HIDDEN), device=dev)
     c_carry = torch.zeros((DEPTH, n, HIDDEN), device=dev)
 
+    bsz = args.batch
+    assert n % bsz == 0, "the captured update needs equal minibatches"
+    static = {"obs_a": torch.zeros((n, t, 43), device=dev), "obs_c": torch.zeros((n, t, 340), device=dev), "act": torch.zeros((n, t, nj), device=dev),
+              "keep": torch.zeros((n, t), device=dev), "logp_on": torch.zeros((n, t, nj), device=dev), "values_on": torch.zeros((n, t), device=dev),
+              "total": torch.zeros((n, t), device=dev), "dones": torch.zeros((n, t), dtype=torch.uint8, device=dev),
+              "succ": torch.zeros((n, t), dtype=torch.uint8, device=dev), "a0": torch.zeros((DEPTH, n, HIDDEN), device=dev),
+              "c0": torch.zeros((DEPTH, n, HIDDEN), device=dev), "ix": torch.zeros((bsz,), dtype=torch.long, device=dev),
+              "loss": torch.zeros((), device=dev)}
+
+    def update_step() -> None:
+        """One PPO update on the minibatch static["ix"] (ppo.py:495-565): every input lives at a fixed address, so the same
+        code runs eagerly or as a captured CUDA graph."""
+        ix = static["ix"]
+        ha, hc = static["a0"][:, ix], static["c0"][:, ix]
+        # only the GRU cells are sequential: the input projections, the output MLPs and the mixture log-probabilities run
+        # once over all (B, T) rows of the minibatch
+        xa, xc = actor.input_proj(static["obs_a"][ix]), critic.input_proj(static["obs_c"][ix])
+        keep = static["keep"][ix]
+        tops_a, tops_c = [], []
+        for s in range(t):
+            h, nh = xa[:, s], []
+            for i, rnn in enumerate(actor.rnns):
+                h = rnn(h, ha[i]); nh.append(h)
+            tops_a.append(h)
+            g, ng = xc[:, s], []
+            for i, rnn in enumerate(critic.rnns):
+                g = rnn(g, hc[i]); ng.append(g)
+            tops_c.append(g)
+            k = keep[:, s][None, :, None]                # recurrent carries restart with the episode
+            ha, hc = torch.stack(nh, dim=0) * k, torch.stack(ng, dim=0) * k
+        pred = actor.output_proj(torch.stack(tops_a, dim=1))
+        logp_off = mixture_log_prob(static["act"][ix], *mixture(pred, nj))
+        values_off = critic.output_proj(torch.stack(tops_c, dim=1))[..., 0]
+        adv, tgt, _ = eng.gae(values_off.detach().contiguous(), static["total"][ix], static["dones"][ix], static["succ"][ix],
+                              0.99, 0.95, normalize_advantages=True)
+        loss, _ = ppo.ppo_loss(ppo.PPOInputs(adv, tgt), ppo.PPOVariables(static["logp_on"][ix], static["values_on"][ix]),
+                               ppo.PPOVariables(logp_off, values_off), cfg)
+        opt.zero_grad(set_to_none=not use_graph)
+        loss.backward()
+        if world > 1:
+            dist_util.allreduce_mean_([q.grad for q in params if q.grad is not None])
+        torch.nn.utils.clip_grad_norm_(params, 2.0)
+        opt.step()
+        static["loss"].copy_(loss.detach())
+
+    roll = {"cur": torch.zeros((n, eng.R), device=dev), "nxt": torch.zeros((n, eng.R), device=dev), "act": torch.zeros((n, nj), device=dev),
+            "logp": torch.zeros((n, nj), device=dev), "val": torch.zeros((n,), device=dev)}
+
+    def rollout_step() -> None:
+        """One closed-loop control step on fixed buffers (rl.py:1164-1211): observation -> actor / critic -> sampled action ->
+        b200sim_step_ctrl; the recurrent carries are updated in place and restart with the episode (rl.py:1100-1123)."""
+        row = roll["cur"]
+        pred, ac = actor(row[:, a_idx] * a_scale, a_carry)
+        mean, std, logw = mixture(pred, nj)
+        act = mixture_sample(mean, std, logw)
+        roll["logp"].copy_(mixture_log_prob(act, mean, std, logw))
+        v, cc = critic(row[:, c_idx] * c_scale, c_carry)
+        roll["val"].copy_(v[:, 0])
+        roll["act"].copy_(act)
+        eng.step(roll["act"], roll["cur"], roll["nxt"])
+        keep = (roll["cur"][:, p["TI_R_DONE"]] == 0).float()[None, :, None]
+        a_carry.copy_(ac * keep); c_carry.copy_(cc * keep)
+
+    def capture_rollout_step() -> None:
+        # the warm-up steps are real steps of real environments; state and carries are put back afterwards
+        saved = [x.clone() for x in (eng.state, eng.keys, eng.act_keys, a_carry, c_carry, roll["cur"])]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                rollout_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g), torch.no_grad():
+            rollout_step()
+        for dst, src in zip((eng.state, eng.keys, eng.act_keys, a_carry, c_carry, roll["cur"]), saved):
+            dst.copy_(src)
+        roll["graph"] = g
+
+    def capture() -> None:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):                           # warm-up on a side stream: optimiser state, cuBLAS workspaces
+                update_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            update_step()
+        static["graph"] = g
+
     def iteration() -> dict[str, float]:
-        nonlocal a_carry, c_carry
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         rec = eng.new_record_buffer(t)
         actions = torch.empty((t, n, nj), device=dev)
         logp_on = torch.empty((n, t, nj), device=dev)
         values_on = torch.empty((n, t), device=dev)
-        a0, c0 = a_carry, c_carry
+        a0, c0 = a_carry.clone(), c_carry.clone()
         with torch.no_grad():
+            roll["cur"].copy_(rec[0])
             for s in range(t):
-                row = rec[s]
-                pred, a_carry = actor(row[:, a_idx] * a_scale, a_carry)
-                mean, std, logw = mixture(pred, nj)
-                act = mixture_sample(mean, std, logw)
-                logp_on[:, s] = mixture_log_prob(act, mean, std, logw)
-                v, c_carry = critic(row[:, c_idx] * c_scale, c_carry)
-                values_on[:, s] = v[:, 0]
-                actions[s] = act
-                eng.step(act, rec[s], rec[s + 1])
-                done = rec[s, :, p["TI_R_DONE"]] != 0      # recurrent carries restart with the episode (rl.py:1100-1123)
-                a_carry = torch.where(done[None, :, None], torch.zeros_like(a_carry), a_carry)
-                c_carry = torch.where(done[None, :, None], torch.zeros_like(c_carry), c_carry)
+                if use_graph:
+                    if "graph" not in roll:
+                        capture_rollout_step()
+                    roll["graph"].replay()
+                else:
+                    rollout_step()
+                rec[s].copy_(roll["cur"])               # pre-step block as it was + the post-step block the engine wrote
+                actions[s].copy_(roll["act"]); logp_on[:, s].copy_(roll["logp"]); values_on[:, s].copy_(roll["val"])
+                roll["cur"].copy_(roll["nxt"])
+            rec[t].copy_(roll["nxt"])
         eng.first_rec = rec[t]
         ev[1].record()
         total, _ = eng.rewards(rec, t)
         dones, succ = eng.flags(rec, t)
         ev[2].record()
-        obs_a = (rec[:t, :, a_idx] * a_scale).transpose(0, 1).contiguous()   # [N, T, 43]
-        obs_c = (rec[:t, :, c_idx] * c_scale).transpose(0, 1).contiguous()
-        act_nt = actions.transpose(0, 1).contiguous()
-        done_nt = dones.bool()
+        data = {"obs_a": (rec[:t, :, a_idx] * a_scale).transpose(0, 1), "obs_c": (rec[:t, :, c_idx] * c_scale).transpose(0, 1),
+                "act": actions.transpose(0, 1), "keep": (dones == 0).float(), "logp_on": logp_on, "values_on": values_on, "total": total,
+                "dones": dones, "succ": succ, "a0": a0, "c0": c0}
+        for k, v in data.items():
+            static[k].copy_(v)
         loss_val = 0.0
         for _ in range(args.passes):
             perm = torch.randperm(n, device=dev)
             for b0 in range(0, n, args.batch):
-                ix = perm[b0 : b0 + args.batch]
-                ha, hc = a0[:, ix], c0[:, ix]
-                # only the GRU cells are sequential: the input projections, the output MLPs and the mixture log-probabilities
-                # run once over all (B, T) rows of the minibatch
-                xa, xc = actor.input_proj(obs_a[ix]), critic.input_proj(obs_c[ix])
-                tops_a, tops_c = [], []
-                for s in range(t):
-                    h, nh = xa[:, s], []
-                    for i, rnn in enumerate(actor.rnns):
-                        h = rnn(h, ha[i]); nh.append(h)
-                    tops_a.append(h)
-                    g, ng = xc[:, s], []
-                    for i, rnn in enumerate(critic.rnns):
-                        g = rnn(g, hc[i]); ng.append(g)
-                    tops_c.append(g)
-                    keep = (~done_nt[ix, s])[None, :, None].to(h.dtype)
-                    ha, hc = torch.stack(nh, dim=0) * keep, torch.stack(ng, dim=0) * keep
-                pred = actor.output_proj(torch.stack(tops_a, dim=1))
-                logp_off = mixture_log_prob(act_nt[ix], *mixture(pred, nj))
-                values_off = critic.output_proj(torch.stack(tops_c, dim=1))[..., 0]
-                adv, tgt, _ = eng.gae(values_off.detach().contiguous(), total[ix].contiguous(), dones[ix].contiguous(), succ[ix].contiguous(),
-                                      0.99, 0.95, normalize_advantages=True)
-                loss, _ = ppo.ppo_loss(ppo.PPOInputs(adv, tgt), ppo.PPOVariables(logp_on[ix].contiguous(), values_on[ix].contiguous()),
-                                       ppo.PPOVariables(logp_off, values_off), cfg)
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                if world > 1:
-                    dist_util.allreduce_mean_([q.grad for q in params if q.grad is not None])
-                torch.nn.utils.clip_grad_norm_(params, 2.0)
-                opt.step()
-                loss_val = loss
+                static["ix"].copy_(perm[b0 : b0 + args.batch])
+                if use_graph:
+                    if "graph" not in static:
+                        capture()
+                    static["graph"].replay()
+                else:
+                    update_step()
+                loss_val = static["loss"]
         ev[3].record()
         torch.cuda.synchronize()
         return {"rollout_ms": ev[0].elapsed_time(ev[1]), "scoring_ms": ev[1].elapsed_time(ev[2]), "update_ms": ev[2].elapsed_time(ev[3]),
@@ -216,7 +290,8 @@ def main() -> None:
             "config": {"envs_per_gpu": n, "rollout": t, "batch_size": args.batch, "num_passes": args.passes,
                        "updates_per_iteration": args.passes * math.ceil(n / args.batch),
                        "networks": "PyTorch eager TF32 (library code): GRU actor 43->512x2->510 (10-mixture), GRU critic 340->512x2->1",
-                       "ours": "engine step (k_rollout, one launch per control step), rewards, flags, GAE, PPO loss forward+backward"},
+                       "ours": "engine step (k_rollout, one launch per control step), rewards, flags, GAE, PPO loss forward+backward",
+                       "launching": "CUDA graphs: one per closed-loop control step, one per PPO update" if use_graph else "eager"},
             "iters": args.iters, "warmup": args.warmup}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
