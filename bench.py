@@ -58,7 +58,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int) -> None:
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.first = index, [], None, 0
 
     def start(self) -> None:
         try:
@@ -67,6 +67,11 @@ class ClockSampler:
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def mark(self) -> None:
+        """The timed region starts here: samples taken earlier (while nvidia-smi was starting up under the warm-up load,
+        where its NVML initialisation cannot perturb a timed step) are dropped from the report."""
+        self.first = len(self.samples)
 
     def _read(self) -> None:
         assert self.proc is not None and self.proc.stdout is not None
@@ -78,7 +83,7 @@ class ClockSampler:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in (self.samples[self.first:] or self.samples):
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 6:
                 continue
@@ -263,13 +268,18 @@ def main() -> None:
             torch.distributed.barrier()
         torch.cuda.synchronize(device)
 
-    for _ in range(max(args.warmup, 3)):
-        hot_path(actions)
-    # ---- device-resident timing (value) + dominant-kernel timing (roofline) ----
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # spawned before the warm-up so that its start-up cost is not paid inside the timed region
+    for _ in range(max(args.warmup, 3)):
+        hot_path(actions)
+    t_wait = time.perf_counter()
+    while sampler.proc is not None and not sampler.samples and time.perf_counter() - t_wait < 3.0:
+        hot_path(actions)  # extra untimed warm-up until nvidia-smi has printed its first sample (rank 0 only)
+        torch.cuda.synchronize(device)
+    # ---- device-resident timing (value) + dominant-kernel timing (roofline) ----
+    barrier()
+    sampler.mark()
     l0 = eng.launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
