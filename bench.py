@@ -125,11 +125,17 @@ def run_reference(args: argparse.Namespace) -> None:
     make_spec, RANDOMIZERS = _task()
     oracle.build()
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers (N > 1); the arm runs on rank 0 alone and is meant to use every
+    # host core, so the OpenMP runtime the oracle library is linked to is told so directly.
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    import ctypes
+    omp_set = oracle.lib("f32").omp_set_num_threads
+    omp_set.argtypes, omp_set.restype = [ctypes.c_int], None
+    omp_set(cores)
     spec = make_spec()
     prog = build_program(spec)
     rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
-    n, t = max(cores * 8, 64), 16
+    n, t = max(cores * 64, 256), 64  # one step = 64 envs per core x a 64-step rollout: 0.5-2 s of work on all cores
     ora = OracleEngine(prog, "f32")
     init = make_env_init(prog, rz, n, seed=0, level=1.0 if WORKLOAD == "kbot" else 0.0)
     st, keys, rec0, _ = ora.init_envs(init.init_keys, init.levels, init.rand)
@@ -172,11 +178,17 @@ def cpu_baseline_leg() -> dict:
     make_spec, RANDOMIZERS = _task()
     oracle.build()
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers (N > 1); the arm runs on rank 0 alone and is meant to use every
+    # host core, so the OpenMP runtime the oracle library is linked to is told so directly.
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    import ctypes
+    omp_set = oracle.lib("f32").omp_set_num_threads
+    omp_set.argtypes, omp_set.restype = [ctypes.c_int], None
+    omp_set(cores)
     spec = make_spec()
     prog = build_program(spec)
     rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
-    n, t = max(cores * 8, 64), 16
+    n, t = max(cores * 64, 256), 64  # one step = 64 envs per core x a 64-step rollout: 0.5-2 s of work on all cores
     ora = OracleEngine(prog, "f32")
     init = make_env_init(prog, rz, n, seed=0, level=1.0 if WORKLOAD == "kbot" else 0.0)
     st, keys, rec0, _ = ora.init_envs(init.init_keys, init.levels, init.rand)
