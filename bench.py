@@ -132,6 +132,7 @@ def run_reference(args: argparse.Namespace) -> None:
     omp_set = oracle.lib("f32").omp_set_num_threads
     omp_set.argtypes, omp_set.restype = [ctypes.c_int], None
     omp_set(cores)
+    cores = int(oracle.lib("f32").omp_get_max_threads())  # what the library will actually fan out to
     spec = make_spec()
     prog = build_program(spec)
     rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
@@ -185,6 +186,7 @@ def cpu_baseline_leg() -> dict:
     omp_set = oracle.lib("f32").omp_set_num_threads
     omp_set.argtypes, omp_set.restype = [ctypes.c_int], None
     omp_set(cores)
+    cores = int(oracle.lib("f32").omp_get_max_threads())  # what the library will actually fan out to
     spec = make_spec()
     prog = build_program(spec)
     rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
