@@ -122,6 +122,42 @@ int b200sim_metrics(const b200sim_model* model, void* stream, int n_envs, int n_
 int b200sim_dataset_pack(void* stream, int n_envs, int n_steps, int rec_size, const float* rec, const float* total,
                          const float* comps, const int32_t* fields, int n_fields, int sample_size, float* out);
 
+/* ---- Recurrent policy replay: the sequential part of get_ppo_variables (ksim/task/ppo.py:417-488 ->
+ * examples/walking.py:674-728: xax.scan of two stacks of GRU(512) cells over the T steps of a minibatch) as persistent
+ * tcgen05 kernels.  One call advances up to B2S_GRU_MAX_PROBLEMS independent GRU layers (e.g. the actor's and the critic's
+ * layer l) over all T steps for B rows; all sequence arrays are TIME-major.  Cell = equinox.nn.GRUCell:
+ *   r = sigmoid(gi_r + gh_r), z = sigmoid(gi_z + gh_z), n = tanh(gi_n + r (gh_n + b_hn)), h' = n + z (h - n),
+ *   gi = x W_ih^T (+ b_i, added here), gh = h W_hh^T; the carry handed on is keep_t h'_t (it restarts from zero after a
+ *   terminal step, walking.py:715-719).  bf16 tensor-core operands, fp32 accumulation, fp32 state and gate arithmetic. */
+typedef struct {
+  const void* w_hh;   /* bf16 [3H][H] (gate order r, z, n) */
+  const float* gi;    /* [T][B][3H] = x_t W_ih^T, without bias (a plain batched GEMM over all T, done by the caller) */
+  const float* b_i;   /* [3H] */
+  const float* b_hn;  /* [H] */
+  const float* h0;    /* [B][H] or NULL (zeros) */
+  void* y;            /* bf16 [T][B][H]: h'_t */
+  void* hst;          /* bf16 [T][B][H]: the state step t started from (what dW_hh = sum_t hst_t^T dgh_t needs) */
+  float* h_last;      /* [B][H] or NULL: the carry after the last step */
+  float* saved;       /* b200sim_gru_saved_floats(T, B) floats for the backward pass, or NULL (inference) */
+} b200sim_gru_fwd;
+typedef struct {
+  const void* w_hh_t; /* bf16 [H][3H] = W_hh^T */
+  const float* dy;    /* [T][B][H]: gradient with respect to y */
+  const float* saved; /* written by the forward call */
+  void* dgi;          /* bf16 [T][B][3H]: gradient w.r.t. gi; its r and z blocks are also the gradient w.r.t. gh_r, gh_z */
+  void* dghn;         /* bf16 [T][B][H]: gradient w.r.t. gh_n (and, summed over (t, b), b_hn) */
+  float* dh0;         /* [B][H] or NULL */
+} b200sim_gru_bwd;
+size_t b200sim_gru_workspace_bytes(int n_problems, int n_steps, int batch, int backward);
+size_t b200sim_gru_saved_floats(int n_steps, int batch);
+/* keep[T][B] (1 = the episode continues after step t, 0 = it ended) or NULL.  The first int of `workspace` is a device-side
+ * status word (B2S_GRU_ERR_*, 0 = ok) the caller may read after synchronising. */
+int b200sim_gru_forward(void* stream, int n_problems, const b200sim_gru_fwd* problems, int n_steps, int batch, const float* keep,
+                        void* workspace, size_t workspace_bytes);
+int b200sim_gru_backward(void* stream, int n_problems, const b200sim_gru_bwd* problems, int n_steps, int batch, const float* keep,
+                         void* workspace, size_t workspace_bytes);
+const char* b200sim_gru_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

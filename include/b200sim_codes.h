@@ -248,6 +248,16 @@
 #define PPO_MAX_CTAS 2368        /* grid cap: 16 resident CTAs (the 2048-thread limit) on each of 148 SMs */
 #define PPO_SCRATCH_BYTES 94720  /* caller-owned device scratch: per-CTA partial sums (<= PPO_MAX_CTAS x 5 doubles) */
 
+/* ---- recurrent replay kernels (b200sim_gru_forward / _backward) ---- */
+#define B2S_GRU_HIDDEN 512       /* hidden size the tensor-core kernels are built for (examples/walking.py:262, kbot train.py) */
+#define B2S_GRU_MAX_PROBLEMS 2   /* GRU layers of different networks run side by side in one launch (actor + critic) */
+/* device-side status word (first int of the workspace): which bounded wait gave up (0 = none) */
+#define B2S_GRU_ERR_ACC 1        /* accumulator-ready barrier */
+#define B2S_GRU_ERR_FLAG 2       /* a peer CTA's state chunk never arrived */
+#define B2S_GRU_ERR_TMEM 3       /* accumulator never drained */
+#define B2S_GRU_ERR_FULL 4       /* bulk copy never landed */
+#define B2S_GRU_ERR_EMPTY 5      /* pipeline stage never freed */
+
 /* ---- error codes ---- */
 #define B2S_OK 0
 #define B2S_ERR_BAD_ARG 1
