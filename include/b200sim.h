@@ -158,6 +158,37 @@ int b200sim_gru_backward(void* stream, int n_problems, const b200sim_gru_bwd* pr
                          void* workspace, size_t workspace_bytes);
 const char* b200sim_gru_last_error(void);
 
+/* ---- Policy head of the replay: the actor's mixture-of-Gaussians distribution of examples/walking.py:129-146 (prediction ->
+ * means + ZEROS bias, clipped to the joint ranges; std = min((softplus + min_std) var_scale, max_std); logits) and
+ * xax.MixtureOfGaussians.log_prob / sample on it.  pred[rows][3 J M] fp32 = [means | raw stds | logits], each [J][M];
+ * action / logp [rows][J]; mean_bias / lo / hi [J] (NULL = none).  M <= 16. */
+int b200sim_mixture_logprob(void* stream, int rows, int n_joints, int n_mix, const float* pred, const float* action,
+                            const float* mean_bias, const float* lo, const float* hi, float min_std, float var_scale,
+                            float max_std, float* logp);
+/* d_pred[rows][3 J M] (fp32, or bf16 when d_pred_bf16) from d_logp[rows][J], or from one value per row (d_logp_per_row: the
+ * layout b200sim_ppo_loss writes, the same gradient for every joint of a row). */
+int b200sim_mixture_logprob_backward(void* stream, int rows, int n_joints, int n_mix, const float* pred, const float* action,
+                                     const float* mean_bias, const float* lo, const float* hi, float min_std, float var_scale,
+                                     float max_std, const float* d_logp, int d_logp_per_row, void* d_pred, int d_pred_bf16);
+/* action ~ the mixture (argmax: the mean of the heaviest component) with a threefry stream keyed by key[2] and the device
+ * word counter[0] (NULL = 0); logp (may be NULL) = log p(action). */
+int b200sim_mixture_sample(void* stream, int rows, int n_joints, int n_mix, const float* pred, const float* mean_bias,
+                           const float* lo, const float* hi, float min_std, float var_scale, float max_std,
+                           const uint32_t* key, const int32_t* counter, int argmax, float* action, float* logp);
+const char* b200sim_policy_last_error(void);
+
+/* ---- Optimiser step of the PPO update (ksim/task/ppo.py:536-565 apply_gradients_with_clipping -> optax chain of
+ * examples/walking.py:373-387: zero_nans, clip_by_global_norm, add_decayed_weights, scale_by_adam, warmup_constant_schedule,
+ * scale(-1)) on flat fp32 buffers of n elements, in place.  step_count[0] (device int32, starts at 0) is advanced by the call;
+ * grads are read as grad_scale * grads (1 / world_size after a sum all-reduce).  params_bf16 (may be NULL): bf16 shadow copy of
+ * the updated parameters.  scratch: b200sim_optimizer_scratch_bytes() bytes.  stats (may be NULL): [0] global gradient norm
+ * before clipping, [1] learning rate used, [2] clip factor.  Deterministic (fixed reduction order). */
+size_t b200sim_optimizer_scratch_bytes(void);
+int b200sim_optimizer_step(void* stream, size_t n, float* params, const float* grads, float* mu, float* nu, void* params_bf16,
+                           int32_t* step_count, float grad_scale, float lr_init, float lr_peak, int warmup_steps, float b1, float b2,
+                           float eps, float weight_decay, float max_norm, void* scratch, float* stats);
+const char* b200sim_optimizer_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

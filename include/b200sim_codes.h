@@ -258,6 +258,9 @@
 #define B2S_GRU_ERR_FULL 4       /* bulk copy never landed */
 #define B2S_GRU_ERR_EMPTY 5      /* pipeline stage never freed */
 
+/* ---- flat-buffer optimiser step (b200sim_optimizer_step) ---- */
+#define B2S_OPTIM_MAX_PARTIALS 1024  /* per-CTA partial sums of the gradient norm (grid = a multiple of the SM count, <= this) */
+
 /* ---- error codes ---- */
 #define B2S_OK 0
 #define B2S_ERR_BAD_ARG 1

@@ -18,6 +18,9 @@ EXPORTS = (
     "b200sim_model_create", "b200sim_model_destroy", "b200sim_model_info", "b200sim_last_error", "b200sim_init_envs",
     "b200sim_step_ctrl", "b200sim_rollout", "b200sim_rewards", "b200sim_gae", "b200sim_extract_flags", "b200sim_dataset_pack",
     "b200sim_metrics", "b200sim_ppo_loss",
+    "b200sim_gru_workspace_bytes", "b200sim_gru_saved_floats", "b200sim_gru_forward", "b200sim_gru_backward", "b200sim_gru_last_error",
+    "b200sim_mixture_logprob", "b200sim_mixture_logprob_backward", "b200sim_mixture_sample", "b200sim_policy_last_error",
+    "b200sim_optimizer_scratch_bytes", "b200sim_optimizer_step", "b200sim_optimizer_last_error",
 )
 
 INFO = dict(STATE_SIZE=0, REC_SIZE=1, KEY_SIZE=2, RAND_SIZE=3, ACTION_SIZE=4, N_REW_COMP=5, REW_CARRY_SIZE=6,
@@ -69,6 +72,23 @@ def lib() -> ctypes.CDLL:
         cdll.b200sim_metrics.restype = ci
         cdll.b200sim_ppo_loss.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp, vp, vp]
         cdll.b200sim_ppo_loss.restype = ci
+        sz, u32p = ctypes.c_size_t, vp
+        cdll.b200sim_gru_workspace_bytes.argtypes, cdll.b200sim_gru_workspace_bytes.restype = [ci, ci, ci, ci], sz
+        cdll.b200sim_gru_saved_floats.argtypes, cdll.b200sim_gru_saved_floats.restype = [ci, ci], sz
+        cdll.b200sim_gru_forward.argtypes, cdll.b200sim_gru_forward.restype = [vp, ci, vp, ci, ci, vp, vp, sz], ci
+        cdll.b200sim_gru_backward.argtypes, cdll.b200sim_gru_backward.restype = [vp, ci, vp, ci, ci, vp, vp, sz], ci
+        cdll.b200sim_gru_last_error.argtypes, cdll.b200sim_gru_last_error.restype = [], ctypes.c_char_p
+        cdll.b200sim_mixture_logprob.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp, cf, cf, cf, vp]
+        cdll.b200sim_mixture_logprob.restype = ci
+        cdll.b200sim_mixture_logprob_backward.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp, cf, cf, cf, vp, ci, vp, ci]
+        cdll.b200sim_mixture_logprob_backward.restype = ci
+        cdll.b200sim_mixture_sample.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, cf, cf, cf, u32p, vp, ci, vp, vp]
+        cdll.b200sim_mixture_sample.restype = ci
+        cdll.b200sim_policy_last_error.argtypes, cdll.b200sim_policy_last_error.restype = [], ctypes.c_char_p
+        cdll.b200sim_optimizer_scratch_bytes.argtypes, cdll.b200sim_optimizer_scratch_bytes.restype = [], sz
+        cdll.b200sim_optimizer_step.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, cf, cf, cf, ci, cf, cf, cf, cf, cf, vp, vp]
+        cdll.b200sim_optimizer_step.restype = ci
+        cdll.b200sim_optimizer_last_error.argtypes, cdll.b200sim_optimizer_last_error.restype = [], ctypes.c_char_p
         _LIB = cdll
     return _LIB
 

@@ -20,7 +20,7 @@
 #if defined(__CUDACC__) && !defined(B2S_EMU)
 #define B2S_DEVICE 1
 #define DEV __device__ __forceinline__
-#define DEVNI __device__ __noinline__
+#define DEVNI static __device__ __noinline__
 #define LANE_FOR(i, n) for (int i = lane; i < (n); i += 32)
 #define WSYNC() __syncwarp()
 // Stage barriers keep a CTA's warps on the same code (shared instruction-cache fills); they carry no data dependence.

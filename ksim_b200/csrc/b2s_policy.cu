@@ -1,0 +1,217 @@
+// Policy-head kernels of the replay path: the actor's mixture-of-Gaussians head of examples/walking.py:129-146
+// (prediction -> means / standard deviations / logits -> xax.MixtureOfGaussians) as one pass each for log-prob, its backward
+// and sampling.  Elementwise HBM-bound work: per (row, joint) 3 M inputs, one output.
+//
+//   mean_k = clip(pred[j M + k] + mean_bias[j], lo[j], hi[j])                       (walking.py:140-143: ZEROS bias, ClipPositions)
+//   std_k  = min((softplus(pred[J M + j M + k]) + min_std) var_scale, max_std)      (walking.py:137)
+//   logw_k = log_softmax(pred[2 J M + j M + ..])_k
+//   log p(x) = logsumexp_k(logw_k - 0.5 ((x - mean_k) / std_k)^2 - log std_k - 0.5 log 2 pi)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/b200sim.h"
+#include "b2s_common.cuh"
+
+namespace {
+
+constexpr int MAXM = 16;
+constexpr float HALF_LOG_2PI = 0.91893853320467274178f;
+
+struct MixArgs {
+  int rows, J, M;
+  const float* pred;       // [rows][3 J M]
+  const float* mean_bias;  // [J] or null
+  const float* lo;         // [J] or null (no clip)
+  const float* hi;
+  float min_std, var_scale, max_std;
+};
+
+struct Comp {
+  float mean[MAXM], std[MAXM], logw[MAXM];
+  bool mean_free[MAXM], std_free[MAXM];
+  float sraw[MAXM];
+};
+
+__device__ __forceinline__ void load_components(const MixArgs& a, int row, int j, Comp& c) {
+  const int JM = a.J * a.M;
+  const float* p = a.pred + (size_t)row * 3 * JM + j * a.M;
+  const float bias = a.mean_bias ? a.mean_bias[j] : 0.0f;
+  const float lo = a.lo ? a.lo[j] : -INFINITY, hi = a.hi ? a.hi[j] : INFINITY;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) {
+    if (k < a.M) {
+      const float raw = p[k] + bias;
+      c.mean_free[k] = raw > lo && raw < hi;
+      c.mean[k] = fminf(fmaxf(raw, lo), hi);
+      const float s = p[JM + k];
+      c.sraw[k] = s;
+      const float sp = s > 20.0f ? s : log1pf(expf(s));
+      const float sd = (sp + a.min_std) * a.var_scale;
+      c.std_free[k] = sd < a.max_std;
+      c.std[k] = fminf(sd, a.max_std);
+      c.logw[k] = p[2 * JM + k];
+      mx = fmaxf(mx, c.logw[k]);
+    }
+  }
+  float se = 0.0f;
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) if (k < a.M) se += expf(c.logw[k] - mx);
+  const float lse = mx + logf(se);
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) if (k < a.M) c.logw[k] -= lse;
+}
+
+// log p(x) and the per-component terms (logw_k + log N(x; mean_k, std_k)) left in t[]
+__device__ __forceinline__ float mixture_logp(const MixArgs& a, const Comp& c, float x, float* t) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) {
+    if (k < a.M) {
+      const float u = (x - c.mean[k]) / c.std[k];
+      t[k] = c.logw[k] - 0.5f * u * u - logf(c.std[k]) - HALF_LOG_2PI;
+      mx = fmaxf(mx, t[k]);
+    }
+  }
+  float se = 0.0f;
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) if (k < a.M) se += expf(t[k] - mx);
+  return mx + logf(se);
+}
+
+__global__ void __launch_bounds__(256) k_mixture_logprob(const MixArgs a, const float* __restrict__ action, float* __restrict__ logp) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)a.rows * a.J) return;
+  const int row = idx / a.J, j = idx - (size_t)row * a.J;
+  Comp c;
+  float t[MAXM];
+  load_components(a, row, j, c);
+  logp[idx] = mixture_logp(a, c, action[idx], t);
+}
+
+// d_pred[row][..] from g = d loss / d logp[row][j] (d_logp_row: one value per row, the PPO loss kernel's layout)
+template <class OutT>
+__global__ void __launch_bounds__(256) k_mixture_logprob_bwd(const MixArgs a, const float* __restrict__ action, const float* __restrict__ d_logp,
+                                                             int per_row, OutT* __restrict__ d_pred) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)a.rows * a.J) return;
+  const int row = idx / a.J, j = idx - (size_t)row * a.J;
+  Comp c;
+  float t[MAXM];
+  load_components(a, row, j, c);
+  const float x = action[idx];
+  const float lp = mixture_logp(a, c, x, t);
+  const float g = per_row ? d_logp[row] : d_logp[idx];
+  const int JM = a.J * a.M;
+  OutT* o = d_pred + (size_t)row * 3 * JM + j * a.M;
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) {
+    if (k < a.M) {
+      const float w = expf(t[k] - lp);  // responsibility of component k
+      const float d = x - c.mean[k], inv = 1.0f / c.std[k];
+      const float dmean = c.mean_free[k] ? g * w * d * inv * inv : 0.0f;
+      const float dstd = g * w * (d * d * inv * inv * inv - inv);
+      const float sig = 1.0f / (1.0f + expf(-c.sraw[k]));
+      const float dsraw = c.std_free[k] ? dstd * a.var_scale * sig : 0.0f;
+      const float dlogit = g * (w - expf(c.logw[k]));
+      o[k] = (OutT)dmean;
+      o[JM + k] = (OutT)dsraw;
+      o[2 * JM + k] = (OutT)dlogit;
+    }
+  }
+}
+
+// Sampling (xax.MixtureOfGaussians.sample: component ~ Categorical(softmax(logits)) by Gumbel-max, then a normal draw) or the
+// mode of the heaviest component (argmax); threefry counter = (call counter, row J + j).  Also returns log p(action).
+__global__ void __launch_bounds__(256) k_mixture_sample(const MixArgs a, const uint32_t* __restrict__ key, const int* __restrict__ counter,
+                                                        int argmax, float* __restrict__ action, float* __restrict__ logp) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)a.rows * a.J) return;
+  const int row = idx / a.J, j = idx - (size_t)row * a.J;
+  Comp c;
+  float t[MAXM];
+  load_components(a, row, j, c);
+  const b2s::U2 sub = b2s::threefry2x32(key[0], key[1], (uint32_t)(counter ? counter[0] : 0), (uint32_t)idx);
+  b2s::Key k2; k2.k0 = sub.a; k2.k1 = sub.b;
+  int best = 0;
+  float bv = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) {
+    if (k < a.M) {
+      float v = c.logw[k];
+      if (!argmax) {
+        const float u = fmaxf(b2s::bits_to_unit(b2s::key_bits(k2, k)), 1e-20f);
+        v -= logf(-logf(u));
+      }
+      if (v > bv) { bv = v; best = k; }
+    }
+  }
+  float mean = 0.0f, sd = 0.0f;
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) if (k == best) { mean = c.mean[k]; sd = c.std[k]; }
+  const float x = argmax ? mean : mean + sd * b2s::key_normal(k2, MAXM);
+  action[idx] = x;
+  if (logp) logp[idx] = mixture_logp(a, c, x, t);
+}
+
+thread_local std::string g_pol_error;
+int pfail(int code, const std::string& msg) { g_pol_error = msg; return code; }
+
+int fill(MixArgs& a, int rows, int J, int M, const float* pred, const float* mean_bias, const float* lo, const float* hi, float min_std,
+         float var_scale, float max_std) {
+  if (rows < 0 || J < 1 || M < 1 || M > MAXM) return pfail(B2S_ERR_UNSUPPORTED, "mixture: 1 <= n_mix <= 16, n_joints >= 1");
+  if (!pred || ((lo == nullptr) != (hi == nullptr))) return pfail(B2S_ERR_BAD_ARG, "null argument");
+  a.rows = rows; a.J = J; a.M = M; a.pred = pred; a.mean_bias = mean_bias; a.lo = lo; a.hi = hi;
+  a.min_std = min_std; a.var_scale = var_scale; a.max_std = max_std;
+  return B2S_OK;
+}
+#define LAUNCH_OK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return pfail(B2S_ERR_CUDA, cudaGetErrorString(e_)); } while (0)
+
+}  // namespace
+
+extern "C" const char* b200sim_policy_last_error(void) { return g_pol_error.c_str(); }
+
+extern "C" int b200sim_mixture_logprob(void* stream, int rows, int n_joints, int n_mix, const float* pred, const float* action,
+                                       const float* mean_bias, const float* lo, const float* hi, float min_std, float var_scale,
+                                       float max_std, float* logp) {
+  MixArgs a;
+  if (int rc = fill(a, rows, n_joints, n_mix, pred, mean_bias, lo, hi, min_std, var_scale, max_std)) return rc;
+  if (rows == 0) return B2S_OK;
+  if (!action || !logp) return pfail(B2S_ERR_BAD_ARG, "null argument");
+  const size_t n = (size_t)rows * n_joints;
+  k_mixture_logprob<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, action, logp);
+  LAUNCH_OK();
+  return B2S_OK;
+}
+
+extern "C" int b200sim_mixture_logprob_backward(void* stream, int rows, int n_joints, int n_mix, const float* pred, const float* action,
+                                                const float* mean_bias, const float* lo, const float* hi, float min_std, float var_scale,
+                                                float max_std, const float* d_logp, int d_logp_per_row, void* d_pred, int d_pred_bf16) {
+  MixArgs a;
+  if (int rc = fill(a, rows, n_joints, n_mix, pred, mean_bias, lo, hi, min_std, var_scale, max_std)) return rc;
+  if (rows == 0) return B2S_OK;
+  if (!action || !d_logp || !d_pred) return pfail(B2S_ERR_BAD_ARG, "null argument");
+  const size_t n = (size_t)rows * n_joints;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (d_pred_bf16)
+    k_mixture_logprob_bwd<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a, action, d_logp, d_logp_per_row, (__nv_bfloat16*)d_pred);
+  else
+    k_mixture_logprob_bwd<float><<<grid, 256, 0, (cudaStream_t)stream>>>(a, action, d_logp, d_logp_per_row, (float*)d_pred);
+  LAUNCH_OK();
+  return B2S_OK;
+}
+
+extern "C" int b200sim_mixture_sample(void* stream, int rows, int n_joints, int n_mix, const float* pred, const float* mean_bias,
+                                      const float* lo, const float* hi, float min_std, float var_scale, float max_std,
+                                      const uint32_t* key, const int32_t* counter, int argmax, float* action, float* logp) {
+  MixArgs a;
+  if (int rc = fill(a, rows, n_joints, n_mix, pred, mean_bias, lo, hi, min_std, var_scale, max_std)) return rc;
+  if (rows == 0) return B2S_OK;
+  if (!action || !key) return pfail(B2S_ERR_BAD_ARG, "null argument");
+  const size_t n = (size_t)rows * n_joints;
+  k_mixture_sample<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, key, counter, argmax, action, logp);
+  LAUNCH_OK();
+  return B2S_OK;
+}

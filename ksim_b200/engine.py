@@ -176,10 +176,20 @@ class B200Engine:
             raise ValueError(f"{name}: expected contiguous {dtype} {shape} on {self.device}, got {t.dtype} {tuple(t.shape)} on {t.device}")
 
     def new_record_buffer(self, n_steps: int) -> torch.Tensor:
-        """rec[T+1][N][R]; slot 0 receives the current pre-step block (observations of the next policy call)."""
+        """rec[T+1][N][R]; slot 0 receives the current pre-step block (observations of the next policy call).  Slot T of a
+        rollout holds only the NEXT step's pre-step block -- scoring passes work on the first T slots."""
         rec = torch.zeros((n_steps + 1, self.num_envs, self.R), dtype=torch.float32, device=self.device)
         rec[0].copy_(self.first_rec)
         return rec
+
+    @staticmethod
+    def _scored_steps(rec: torch.Tensor, n_steps: int | None) -> int:
+        """Record buffers are ``[T+1][N][R]`` (``rollout`` / ``new_record_buffer``): the reference's ``get_rewards`` works on
+        exactly the T transitions (rl.py:189-245), so the default is ``rec.shape[0] - 1``; slot T is never a transition."""
+        t = int(rec.shape[0]) - 1 if n_steps is None else int(n_steps)
+        if not 0 <= t <= int(rec.shape[0]):
+            raise ValueError(f"n_steps {t} outside a record buffer of {int(rec.shape[0])} slots")
+        return t
 
     def view(self, rec: torch.Tensor) -> TrajectoryView:
         return TrajectoryView(rec, self.program)
@@ -217,25 +227,29 @@ class B200Engine:
         self.launches += 1
 
     def rollout(self, actions: torch.Tensor, rec: torch.Tensor | None = None) -> torch.Tensor:
-        """T control steps with given ``actions[T][N][NA]`` in one launch (``_single_unroll``'s scan, rl.py:1620)."""
+        """T control steps with given ``actions[T][N][NA]`` in one launch (``_single_unroll``'s scan, rl.py:1620).  ``rec`` may
+        be a caller-owned ``[T+1][N][R]`` buffer that is reused between calls: its slot 0 is refreshed here from the
+        engine-owned pre-step block (``first_rec``), which is in turn refreshed from slot T after the launch."""
         t, n = int(actions.shape[0]), self.num_envs
         self._chk(actions, (t, n, self.NA), torch.float32, "actions")
         if rec is None:
             rec = self.new_record_buffer(t)
-        self._chk(rec, (t + 1, n, self.R), torch.float32, "rec")
+        else:
+            self._chk(rec, (t + 1, n, self.R), torch.float32, "rec")
+            rec[0].copy_(self.first_rec)
         if t == 0 or n == 0:
             return rec
         with torch.cuda.device(self.device):
             binding.check(self.lib.b200sim_rollout(self._handle, self._stream(), n, t, _ptr(actions), _ptr(self.rand), _ptr(self.state),
                                                    _ptr(self.keys), _ptr(rec)), "b200sim_rollout")
         self.launches += 1
-        self.first_rec = rec[t]  # pre-step block of the next rollout
+        self.first_rec.copy_(rec[t])  # pre-step block of the next rollout (engine-owned: set_curriculum_level patches it)
         return rec
 
     # ----------------------------------------------------------------------------------------------- scoring
     def rewards(self, rec: torch.Tensor, n_steps: int | None = None) -> tuple[torch.Tensor, torch.Tensor]:
         """``get_rewards`` for every env (rl.py:189-245): returns total[N][T], components[K][N][T]; updates the carry."""
-        t = int(rec.shape[0]) if n_steps is None else int(n_steps)
+        t = self._scored_steps(rec, n_steps)
         n, k = self.num_envs, self.program["TI_N_REW_COMP"]
         total = torch.empty((n, t), dtype=torch.float32, device=self.device)
         comps = torch.empty((max(k, 1), n, t), dtype=torch.float32, device=self.device)
@@ -250,7 +264,7 @@ class B200Engine:
         (types.py:72-76), ``get_termination_metrics`` / ``get_reward_metrics`` (rl.py:1544-1573), the inputs of
         ``EpisodeLengthCurriculum`` / ``DistanceFromOriginCurriculum`` / ``StepWhenSaturated`` (curriculum.py:125,187,262).
         Returns 0-d / 1-d device tensors; ``episode_length`` and ``deaths`` are per environment."""
-        t = int(rec.shape[0]) if n_steps is None else int(n_steps)
+        t = self._scored_steps(rec, n_steps)
         n, k = self.num_envs, self.program["TI_N_REW_COMP"]
         width = 13 + k
         per_env = torch.empty((n, width), dtype=torch.float32, device=self.device)

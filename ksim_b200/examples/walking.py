@@ -4,7 +4,7 @@ with this package's mirror classes.  BASELINE.json configs 1, 2 and 4 run this s
 
 from __future__ import annotations
 
-__all__ = ["WalkingConfig", "load_humanoid", "make_spec", "RANDOMIZERS"]
+__all__ = ["WalkingConfig", "load_humanoid", "make_spec", "RANDOMIZERS", "ZEROS", "ACTOR_INPUTS", "CRITIC_INPUTS", "network_columns", "make_model"]
 
 import math
 from dataclasses import dataclass, field
@@ -143,3 +143,46 @@ def make_spec(config: WalkingConfig | None = None) -> TaskSpec:
         observations=obs, commands=cmds, rewards=rews, terminations=terms,
         randomized_fields=("dof_frictionloss", "dof_armature", "body_mass", "dof_damping"),
     )
+
+
+# examples/walking.py:19-37: per-joint bias added to the mixture means (all zero for the humanoid), in actuator order
+ZEROS = ("abdomen_z", "abdomen_y", "abdomen_x", "hip_x_right", "hip_z_right", "hip_y_right", "knee_right", "hip_x_left", "hip_z_left",
+         "hip_y_left", "knee_left", "shoulder1_right", "shoulder2_right", "elbow_right", "shoulder1_left", "shoulder2_left", "elbow_left")
+
+# run_actor (walking.py:579-614) and run_critic (:616-672): (observation name, scale) in concatenation order, then the command
+# columns (LinearVelocityCommandValue fields vel, yaw, xvel, yvel = columns 0..3 of "linvel"; AngularVelocityCommandValue.vel = 0)
+ACTOR_INPUTS = ((("noisy_joint_position", 1.0), ("noisy_joint_velocity", 0.1), ("noisy_imu_projected_gravity", 1.0), ("noisy_imu_gyro", 1.0)),
+                (("linvel", 0), ("linvel", 1), ("angvel", 0)))
+CRITIC_INPUTS = ((("joint_position", 1.0), ("joint_velocity", 0.1), ("center_of_mass_inertia", 1.0), ("center_of_mass_velocity", 1.0),
+                  ("imu_acc", 1.0), ("imu_gyro", 1.0), ("projected_gravity", 1.0), ("actuator_force", 0.01), ("base_position", 1.0),
+                  ("base_orientation", 1.0), ("base_linear_velocity", 1.0), ("base_angular_velocity", 1.0), ("feet_force", 1.0)),
+                 (("linvel", 0), ("linvel", 1), ("linvel", 2), ("linvel", 3), ("angvel", 0)))
+
+
+def network_columns(program, inputs) -> tuple[list[int], list[float]]:  # noqa: ANN001
+    """Record columns and scales that assemble a network input row from a pre-step record block: the gather ``run_actor`` /
+    ``run_critic`` do by name on the observation / command dicts."""
+    ob, cm = program["TI_R_OBS"], program["TI_R_CMD"]
+    idx: list[int] = []
+    scale: list[float] = []
+    for name, sc in inputs[0]:
+        off, dim, _ = program.obs_slices[name]
+        idx += list(range(ob + off, ob + off + dim))
+        scale += [sc] * dim
+    for name, col in inputs[1]:
+        off, dim = program.cmd_slices[name]
+        if not 0 <= col < dim:
+            raise ValueError(f"command {name} has {dim} columns")
+        idx.append(cm + off + col)
+        scale.append(1.0)
+    return idx, scale
+
+
+def make_model(spec: TaskSpec, hidden_size: int = 512, depth: int = 2, num_hidden_layers: int = 2, num_mixtures: int = 10):  # noqa: ANN201
+    """``WalkingTask.get_model`` (walking.py:556-571)."""
+    from ksim_b200.policy import Model
+
+    rng = spec.model.jnt_range[1:]  # ksim.ClipPositions.from_physics_model (actions.py:196-200): every joint after the root
+    return Model(num_actor_inputs=43, num_critic_inputs=340, num_joints=len(ZEROS), hidden_size=hidden_size, depth=depth,
+                 num_hidden_layers=num_hidden_layers, num_mixtures=num_mixtures, min_std=0.01, max_std=1.0, var_scale=0.5,
+                 mean_bias=[0.0] * len(ZEROS), clip_lo=rng[:, 0], clip_hi=rng[:, 1])

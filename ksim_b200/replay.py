@@ -15,7 +15,7 @@ the tensor-core path raises.
 
 from __future__ import annotations
 
-__all__ = ["GRUStack", "gru_stacks_forward", "gru_stack_reference", "gru_cell_reference", "HIDDEN"]
+__all__ = ["GRUStack", "gru_stacks_forward", "gru_stack_reference", "gru_cell_reference", "HIDDEN", "shadow"]
 
 import ctypes
 import math
@@ -43,16 +43,7 @@ def _p(t: torch.Tensor | None) -> int | None:
 
 
 def _lib() -> ctypes.CDLL:
-    lib = binding.lib()
-    if not getattr(lib, "_gru_ready", False):
-        vp, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
-        lib.b200sim_gru_workspace_bytes.argtypes, lib.b200sim_gru_workspace_bytes.restype = [ci, ci, ci, ci], sz
-        lib.b200sim_gru_saved_floats.argtypes, lib.b200sim_gru_saved_floats.restype = [ci, ci], sz
-        lib.b200sim_gru_forward.argtypes, lib.b200sim_gru_forward.restype = [vp, ci, vp, ci, ci, vp, vp, sz], ci
-        lib.b200sim_gru_backward.argtypes, lib.b200sim_gru_backward.restype = [vp, ci, vp, ci, ci, vp, vp, sz], ci
-        lib.b200sim_gru_last_error.argtypes, lib.b200sim_gru_last_error.restype = [], ctypes.c_char_p
-        lib._gru_ready = True
-    return lib
+    return binding.lib()
 
 
 def _check(rc: int, what: str) -> None:
@@ -78,6 +69,13 @@ def last_status(n: int, t: int, b: int, backward: bool, device: torch.device) ->
     """Device-side status word of the most recent launch of that shape (0 = ok, else ``B2S_GRU_ERR_*``).  Synchronises."""
     ws = _WORKSPACES.get((n, t, b, backward, torch.device(device)))
     return 0 if ws is None else int(ws[:4].view(torch.int32).item())
+
+
+def shadow(p: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of a parameter for the tensor-core GEMMs: the shadow ``ksim_b200.optim.FlatParams`` keeps up to date inside
+    the optimiser step (``p.shadow``), else a fresh cast."""
+    s = getattr(p, "shadow", None)
+    return s if s is not None else p.detach().to(torch.bfloat16)
 
 
 def _mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -169,7 +167,7 @@ class _GruStacksFn(torch.autograd.Function):
             nxt = []
             for s in range(n_stacks):
                 w_ih, w_hh, bias, bias_n = params[(s * depth + layer) * 4 : (s * depth + layer) * 4 + 4]
-                w_ih16, w_hh16 = w_ih.detach().to(torch.bfloat16), w_hh.detach().to(torch.bfloat16).contiguous()
+                w_ih16, w_hh16 = shadow(w_ih), shadow(w_hh).contiguous()
                 x2 = cur[s].view(t_ * b_, -1)
                 gi = _mm(x2, w_ih16.t())  # [T B, 3H] fp32
                 y = torch.empty((t_, b_, hd), dtype=torch.bfloat16, device=dev)

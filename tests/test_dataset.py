@@ -72,7 +72,7 @@ def test_trajectory_metrics_match_the_reference_formulas(walking_spec, walking_r
     eng = B200Engine(walking_spec, n, randomizers=walking_randomizers, seed=5, curriculum_level=1.0)
     rec = eng.rollout(0.5 * torch.randn((t, n, eng.NA), device="cuda"))
     total, comps = eng.rewards(rec, t)
-    got = {k: v.cpu().numpy() for k, v in eng.metrics(rec[:t], total, comps).items()}
+    got = {k: v.cpu().numpy() for k, v in eng.metrics(rec, total, comps).items()}
     tv = eng.view(rec[:t])
     done = tv.done.cpu().numpy().T                      # (N, T)
     timestep = tv.timestep.cpu().numpy().T
