@@ -125,27 +125,28 @@ int b200sim_dataset_pack(void* stream, int n_envs, int n_steps, int rec_size, co
 /* ---- Recurrent policy replay: the sequential part of get_ppo_variables (ksim/task/ppo.py:417-488 ->
  * examples/walking.py:674-728: xax.scan of two stacks of GRU(512) cells over the T steps of a minibatch) as persistent
  * tcgen05 kernels.  One call advances up to B2S_GRU_MAX_PROBLEMS independent GRU layers (e.g. the actor's and the critic's
- * layer l) over all T steps for B rows; all sequence arrays are TIME-major.  Cell = equinox.nn.GRUCell:
+ * layer l) over all T steps for B rows.  Sequence arrays are FEATURE-major, [features][T B] with column t B + b, so that the
+ * kernels' accesses (one thread per batch row) are coalesced; they are plain transposed operands for the GEMMs around.  Cell = equinox.nn.GRUCell:
  *   r = sigmoid(gi_r + gh_r), z = sigmoid(gi_z + gh_z), n = tanh(gi_n + r (gh_n + b_hn)), h' = n + z (h - n),
  *   gi = x W_ih^T (+ b_i, added here), gh = h W_hh^T; the carry handed on is keep_t h'_t (it restarts from zero after a
  *   terminal step, walking.py:715-719).  bf16 tensor-core operands, fp32 accumulation, fp32 state and gate arithmetic. */
 typedef struct {
   const void* w_hh;   /* bf16 [3H][H] (gate order r, z, n) */
-  const float* gi;    /* [T][B][3H] = x_t W_ih^T, without bias (a plain batched GEMM over all T, done by the caller) */
+  const float* gi;    /* [3H][T B] = W_ih x^T, without bias (a plain batched GEMM over all T, done by the caller) */
   const float* b_i;   /* [3H] */
   const float* b_hn;  /* [H] */
   const float* h0;    /* [B][H] or NULL (zeros) */
-  void* y;            /* bf16 [T][B][H]: h'_t */
-  void* hst;          /* bf16 [T][B][H]: the state step t started from (what dW_hh = sum_t hst_t^T dgh_t needs) */
+  void* y;            /* bf16 [H][T B]: h'_t */
+  void* hst;          /* bf16 [H][T B]: the state step t started from (what dW_hh = sum_t dgh_t^T hst_t needs) */
   float* h_last;      /* [B][H] or NULL: the carry after the last step */
   float* saved;       /* b200sim_gru_saved_floats(T, B) floats for the backward pass, or NULL (inference) */
 } b200sim_gru_fwd;
 typedef struct {
   const void* w_hh_t; /* bf16 [H][3H] = W_hh^T */
-  const float* dy;    /* [T][B][H]: gradient with respect to y */
+  const float* dy;    /* [H][T B]: gradient with respect to y */
   const float* saved; /* written by the forward call */
-  void* dgi;          /* bf16 [T][B][3H]: gradient w.r.t. gi; its r and z blocks are also the gradient w.r.t. gh_r, gh_z */
-  void* dghn;         /* bf16 [T][B][H]: gradient w.r.t. gh_n (and, summed over (t, b), b_hn) */
+  void* dgi;          /* bf16 [3H][T B]: gradient w.r.t. gi; its r and z blocks are also the gradient w.r.t. gh_r, gh_z */
+  void* dghn;         /* bf16 [H][T B]: gradient w.r.t. gh_n (and, summed over (t, b), b_hn) */
   float* dh0;         /* [B][H] or NULL */
 } b200sim_gru_bwd;
 size_t b200sim_gru_workspace_bytes(int n_problems, int n_steps, int batch, int backward);

@@ -257,6 +257,7 @@
 #define B2S_GRU_ERR_TMEM 3       /* accumulator never drained */
 #define B2S_GRU_ERR_FULL 4       /* bulk copy never landed */
 #define B2S_GRU_ERR_EMPTY 5      /* pipeline stage never freed */
+#define B2S_GRU_ERR_PEERS 6      /* a peer CTA of the cluster never finished reading the previous state */
 
 /* ---- flat-buffer optimiser step (b200sim_optimizer_step) ---- */
 #define B2S_OPTIM_MAX_PARTIALS 1024  /* per-CTA partial sums of the gradient norm (grid = a multiple of the SM count, <= this) */

@@ -40,7 +40,10 @@ constexpr int U = 32;                // hidden units per CTA
 constexpr int NCH = H / U;           // CTAs (= state chunks) per group
 constexpr int MT = 128;              // batch rows per group = UMMA M
 constexpr int NEPI = 256;            // epilogue threads: warps 0-7; warp w reads TMEM lanes 32 (w % 4).., units 16 (w / 4)..
-constexpr int NTHREADS = NEPI + 64;  // + warp 8 (bulk-copy producer) + warp 9 (MMA issuer, TMEM owner)
+constexpr int NTHREADS = NEPI + 64;  // backward: + warp 8 (bulk-copy producer) + warp 9 (MMA issuer, TMEM owner)
+constexpr int FULL_CH = 16;                    // forward: state chunks per arrival barrier (the MMA issuer waits NCH / FULL_CH times a step)
+constexpr int NFULL = NCH / FULL_CH;
+constexpr int FWD_THREADS = NEPI + 32;  // forward: + warp 8 (MMA issuer, TMEM owner); chunks arrive by multicast, no producer
 constexpr uint32_t SPIN = 1u << 22;  // bounded waits: a lost signal ends the kernel with an error code, not a hung GPU
 
 constexpr int W_BYTES = 3 * U * H * 2;         // 98304: the CTA's weight slice
@@ -55,12 +58,12 @@ constexpr int SAVED_BLOCK = SAVED_Q * MT * U;  // floats per (step, group, chunk
 
 struct FwdProblem {
   const bf16* w;       // W_hh [3H][H]
-  const float* gi;     // [T][B][3H] = x W_ih^T (bias not included)
+  const float* gi;     // feature-major [3H][T B] = W_ih x^T (bias not included)
   const float* b_i;    // [3H]
   const float* b_hn;   // [H]
   const float* h0;     // [B][H] or null (zeros)
-  bf16* y;             // [T][B][H]   h'_t (what the next layer / the output MLP reads)
-  bf16* hst;           // [T][B][H]   the state step t started from (keep_{t-1} h'_{t-1}; h0 for t = 0)
+  bf16* y;             // feature-major [H][T B]: h'_t (what the next layer / the output MLP reads)
+  bf16* hst;           // feature-major [H][T B]: the state step t started from (keep_{t-1} h'_{t-1}; h0 for t = 0)
   float* h_last;       // [B][H] or null: keep_{T-1} h'_{T-1}
   float* saved;        // [T][n_mt][NCH][SAVED_BLOCK] or null (no backward wanted)
   bf16* xchg;          // [(T+1)][n_mt][NCH][FWD_CH / 2] state chunks in core-matrix order
@@ -76,10 +79,10 @@ struct FwdParams {
 
 struct BwdProblem {
   const bf16* wt;      // W_hh^T [H][3H]
-  const float* dy;     // [T][B][H] gradient with respect to y
+  const float* dy;     // feature-major [H][T B]: gradient with respect to y
   const float* saved;
-  bf16* dgi;           // [T][B][3H] gradient with respect to gi (its r and z blocks are also the gradient w.r.t. gh_r, gh_z)
-  bf16* dghn;          // [T][B][H]  gradient with respect to gh_n
+  bf16* dgi;           // feature-major [3H][T B]: gradient w.r.t. gi (its r and z blocks are also the gradient w.r.t. gh_r, gh_z)
+  bf16* dghn;          // feature-major [H][T B]: gradient with respect to gh_n
   float* dh0;          // [B][H] or null
   bf16* xchg;          // [T][n_mt][NCH][BWD_CH / 2]
   int* flags;
@@ -91,6 +94,20 @@ struct BwdParams {
   int* status;
   uint32_t lbo_sbo_swap;
 };
+
+#ifdef B2S_GRU_TRACE
+// debug build only (B2S_EXTRA_NVCC=-DB2S_GRU_TRACE): SM-clock stamps of CTA 0's roles, 8 points per step (tools/gru_trace.py)
+__device__ long long g_trace[8 * 256];
+__device__ long long g_trace_ch[16 * 256];
+__device__ long long g_trace_ch0[16 * 256];
+#define TRACE_CH0(t, ch) do { if (blockIdx.x == 0 && (t) < 256) g_trace_ch0[(t) * 16 + (ch)] = clock64(); } while (0)
+#define TRACE_CH(t, ch) do { if (blockIdx.x == 0 && (t) < 256) g_trace_ch[(t) * 16 + (ch)] = clock64(); } while (0)
+#define TRACE(t, point) do { if (blockIdx.x == 0 && (t) < 256) g_trace[(t) * 8 + (point)] = clock64(); } while (0)
+#else
+#define TRACE(t, point) do { } while (0)
+#define TRACE_CH(t, ch) do { } while (0)
+#define TRACE_CH0(t, ch) do { } while (0)
+#endif
 
 __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, volatile int* s_abort, int* status, int code) {
   if (*s_abort) return false;
@@ -108,47 +125,59 @@ __device__ __forceinline__ bool wait_flag(const int* flag, int target, volatile 
 }
 
 __device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t swap) {
-  return swap ? smem_desc(addr, sbo, lbo) : smem_desc(addr, lbo, sbo);
+  return (swap & 1) ? smem_desc(addr, sbo, lbo) : smem_desc(addr, lbo, sbo);
 }
 
 // ------------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(NTHREADS, 1) k_gru_fwd(const FwdParams p) {
+// One thread-block CLUSTER of 16 CTAs = one group.  State exchange per step, with no flags and no polling of global memory:
+//   * the epilogue threads of CTA c store the CTA's bf16 chunk of the next state to the exchange buffer (L2), and one thread
+//     then issues ONE multicast bulk copy of that chunk (cp.async.bulk ... .multicast::cluster) which lands at sA + c * FWD_CH
+//     in all 16 CTAs and completes on full[c] of each of them: one L2 read feeds 16 SMs, the arrival is the signal;
+//   * before overwriting the peers' state tiles the sender waits for `peers_done`, on which the MMA issuer of every CTA of
+//     the cluster arrives (tcgen05.commit ... .multicast::cluster) when its MMAs of the previous step have completed.
+__global__ void __launch_bounds__(FWD_THREADS, 1) k_gru_fwd(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sB = smem;
   uint8_t* sA = smem + W_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + W_BYTES + FWD_A);  // [NCH]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + W_BYTES + FWD_A);  // [NFULL]: chunks FULL_CH q .. FULL_CH q + FULL_CH - 1
   uint64_t* acc_full = full + NCH;
   uint64_t* tmem_empty = full + NCH + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(full + NCH + 2);
+  uint64_t* peers_done = full + NCH + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(full + NCH + 3);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   float* s_bias = reinterpret_cast<float*>(smem + W_BYTES + FWD_A + 256);  // b_i slice [3][U], b_hn slice [U]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int c = blockIdx.x % NCH, slot = blockIdx.x / NCH, n_slots = gridDim.x / NCH;
+  const int c = (int)cluster_ctarank(), slot = (int)cluster_id_x(), n_slots = (int)cluster_count_x();
   const int n_groups = p.n_problems * p.n_mt, T = p.T, B = p.B;
+  const size_t TB = (size_t)T * B;
+  constexpr uint16_t ALL = (uint16_t)((1u << NCH) - 1);
 
   if (tid == 0) {
-    for (int i = 0; i < NCH; i++) mbar_init(&full[i], 1);
+    for (int i = 0; i < NFULL; i++) mbar_init(&full[i], 1);
     mbar_init(acc_full, 1);
     mbar_init(tmem_empty, NEPI);
+    mbar_init(peers_done, NCH);
     *s_abort = 0;
     mbar_fence_init();
+    for (int i = 0; i < NFULL; i++) mbar_arrive_expect_tx(&full[i], FULL_CH * FWD_CH);  // phase 0 armed: FULL_CH chunks per phase
   }
-  if (warp == 9) tmem_alloc(s_tmem, 128);
+  if (warp == 8) tmem_alloc(s_tmem, 128);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peers' barriers exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
   constexpr uint32_t IDESC = idesc_bf16(MT, 3 * U);
 
   int loaded = -1;
-  uint32_t base = 0;  // steps this CTA has run so far (mbarrier phase bookkeeping, identical in every role)
+  uint32_t base = 0;  // steps this CTA has run so far (mbarrier phase bookkeeping, identical in every role and every CTA)
   for (int g = slot; g < n_groups; g += n_slots, base += T) {
     const int pi = g / p.n_mt, mt = g % p.n_mt;
     const FwdProblem& q = p.pr[pi];
     if (pi != loaded) {
       __syncthreads();
       // weight slice -> K-major core matrices: B row n = gate * U + j  <->  W_hh row gate * H + c U + j
-      for (int idx = tid; idx < 3 * U * (H / 8); idx += NTHREADS) {
+      for (int idx = tid; idx < 3 * U * (H / 8); idx += FWD_THREADS) {
         const int n = idx / (H / 8), kc = idx % (H / 8);
         const uint4 v = *reinterpret_cast<const uint4*>(q.w + ((size_t)((n / U) * H + c * U + (n % U)) * H + kc * 8));
         *reinterpret_cast<uint4*>(sB + kc * (3 * U * 16) + n * 16) = v;
@@ -159,7 +188,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_fwd(const FwdParams p) {
       __syncthreads();
       loaded = pi;
     }
-    int* flags = q.flags + mt * NCH;
     if (warp < 8) {
       // ------------------------------------------------------------------ epilogue: gates, state, outputs
       const int row = (warp & 3) * 32 + lane, half = warp >> 2, j0 = half * 16;
@@ -176,45 +204,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_fwd(const FwdParams p) {
           h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
         }
       }
+      // state s (the state step s starts from) goes out first; the step's bulky outputs (y, hst, saved) are stored afterwards
+      uint4 v0, v1;
       auto publish = [&](int s) {
-        const uint4 v0 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-        const uint4 v1 = make_uint4(pack_bf16(h[8], h[9]), pack_bf16(h[10], h[11]), pack_bf16(h[12], h[13]), pack_bf16(h[14], h[15]));
+        v0 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+        v1 = make_uint4(pack_bf16(h[8], h[9]), pack_bf16(h[10], h[11]), pack_bf16(h[12], h[13]), pack_bf16(h[14], h[15]));
         bf16* dst = q.xchg + (((size_t)s * p.n_mt + mt) * NCH + c) * (FWD_CH / 2);
         *reinterpret_cast<uint4*>(dst + ((2 * half) * MT + row) * 8) = v0;
         *reinterpret_cast<uint4*>(dst + ((2 * half + 1) * MT + row) * 8) = v1;
-        if (s < T && live) {
-          bf16* hs = q.hst + ((size_t)s * B + grow) * H + ucol;
-          *reinterpret_cast<uint4*>(hs) = v0;
-          *reinterpret_cast<uint4*>(hs + 8) = v1;
-        }
         __syncwarp();
         named_bar_sync(1, NEPI);
-        if (tid == 0) {
-          __threadfence();
-          st_release(&flags[c], s + 1);
+        if (tid == 0 && !(p.lbo_sbo_swap & 2)) {
+          // every CTA of the cluster has finished the MMAs that read the previous state: the tiles may be overwritten
+          if (s > 0) TRACE(s - 1, 3);
+          if (base + s > 0) wait_bar(peers_done, (base + s - 1) & 1, s_abort, p.status, B2S_GRU_ERR_PEERS);
+          if (s > 0) TRACE(s - 1, 7);
+          fence_proxy_async();  // the chunk was written through the generic proxy; the bulk copy reads it through the async proxy
+          bulk_g2s_multicast(sA + c * FWD_CH, dst, FWD_CH, &full[c / FULL_CH], ALL);
         }
       };
+      auto store_cols = [&](bf16* base_ptr, int s, const uint4& a, const uint4& b) {  // feature-major [H][T B], lanes = batch rows
+        if (live) {
+          uint16_t* o = reinterpret_cast<uint16_t*>(base_ptr) + (size_t)ucol * TB + (size_t)s * B + grow;
+          const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            o[(size_t)(2 * i) * TB] = (uint16_t)(w[i] & 0xffffu);
+            o[(size_t)(2 * i + 1) * TB] = (uint16_t)(w[i] >> 16);
+          }
+        }
+      };
+      auto store_hst = [&](int s) { if (!(p.lbo_sbo_swap & 4)) store_cols(q.hst, s, v0, v1); };
       publish(0);
+      store_hst(0);
       for (int t = 0; t < T; t++) {
         float gr[16], gz[16], gn[16];
         float kp = 1.0f;
-        if (live) {
-          const float* gp = q.gi + ((size_t)t * B + grow) * (3 * H) + ucol;
+        if (live && !(p.lbo_sbo_swap & 8)) {
+          // feature-major gi [3H][T B]: consecutive lanes (batch rows) read consecutive addresses
+          const float* gp = q.gi + (size_t)ucol * TB + (size_t)t * B + grow;
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float4 a = __ldcs(reinterpret_cast<const float4*>(gp + 4 * i));
-            const float4 b = __ldcs(reinterpret_cast<const float4*>(gp + H + 4 * i));
-            const float4 d = __ldcs(reinterpret_cast<const float4*>(gp + 2 * H + 4 * i));
-            gr[4 * i] = a.x; gr[4 * i + 1] = a.y; gr[4 * i + 2] = a.z; gr[4 * i + 3] = a.w;
-            gz[4 * i] = b.x; gz[4 * i + 1] = b.y; gz[4 * i + 2] = b.z; gz[4 * i + 3] = b.w;
-            gn[4 * i] = d.x; gn[4 * i + 1] = d.y; gn[4 * i + 2] = d.z; gn[4 * i + 3] = d.w;
+          for (int i = 0; i < 16; i++) {
+            gr[i] = ld_stream_f32(gp + (size_t)i * TB);
+            gz[i] = ld_stream_f32(gp + (size_t)(H + i) * TB);
+            gn[i] = ld_stream_f32(gp + (size_t)(2 * H + i) * TB);
           }
           if (p.keep) kp = p.keep[(size_t)t * B + grow];
         } else {
 #pragma unroll
           for (int i = 0; i < 16; i++) gr[i] = gz[i] = gn[i] = 0.0f;
         }
-        wait_bar(acc_full, (base + t) & 1, s_abort, p.status, B2S_GRU_ERR_ACC);
+        if (lane == 0) wait_bar(acc_full, (base + t) & 1, s_abort, p.status, B2S_GRU_ERR_ACC);  // one poller per warp
+        if (tid == 0) TRACE(t, 0);
         __syncwarp();
         tc_fence_after();
         const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)j0;
@@ -233,7 +274,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_fwd(const FwdParams p) {
           a[i] += s_bias[3 * U + j0 + i];                                   // hn = gh_n + b_hn
           gn[i] = tanh_fast(gn[i] + s_bias[2 * U + j0 + i] + gr[i] * a[i]);  // n
         }
-        if (q.saved) {
+        float hm[16];   // h - n (saved for the backward pass)
+#pragma unroll
+        for (int i = 0; i < 16; i++) { hm[i] = h[i] - gn[i]; h[i] = fmaf(gz[i], hm[i], gn[i]); }  // h' = n + z (h - n)
+        const uint4 y0 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+        const uint4 y1 = make_uint4(pack_bf16(h[8], h[9]), pack_bf16(h[10], h[11]), pack_bf16(h[12], h[13]), pack_bf16(h[14], h[15]));
+#pragma unroll
+        for (int i = 0; i < 16; i++) h[i] *= kp;  // the carry restarts from zero after a terminal step
+        if (tid == 0) TRACE(t, 1);
+        if (t + 1 < T) {
+          publish(t + 1);
+          if (tid == 0) TRACE(t, 2);
+          store_hst(t + 1);
+        }
+        if (!(p.lbo_sbo_swap & 4)) store_cols(q.y, t, y0, y1);
+        if (q.saved && !(p.lbo_sbo_swap & 4)) {
           float* sv = q.saved + (((size_t)t * p.n_mt + mt) * NCH + c) * SAVED_BLOCK;
 #pragma unroll
           for (int i = 0; i < 4; i++) {
@@ -242,39 +297,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_fwd(const FwdParams p) {
             __stcs(reinterpret_cast<float4*>(sv + MT * U + o), make_float4(gz[4 * i], gz[4 * i + 1], gz[4 * i + 2], gz[4 * i + 3]));
             __stcs(reinterpret_cast<float4*>(sv + 2 * MT * U + o), make_float4(gn[4 * i], gn[4 * i + 1], gn[4 * i + 2], gn[4 * i + 3]));
             __stcs(reinterpret_cast<float4*>(sv + 3 * MT * U + o), make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]));
-            __stcs(reinterpret_cast<float4*>(sv + 4 * MT * U + o),
-                   make_float4(h[4 * i] - gn[4 * i], h[4 * i + 1] - gn[4 * i + 1], h[4 * i + 2] - gn[4 * i + 2], h[4 * i + 3] - gn[4 * i + 3]));
+            __stcs(reinterpret_cast<float4*>(sv + 4 * MT * U + o), make_float4(hm[4 * i], hm[4 * i + 1], hm[4 * i + 2], hm[4 * i + 3]));
           }
         }
-#pragma unroll
-        for (int i = 0; i < 16; i++) h[i] = fmaf(gz[i], h[i] - gn[i], gn[i]);  // h' = n + z (h - n)
-        if (live) {
-          bf16* yp = q.y + ((size_t)t * B + grow) * H + ucol;
-          *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-          *reinterpret_cast<uint4*>(yp + 8) =
-              make_uint4(pack_bf16(h[8], h[9]), pack_bf16(h[10], h[11]), pack_bf16(h[12], h[13]), pack_bf16(h[14], h[15]));
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++) h[i] *= kp;  // the carry restarts from zero after a terminal step
-        publish(t + 1);
       }
       if (live && q.h_last) {
 #pragma unroll
         for (int i = 0; i < 4; i++)
           *reinterpret_cast<float4*>(q.h_last + (size_t)grow * H + ucol + 4 * i) = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-      }
-    } else if (warp == 8) {
-      // ------------------------------------------------------------------ producer: lane l gathers chunk l of every step
-      for (int t = 0; t < T; t++) {
-        if (lane < NCH) {
-          const uint32_t gs = base + t;
-          if (gs > 0) wait_bar(acc_full, (gs - 1) & 1, s_abort, p.status, B2S_GRU_ERR_ACC);  // the previous step's MMAs have read sA
-          wait_flag(&flags[lane], t + 1, s_abort, p.status, B2S_GRU_ERR_FLAG);
-          fence_proxy_async();
-          mbar_arrive_expect_tx(&full[lane], FWD_CH);
-          bulk_g2s(sA + lane * FWD_CH, q.xchg + (((size_t)t * p.n_mt + mt) * NCH + lane) * (FWD_CH / 2), FWD_CH, &full[lane]);
-        }
-        __syncwarp();
       }
     } else if (lane == 0) {
       // ------------------------------------------------------------------ MMA issuer: gh_t[128 x 96] = h_{t-1}[128 x 512] W^T
@@ -284,23 +314,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_fwd(const FwdParams p) {
         if (gs > 0) wait_bar(tmem_empty, (gs - 1) & 1, s_abort, p.status, B2S_GRU_ERR_TMEM);
         tc_fence_after();
         for (int ch = 0; ch < NCH; ch++) {
-          wait_bar(&full[ch], gs & 1, s_abort, p.status, B2S_GRU_ERR_FULL);
-          tc_fence_after();
+          if (ch % FULL_CH == 0 && !(p.lbo_sbo_swap & 2)) {
+            TRACE_CH0(t, ch);
+            wait_bar(&full[ch / FULL_CH], gs & 1, s_abort, p.status, B2S_GRU_ERR_FULL);
+            mbar_arrive_expect_tx(&full[ch / FULL_CH], FULL_CH * FWD_CH);  // arms the next phase (the next step's chunks)
+            if (ch == 0) TRACE(t, 4);
+            if (ch == NCH - FULL_CH) TRACE(t, 5);
+            TRACE_CH(t, ch);
+            tc_fence_after();
+          }
 #pragma unroll
           for (int k2 = 0; k2 < U / 16; k2++) {
             const uint64_t da = desc(a0 + ch * FWD_CH + k2 * 2 * (MT * 16), MT * 16, 128, p.lbo_sbo_swap);
             const uint64_t db = desc(b0 + (ch * (U / 8) + k2 * 2) * (3 * U * 16), 3 * U * 16, 128, p.lbo_sbo_swap);
             mma_bf16_ss(tmem, da, db, IDESC, (ch | k2) != 0);
           }
+          if (ch % FULL_CH != 0) TRACE_CH0(t, ch);   // after this chunk's MMAs were issued
         }
         mma_commit(acc_full);
+        if (!(p.lbo_sbo_swap & 2)) mma_commit_multicast(peers_done, ALL);
+        TRACE(t, 6);
       }
     }
     __syncwarp();  // roles reconverge before the next CTA-wide barrier
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, 128);
+  cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
+  if (warp == 8) tmem_dealloc(tmem, 128);
 }
 
 // ----------------------------------------------------------------------------------------------------- backward
@@ -322,6 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
   const int c = blockIdx.x % NCH, slot = blockIdx.x / NCH, n_slots = gridDim.x / NCH;
   const int n_groups = p.n_problems * p.n_mt, T = p.T, B = p.B;
 
+  const size_t TB = (size_t)T * B;
   if (tid == 0) {
     for (int i = 0; i < BWD_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(acc_full, 1);
@@ -384,12 +426,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
           hmn[4 * i] = f.x; hmn[4 * i + 1] = f.y; hmn[4 * i + 2] = f.z; hmn[4 * i + 3] = f.w;
         }
         if (live) {
-          const float* dp = q.dy + ((size_t)t * B + grow) * H + ucol;
+          const float* dp = q.dy + (size_t)ucol * TB + (size_t)t * B + grow;  // feature-major dy [H][T B]
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float4 a = __ldcs(reinterpret_cast<const float4*>(dp + 4 * i));
-            dy[4 * i] = a.x; dy[4 * i + 1] = a.y; dy[4 * i + 2] = a.z; dy[4 * i + 3] = a.w;
-          }
+          for (int i = 0; i < 16; i++) dy[i] = ld_stream_f32(dp + (size_t)i * TB);
           if (p.keep) kp = p.keep[(size_t)t * B + grow];
         } else {
 #pragma unroll
@@ -408,15 +447,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
         }
         auto pk = [](const float* v, int o) { return make_uint4(pack_bf16(v[o], v[o + 1]), pack_bf16(v[o + 2], v[o + 3]), pack_bf16(v[o + 4], v[o + 5]), pack_bf16(v[o + 6], v[o + 7])); };
         const uint4 r0 = pk(dr_, 0), r1 = pk(dr_, 8), z0 = pk(dz_, 0), z1 = pk(dz_, 8), n0 = pk(dn_, 0), n1 = pk(dn_, 8), g0 = pk(dg_, 0), g1 = pk(dg_, 8);
-        if (live) {
-          bf16* o = q.dgi + ((size_t)t * B + grow) * (3 * H) + ucol;
-          *reinterpret_cast<uint4*>(o) = r0; *reinterpret_cast<uint4*>(o + 8) = r1;
-          *reinterpret_cast<uint4*>(o + H) = z0; *reinterpret_cast<uint4*>(o + H + 8) = z1;
-          *reinterpret_cast<uint4*>(o + 2 * H) = n0; *reinterpret_cast<uint4*>(o + 2 * H + 8) = n1;
-          bf16* og = q.dghn + ((size_t)t * B + grow) * H + ucol;
-          *reinterpret_cast<uint4*>(og) = g0; *reinterpret_cast<uint4*>(og + 8) = g1;
-        }
-        // the chunk the peers multiply with W_hh: K order gate * 32 + j  ->  core-matrix column gate * 4 + j / 8
+        // the chunk the peers multiply with W_hh goes out first (K order gate * 32 + j -> core-matrix column gate * 4 + j / 8);
+        // the step's own outputs (dgi, dghn) are stored after the flag, off the exchange's critical path
         bf16* dst = q.xchg + (((size_t)s * p.n_mt + mt) * NCH + c) * (BWD_CH / 2);
         *reinterpret_cast<uint4*>(dst + ((0 + 2 * half) * MT + row) * 8) = r0;
         *reinterpret_cast<uint4*>(dst + ((1 + 2 * half) * MT + row) * 8) = r1;
@@ -430,7 +462,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
           __threadfence();
           st_release(&flags[c], s + 1);
         }
-        wait_bar(acc_full, (base + s) & 1, s_abort, p.status, B2S_GRU_ERR_ACC);
+        if (live) {  // feature-major dgi [3H][T B], dghn [H][T B]: lanes = batch rows
+          uint16_t* o = reinterpret_cast<uint16_t*>(q.dgi) + (size_t)ucol * TB + (size_t)t * B + grow;
+          uint16_t* og = reinterpret_cast<uint16_t*>(q.dghn) + (size_t)ucol * TB + (size_t)t * B + grow;
+          const uint32_t wr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w}, wz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+          const uint32_t wn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w}, wg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            o[(size_t)(2 * i) * TB] = (uint16_t)(wr[i] & 0xffffu);              o[(size_t)(2 * i + 1) * TB] = (uint16_t)(wr[i] >> 16);
+            o[(size_t)(H + 2 * i) * TB] = (uint16_t)(wz[i] & 0xffffu);          o[(size_t)(H + 2 * i + 1) * TB] = (uint16_t)(wz[i] >> 16);
+            o[(size_t)(2 * H + 2 * i) * TB] = (uint16_t)(wn[i] & 0xffffu);      o[(size_t)(2 * H + 2 * i + 1) * TB] = (uint16_t)(wn[i] >> 16);
+            og[(size_t)(2 * i) * TB] = (uint16_t)(wg[i] & 0xffffu);             og[(size_t)(2 * i + 1) * TB] = (uint16_t)(wg[i] >> 16);
+          }
+        }
+        if (lane == 0) wait_bar(acc_full, (base + s) & 1, s_abort, p.status, B2S_GRU_ERR_ACC);  // one poller per warp
         __syncwarp();
         tc_fence_after();
         float a[16];
@@ -519,11 +564,55 @@ int launch(void (*kernel)(const P), const P& prm, int smem_bytes, int n_groups, 
   return B2S_OK;
 }
 
+// The forward kernel runs one 16-CTA thread-block cluster per group (non-portable cluster size: one cluster per GPC).
+int launch_fwd(const FwdParams& prm, int n_groups, void* stream) {
+  static thread_local int max_clusters = -1;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCH; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(FWD_THREADS); cfg.dynamicSmemBytes = FWD_SMEM; cfg.stream = (cudaStream_t)stream; cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    if (cudaFuncSetAttribute(k_gru_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gru_fwd, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+      return gfail(B2S_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(cudaGetLastError()));
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cfg.gridDim = dim3((sms / NCH) * NCH);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_gru_fwd, &cfg) != cudaSuccess)
+      return gfail(B2S_ERR_CUDA, std::string("cudaOccupancyMaxActiveClusters: ") + cudaGetErrorString(cudaGetLastError()));
+    max_clusters = n;
+    if (getenv("B2S_GRU_DEBUG")) fprintf(stderr, "[b200sim] k_gru_fwd: %d co-resident 16-CTA clusters on %d SMs\n", n, sms);
+  }
+  int slots = max_clusters;
+  if (const char* e = getenv("B2S_GRU_SLOTS")) { const int v = atoi(e); if (v >= 1 && v < slots) slots = v; }
+  if (n_groups < slots) slots = n_groups;
+  if (slots < 1) return gfail(B2S_ERR_CUDA, "no 16-CTA cluster of the forward kernel fits on this device");
+  cfg.gridDim = dim3(slots * NCH);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_gru_fwd, prm);
+  if (e != cudaSuccess) return gfail(B2S_ERR_CUDA, std::string("gru forward launch: ") + cudaGetErrorString(e));
+  return B2S_OK;
+}
+
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
 extern "C" const char* b200sim_gru_last_error(void) { return g_gru_error.c_str(); }
+
+#ifdef B2S_GRU_TRACE
+extern "C" int b200sim_debug_gru_trace(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * (n < 8 * 256 ? n : 8 * 256));
+}
+extern "C" int b200sim_debug_gru_trace_ch0(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace_ch0, sizeof(long long) * (n < 16 * 256 ? n : 16 * 256));
+}
+extern "C" int b200sim_debug_gru_trace_ch(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace_ch, sizeof(long long) * (n < 16 * 256 ? n : 16 * 256));
+}
+#endif
 
 extern "C" size_t b200sim_gru_workspace_bytes(int n_problems, int n_steps, int batch, int backward) {
   if (n_problems < 1 || n_steps < 0 || batch < 0) return 0;
@@ -539,7 +628,8 @@ extern "C" int b200sim_gru_forward(void* stream, int n_problems, const b200sim_g
   if (!workspace || workspace_bytes < b200sim_gru_workspace_bytes(n_problems, n_steps, batch, 0)) return gfail(B2S_ERR_BAD_ARG, "workspace too small");
   FwdParams prm{};
   prm.n_problems = n_problems; prm.T = n_steps; prm.B = batch; prm.n_mt = (batch + MT - 1) / MT; prm.keep = keep;
-  prm.lbo_sbo_swap = getenv("B2S_GRU_SWAP") ? 1 : 0;
+  prm.lbo_sbo_swap = (getenv("B2S_GRU_SWAP") ? 1 : 0) | (getenv("B2S_GRU_NOXCHG") ? 2 : 0) | (getenv("B2S_GRU_NOSTORE") ? 4 : 0) |
+                     (getenv("B2S_GRU_NOLOAD") ? 8 : 0);  // debug / timing experiments only
   uint8_t* ws = (uint8_t*)workspace;
   prm.status = (int*)ws;
   const size_t flag_bytes = align256((size_t)prm.n_mt * NCH * sizeof(int));
@@ -557,7 +647,7 @@ extern "C" int b200sim_gru_forward(void* stream, int n_problems, const b200sim_g
   }
   cudaError_t e = cudaMemsetAsync(ws, 0, 256 + (size_t)n_problems * flag_bytes, (cudaStream_t)stream);
   if (e != cudaSuccess) return gfail(B2S_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
-  return launch<FwdParams>(k_gru_fwd, prm, FWD_SMEM, n_problems * prm.n_mt, stream);
+  return launch_fwd(prm, n_problems * prm.n_mt, stream);
 }
 
 extern "C" int b200sim_gru_backward(void* stream, int n_problems, const b200sim_gru_bwd* pr, int n_steps, int batch, const float* keep,

@@ -9,7 +9,8 @@ keeps the reference's parameterisation (``eqx.nn.GRUCell``: ``weight_ih [3H, I]`
 ONE persistent tcgen05 kernel per layer and direction; the batched GEMMs around it are plain library GEMMs (bf16 operands,
 fp32 accumulation) issued through torch.  ``gru_stack_reference`` is the fp32 restatement the tests compare against.
 
-All sequence tensors are time-major ``[T, B, ...]``.  There is no fallback: without ``libb200sim.so`` or off a CUDA device
+All sequence tensors are time-major ``[T, B, ...]`` at this module's interface (feature-major ``[features, T B]`` between
+the kernels and the GEMMs inside).  There is no fallback: without ``libb200sim.so`` or off a CUDA device
 the tensor-core path raises.
 """
 
@@ -141,7 +142,9 @@ def gru_stack_reference(stack: GRUStack, x: torch.Tensor, carry: torch.Tensor | 
 
 class _GruStacksFn(torch.autograd.Function):
     """Up to ``B2S_GRU_MAX_PROBLEMS`` GRU stacks of equal depth over the same ``(T, B)`` batch, layer by layer; each layer of
-    all stacks is one persistent kernel launch per direction."""
+    all stacks is one persistent kernel launch per direction.  Between the kernels and the library GEMMs every sequence array
+    is FEATURE-major (``[features, T B]``): coalesced for the kernels (one thread per batch row), a transposed operand for the
+    GEMMs, and row sums for the bias gradients."""
 
     @staticmethod
     def forward(ctx, n_stacks: int, depth: int, keep: torch.Tensor | None, want_grad: bool, *args: torch.Tensor):  # noqa: ANN001, ANN205
@@ -149,6 +152,7 @@ class _GruStacksFn(torch.autograd.Function):
         xs, h0s = args[:n_stacks], args[n_stacks : 2 * n_stacks]
         params = args[2 * n_stacks :]  # per stack, per layer: w_ih, w_hh, bias, bias_n
         t_, b_ = int(xs[0].shape[0]), int(xs[0].shape[1])
+        tb = t_ * b_
         dev = xs[0].device
         if dev.type != "cuda":
             raise binding.B200SimError("the GRU replay kernels need CUDA tensors; there is no CPU path")
@@ -157,7 +161,9 @@ class _GruStacksFn(torch.autograd.Function):
             keep = keep.to(torch.float32).contiguous()
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         n_saved = int(lib.b200sim_gru_saved_floats(t_, b_))
-        cur = [x.to(torch.bfloat16).contiguous() for x in xs]
+        # layer inputs as [I, T B] operands: the first is a transposed view of the row-major input, the others are the
+        # feature-major outputs of the layer below
+        cur = [x.detach().to(torch.bfloat16).reshape(tb, -1).t() for x in xs]
         saved_layers = []
         h_last = [torch.empty((depth, b_, hd), dtype=torch.float32, device=dev) for _ in range(n_stacks)]
         ws = _workspace(n_stacks, t_, b_, False, dev)
@@ -168,10 +174,9 @@ class _GruStacksFn(torch.autograd.Function):
             for s in range(n_stacks):
                 w_ih, w_hh, bias, bias_n = params[(s * depth + layer) * 4 : (s * depth + layer) * 4 + 4]
                 w_ih16, w_hh16 = shadow(w_ih), shadow(w_hh).contiguous()
-                x2 = cur[s].view(t_ * b_, -1)
-                gi = _mm(x2, w_ih16.t())  # [T B, 3H] fp32
-                y = torch.empty((t_, b_, hd), dtype=torch.bfloat16, device=dev)
-                hst = torch.empty((t_, b_, hd), dtype=torch.bfloat16, device=dev)
+                gi = _mm(w_ih16, cur[s])  # [3H, T B] fp32
+                y = torch.empty((hd, tb), dtype=torch.bfloat16, device=dev)
+                hst = torch.empty((hd, tb), dtype=torch.bfloat16, device=dev)
                 sv = torch.empty(n_saved, dtype=torch.float32, device=dev) if want_grad else None
                 h0 = None if h0s[s] is None else h0s[s][layer].to(torch.float32).contiguous()
                 bi, bn = bias.detach().float().contiguous(), bias_n.detach().float().contiguous()
@@ -189,9 +194,10 @@ class _GruStacksFn(torch.autograd.Function):
         ctx.n_stacks, ctx.depth, ctx.shape, ctx.keep = n_stacks, depth, (t_, b_), keep
         ctx.saved_layers = saved_layers
         ctx.x_dtypes = [x.dtype for x in xs]
+        ctx.x_shapes = [tuple(x.shape) for x in xs]
         outs = []
         for s in range(n_stacks):
-            outs += [cur[s], h_last[s]]
+            outs += [cur[s].t().unflatten(0, (t_, b_)), h_last[s]]  # [T, B, H] view of the feature-major top output
             ctx.mark_non_differentiable(h_last[s])
         return tuple(outs)
 
@@ -199,24 +205,27 @@ class _GruStacksFn(torch.autograd.Function):
     def backward(ctx, *grads: torch.Tensor):  # noqa: ANN205
         lib = _lib()
         n_stacks, depth, (t_, b_), keep = ctx.n_stacks, ctx.depth, ctx.shape, ctx.keep
+        tb = t_ * b_
         hd = HIDDEN
         dev = ctx.saved_layers[0][0].device
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         ws = _workspace(n_stacks, t_, b_, True, dev)
-        dy = []
+        dy = []  # feature-major fp32 [H, T B]
         for s in range(n_stacks):
             g = grads[2 * s]
-            dy.append(torch.zeros((t_, b_, hd), dtype=torch.float32, device=dev) if g is None else g.to(torch.float32).contiguous())
+            dy.append(torch.zeros((hd, tb), dtype=torch.float32, device=dev) if g is None
+                      else g.reshape(tb, hd).t().to(torch.float32).contiguous())
         pgrads: list[list[torch.Tensor | None]] = [[None] * (4 * depth) for _ in range(n_stacks)]
+        dx: list[torch.Tensor | None] = [None] * n_stacks
         for layer in reversed(range(depth)):
             probs = (_BwdProblem * n_stacks)()
             outs = []
             hold = []
             for s in range(n_stacks):
-                x16, w_ih16, w_hh16, hst, sv = ctx.saved_layers[layer * n_stacks + s]
+                x_in, w_ih16, w_hh16, hst, sv = ctx.saved_layers[layer * n_stacks + s]
                 w_hh_t = w_hh16.t().contiguous()
-                dgi = torch.empty((t_, b_, 3 * hd), dtype=torch.bfloat16, device=dev)
-                dghn = torch.empty((t_, b_, hd), dtype=torch.bfloat16, device=dev)
+                dgi = torch.empty((3 * hd, tb), dtype=torch.bfloat16, device=dev)
+                dghn = torch.empty((hd, tb), dtype=torch.bfloat16, device=dev)
                 p = probs[s]
                 p.w_hh_t, p.dy, p.saved, p.dgi, p.dghn, p.dh0 = _p(w_hh_t), _p(dy[s]), _p(sv), _p(dgi), _p(dghn), None
                 outs.append((dgi, dghn))
@@ -225,19 +234,22 @@ class _GruStacksFn(torch.autograd.Function):
                 _check(lib.b200sim_gru_backward(stream, n_stacks, ctypes.byref(probs), t_, b_, _p(keep), _p(ws), ws.numel()), "b200sim_gru_backward")
             del hold
             for s in range(n_stacks):
-                x16, w_ih16, w_hh16, hst, sv = ctx.saved_layers[layer * n_stacks + s]
+                x_in, w_ih16, w_hh16, hst, sv = ctx.saved_layers[layer * n_stacks + s]
                 dgi, dghn = outs[s]
-                dgi2, dghn2, hst2 = dgi.view(t_ * b_, 3 * hd), dghn.view(t_ * b_, hd), hst.view(t_ * b_, hd)
-                g_w_ih = _mm(dgi2.t(), x16.view(t_ * b_, -1))
-                g_w_hh = torch.cat([_mm(dgi2[:, : 2 * hd].t(), hst2), _mm(dghn2.t(), hst2)], dim=0)
-                g_b = dgi2.sum(0, dtype=torch.float32)
-                g_bn = dghn2.sum(0, dtype=torch.float32)
+                hst_r = hst.t()  # [T B, H] operand
+                g_w_ih = _mm(dgi, x_in.t())
+                g_w_hh = torch.cat([_mm(dgi[: 2 * hd], hst_r), _mm(dghn, hst_r)], dim=0)
+                g_b = dgi.sum(1, dtype=torch.float32)
+                g_bn = dghn.sum(1, dtype=torch.float32)
                 pgrads[s][layer * 4 : layer * 4 + 4] = [g_w_ih, g_w_hh, g_b, g_bn]
-                dy[s] = _mm(dgi2, w_ih16).view(t_, b_, -1)  # gradient w.r.t. this layer's input = the layer below's dy
+                if layer > 0:
+                    dy[s] = _mm(w_ih16.t(), dgi)  # [H, T B]: gradient w.r.t. the layer below's feature-major output
+                else:
+                    dx[s] = _mm(dgi.t(), w_ih16).view(ctx.x_shapes[s]).to(ctx.x_dtypes[s])  # row-major, like the input
         flat: list[torch.Tensor | None] = []
         for s in range(n_stacks):
             flat += pgrads[s]
-        return (None, None, None, None, *[d.to(dt) for d, dt in zip(dy, ctx.x_dtypes)], *([None] * n_stacks), *flat)
+        return (None, None, None, None, *dx, *([None] * n_stacks), *flat)
 
 
 def gru_stacks_forward(stacks: Sequence[GRUStack], xs: Sequence[torch.Tensor], carries: Sequence[torch.Tensor | None],
