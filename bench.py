@@ -98,25 +98,33 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+PPO_UPDATES_PER_STEP = 32   # num_passes 4 x (4096 envs / batch 512): gradient all-reduces of one PPO iteration (examples/walking.py:772-776)
+PPO_GRAD_FLOATS = 7_809_024  # actor 43->512->2xGRU(512)->MLP->510 + critic 340->512->2xGRU(512)->MLP->1
+
+
 def _config(n_gpus: int) -> dict:
+    """The same dict for both arms (the reference arm times a bounded SAMPLE of this workload and says so in ``cpu_baseline``)."""
     name = ("K-Bot walking (examples/kbot/train.py task incl. its own commands / observations / rewards, level 1: actuator noise, latency, "
             "drop, force pushes, seven randomizers)"
             if WORKLOAD == "kbot" else "humanoid walking (examples/walking.py plugin set)")
     return {"workload": f"{name} {ENVS_PER_GPU} envs x rollout {ROLLOUT} per GPU: physics+obs+termination+"
                         "reset+reward+GAE", "envs_per_gpu": ENVS_PER_GPU, "rollout": ROLLOUT, "total_envs": ENVS_PER_GPU * n_gpus,
             "physics_substeps_per_env_step": 5, "policy": "synthetic: a_t = 0.3*N(0,1), values = 0", "parallelism": f"env-sharded x{n_gpus}",
-            "l2_note": L2_NOTE}
+            "collective": (f"{PPO_UPDATES_PER_STEP} x NCCL all-reduce of the {PPO_GRAD_FLOATS * 4 / 1e6:.1f} MB flat PPO gradient inside every timed "
+                           "step when n_gpus > 1 (BASELINE.json configs[3]); none at n_gpus = 1")}
 
 
-def run_reference(args: argparse.Namespace) -> None:
-    """The CPU implementation of the same path (the C oracle, f32, OpenMP over envs) on the host cores.
+def _cpu_arm(seconds: float | None, steps: int = 0, warmup: int = 0) -> dict:
+    """The CPU implementation of the same path (the C oracle, f32, OpenMP over envs) timed on the host cores: either `steps`
+    timed steps after `warmup`, or as many steps as fit in `seconds`.  One step is a bounded SAMPLE of the workload:
+    64 envs per host core x a 64-step rollout -> rewards -> GAE.
 
-    The reference's own CPU path is MJX on the JAX CPU backend; neither jax nor mujoco exists in this image
-    (DESIGN.md), so `kind` is "port".  Each step is a bounded sample of the workload: `sample_envs` x `sample_steps`.
+    The reference's own CPU path is MJX on the JAX CPU backend; neither jax nor mujoco exists in this image, so
+    `kind` is "port".  The timing legs use a host-tuned build of the port (-O3 -march=native, oracle.build_perf) when it
+    compiles on this box, else the checker's build; `build` says which.
     """
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    import ctypes
+
     import oracle
     from ksim_b200.envinit import make_env_init
     from ksim_b200.program import build_program
@@ -124,11 +132,14 @@ def run_reference(args: argparse.Namespace) -> None:
 
     make_spec, RANDOMIZERS = _task()
     oracle.build()
+    try:
+        build = "perf: gcc " + oracle.build_perf()
+    except Exception as e:  # noqa: BLE001  (no compiler on the box, or the f32 library is already loaded)
+        build = f"checker build (-O2 -ffp-contract=off); perf build unavailable: {type(e).__name__}"
     cores = os.cpu_count() or 1
     # torchrun exports OMP_NUM_THREADS=1 to its workers (N > 1); the arm runs on rank 0 alone and is meant to use every
     # host core, so the OpenMP runtime the oracle library is linked to is told so directly.
     os.environ["OMP_NUM_THREADS"] = str(cores)
-    import ctypes
     omp_set = oracle.lib("f32").omp_set_num_threads
     omp_set.argtypes, omp_set.restype = [ctypes.c_int], None
     omp_set(cores)
@@ -152,60 +163,36 @@ def run_reference(args: argparse.Namespace) -> None:
         ora.gae(np.zeros_like(total), total, (rec[:t, :, d] != 0).T, (rec[:t, :, s] != 0).T, GAMMA, LAM, 0)
         rec[0] = rec[t]
 
-    for _ in range(args.warmup):
+    for _ in range(max(warmup, 1)):
         one()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    reps, t0 = 0, time.perf_counter()
+    while (reps < steps) if seconds is None else (time.perf_counter() - t0 < seconds or reps == 0):
         one()
-    dt = (time.perf_counter() - t0) / args.steps
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
     value = n * t / dt
-    sample = f"{n} envs x {t} control steps per step (same plugin set), f32 C oracle, OpenMP over envs"
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "per_core": value / cores, "build": build,
+            "sample_envs": n, "sample_steps": t, "sample_reps": reps, "ms_per_sample": dt * 1e3,
+            "sample": f"{reps} x ({n} envs x {t} control steps: rollout + rewards + GAE, same plugin set) of the {ENVS_PER_GPU} x {ROLLOUT} "
+                      "workload, f32 C port of the path, OpenMP over envs"}
+
+
+def run_reference(args: argparse.Namespace) -> None:
+    """`--impl reference`: rank 0 alone times the CPU arm and prints its line; the other ranks exit quietly."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cb = _cpu_arm(None, steps=args.steps, warmup=args.warmup)
     _emit(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": _config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": cb["ms_per_sample"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": _config(args.gpus), "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def cpu_baseline_leg() -> dict:
-    """Bounded CPU sample (~10-20 s) of the same workload for the `cpu_baseline` object (rank 0, N=1 only)."""
-    import oracle
-    from ksim_b200.envinit import make_env_init
-    from ksim_b200.program import build_program
-    from oracle import OracleEngine
-
-    make_spec, RANDOMIZERS = _task()
-    oracle.build()
-    cores = os.cpu_count() or 1
-    # torchrun exports OMP_NUM_THREADS=1 to its workers (N > 1); the arm runs on rank 0 alone and is meant to use every
-    # host core, so the OpenMP runtime the oracle library is linked to is told so directly.
-    os.environ["OMP_NUM_THREADS"] = str(cores)
-    import ctypes
-    omp_set = oracle.lib("f32").omp_set_num_threads
-    omp_set.argtypes, omp_set.restype = [ctypes.c_int], None
-    omp_set(cores)
-    cores = int(oracle.lib("f32").omp_get_max_threads())  # what the library will actually fan out to
-    spec = make_spec()
-    prog = build_program(spec)
-    rz = {k: f(spec.model) for k, f in RANDOMIZERS.items()}
-    n, t = max(cores * 64, 256), 64  # one step = 64 envs per core x a 64-step rollout: 0.5-2 s of work on all cores
-    ora = OracleEngine(prog, "f32")
-    init = make_env_init(prog, rz, n, seed=0, level=1.0 if WORKLOAD == "kbot" else 0.0)
-    st, keys, rec0, _ = ora.init_envs(init.init_keys, init.levels, init.rand)
-    rec = np.zeros((t + 1, n, prog.rec_size), np.float32)
-    rec[0] = rec0
-    actions = (0.3 * np.random.RandomState(1).randn(t, n, prog.action_size)).astype(np.float32)
-    ora.rollout(actions, init.rand, st, keys, rec)  # warm
-    reps, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < 10.0:
-        rec[0] = rec[t]
-        ora.rollout(actions, init.rand, st, keys, rec)
-        reps += 1
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": n * t / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{reps} x ({n} envs x {t} control steps), f32 C oracle of the same path, OpenMP over envs, ~10 s"}
+    """Bounded CPU sample (~10 s) of the same workload for the `cpu_baseline` object (rank 0, N=1 only)."""
+    return _cpu_arm(10.0)
 
 
 _JSON_FD = 1
@@ -215,6 +202,90 @@ def _emit(line: str) -> None:
     """The ONE stdout line of the contract.  Everything else a library prints to fd 1 (NCCL announces its version there when
     the first communicator is built) has been routed to stderr by main()."""
     os.write(_JSON_FD, (line + "\n").encode())
+
+
+def _extras(eng, actions, rec, device, rank: int, world: int, args: argparse.Namespace) -> dict:  # noqa: ANN001
+    """Measurements beside the headline, every one device-timed after its own warm-up, max over ranks:
+
+    * ``closed_loop``: the rollout as a real PPO loop drives it -- ONE ``b200sim_step_ctrl`` launch per control step (the policy
+      would run between launches; here the next action block is already resident), same environments, same workload;
+    * ``ppo_iteration`` (humanoid only): ``ksim_b200.trainer.PPOTrainer.iteration`` -- closed-loop rollout with the random-init
+      GRU policy, rewards, on-policy replay, 32 minibatch steps (replay + GAE + loss + backward + optimiser; at N > 1 the NCCL
+      all-reduce of the flat gradient is inside every captured step), closing replay -- at the reference's default rollout of
+      24 frames and at this benchmark's rollout;
+    * ``secondary`` (N = 1, humanoid runs only): the K-Bot workload (BASELINE.json configs[2]) through the same hot path."""
+    import torch
+
+    from ksim_b200 import distributed as D
+
+    out: dict = {}
+    t, n = int(actions.shape[0]), eng.num_envs
+    stream = torch.cuda.current_stream(device)
+
+    def timed(fn, reps: int) -> float:  # noqa: ANN001
+        fn()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize(device)
+        return D.max_over_ranks(a.elapsed_time(b) / reps, device)
+
+    def closed_loop() -> None:
+        rec[0].copy_(eng.first_rec)
+        for s in range(t):
+            eng.step(actions[s], rec[s], rec[s + 1])
+        eng.first_rec.copy_(rec[t])
+
+    l0 = eng.launches
+    ms = timed(closed_loop, max(args.steps // 2, 2))
+    out["closed_loop"] = {"value": n * t * world / (ms * 1e-3), "unit": UNIT, "ms_per_rollout": ms, "launches_per_rollout": t,
+                          "gpu_launches": eng.launches - l0, "what": "one b200sim_step_ctrl launch per control step, actions resident"}
+    if WORKLOAD == "humanoid" and ENVS_PER_GPU % 512 == 0:
+        from ksim_b200.examples import walking
+        from ksim_b200.trainer import PPOConfig, PPOTrainer
+
+        ppo_out = {}
+        for frames in sorted({24, t}):
+            torch.manual_seed(0)
+            model = walking.make_model(eng.spec).to(device)
+            tr = PPOTrainer(eng, model, walking.network_columns(eng.program, walking.ACTOR_INPUTS),
+                            walking.network_columns(eng.program, walking.CRITIC_INPUTS),
+                            PPOConfig(batch_size=512, num_passes=4, rollout_length_frames=frames), use_graphs=True, seed=rank)
+            for _ in range(2):
+                tr.iteration()
+            if world > 1:
+                torch.distributed.barrier()
+            runs = [tr.iteration() for _ in range(3)]
+            mean = {k: D.max_over_ranks(sum(r[k] for r in runs) / len(runs), device) for k in runs[0]}
+            ppo_out[f"rollout_{frames}"] = {"iteration_ms": mean["iteration_ms"], "rollout_ms": mean["rollout_ms"], "scoring_ms": mean["scoring_ms"],
+                                            "update_ms": mean["update_ms"], "env_steps_per_s": n * frames * world / (mean["iteration_ms"] * 1e-3),
+                                            "final_loss": float(tr.loss)}
+            del tr, model
+            torch.cuda.empty_cache()
+        out["ppo_iteration"] = {
+            **ppo_out, "unit": "ms", "envs_per_gpu": n, "batch_size": 512, "num_passes": 4, "updates_per_iteration": 4 * (n // 512),
+            "gradient_allreduce": (f"in-place NCCL all-reduce of the {PPO_GRAD_FLOATS * 4 / 1e6:.1f} MB flat gradient inside every captured "
+                                   "minibatch step") if world > 1 else "none (single rank)",
+            "ours": "engine step, rewards, flags, GAE, PPO loss fwd+bwd, GRU sequence kernels (tcgen05), mixture head, optimiser step",
+            "library": "batched affine maps (cuBLAS bf16 through torch), gathers, NCCL"}
+    return out
+
+
+def _secondary_kbot(args: argparse.Namespace) -> dict | None:
+    """The K-Bot line (BASELINE.json configs[2]) from a child process of the same script, attached to the humanoid line."""
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--workload", "kbot", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-extras"]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+        line = json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+    keep = ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline", "config")
+    return {k: line[k] for k in keep if k in line}
 
 
 def main() -> None:
@@ -232,6 +303,7 @@ def main() -> None:
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (env-count sweeps, BASELINE.json configs[4]); "
                     "the default is the configuration the metric is quoted on")
     ap.add_argument("--rollout", type=int, default=None, help="control steps per rollout")
+    ap.add_argument("--no-extras", action="store_true", help="skip the closed-loop, PPO-iteration and K-Bot secondary measurements")
     args = ap.parse_args()
     global WORKLOAD, ENVS_PER_GPU, ROLLOUT, METRIC, GAMMA, LAM
     if args.workload == "kbot":
@@ -268,12 +340,21 @@ def main() -> None:
     values = torch.zeros((n, t), device=device)
     rec = eng.new_record_buffer(t)
     stream = torch.cuda.current_stream(device)
+    # BASELINE.json configs[3]: "per-GPU env slices + NCCL PPO grad allreduce" -- at N > 1 every timed step carries the gradient
+    # all-reduces of one PPO iteration on the flat gradient buffer; nothing at N = 1
+    grad = torch.zeros(PPO_GRAD_FLOATS, device=device) if world > 1 else None
+
+    def collective() -> None:
+        if grad is not None:
+            for _ in range(PPO_UPDATES_PER_STEP):
+                torch.distributed.all_reduce(grad)
 
     def hot_path(acts: torch.Tensor) -> torch.Tensor:
         eng.rollout(acts, rec)
         total, _ = eng.rewards(rec, t)
         dones, succ = eng.flags(rec, t)
         adv, tgt, ret = eng.gae(values, total, dones, succ, GAMMA, LAM)
+        collective()
         return adv  # (the engine hands this rollout's final pre-step block to the next one itself)
 
     def barrier() -> None:
@@ -317,6 +398,7 @@ def main() -> None:
         total, _ = eng.rewards(rec, t)
         dones, succ = eng.flags(rec, t)
         eng.gae(values, total, dones, succ, GAMMA, LAM)
+        collective()
         sev[i][1].record(stream)
     ev[1].record(stream)
     barrier()
@@ -337,6 +419,7 @@ def main() -> None:
         total, _ = eng.rewards(rec, t)
         dones, succ = eng.flags(rec, t)
         adv, _, _ = eng.gae(values, total, dones, succ, GAMMA, LAM)
+        collective()
         host_adv.copy_(adv, non_blocking=True)
         host_total.copy_(total, non_blocking=True)
         torch.cuda.synchronize(device)  # the caller reads the result
@@ -350,6 +433,7 @@ def main() -> None:
     ev2[1].record(stream)
     barrier()
     e2e_ms = D.max_over_ranks(ev2[0].elapsed_time(ev2[1]) / args.steps, device)
+    extras = {} if args.no_extras else _extras(eng, actions, rec, device, rank, world, args)
     clocks = sampler.stop() if rank == 0 else {}
     nonfinite = float(eng.state[:, eng.program["TI_S_NONFINITE"]].sum())
     if nonfinite:
@@ -376,11 +460,12 @@ def main() -> None:
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": _config(world),
+        "config": _config(world), "l2_note": L2_NOTE,
         "e2e": {"value": env_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_actions.numel() * 4),
                 "d2h_bytes_per_step": int((host_adv.numel() + host_total.numel()) * 4), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "profiles/r01_traffic.json (one ncu capture of this configuration, committed; not measured in this run)" if traffic else None,
                      "algorithmic_bytes_per_launch": n * t * bytes_per_env_step,
                      "kernel": "k_rollout<DimsKbot>" if WORKLOAD == "kbot" else "k_rollout<DimsHumanoid>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms,
                      "algorithmic_bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src,
@@ -389,6 +474,11 @@ def main() -> None:
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg()
+    out.update(extras)
+    if world == 1 and WORKLOAD == "humanoid" and not args.no_extras:
+        del eng
+        torch.cuda.empty_cache()
+        out["secondary"] = _secondary_kbot(args)
     _emit(json.dumps(out))
     D.shutdown()
 

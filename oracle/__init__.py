@@ -24,11 +24,34 @@ def build(force: bool = False) -> None:
     subprocess.run(["make", "-C", str(_DIR)], check=True, capture_output=True)
 
 
+_PERF_FLAGS = "-O3 -march=native -fPIC -std=c11 -fopenmp -ffp-contract=fast -w"
+_PERF: Path | None = None
+
+
+def build_perf() -> str:
+    """A second f32 build tuned for THIS host (``-O3 -march=native``, contraction allowed) for the timing legs of ``bench.py``
+    only: the CPU baseline should not be handicapped by the checker's conservative flags (``-O2 -ffp-contract=off``, which keep
+    the f32 oracle's rounding reproducible).  Compiled where it runs (``-march=native`` must match the host), into
+    ``oracle/_perf/``; every later ``lib("f32")`` of this process loads it.  Returns the flags used, or raises."""
+    global _PERF
+    out = _DIR / "_perf"
+    out.mkdir(exist_ok=True)
+    target = out / "liboracle_f32.so"
+    cmd = ["gcc", *_PERF_FLAGS.split(), "-DREAL=float", "-DORACLE_F32", "-shared", "-o", str(target), "physics.c", "model_io.c", "engine.c", "-lm"]
+    subprocess.run(cmd, check=True, capture_output=True, cwd=str(_DIR))
+    if "f32" in _LIBS:
+        raise RuntimeError("build_perf() must run before the f32 oracle library is first loaded")
+    _PERF = target
+    return _PERF_FLAGS
+
+
 def lib(precision: str = "f64") -> ctypes.CDLL:
     if precision not in ("f64", "f32"):
         raise ValueError(precision)
     if precision not in _LIBS:
         path = _DIR / f"liboracle_{precision}.so"
+        if precision == "f32" and _PERF is not None:
+            path = _PERF
         if not path.exists():
             build()
         cdll = ctypes.CDLL(str(path))

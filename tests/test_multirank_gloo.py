@@ -46,6 +46,20 @@ def _worker(rank: int, world: int, port: int, total_envs: int, out_dir: str) -> 
     # gradient averaging (the PPO step's one collective): mixed shapes / dtypes, small bucket to force several flushes
     grads = [torch.full((5, 3), float(rank + 1)), torch.full((7,), 10.0 * (rank + 1)), torch.full((2, 2), float(rank), dtype=torch.float64)]
     D.allreduce_mean_(grads, bucket_bytes=64)
+    # the PPO update's collective as the trainer issues it: one in-place all-reduce of the flat gradient buffer; a rank whose
+    # backward left some parameter without a gradient still reduces the same number of elements (zeros in the flat buffer)
+    from ksim_b200 import optim, policy
+
+    torch.manual_seed(0)
+    mlp = policy.MLP(6, 3, 8, 2, "elu")
+    fp = optim.FlatParams(mlp)
+    fp.zero_grad()
+    xin = torch.full((4, 6), float(rank + 1))
+    (mlp.layers[0].reference(xin).sum() if rank == 1 else mlp.reference(xin).sum()).backward()  # rank 1: only layer 0 gets a gradient
+    local = fp.grad.clone()
+    scale = fp.allreduce_grads()
+    np.save(os.path.join(out_dir, f"flat_local_{rank}.npy"), local.numpy())
+    np.save(os.path.join(out_dir, f"flat_reduced_{rank}.npy"), (fp.grad * scale).numpy())
     if rank == 0:
         np.save(os.path.join(out_dir, "reduced.npy"), np.array([t, work, mean, std]))
         np.save(os.path.join(out_dir, "grads.npy"), np.array([float(g.reshape(-1)[0]) for g in grads]))
@@ -73,6 +87,10 @@ def test_two_rank_sharding_matches_single_process(tmp_path) -> None:  # noqa: AN
     assert mean == pytest.approx(np.arange(total).mean()) and std == pytest.approx(np.arange(total).std())
     assert [shard_range(total, r, world) for r in range(world)] == [(0, 7), (7, 13)]
     np.testing.assert_allclose(np.load(tmp_path / "grads.npy"), [1.5, 15.0, 0.5])
+    local = [np.load(tmp_path / f"flat_local_{r}.npy") for r in range(world)]
+    for r in range(world):
+        np.testing.assert_allclose(np.load(tmp_path / f"flat_reduced_{r}.npy"), (local[0] + local[1]) / 2, rtol=1e-6, atol=1e-7)
+    assert np.abs(local[1]).sum() > 0 and (local[1] == 0).sum() > (local[0] == 0).sum()
 
 
 def test_allreduce_mean_single_process_is_identity() -> None:
