@@ -122,6 +122,24 @@ int b200sim_metrics(const b200sim_model* model, void* stream, int n_envs, int n_
 int b200sim_dataset_pack(void* stream, int n_envs, int n_steps, int rec_size, const float* rec, const float* total,
                          const float* comps, const int32_t* fields, int n_fields, int sample_size, float* out);
 
+/* ---- The engine alone: ksim's PhysicsEngine.reset / .step (ksim/engine.py:171-199; MjxEngine :205-361) without the task layer
+ * the fused control step adds -- what RLTask._step_physics (rl.py:1143-1157) and the reset path (rl.py:1072-1080) call.  `rng`
+ * [N][2] u32 is the key the caller hands to engine.step / engine.reset for each environment; `state` / `keys` are the same
+ * opaque per-environment blocks as above (task-side fields are left untouched by step and zeroed by reset); `data` [N][DATA]
+ * receives the physics_state.data fields the reference's plugins read, laid out as B2S_DATA_* (include/b200sim_codes.h);
+ * b200sim_data_layout writes the B2S_DATA_N_FIELDS + 1 float offsets (the last one is DATA, the block size). */
+int b200sim_data_layout(const b200sim_model* model, int32_t* offsets);
+int b200sim_engine_reset(const b200sim_model* model, void* stream, int n_envs, const uint32_t* rng, const float* levels,
+                         const float* rand, float* state, uint32_t* keys, float* data);
+int b200sim_engine_step(const b200sim_model* model, void* stream, int n_envs, const float* action, const uint32_t* rng,
+                        const float* rand, float* state, uint32_t* keys, float* data);
+/* get_terminations (rl.py:288-299) of the task program on data blocks: codes[N][n_terminations] int32 in {-1, 0, +1};
+ * done[N] = any(code != 0), success[N] = all(code != -1) & done (rl.py:1049-1050); done / success may be NULL.  A contact is
+ * matched to the model's contact pairs by its (geom1, geom2); a pair the model does not hold counts as not in contact. */
+int b200sim_terminations(const b200sim_model* model, void* stream, int n_envs, const float* data, const float* levels,
+                         int32_t* codes, uint8_t* done, uint8_t* success);
+const char* b200sim_engine_last_error(void);
+
 /* ---- Recurrent policy replay: the sequential part of get_ppo_variables (ksim/task/ppo.py:417-488 ->
  * examples/walking.py:674-728: xax.scan of two stacks of GRU(512) cells over the T steps of a minibatch) as persistent
  * tcgen05 kernels.  One call advances up to B2S_GRU_MAX_PROBLEMS independent GRU layers (e.g. the actor's and the critic's

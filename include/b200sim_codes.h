@@ -259,6 +259,31 @@
 #define B2S_GRU_ERR_EMPTY 5      /* pipeline stage never freed */
 #define B2S_GRU_ERR_PEERS 6      /* a peer CTA of the cluster never finished reading the previous state */
 
+/* ---- fields of the per-environment data block of b200sim_engine_step / _reset (the physics_state.data.* the reference's
+ * plugins read), in block order; b200sim_data_layout returns their float offsets ---- */
+#define B2S_DATA_QPOS 0            /* [nq] */
+#define B2S_DATA_QVEL 1            /* [nv] */
+#define B2S_DATA_QACC 2            /* [nv] */
+#define B2S_DATA_CTRL 3            /* [nu] */
+#define B2S_DATA_TIME 4            /* [1] */
+#define B2S_DATA_XPOS 5            /* [nbody][3] */
+#define B2S_DATA_XQUAT 6           /* [nbody][4] wxyz */
+#define B2S_DATA_CINERT 7          /* [nbody][10] */
+#define B2S_DATA_CVEL 8            /* [nbody][6] */
+#define B2S_DATA_ACTUATOR_FORCE 9  /* [nu] */
+#define B2S_DATA_SENSORDATA 10     /* [nsensordata] */
+#define B2S_DATA_CFRC_EXT 11       /* [nbody][6] */
+#define B2S_DATA_SITE_XPOS 12      /* [nsite][3] */
+#define B2S_DATA_SITE_XMAT 13      /* [nsite][9] */
+#define B2S_DATA_SUBTREE_COM 14    /* [nbody][3] */
+#define B2S_DATA_XFRC_APPLIED 15   /* [nbody][6] */
+#define B2S_DATA_NCON 16           /* [1]: candidate contacts (fixed per model, as in MJX); a contact is active when dist < 0 */
+#define B2S_DATA_CONTACT_GEOM1 17  /* [ncon] geom ids, stored as floats */
+#define B2S_DATA_CONTACT_GEOM2 18  /* [ncon] */
+#define B2S_DATA_CONTACT_DIST 19   /* [ncon] */
+#define B2S_DATA_CONTACT_POS 20    /* [ncon][3] */
+#define B2S_DATA_N_FIELDS 21
+
 /* ---- flat-buffer optimiser step (b200sim_optimizer_step) ---- */
 #define B2S_OPTIM_MAX_PARTIALS 1024  /* per-CTA partial sums of the gradient norm (grid = a multiple of the SM count, <= this) */
 

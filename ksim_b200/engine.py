@@ -14,7 +14,7 @@ fails loudly when the CUDA library is missing (ksim_b200/binding.py).
 
 from __future__ import annotations
 
-__all__ = ["B200Engine", "TrajectoryView", "get_physics_engine"]
+__all__ = ["B200Engine", "TrajectoryView", "PhysicsData", "ContactData", "get_physics_engine"]
 
 import ctypes
 from dataclasses import dataclass
@@ -117,6 +117,76 @@ class TrajectoryView:
         return {k: flat[..., i].to(torch.int32) for i, k in enumerate(names)}
 
 
+@dataclass
+class ContactData:
+    """``physics_state.data.contact`` as the plugins read it (utils/mujoco.py:175-217, terminations.py:84-99): fixed candidate
+    slots, a contact is active when ``dist < 0``."""
+
+    geom1: torch.Tensor   # [N, ncon] int32
+    geom2: torch.Tensor
+    dist: torch.Tensor    # [N, ncon]
+    pos: torch.Tensor     # [N, ncon, 3]
+
+    @property
+    def geom(self) -> torch.Tensor:
+        return torch.stack([self.geom1, self.geom2], dim=-1)
+
+
+@dataclass
+class PhysicsData:
+    """Named views into the data blocks ``b200sim_engine_step`` / ``_reset`` write -- the fields of ``physics_state.data`` the
+    reference's Observation / Reward / Termination / Command / Event plugins read, batched over environments."""
+
+    block: torch.Tensor           # [N, DATA] fp32
+    offsets: tuple[int, ...]      # B2S_DATA_N_FIELDS + 1 float offsets
+    model: object
+
+    def _f(self, field: int, *shape: int) -> torch.Tensor:
+        v = self.block[:, self.offsets[field] : self.offsets[field + 1]]
+        return v.unflatten(-1, shape) if shape else v
+
+    @property
+    def qpos(self) -> torch.Tensor: return self._f(C.B2S_DATA_QPOS)                                    # noqa: E704
+    @property
+    def qvel(self) -> torch.Tensor: return self._f(C.B2S_DATA_QVEL)                                    # noqa: E704
+    @property
+    def qacc(self) -> torch.Tensor: return self._f(C.B2S_DATA_QACC)                                    # noqa: E704
+    @property
+    def ctrl(self) -> torch.Tensor: return self._f(C.B2S_DATA_CTRL)                                    # noqa: E704
+    @property
+    def time(self) -> torch.Tensor: return self._f(C.B2S_DATA_TIME)[:, 0]                              # noqa: E704
+    @property
+    def xpos(self) -> torch.Tensor: return self._f(C.B2S_DATA_XPOS, self.model.nbody, 3)               # noqa: E704
+    @property
+    def xquat(self) -> torch.Tensor: return self._f(C.B2S_DATA_XQUAT, self.model.nbody, 4)             # noqa: E704
+    @property
+    def cinert(self) -> torch.Tensor: return self._f(C.B2S_DATA_CINERT, self.model.nbody, 10)          # noqa: E704
+    @property
+    def cvel(self) -> torch.Tensor: return self._f(C.B2S_DATA_CVEL, self.model.nbody, 6)               # noqa: E704
+    @property
+    def actuator_force(self) -> torch.Tensor: return self._f(C.B2S_DATA_ACTUATOR_FORCE)                # noqa: E704
+    @property
+    def sensordata(self) -> torch.Tensor: return self._f(C.B2S_DATA_SENSORDATA)                        # noqa: E704
+    @property
+    def cfrc_ext(self) -> torch.Tensor: return self._f(C.B2S_DATA_CFRC_EXT, self.model.nbody, 6)       # noqa: E704
+    @property
+    def site_xpos(self) -> torch.Tensor: return self._f(C.B2S_DATA_SITE_XPOS, self.model.nsite, 3)     # noqa: E704
+    @property
+    def site_xmat(self) -> torch.Tensor: return self._f(C.B2S_DATA_SITE_XMAT, self.model.nsite, 3, 3)  # noqa: E704
+    @property
+    def subtree_com(self) -> torch.Tensor: return self._f(C.B2S_DATA_SUBTREE_COM, self.model.nbody, 3)  # noqa: E704
+    @property
+    def xfrc_applied(self) -> torch.Tensor: return self._f(C.B2S_DATA_XFRC_APPLIED, self.model.nbody, 6)  # noqa: E704
+    @property
+    def ncon(self) -> torch.Tensor: return self._f(C.B2S_DATA_NCON)[:, 0].to(torch.int32)              # noqa: E704
+
+    @property
+    def contact(self) -> ContactData:
+        nc = self.offsets[C.B2S_DATA_CONTACT_GEOM2] - self.offsets[C.B2S_DATA_CONTACT_GEOM1]
+        return ContactData(self._f(C.B2S_DATA_CONTACT_GEOM1).to(torch.int32), self._f(C.B2S_DATA_CONTACT_GEOM2).to(torch.int32),
+                           self._f(C.B2S_DATA_CONTACT_DIST), self._f(C.B2S_DATA_CONTACT_POS, nc, 3))
+
+
 class B200Engine:
     """Batched drop-in for ``MjxEngine`` + the rollout functions around it (see module docstring)."""
 
@@ -193,6 +263,68 @@ class B200Engine:
 
     def view(self, rec: torch.Tensor) -> TrajectoryView:
         return TrajectoryView(rec, self.program)
+
+    # ----------------------------------------------------------------------- the engine alone (PhysicsEngine)
+    def data_layout(self) -> tuple[int, ...]:
+        offs = (ctypes.c_int32 * (C.B2S_DATA_N_FIELDS + 1))()
+        binding.check(self.lib.b200sim_data_layout(self._handle, offs), "b200sim_data_layout")
+        return tuple(int(x) for x in offs)
+
+    def new_data(self) -> PhysicsData:
+        offs = self.data_layout()
+        return PhysicsData(torch.zeros((self.num_envs, offs[-1]), dtype=torch.float32, device=self.device), offs, self.spec.model)
+
+    def _api_check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self.lib.b200sim_engine_last_error()
+            raise binding.B200SimError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
+
+    def engine_reset(self, rng: torch.Tensor, curriculum_level: torch.Tensor | float = 0.0, data: PhysicsData | None = None) -> PhysicsData:
+        """``PhysicsEngine.reset(physics_model, curriculum_level, rng)`` (ksim/engine.py:205-246) for every environment, without the
+        task layer: ``rng [N, 2]`` int32 (uint32 bit patterns) is the key each environment's reset consumes.  The physics state
+        lands in ``self.state`` (the ``PhysicsState``), its ``data`` fields in the returned ``PhysicsData``."""
+        n = self.num_envs
+        self._chk(rng, (n, 2), torch.int32, "rng")
+        lv = curriculum_level if torch.is_tensor(curriculum_level) else torch.full((n,), float(curriculum_level), device=self.device)
+        self._chk(lv, (n,), torch.float32, "curriculum_level")
+        data = self.new_data() if data is None else data
+        with torch.cuda.device(self.device):
+            self._api_check(self.lib.b200sim_engine_reset(self._handle, self._stream(), n, _ptr(rng), _ptr(lv), _ptr(self.rand), _ptr(self.state),
+                                                          _ptr(self.keys), _ptr(data.block)), "b200sim_engine_reset")
+        self.launches += 1
+        self.levels.copy_(lv)
+        return data
+
+    def engine_step(self, action: torch.Tensor, rng: torch.Tensor, data: PhysicsData | None = None) -> PhysicsData:
+        """``PhysicsEngine.step(action, physics_model, physics_state, curriculum_level, rng)`` (ksim/engine.py:259-361) for every
+        environment: actuators + events + the physics sub-steps of one control step, nothing else (no observation, termination,
+        reset-on-done or command update -- ``RLTask._step_physics``, rl.py:1143-1157, is exactly this call)."""
+        n = self.num_envs
+        self._chk(action, (n, self.NA), torch.float32, "action")
+        self._chk(rng, (n, 2), torch.int32, "rng")
+        data = self.new_data() if data is None else data
+        with torch.cuda.device(self.device):
+            self._api_check(self.lib.b200sim_engine_step(self._handle, self._stream(), n, _ptr(action), _ptr(rng), _ptr(self.rand),
+                                                         _ptr(self.state), _ptr(self.keys), _ptr(data.block)), "b200sim_engine_step")
+        self.launches += 1
+        return data
+
+    def get_terminations(self, data: PhysicsData, curriculum_level: torch.Tensor | None = None,
+                         ) -> tuple[dict[str, torch.Tensor], torch.Tensor, torch.Tensor]:
+        """``get_terminations`` (rl.py:288-299) of the task's Termination plugins on a ``PhysicsData``: ``({name: code [N] int32},
+        done [N] bool, success [N] bool)`` with ``done = any(code != 0)``, ``success = all(code != -1) & done`` (rl.py:1049-1050)."""
+        n = int(data.block.shape[0])
+        names = self.program.termination_names
+        codes = torch.zeros((n, max(len(names), 1)), dtype=torch.int32, device=self.device)
+        done = torch.zeros((n,), dtype=torch.uint8, device=self.device)
+        succ = torch.zeros((n,), dtype=torch.uint8, device=self.device)
+        lv = self.levels[:n].contiguous() if curriculum_level is None else curriculum_level
+        self._chk(lv, (n,), torch.float32, "curriculum_level")
+        with torch.cuda.device(self.device):
+            self._api_check(self.lib.b200sim_terminations(self._handle, self._stream(), n, _ptr(data.block), _ptr(lv), _ptr(codes), _ptr(done),
+                                                          _ptr(succ)), "b200sim_terminations")
+        self.launches += 1
+        return {k: codes[:, i] for i, k in enumerate(names)}, done != 0, succ != 0
 
     # ------------------------------------------------------------------------------------------------- reset
     def reset(self, seed: int = 0, curriculum_level: float = 0.0, env_offset: int = 0, total_envs: int | None = None) -> None:
