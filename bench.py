@@ -276,6 +276,17 @@ def _extras(eng, actions, rec, device, rank: int, world: int, args: argparse.Nam
     return out
 
 
+def _mjx_baseline() -> dict:
+    """The reference's own MjxEngine on the JAX CPU backend (baseline/run_mjx_cpu.py) when jax + mujoco-mjx + a reference
+    checkout exist on this box; otherwise the one-line reason (they do not exist in this repository's image)."""
+    try:
+        res = subprocess.run([sys.executable, str(ROOT / "baseline" / "run_mjx_cpu.py"), "--envs", "256", "--steps", "64", "--reps", "1"],
+                             capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+        return json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"impl": "mjx", "unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def _secondary_kbot(args: argparse.Namespace) -> dict | None:
     """The K-Bot line (BASELINE.json configs[2]) from a child process of the same script, attached to the humanoid line."""
     cmd = [sys.executable, str(ROOT / "bench.py"), "--workload", "kbot", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-extras"]
@@ -476,6 +487,7 @@ def main() -> None:
         out["cpu_baseline"] = cpu_baseline_leg()
     out.update(extras)
     if world == 1 and WORKLOAD == "humanoid" and not args.no_extras:
+        out["mjx_baseline"] = _mjx_baseline()
         del eng
         torch.cuda.empty_cache()
         out["secondary"] = _secondary_kbot(args)

@@ -223,6 +223,39 @@ class OracleEngine:
         if rc != 0:
             raise RuntimeError(f"o_step_ctrl -> {rc}")
 
+    # ---- the engine alone (PhysicsEngine.reset / .step): data blocks in the B2S_DATA_* layout of include/b200sim_codes.h
+    def data_size(self, ncon: int) -> int:
+        return int(self.lib.o_data_size(ctypes.c_void_p(self.model.ptr), ctypes.c_int(ncon)))
+
+    def engine_reset(self, rng: np.ndarray, levels: np.ndarray, rand: np.ndarray, ncon: int) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """rng [N][2] uint32 -> (state [N][S], keys [N][K], data [N][DATA])."""
+        n = rng.shape[0]
+        rng = np.ascontiguousarray(rng, dtype=np.uint32).reshape(n, 2)
+        levels = np.ascontiguousarray(levels, dtype=self.real)
+        rand = np.ascontiguousarray(rand, dtype=self.real).reshape(n, self.RAND)
+        state = np.zeros((n, self.S), dtype=self.real)
+        keys = np.zeros((n, self.K), dtype=np.uint32)
+        data = np.zeros((n, self.data_size(ncon)), dtype=self.real)
+        rc = self.lib.o_engine_reset(ctypes.c_void_p(self.model.ptr), self._p(self.ti), self._p(self.tf), ctypes.c_int(n), self._p(rng),
+                                     self._p(levels), self._p(rand), self._p(state), self._p(keys), ctypes.c_int(ncon), self._p(data))
+        if rc != 0:
+            raise RuntimeError(f"o_engine_reset -> {rc}")
+        return state, keys, data
+
+    def engine_step(self, action: np.ndarray, rng: np.ndarray, rand: np.ndarray, state: np.ndarray, keys: np.ndarray, ncon: int) -> np.ndarray:
+        """Advances ``state`` / ``keys`` in place by one control step of the engine alone; returns data [N][DATA]."""
+        n = state.shape[0]
+        action = np.ascontiguousarray(action, dtype=self.real).reshape(n, self.NA)
+        rng = np.ascontiguousarray(rng, dtype=np.uint32).reshape(n, 2)
+        rand = np.ascontiguousarray(rand, dtype=self.real).reshape(n, self.RAND)
+        assert state.flags["C_CONTIGUOUS"] and keys.flags["C_CONTIGUOUS"] and state.dtype == self.real
+        data = np.zeros((n, self.data_size(ncon)), dtype=self.real)
+        rc = self.lib.o_engine_step(ctypes.c_void_p(self.model.ptr), self._p(self.ti), self._p(self.tf), ctypes.c_int(n), self._p(action),
+                                    self._p(rng), self._p(rand), self._p(state), self._p(keys), ctypes.c_int(ncon), self._p(data))
+        if rc != 0:
+            raise RuntimeError(f"o_engine_step -> {rc}")
+        return data
+
     def rollout(self, actions: np.ndarray, rand: np.ndarray, state: np.ndarray, keys: np.ndarray, rec: np.ndarray) -> None:
         """actions [T][N][NA]; rec [T+1][N][R] with slot 0's pre-step block valid."""
         for t in range(actions.shape[0]):

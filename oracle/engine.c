@@ -1023,6 +1023,102 @@ int o_step_ctrl(const OModel* base, const int* ti, const REAL* tf, int N, const 
   return B2S_OK;
 }
 
+/* ---- the engine alone (PhysicsEngine.reset / .step, ksim/engine.py:205-361), the checker of b200sim_engine_reset / _step and
+ * the entry point MJX fixtures are compared through (scripts/gen_mjx_fixtures.py): `rng` [N][2] is the key the caller hands to
+ * engine.reset / engine.step; `data` [N][DATA] uses the B2S_DATA_* block layout of include/b200sim_codes.h. */
+static int data_offsets(const OModel* m, int ncon, int* off) {
+  const int size[B2S_DATA_N_FIELDS] = {m->nq, m->nv, m->nv, m->nu, 1, 3 * m->nbody, 4 * m->nbody, 10 * m->nbody, 6 * m->nbody, m->nu,
+                                       m->nsensordata, 6 * m->nbody, 3 * m->nsite, 9 * m->nsite, 3 * m->nbody, 6 * m->nbody, 1, ncon, ncon,
+                                       ncon, 3 * ncon};
+  int o = 0;
+  for (int i = 0; i < B2S_DATA_N_FIELDS; i++) { off[i] = o; o += size[i]; }
+  off[B2S_DATA_N_FIELDS] = o;
+  return o;
+}
+static void write_data(const OModel* m, const OData* d, int ncon, REAL* out) {
+  int off[B2S_DATA_N_FIELDS + 1];
+  data_offsets(m, ncon, off);
+  memcpy(out + off[B2S_DATA_QPOS], d->qpos, m->nq * sizeof(REAL));
+  memcpy(out + off[B2S_DATA_QVEL], d->qvel, m->nv * sizeof(REAL));
+  memcpy(out + off[B2S_DATA_QACC], d->qacc, m->nv * sizeof(REAL));
+  memcpy(out + off[B2S_DATA_CTRL], d->ctrl, m->nu * sizeof(REAL));
+  out[off[B2S_DATA_TIME]] = d->time;
+  memcpy(out + off[B2S_DATA_ACTUATOR_FORCE], d->actuator_force, m->nu * sizeof(REAL));
+  memcpy(out + off[B2S_DATA_SENSORDATA], d->sensordata, m->nsensordata * sizeof(REAL));
+  for (int b = 0; b < m->nbody; b++) {
+    memcpy(out + off[B2S_DATA_XPOS] + 3 * b, d->xpos[b], 3 * sizeof(REAL));
+    memcpy(out + off[B2S_DATA_XQUAT] + 4 * b, d->xquat[b], 4 * sizeof(REAL));
+    memcpy(out + off[B2S_DATA_CINERT] + 10 * b, d->cinert[b], 10 * sizeof(REAL));
+    memcpy(out + off[B2S_DATA_CVEL] + 6 * b, d->cvel[b], 6 * sizeof(REAL));
+    memcpy(out + off[B2S_DATA_CFRC_EXT] + 6 * b, d->cfrc_ext[b], 6 * sizeof(REAL));
+    memcpy(out + off[B2S_DATA_SUBTREE_COM] + 3 * b, d->subtree_com[b], 3 * sizeof(REAL));
+    memcpy(out + off[B2S_DATA_XFRC_APPLIED] + 6 * b, d->xfrc_applied[b], 6 * sizeof(REAL));
+  }
+  for (int s = 0; s < m->nsite; s++) {
+    memcpy(out + off[B2S_DATA_SITE_XPOS] + 3 * s, d->site_xpos[s], 3 * sizeof(REAL));
+    memcpy(out + off[B2S_DATA_SITE_XMAT] + 9 * s, d->site_xmat[s], 9 * sizeof(REAL));
+  }
+  out[off[B2S_DATA_NCON]] = (REAL)ncon;
+  for (int c = 0; c < ncon; c++) {
+    const int live = c < d->ncon;
+    out[off[B2S_DATA_CONTACT_GEOM1] + c] = live ? (REAL)d->contact[c].geom1 : 0;
+    out[off[B2S_DATA_CONTACT_GEOM2] + c] = live ? (REAL)d->contact[c].geom2 : 0;
+    out[off[B2S_DATA_CONTACT_DIST] + c] = live ? d->contact[c].dist : 1;
+    for (int k = 0; k < 3; k++) out[off[B2S_DATA_CONTACT_POS] + 3 * c + k] = live ? d->contact[c].pos[k] : 0;
+  }
+}
+int o_data_size(const OModel* base, int ncon) {
+  int off[B2S_DATA_N_FIELDS + 1];
+  return data_offsets(base, ncon, off);
+}
+
+int o_engine_reset(const OModel* base, const int* ti, const REAL* tf, int N, const uint32_t* rng, const REAL* levels, const REAL* rand,
+                   REAL* state, uint32_t* keys, int ncon, REAL* data) {
+  Task t;
+  task_init(&t, ti, tf);
+  if (ti[TI_MAGIC] != B2S_TASK_MAGIC) return B2S_ERR_BAD_BLOB;
+  const int DATA = o_data_size(base, ncon);
+#pragma omp parallel for schedule(static)
+  for (int n = 0; n < N; n++) {
+    Env* e = (Env*)calloc(1, sizeof(Env));
+    apply_overrides(&t, base, &e->model, rand + (size_t)n * t.RAND);
+    e->level = levels[n];
+    Key k = {rng[2 * n], rng[2 * n + 1]};
+    engine_reset(&t, e, k);
+    write_data(&e->model, &e->d, ncon, data + (size_t)n * DATA);
+    env_pack(&t, e, state + (size_t)n * t.S, keys + (size_t)n * t.K);
+    free(e);
+  }
+  return B2S_OK;
+}
+
+int o_engine_step(const OModel* base, const int* ti, const REAL* tf, int N, const REAL* action, const uint32_t* rng, const REAL* rand,
+                  REAL* state, uint32_t* keys, int ncon, REAL* data) {
+  Task t;
+  task_init(&t, ti, tf);
+  if (ti[TI_MAGIC] != B2S_TASK_MAGIC) return B2S_ERR_BAD_BLOB;
+  const int na = ti[TI_ACTION_SIZE], DATA = o_data_size(base, ncon);
+  const REAL aclip = (t.tf + ti[TI_ENGINE_FOFF])[6];
+#pragma omp parallel for schedule(static)
+  for (int n = 0; n < N; n++) {
+    Env* e = (Env*)calloc(1, sizeof(Env));
+    apply_overrides(&t, base, &e->model, rand + (size_t)n * t.RAND);
+    env_unpack(&t, e, state + (size_t)n * t.S, keys + (size_t)n * t.K);
+    REAL act[O_MAXNU * 2];
+    for (int i = 0; i < na; i++) {
+      REAL a = action[(size_t)n * na + i];
+      if (a != a) a = 0;
+      act[i] = a < -aclip ? -aclip : (a > aclip ? aclip : a);
+    }
+    Key k = {rng[2 * n], rng[2 * n + 1]};
+    engine_step(&t, e, act, k);
+    write_data(&e->model, &e->d, ncon, data + (size_t)n * DATA);
+    env_pack(&t, e, state + (size_t)n * t.S, keys + (size_t)n * t.K);
+    free(e);
+  }
+  return B2S_OK;
+}
+
 /* ------------------------------------------------------------------------------------------- rewards */
 
 static REAL exp_kernel_pen(REAL x, REAL scale, REAL sq, REAL ab) {

@@ -184,3 +184,79 @@ def test_engine_reset_matches_the_fused_initialisation(walking_spec, walking_ran
         torch.testing.assert_close(eng.state[:, p[slot] : p[slot] + width], want[:, p[slot] : p[slot] + width], rtol=0, atol=0, msg=slot)
     torch.testing.assert_close(d.qpos, eng.state[:, p["TI_S_QPOS"] : p["TI_S_QPOS"] + nq], rtol=0, atol=0)
     assert float(d.qvel.abs().max()) == 0.0 and float(d.time.abs().max()) == 0.0
+
+
+def _oracle_setup(spec, randomizers, n, seed, level):  # noqa: ANN001, ANN202
+    from ksim_b200.envinit import make_env_init
+    from ksim_b200.program import build_program
+    from oracle import OracleEngine
+
+    prog = build_program(spec)
+    init = make_env_init(prog, randomizers, n, seed=seed, level=level)
+    ora = OracleEngine(prog, "f32")
+    return prog, init, ora
+
+
+def test_oracle_engine_step_is_its_fused_step_minus_the_task_layer(oracle_built, walking_spec, walking_randomizers) -> None:  # noqa: ANN001
+    """CPU: the oracle's engine-only entry points (the checker of the CUDA ones, and the entry MJX fixtures are compared
+    through) against its own fused control step."""
+    n = 8
+    prog, init, ora = _oracle_setup(walking_spec, walking_randomizers, n, 3, 0.5)
+    st, keys, rec0, _ = ora.init_envs(init.init_keys, init.levels, init.rand)
+    st2, _, data0 = ora.engine_reset(init.init_keys[:, 0:2], init.levels, init.rand, 2)
+    nq = walking_spec.model.nq
+    q = prog["TI_S_QPOS"]
+    np.testing.assert_array_equal(st2[:, q : q + nq], st[:, q : q + nq])
+    np.testing.assert_array_equal(data0[:, :nq], st[:, q : q + nq])
+    act = (0.3 * np.random.RandomState(0).randn(n, prog.action_size)).astype(np.float32)
+    st_a, keys_a = st.copy(), keys.copy()
+    d = ora.engine_step(act, rng.split(keys[:, :2], 3)[:, 1, :], init.rand, st_a, keys_a, 2)
+    rec = np.zeros((2, n, prog.rec_size), np.float32)
+    rec[0] = rec0
+    ora.step_ctrl(act, init.rand, st, keys, rec[0], rec[1])
+    o = prog["TI_R_QPOS"]
+    np.testing.assert_array_equal(d[:, :nq], rec[0][:, o : o + nq])
+    assert d.shape[1] == ora.data_size(2) and np.isfinite(d).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["walking", "kbot"])
+def test_engine_entry_points_match_the_oracle(oracle_built, task, request) -> None:  # noqa: ANN001
+    """CUDA ``b200sim_engine_reset`` / ``_step`` against the oracle's, whole data block (every ``physics_state.data`` field a
+    plugin reads): fp32 tolerance 2e-4 absolute + 2e-4 relative over two control steps from the same keys and actions."""
+    import torch
+
+    from ksim_b200.engine import B200Engine
+
+    spec = request.getfixturevalue(f"{task}_spec")
+    rz = request.getfixturevalue(f"{task}_randomizers")
+    n, level = 48, 1.0 if task == "kbot" else 0.5
+    prog, init, ora = _oracle_setup(spec, rz, n, 4, level)
+    eng = B200Engine(spec, n, device="cuda:0", randomizers=rz, seed=4, curriculum_level=level)
+    keys_r = np.ascontiguousarray(init.init_keys[:, 0:2])
+    d = eng.engine_reset(torch.from_numpy(keys_r.view(np.int32)).cuda(), torch.from_numpy(init.levels).cuda())
+    ncon = d.contact.geom1.shape[1]
+    st, keys, d_o = ora.engine_reset(keys_r, init.levels, init.rand, ncon)
+    off = d.offsets
+
+    def compare(got: np.ndarray, want: np.ndarray, what: str) -> None:
+        for name in ("QPOS", "QVEL", "QACC", "CTRL", "TIME", "XPOS", "XQUAT", "CINERT", "CVEL", "ACTUATOR_FORCE", "SENSORDATA", "SITE_XPOS",
+                     "SITE_XMAT", "SUBTREE_COM", "XFRC_APPLIED", "CFRC_EXT"):
+            f = getattr(C, f"B2S_DATA_{name}")
+            a, b = got[:, off[f] : off[f + 1]], want[:, off[f] : off[f + 1]]
+            scale = max(float(np.abs(b).max()), 1.0)
+            bad = np.abs(a - b) > 2e-4 * scale + 2e-4 * np.abs(b)
+            # contact forces flip with ulp-level changes of a penetration depth: allow isolated environments to differ there
+            limit = 0.05 if name in ("CFRC_EXT", "QACC", "SENSORDATA", "ACTUATOR_FORCE") else 0.0
+            assert bad.any(axis=1).mean() <= limit, f"{what}: {name} differs in {bad.any(axis=1).sum()} of {n} envs (max {np.abs(a - b).max():.3e})"
+
+    compare(d.block.cpu().numpy(), d_o, "reset")
+    np.testing.assert_allclose(eng.state.cpu().numpy(), st, rtol=2e-4, atol=2e-4)
+    r = np.random.RandomState(1)
+    for step in range(2):
+        action = (0.3 * r.randn(n, prog.action_size)).astype(np.float32)
+        key = r.randint(0, 2**32, size=(n, 2), dtype=np.uint64).astype(np.uint32)
+        eng.state.copy_(torch.from_numpy(st).cuda())       # resynchronised: the comparison is per step, not accumulated
+        d = eng.engine_step(torch.from_numpy(action).cuda(), torch.from_numpy(key.view(np.int32)).cuda())
+        d_o = ora.engine_step(action, key, init.rand, st, keys, ncon)
+        compare(d.block.cpu().numpy(), d_o, f"step {step}")
