@@ -55,6 +55,8 @@ enum {
 int b200sim_model_create(const void* blob, size_t nbytes, b200sim_model** out);
 void b200sim_model_destroy(b200sim_model* model);
 int b200sim_model_info(const b200sim_model* model, int what);
+/* Options of a model handle (B2S_OPT_* / values in include/b200sim_codes.h); affects launches issued after the call. */
+int b200sim_model_set_option(b200sim_model* model, int option, int value);
 const char* b200sim_last_error(void);
 
 /* init_keys[N][10] u32: (reset, command, obs-carry, obs-bias, env) keys; levels[N]; rec0[N][R] receives the first

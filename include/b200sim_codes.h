@@ -259,6 +259,11 @@
 #define B2S_GRU_ERR_EMPTY 5      /* pipeline stage never freed */
 #define B2S_GRU_ERR_PEERS 6      /* a peer CTA of the cluster never finished reading the previous state */
 
+/* ---- b200sim_model_set_option ---- */
+#define B2S_OPT_SOLVER 0
+#define B2S_SOLVER_FAST 0        /* constraint-space / factor-reusing Newton, exact one-pass line search (default) */
+#define B2S_SOLVER_REFERENCE 1   /* the reference-shaped iteration: primal Newton, bracketing line search, both at the model's caps */
+
 /* ---- fields of the per-environment data block of b200sim_engine_step / _reset (the physics_state.data.* the reference's
  * plugins read), in block order; b200sim_data_layout returns their float offsets ---- */
 #define B2S_DATA_QPOS 0            /* [nq] */

@@ -15,7 +15,7 @@ _LIB: ctypes.CDLL | None = None
 
 # every symbol include/b200sim.h declares (tests assert the library exports exactly these)
 EXPORTS = (
-    "b200sim_model_create", "b200sim_model_destroy", "b200sim_model_info", "b200sim_last_error", "b200sim_init_envs",
+    "b200sim_model_create", "b200sim_model_destroy", "b200sim_model_info", "b200sim_model_set_option", "b200sim_last_error", "b200sim_init_envs",
     "b200sim_step_ctrl", "b200sim_rollout", "b200sim_rewards", "b200sim_gae", "b200sim_extract_flags", "b200sim_dataset_pack",
     "b200sim_metrics", "b200sim_ppo_loss",
     "b200sim_gru_workspace_bytes", "b200sim_gru_saved_floats", "b200sim_gru_forward", "b200sim_gru_backward", "b200sim_gru_last_error",
@@ -53,6 +53,7 @@ def lib() -> ctypes.CDLL:
         cdll.b200sim_model_destroy.restype = None
         cdll.b200sim_model_info.argtypes = [vp, ci]
         cdll.b200sim_model_info.restype = ci
+        cdll.b200sim_model_set_option.argtypes, cdll.b200sim_model_set_option.restype = [vp, ci, ci], ci
         cdll.b200sim_last_error.argtypes = []
         cdll.b200sim_last_error.restype = ctypes.c_char_p
         cdll.b200sim_init_envs.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp]

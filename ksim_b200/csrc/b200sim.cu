@@ -362,6 +362,18 @@ __global__ void __launch_bounds__(256) k_dataset_pack(int n_envs, int n_steps, i
 
 static thread_local std::string g_last_error;
 static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+extern "C" int b200sim_model_set_option(b200sim_model* mo, int option, int value) {
+  if (!mo) return fail(B2S_ERR_BAD_ARG, "null model");
+  if (option == B2S_OPT_SOLVER && (value == B2S_SOLVER_FAST || value == B2S_SOLVER_REFERENCE)) {
+    // bits 8 / 9 / 10 of sync_mask: constraint-space Newton off, factor-reusing dof-space Newton off, exact line search off
+    // (b2s_physics.cuh: dual_enabled / newton_dof_enabled / exact_ls_enabled) -> the reference-shaped solve_primal runs
+    const int ref_bits = (1 << 8) | (1 << 9) | (1 << 10);
+    mo->mdl.sync_mask = value == B2S_SOLVER_REFERENCE ? (mo->mdl.sync_mask | ref_bits) : (mo->mdl.sync_mask & ~ref_bits);
+    return B2S_OK;
+  }
+  return fail(B2S_ERR_BAD_ARG, "unknown option or value");
+}
+
 #define CUDA_OK(expr)                                                                                  \
   do {                                                                                                 \
     cudaError_t e_ = (expr);                                                                           \

@@ -39,7 +39,10 @@ __device__ __forceinline__ void write_data(const Mdl& m, const Work<D>& w, const
   LANE_FOR(i, nq) out[l.off[B2S_DATA_QPOS] + i] = w.qpos[i];
   LANE_FOR(i, nv) { out[l.off[B2S_DATA_QVEL] + i] = w.qvel[i]; out[l.off[B2S_DATA_QACC] + i] = w.qacc[i]; }
   LANE_FOR(i, nu) { out[l.off[B2S_DATA_CTRL] + i] = w.ctrl[i]; out[l.off[B2S_DATA_ACTUATOR_FORCE] + i] = w.actuator_force[i]; }
-  LANE_FOR(i, 3 * nb) { out[l.off[B2S_DATA_XPOS] + i] = w.xpos[i % 3][i / 3]; out[l.off[B2S_DATA_SUBTREE_COM] + i] = w.subtree_com[i % 3][i / 3]; }
+  LANE_FOR(i, 3 * nb) {
+    out[l.off[B2S_DATA_XPOS] + i] = w.xpos[i % 3][i / 3];
+    if (i >= 3) out[l.off[B2S_DATA_SUBTREE_COM] + i] = w.subtree_com[i % 3][i / 3];
+  }
   LANE_FOR(i, 4 * nb) out[l.off[B2S_DATA_XQUAT] + i] = w.xquat[i & 3][i >> 2];
   LANE_FOR(i, 10 * nb) out[l.off[B2S_DATA_CINERT] + i] = w.cinert[i % 10][i / 10];
   LANE_FOR(i, 6 * nb) {
@@ -58,7 +61,15 @@ __device__ __forceinline__ void write_data(const Mdl& m, const Work<D>& w, const
     out[l.off[B2S_DATA_CONTACT_POS] + 3 * c + 1] = w.con_pos[1][c];
     out[l.off[B2S_DATA_CONTACT_POS] + 3 * c + 2] = w.con_pos[2][c];
   }
-  if (lane == 0) { out[l.off[B2S_DATA_TIME]] = w.time; out[l.off[B2S_DATA_NCON]] = (float)nc; }
+  if (lane == 0) {
+    out[l.off[B2S_DATA_TIME]] = w.time;
+    out[l.off[B2S_DATA_NCON]] = (float)nc;
+    // subtree_com[0] (the world's subtree = the whole model): the kernels never need it and leave it unaccumulated
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    for (int b = 1; b < nb; b++) { cx += w.body_mass[b] * w.xipos[0][b]; cy += w.body_mass[b] * w.xipos[1][b]; cz += w.body_mass[b] * w.xipos[2][b]; }
+    const float sm = fmaxf(MF(m, MH_BODY_SUBTREEMASS)[0], MINVAL);  // nominal subtree mass, as for the other bodies
+    out[l.off[B2S_DATA_SUBTREE_COM]] = cx / sm; out[l.off[B2S_DATA_SUBTREE_COM] + 1] = cy / sm; out[l.off[B2S_DATA_SUBTREE_COM] + 2] = cz / sm;
+  }
 }
 
 // engine.step (ksim/engine.py:259-361): action -> ctrl (latency blend, drop mask), actuators, events, nsub x mjx.step.

@@ -208,6 +208,9 @@ class B200Engine:
         with torch.cuda.device(self.device):
             buf = (ctypes.c_char * len(self.blob)).from_buffer_copy(self.blob)
             binding.check(self.lib.b200sim_model_create(buf, len(self.blob), ctypes.byref(self._handle)), "b200sim_model_create")
+        binding.check(self.lib.b200sim_model_set_option(self._handle, C.B2S_OPT_SOLVER,
+                                                        C.B2S_SOLVER_REFERENCE if spec.config.solver == "reference" else C.B2S_SOLVER_FAST),
+                      "b200sim_model_set_option")
         p = self.program
         self.S, self.R, self.K, self.RAND, self.NA = p.state_size, p.rec_size, p.key_size, p.rand_size, p.action_size
         for name, want in (("STATE_SIZE", self.S), ("REC_SIZE", self.R), ("KEY_SIZE", self.K), ("RAND_SIZE", self.RAND),

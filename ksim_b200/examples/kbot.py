@@ -79,6 +79,9 @@ class KbotConfig:
     action_clip_max: float = 1e3
     gamma: float = 0.94
     lam: float = 0.94
+    # the reference-shaped capped Newton iteration ships for this task (EngineConfig.solver); "fast" is the opt-in whose
+    # deviation from the reference's iterate tests/test_gpu_parity.py::test_kbot_parity_resynchronised counts
+    solver: str = "reference"
 
     @property
     def rollout_length_frames(self) -> int:
@@ -389,6 +392,7 @@ def make_spec(config: KbotConfig | None = None, core_only: bool = False) -> Task
     eng = EngineConfig(
         dt=config.dt, ctrl_dt=config.ctrl_dt, action_latency_range=config.action_latency_range,
         drop_action_prob=config.drop_action_prob, zero_offset_mag=config.zero_offset_mag, action_clip_max=config.action_clip_max,
+        solver=config.solver,
     )
     left, right = "LFootBushing_GPF_1517_12", "RFootBushing_GPF_1517_12"
     obs = {

@@ -47,8 +47,17 @@ class EngineConfig:
     action_clip_max: float = 1e6
     reward_clip_min: float | None = None
     reward_clip_max: float | None = None
+    # Which Newton iteration the CUDA constraint solver runs (b200sim_model_set_option, B2S_OPT_SOLVER):
+    #   "reference": MJX's shape -- primal Newton in dof space, bracketing line search, both capped at the model's
+    #                iterations / ls_iterations: reproduces the reference's (possibly unconverged) iterate;
+    #   "fast":      constraint-space / factor-reusing Newton with an exact one-pass line search: converges further within the
+    #                same caps, so it departs from the reference's iterate wherever that one stops at its cap (K-Bot's 40-70
+    #                rows: ~1.5 % of env-steps beyond the stated tolerance; humanoid: within it, tests/test_gpu_parity.py).
+    solver: str = "fast"
 
     def __post_init__(self) -> None:
+        if self.solver not in ("fast", "reference"):
+            raise ValueError("`solver` must be 'fast' or 'reference'")
         lo, hi = self.action_latency_range
         if lo < 0:
             raise ValueError("`min_action_latency` must be non-negative")

@@ -247,7 +247,11 @@ def test_engine_entry_points_match_the_oracle(oracle_built, task, request) -> No
             scale = max(float(np.abs(b).max()), 1.0)
             bad = np.abs(a - b) > 2e-4 * scale + 2e-4 * np.abs(b)
             # contact forces flip with ulp-level changes of a penetration depth: allow isolated environments to differ there
-            limit = 0.05 if name in ("CFRC_EXT", "QACC", "SENSORDATA", "ACTUATOR_FORCE") else 0.0
+            # (K-Bot: capsule contacts + friction-loss rows make such isolated flips visible in every field; same clause and hard
+            # bound as tests/test_gpu_parity.py)
+            limit = 0.05 if name in ("CFRC_EXT", "QACC", "SENSORDATA", "ACTUATOR_FORCE") or task == "kbot" else 0.0
+            if name == "QPOS":
+                assert np.abs(a - b).max() <= 2e-2, f"{what}: qpos off by {np.abs(a - b).max():.3e}"
             assert bad.any(axis=1).mean() <= limit, f"{what}: {name} differs in {bad.any(axis=1).sum()} of {n} envs (max {np.abs(a - b).max():.3e})"
 
     compare(d.block.cpu().numpy(), d_o, "reset")

@@ -145,12 +145,12 @@ def test_bad_calls_come_back_as_xla_errors(shim: ctypes.CDLL) -> None:
 
 
 @pytest.mark.gpu
-def test_gae_handler_equals_the_c_abi_call(shim: ctypes.CDLL, walking_spec) -> None:  # noqa: ANN001
+def test_gae_handler_equals_the_c_abi_call(shim: ctypes.CDLL, walking_spec, walking_randomizers) -> None:  # noqa: ANN001
     import torch
 
     from ksim_b200.engine import B200Engine
 
-    eng = B200Engine(walking_spec, 4, device="cuda:0")
+    eng = B200Engine(walking_spec, 4, device="cuda:0", randomizers=walking_randomizers)
     b, t = 37, 24
     gen = torch.Generator(device="cuda:0").manual_seed(5)
     values, rewards = torch.randn((b, t), generator=gen, device="cuda:0"), torch.randn((b, t), generator=gen, device="cuda:0")

@@ -248,29 +248,32 @@ def test_edge_cases(ctx) -> None:  # noqa: ANN001
         eng.step(torch.zeros((7, eng.NA), device="cuda"), rec[0], rec[1])
 
 
-def test_kbot_parity_resynchronised(ctx, kbot_spec, kbot_randomizers) -> None:  # noqa: ANN001
+@pytest.mark.parametrize("solver", ["reference", "fast"])
+def test_kbot_parity_resynchronised(ctx, kbot_randomizers, solver) -> None:  # noqa: ANN001
     """BASELINE config 3's task (examples/kbot/train.py incl. its own plugins) through the K-Bot-sized instantiation
     (variant 1): capsule/plane contacts with pyramidal cones, friction-loss rows, per-joint PD gains with action noise,
     latency, drop, force pushes, five randomizers.  Resynchronised single-step protocol, stated tolerances
     qpos 3e-4, qvel 3e-2 + 5e-3 |v|; keys, done / success / termination codes bit-exact.
 
-    Two references.  (a) The f32 oracle at the reference's solver caps (8 Newton x 8 line-search iterations).  With 40-70
-    constraint rows that iteration often stops at its cap before converging, so its output there is an unconverged
-    iterate; the CUDA solver (exact line search, factor reuse, up to 16 cheap iterations) converges further and differs
-    from it in those env-steps.  They are COUNTED (<= 3 %), and hard-bounded (qpos 2e-2, qvel 2.0).  (b) The f64 oracle run
-    to convergence (60 x 240 iterations) from the same state: the minimum both iterations approximate.  Against it the
-    CUDA path must be inside the tolerance on all but isolated (<= 0.3 %) env-steps -- measured: CUDA 1 of 960, the
-    reference-shaped f32 iteration 11 of 960 (tools/emu_accuracy.py)."""
+    ``solver="reference"`` (what ships for this task, ``KbotConfig.solver``): the reference-shaped iteration -- primal Newton,
+    bracketing line search, both at the reference's caps (8 x 8).  The bar is the reference's iterate, converged or not: against
+    the f32 oracle at the same caps at most 0.3 % of env-steps may fall outside the tolerance (contact / limit rows that switch
+    within an fp32 ulp), hard-bounded (qpos 2e-2, qvel 2.0).
+
+    ``solver="fast"`` (opt-in): constraint-space / factor-reusing Newton with an exact line search.  With 40-70 constraint rows
+    the reference's iteration often stops at its cap before converging; the fast solver converges further and therefore
+    DEPARTS from the reference's iterate in those env-steps.  The departure is reported and bounded (<= 3 % of env-steps vs the
+    capped oracle), and the solver is held to 0.3 % against the f64 oracle run to convergence (60 x 240 iterations)."""
     from ksim_b200.examples.kbot import KbotConfig, make_spec
     from ksim_b200.program import build_program
     from oracle import OracleEngine
 
     n, steps = 32, 30
-    eng = _engine(kbot_spec, kbot_randomizers, n, level=1.0, seed=5)
+    eng = _engine(make_spec(KbotConfig(solver=solver)), kbot_randomizers, n, level=1.0, seed=5)
     assert eng.info("VARIANT") == 1
     ora, st, keys, rec0, _ = _oracle_init(eng)
     conv = OracleEngine(build_program(make_spec(KbotConfig(iterations=60, ls_iterations=240))), "f64")
-    p, m = eng.program, kbot_spec.model
+    p, m = eng.program, eng.spec.model
     np.testing.assert_array_equal(_np(eng.keys).view(np.uint32), keys)
     np.testing.assert_allclose(_np(eng.state), st, rtol=1e-3, atol=5e-5)
     actions = (0.3 * np.random.RandomState(6).randn(steps, n, eng.NA)).astype(np.float32)
@@ -303,8 +306,14 @@ def test_kbot_parity_resynchronised(ctx, kbot_spec, kbot_randomizers) -> None:  
             else:
                 n_bad_conv += int(bad.sum())
         rec_o[0] = rec_o[1]
-    assert n_bad_conv <= max(1, int(0.003 * n * steps)), f"{n_bad_conv} of {n * steps} env-steps away from the converged solution"
-    assert n_bad <= int(0.03 * n * steps), f"{n_bad} of {n * steps} env-steps away from the reference-capped iteration"
+    total = n * steps
+    print(f"kbot solver={solver}: {n_bad} of {total} env-steps beyond tolerance vs the reference-capped oracle, "
+          f"{n_bad_conv} vs the converged f64 oracle")
+    if solver == "reference":
+        assert n_bad <= max(1, int(0.003 * total)), f"{n_bad} of {total} env-steps away from the reference-capped iteration"
+    else:
+        assert n_bad_conv <= max(1, int(0.003 * total)), f"{n_bad_conv} of {total} env-steps away from the converged solution"
+        assert n_bad <= int(0.03 * total), f"{n_bad} of {total} env-steps away from the reference-capped iteration"
     assert float(eng.state[:, p["TI_S_NONFINITE"]].sum()) == 0.0
 
 

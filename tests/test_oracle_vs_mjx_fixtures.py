@@ -36,11 +36,10 @@ def test_oracle_matches_mjx_fixture(oracle_built, task, request) -> None:  # noq
     prog = build_program(spec)
     ora = OracleEngine(prog, "f32")
     n, t = int(fx["n_envs"]), int(fx["n_steps"])
-    rand = np.zeros((n, max(prog.rand_size, 1)), np.float32)
-    if prog.rand_size:
-        from ksim_b200.envinit import make_env_init
-        rand = make_env_init(prog, {}, n, seed=0).rand      # identity overrides: the fixture uses the shared base model
     m = spec.model
+    rand = np.zeros((n, max(prog.rand_size, 1)), np.float32)
+    for name, sl in prog.rand_slices.items():               # identity overrides: the fixture uses the shared base model
+        rand[:, sl[0] : sl[0] + sl[1]] = np.asarray(m.arrays[name], dtype=np.float32).reshape(-1)[: sl[1]]
     ncon = m.ncon if hasattr(m, "ncon") else 2
     state, keys, data = ora.engine_reset(fx["reset_keys"], fx["level"].astype(np.float32), rand, ncon)
     off = np.cumsum([0, m.nq, m.nv, m.nv, m.nu, 1])
