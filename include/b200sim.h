@@ -198,6 +198,13 @@ int b200sim_mixture_sample(void* stream, int rows, int n_joints, int n_mix, cons
                            const uint32_t* key, const int32_t* counter, int argmax, float* action, float* logp);
 const char* b200sim_policy_last_error(void);
 
+/* ---- Metric histograms: RLTask.get_histogram (ksim/task/rl.py:1521-1541) = jnp.histogram(arr.flatten(), bins) over [min, max]
+ * (widened by +-0.5 when min == max; last bin closed on the right) plus min / max / sum / sum of squares / mean.  counts[bins]
+ * int32; limits[bins] = the upper edge of every bin (edges[1:], as the reference stores them); stats[5] = {min, max, sum,
+ * sum_squares, mean}; scratch: b200sim_histogram_scratch_bytes() bytes.  bins <= 1024.  Counts are exact and deterministic. */
+size_t b200sim_histogram_scratch_bytes(void);
+int b200sim_histogram(void* stream, size_t n, const float* x, int bins, int32_t* counts, float* limits, float* stats, void* scratch);
+
 /* ---- Optimiser step of the PPO update (ksim/task/ppo.py:536-565 apply_gradients_with_clipping -> optax chain of
  * examples/walking.py:373-387: zero_nans, clip_by_global_norm, add_decayed_weights, scale_by_adam, warmup_constant_schedule,
  * scale(-1)) on flat fp32 buffers of n elements, in place.  step_count[0] (device int32, starts at 0) is advanced by the call;

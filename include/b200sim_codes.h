@@ -83,6 +83,9 @@
 #define TI_R_TIME 61
 #define TI_R_LEVEL 62
 #define TI_R_TERM 63
+#define TI_R_AUX 65          /* aux_outputs region of a record (Trajectory.aux_outputs, types.py:48-70): written by the host's
+                                postprocess_trajectory hook between rollout and rewards, never by the kernels */
+#define TI_AUX_SIZE 66
 #define TI_S_XFRC 64         /* 6 floats wrench + body id handled via event params; -1 if unused */
 #define TI_HEADER_SIZE 72
 
@@ -215,6 +218,7 @@
 #define REW_REACHABILITY 38
 #define REW_SYMMETRY 39
 #define REW_PAIRWISE_SYMMETRY 40
+#define REW_AMP 41               /* ksim/task/amp.py:100-112: max(0, 1 - 0.25 (logit - 1)^2) of an aux output; ints [aux offset] */
 #define REW_KBOT_SINGLE_FOOT_CONTACT 16
 #define REW_KBOT_NO_CONTACT 17
 #define REW_KBOT_FEET_AIRTIME 18
@@ -288,6 +292,9 @@
 #define B2S_DATA_CONTACT_DIST 19   /* [ncon] */
 #define B2S_DATA_CONTACT_POS 20    /* [ncon][3] */
 #define B2S_DATA_N_FIELDS 21
+
+/* ---- metric histograms (b200sim_histogram) ---- */
+#define B2S_HIST_MAX_CTAS 592    /* 4 x 148: per-CTA partial statistics in the scratch buffer */
 
 /* ---- flat-buffer optimiser step (b200sim_optimizer_step) ---- */
 #define B2S_OPTIM_MAX_PARTIALS 1024  /* per-CTA partial sums of the gradient norm (grid = a multiple of the SM count, <= this) */

@@ -151,4 +151,17 @@ class PositionVelocityActuator(PositionActuators):
         return 0
 
     def encode(self, model: Model) -> tuple[list[int], list[float]]:
-        raise NotImplementedError("PositionVelocityActuator is not yet supported by the CUDA engine")
+        """``get_ctrl`` (actuators.py:261-293): ``split(rng, 3)`` -> position, velocity and torque noise; ``ctrl = kps (noisy
+        position target - q) + kds (noisy velocity target - qdot)``, torque noise, clip to ``ctrl_clip`` -- no action scale, no
+        biases, no gain / limit scales (those belong to ``get_stateful_ctrl``).  Note on the reference: the class derives from
+        the *stateful* ``PositionActuators``, so ``MjxEngine.step`` (engine.py:293-301) dispatches to the inherited
+        ``get_stateful_ctrl`` with the 2 nu-long action and fails on the shape check; no reference example uses the class.  The
+        engine here runs the class's own ``get_ctrl``.  Layout: the ``PositionActuators`` block (unused slots neutral) with the
+        velocity noise appended."""
+        ani, anf = encode_noise(self.action_noise)
+        tni, tnf = encode_noise(self.torque_noise)
+        vni, vnf = encode_noise(self.vel_action_noise)
+        ints = ani + tni + [-1] * 5 + vni
+        floats = [1.0] + anf + tnf + [0.0] * 15
+        floats += [float(v) for v in self.kps] + [float(v) for v in self.kds] + [float(v) for v in self.ctrl_clip] + vnf
+        return ints, floats

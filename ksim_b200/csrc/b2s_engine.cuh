@@ -152,6 +152,22 @@ DEV void actuators_ctrl(const Mdl& m, Work<D>& w, const float* ctrl_in, Key rng,
   const float action_scale = af[0];
   const float* an_f = af + 1; const float* tn_f = an_f + NOISE_NF;
   const float* kp = tn_f + NOISE_NF + 15; const float* kd = kp + nu; const float* clip = kd + nu;
+  if (ti[TI_ACT_TYPE] == ACT_POSITION_VELOCITY) {
+    // PositionVelocityActuator.get_ctrl (actuators.py:261-293): action = [position targets | velocity targets]
+    const int* vn_i = ai + 2 * NOISE_NI + 5;
+    const float* vn_f = clip + nu;
+    const KeyFan fan3 = key_fan(rng, LANE_PASS);
+    const Key pos_rng = key_child(fan3, 0), vel_rng = key_child(fan3, 1), tor_rng = key_child(fan3, 2);
+    LANE_FOR(i, nu) {
+      const float tp = noise_apply(an_i, an_f, ctrl_in[i], pos_rng, i, level);
+      const float tv = noise_apply(vn_i, vn_f, ctrl_in[nu + i], vel_rng, i, level);
+      float c = kp[i] * (tp - (w.qpos[7 + i] - w.zero_off[i])) + kd[i] * (tv - w.qvel[6 + i]);
+      c = noise_apply(tn_i, tn_f, c, tor_rng, i, level);
+      w.torque[i] = clipf(c, -clip[i], clip[i]);
+    }
+    WSYNC();
+    return;
+  }
   const float kp_scale = w.act_state[2 * nu], kd_scale = w.act_state[2 * nu + 1], tl_scale = w.act_state[2 * nu + 2];
   const KeyFan fan = key_fan(rng, LANE_PASS);
   const Key pos_rng = key_child(fan, 0), tor_rng = key_child(fan, 1);

@@ -215,3 +215,99 @@ extern "C" int b200sim_mixture_sample(void* stream, int rows, int n_joints, int 
   LAUNCH_OK();
   return B2S_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Metric histograms (RLTask.get_histogram, ksim/task/rl.py:1521-1541: every logged metric array with more than one element is
+// reduced to jnp.histogram(arr, bins) + min / max / sum / sum of squares / mean).  Two HBM-bound passes over the array:
+// (1) per-CTA min / max / sum / sum of squares -> partials; (2) every CTA re-reduces the partials in a fixed order, derives the
+// bin edges (numpy's rule: [min, max], widened by +-0.5 when they coincide; the last bin is closed on the right), counts
+// into a shared-memory histogram and merges it with integer atomics (exact and order-independent).
+namespace {
+
+constexpr int HNT = 256;
+constexpr int HMAXBINS = 1024;
+
+__global__ void __launch_bounds__(HNT) k_hist_stats(size_t n, const float* __restrict__ x, float* __restrict__ partial) {
+  __shared__ float s_mn[HNT / 32], s_mx[HNT / 32];
+  __shared__ double s_sum[HNT / 32], s_sq[HNT / 32];
+  float mn = INFINITY, mx = -INFINITY;
+  double sum = 0.0, sq = 0.0;
+  for (size_t i = (size_t)blockIdx.x * HNT + threadIdx.x; i < n; i += (size_t)gridDim.x * HNT) {
+    const float v = x[i];
+    mn = fminf(mn, v); mx = fmaxf(mx, v);
+    sum += v; sq += (double)v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s_mn[w] = mn; s_mx[w] = mx; s_sum[w] = sum; s_sq[w] = sq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < HNT / 32; k++) { mn = fminf(mn, s_mn[k]); mx = fmaxf(mx, s_mx[k]); sum += s_sum[k]; sq += s_sq[k]; }
+    float* p = partial + 6 * blockIdx.x;   // min, max, sum (double), sum of squares (double)
+    p[0] = mn; p[1] = mx;
+    *reinterpret_cast<double*>(p + 2) = sum;
+    *reinterpret_cast<double*>(p + 4) = sq;
+  }
+}
+
+__global__ void __launch_bounds__(HNT) k_hist_count(size_t n, const float* __restrict__ x, const float* __restrict__ partial, int n_partial,
+                                                    int bins, int* __restrict__ counts, float* __restrict__ limits, float* __restrict__ stats) {
+  __shared__ int s_cnt[HMAXBINS];
+  __shared__ float s_lo, s_hi;
+  for (int b = threadIdx.x; b < bins; b += HNT) s_cnt[b] = 0;
+  if (threadIdx.x == 0) {
+    float mn = INFINITY, mx = -INFINITY;
+    double sum = 0.0, sq = 0.0;
+    for (int k = 0; k < n_partial; k++) {
+      const float* p = partial + 6 * k;
+      mn = fminf(mn, p[0]); mx = fmaxf(mx, p[1]);
+      sum += *reinterpret_cast<const double*>(p + 2);
+      sq += *reinterpret_cast<const double*>(p + 4);
+    }
+    float lo = mn, hi = mx;
+    if (lo == hi) { lo -= 0.5f; hi += 0.5f; }
+    s_lo = lo; s_hi = hi;
+    if (blockIdx.x == 0) {
+      stats[0] = mn; stats[1] = mx; stats[2] = (float)sum; stats[3] = (float)sq; stats[4] = (float)(sum / (double)n);
+      for (int b = 0; b < bins; b++) limits[b] = b + 1 == bins ? hi : lo + (hi - lo) * ((float)(b + 1) / (float)bins);  // edges[1:]
+    }
+  }
+  __syncthreads();
+  const float lo = s_lo, hi = s_hi, scale = (float)bins / (hi - lo);
+  for (size_t i = (size_t)blockIdx.x * HNT + threadIdx.x; i < n; i += (size_t)gridDim.x * HNT) {
+    const float v = x[i];
+    int b = (int)((v - lo) * scale);
+    b = b < 0 ? 0 : (b >= bins ? bins - 1 : b);
+    // settle the candidate against the edges themselves (searchsorted semantics; the product above can be one bin off)
+    const float e0 = lo + (hi - lo) * ((float)b / (float)bins), e1 = lo + (hi - lo) * ((float)(b + 1) / (float)bins);
+    if (v < e0 && b > 0) b--;
+    else if (v >= e1 && b + 1 < bins) b++;
+    atomicAdd(&s_cnt[b], 1);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < bins; b += HNT)
+    if (s_cnt[b]) atomicAdd(&counts[b], s_cnt[b]);
+}
+
+}  // namespace
+
+extern "C" size_t b200sim_histogram_scratch_bytes(void) { return (size_t)B2S_HIST_MAX_CTAS * 6 * sizeof(float); }
+
+extern "C" int b200sim_histogram(void* stream, size_t n, const float* x, int bins, int32_t* counts, float* limits, float* stats, void* scratch) {
+  if (bins < 1 || bins > HMAXBINS) return pfail(B2S_ERR_UNSUPPORTED, "histogram: 1 <= bins <= 1024");
+  if (n == 0 || !x || !counts || !limits || !stats || !scratch) return pfail(B2S_ERR_BAD_ARG, "null argument or empty array");
+  size_t want = (n + HNT - 1) / HNT;
+  const int grid = (int)(want < (size_t)B2S_HIST_MAX_CTAS ? want : (size_t)B2S_HIST_MAX_CTAS);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * bins, s) != cudaSuccess) return pfail(B2S_ERR_CUDA, "cudaMemsetAsync");
+  k_hist_stats<<<grid, HNT, 0, s>>>(n, x, (float*)scratch);
+  k_hist_count<<<grid, HNT, 0, s>>>(n, x, (const float*)scratch, grid, bins, counts, limits, stats);
+  LAUNCH_OK();
+  return B2S_OK;
+}

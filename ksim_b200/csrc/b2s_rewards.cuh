@@ -47,6 +47,12 @@ DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, floa
     if (cr && done_last) { LANE_FOR(k, cdim) cr[k] = 0.0f; }
     WSYNC();
     switch (type) {
+      case REW_AMP:
+        LANE_FOR(s, T) {
+          const float d = REC(s, ti[TI_R_AUX] + xi[0]) - 1.0f;
+          OUT(0, s) = fmaxf(0.0f, 1.0f - 0.25f * d * d);
+        }
+        break;
       case REW_STAY_ALIVE:
         LANE_FOR(s, T) {
           const float alive = 1.0f / xf[0];

@@ -111,6 +111,12 @@ class TrajectoryView:
         return {k: flat[..., off : off + dim] for k, (off, dim) in self.program.event_slices.items()}
 
     @property
+    def aux_outputs(self) -> dict[str, torch.Tensor]:
+        """``Trajectory.aux_outputs``: writable views ``[..., dim]`` of the record's aux region, one per declared output."""
+        off = self.program["TI_R_AUX"]
+        return {k: self.rec[..., off + o : off + o + d] for k, (o, d) in self.program.aux_slices.items()}
+
+    @property
     def termination_components(self) -> dict[str, torch.Tensor]:
         names = self.program.termination_names
         flat = self._blk("TI_R_TERM", len(names))
@@ -394,6 +400,24 @@ class B200Engine:
         self.launches += 1
         return total, comps
 
+    def postprocess_and_rewards(self, rec: torch.Tensor, n_steps: int | None = None,
+                                postprocess_trajectory=None) -> tuple[torch.Tensor, torch.Tensor]:  # noqa: ANN001
+        """What ``_single_unroll`` does after the scan (rl.py:1636-1660): ``postprocess_trajectory(trajectory)`` -- the hook AMP /
+        teacher tasks override (amp.py:327-358, teacher.py:113-136) -- then ``get_rewards``.  The hook receives the
+        ``TrajectoryView`` of the T transitions and returns ``{aux output name: tensor [T, N] or [T, N, dim]}``; the values are
+        stored in the records' aux region (``TaskSpec.aux_outputs`` declares the slots) where the rewards pass reads them."""
+        t = self._scored_steps(rec, n_steps)
+        hook = postprocess_trajectory if postprocess_trajectory is not None else getattr(self, "postprocess_trajectory", None)
+        if hook is not None:
+            view = self.view(rec[:t])
+            slots = view.aux_outputs
+            for name, value in hook(view).items():
+                if name not in slots:
+                    raise KeyError(f"postprocess_trajectory returned '{name}', the task declares aux outputs {sorted(slots)}")
+                dst = slots[name]
+                dst.copy_(value.reshape(dst.shape).to(dst.dtype))
+        return self.rewards(rec, t)
+
     def metrics(self, rec: torch.Tensor, total: torch.Tensor, comps: torch.Tensor, n_steps: int | None = None) -> dict[str, torch.Tensor]:
         """The per-iteration trajectory reductions the curricula and the logger consume: ``Trajectory.episode_length``
         (types.py:72-76), ``get_termination_metrics`` / ``get_reward_metrics`` (rl.py:1544-1573), the inputs of
@@ -415,6 +439,25 @@ class B200Engine:
         for i, name in enumerate(self.program.reward_components):
             res[f"reward/{name}"] = out[13 + i]
         return res
+
+    def get_histogram(self, arr: torch.Tensor, bins: int = 100) -> dict[str, torch.Tensor]:
+        """``RLTask.get_histogram`` (rl.py:1521-1541), the reduction ``_rl_train_loop_step`` applies to every logged metric with
+        more than one element (rl.py:1815): ``counts`` (int32 ``[bins]``), ``limits`` (upper bin edges), ``min``, ``max``, ``sum``,
+        ``sum_squares``, ``mean`` -- the fields of ``xax.Histogram``."""
+        x = arr.detach().to(torch.float32).contiguous().reshape(-1)
+        if x.device != self.device or x.numel() == 0:
+            raise ValueError("get_histogram needs a non-empty tensor on the engine's device")
+        counts = torch.empty((bins,), dtype=torch.int32, device=self.device)
+        limits = torch.empty((bins,), dtype=torch.float32, device=self.device)
+        stats = torch.empty((5,), dtype=torch.float32, device=self.device)
+        scratch = torch.empty(int(self.lib.b200sim_histogram_scratch_bytes()), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.b200sim_histogram(self._stream(), x.numel(), _ptr(x), bins, _ptr(counts), _ptr(limits), _ptr(stats), _ptr(scratch))
+        if rc != 0:
+            msg = self.lib.b200sim_policy_last_error()
+            raise binding.B200SimError(f"b200sim_histogram failed with code {rc}: {msg.decode() if msg else ''}")
+        self.launches += 2
+        return {"counts": counts, "limits": limits, "min": stats[0], "max": stats[1], "sum": stats[2], "sum_squares": stats[3], "mean": stats[4]}
 
     def set_curriculum_level(self, level: float) -> None:
         """The level the next rollout runs at.  The reference passes ``curriculum_state.level`` to every ``step_engine`` call

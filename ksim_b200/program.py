@@ -108,6 +108,10 @@ class TaskSpec:
     rewards: Mapping[str, Reward] = field(default_factory=dict)
     terminations: Mapping[str, Termination] = field(default_factory=dict)
     randomized_fields: tuple[str, ...] = ()
+    # Trajectory.aux_outputs (types.py:48-70): name -> floats per (env, step).  The slots live in every record and are filled
+    # by the postprocess_trajectory hook (rl.py:1590; AMP's discriminator logits amp.py:327-358, a teacher's outputs
+    # teacher.py:113-136) between the rollout and the rewards pass; rewards read them by name (AMPReward).
+    aux_outputs: Mapping[str, int] = field(default_factory=dict)
 
 
 @dataclass
@@ -121,6 +125,7 @@ class TaskProgram:
     reward_components: list[str]
     termination_names: list[str]
     rand_slices: dict[str, tuple[int, int]]
+    aux_slices: dict[str, tuple[int, int]] = field(default_factory=dict)
 
     def __getitem__(self, key: str) -> int:
         return int(self.ti[getattr(C, key)])
@@ -152,8 +157,14 @@ class TaskProgram:
 
 class _Ctx:
     def __init__(self, model: Model, obs: dict[str, tuple[int, int, tuple[int, ...]]], cmds: Mapping[str, Command],
-                 cmd_slices: dict[str, tuple[int, int]]) -> None:
-        self.model, self.obs, self.cmds, self.cmd_slices = model, obs, cmds, cmd_slices
+                 cmd_slices: dict[str, tuple[int, int]], aux_slices: dict[str, tuple[int, int]] | None = None) -> None:
+        self.model, self.obs, self.cmds, self.cmd_slices, self.aux_slices = model, obs, cmds, cmd_slices, aux_slices or {}
+
+    def aux_offset(self, name: str) -> int:
+        """Float offset of an aux output inside a record's aux region."""
+        if name not in self.aux_slices:
+            raise KeyError(f"aux output '{name}' not found; the task's aux_outputs are {sorted(self.aux_slices)}")
+        return self.aux_slices[name][0]
 
     def obs_offset(self, name: str) -> int:
         if name not in self.obs:
@@ -292,8 +303,17 @@ def build_program(spec: TaskSpec) -> TaskProgram:
         coff += dim
     ints[C.TI_CMD_SIZE] = coff
 
+    # aux outputs (filled by the postprocess_trajectory hook; read by rewards)
+    aux_slices: dict[str, tuple[int, int]] = {}
+    aoff = 0
+    for name, dim in spec.aux_outputs.items():
+        if int(dim) < 1:
+            raise ValueError(f"aux output '{name}' needs at least one float per step")
+        aux_slices[name] = (aoff, int(dim))
+        aoff += int(dim)
+
     # rewards
-    ctx = _Ctx(m, obs_slices, spec.commands, cmd_slices)
+    ctx = _Ctx(m, obs_slices, spec.commands, cmd_slices, aux_slices)
     rew_names = list(spec.rewards)
     ints[C.TI_N_REW] = len(rew_names)
     ints[C.TI_REW_TAB] = base = table(len(rew_names))
@@ -349,6 +369,8 @@ def build_program(spec: TaskSpec) -> TaskProgram:
     alloc(C.TI_R_QPOS, m.nq); alloc(C.TI_R_QVEL, m.nv); alloc(C.TI_R_XPOS, 3 * m.nbody); alloc(C.TI_R_XQUAT, 4 * m.nbody)
     alloc(C.TI_R_CTRL, m.nu); alloc(C.TI_R_EVENT, eoff); alloc(C.TI_R_ACTION, na); alloc(C.TI_R_DONE, 1)
     alloc(C.TI_R_SUCCESS, 1); alloc(C.TI_R_TIME, 1); alloc(C.TI_R_TERM, len(term_names))
+    alloc(C.TI_R_AUX, aoff)
+    ints[C.TI_AUX_SIZE] = aoff
     ints[C.TI_REC_SIZE] = _pad4(off)
 
     tf = np.array(floats, dtype=np.float64)
@@ -357,4 +379,4 @@ def build_program(spec: TaskSpec) -> TaskProgram:
     assert not any(math.isinf(v) for v in tf32.tolist())
     return TaskProgram(ti=np.array(ints, dtype=np.int32), tf=tf32, spec=spec, obs_slices=obs_slices, cmd_slices=cmd_slices,
                        event_slices=event_slices, reward_components=comp_names, termination_names=term_names,
-                       rand_slices=rand_slices)
+                       rand_slices=rand_slices, aux_slices=aux_slices)

@@ -8,7 +8,7 @@ command names to record offsets.
 
 from __future__ import annotations
 
-__all__ = [
+__all__ = ["AMPReward", "DISCRIMINATOR_OUTPUT_KEY", 
     "Reward", "StatefulReward", "StayAliveReward", "UprightReward", "LinearVelocityReward", "AngularVelocityReward",
     "FeetAirTimeReward", "SparseTargetHeightReward", "ForcePenalty", "MotionlessAtRestPenalty",
     "ActionVelocityPenalty", "ActionAccelerationPenalty", "ActionJerkPenalty", "BaseHeightReward",
@@ -45,6 +45,7 @@ class EncodeContext(Protocol):
     def obs_shape(self, name: str) -> tuple[int, ...]: ...
     def cmd_offset(self, name: str, field: str | None = None) -> int: ...
     def cmd_type(self, name: str) -> type: ...
+    def aux_offset(self, name: str) -> int: ...
 
 
 def _norm_flag(norm: str) -> int:
@@ -83,6 +84,26 @@ class StayAliveReward(Reward):
     def encode(self, ctx: EncodeContext) -> Encoded:
         has = self.success_reward is not None
         return C.REW_STAY_ALIVE, [int(has)], [float(self.balance), float(self.success_reward or 0.0)], [""], 0
+
+
+DISCRIMINATOR_OUTPUT_KEY = "_discriminator_logits"  # ksim/task/amp.py
+
+
+@attrs.define(frozen=True, kw_only=True)
+class AMPReward(Reward):
+    """``ksim.task.amp.AMPReward`` (amp.py:100-112): ``max(0, 1 - 0.25 (logit - 1)^2)`` of the discriminator logits the task's
+    ``postprocess_trajectory`` hook wrote into ``trajectory.aux_outputs``; the task must declare that aux output
+    (``TaskSpec.aux_outputs``), as the reference raises when it is missing."""
+
+    aux_output: str = attrs.field(default=DISCRIMINATOR_OUTPUT_KEY)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        try:
+            off = ctx.aux_offset(self.aux_output)
+        except KeyError as e:
+            raise ValueError("AMPReward auxiliary output is missing! Make sure you are using it within the context of an AMP task, "
+                             "which populates the auxiliary output for you.") from e
+        return C.REW_AMP, [off], [], [""], 0
 
 
 @attrs.define(frozen=True, kw_only=True)

@@ -202,7 +202,7 @@ typedef struct {
   OModel model;
   OData d;
   REAL level;
-  REAL last_ctrl[O_MAXNU], latency, zero_off[O_MAXNU];
+  REAL last_ctrl[2 * O_MAXNU], latency, zero_off[O_MAXNU];
   REAL event[32], act_state[2 * O_MAXNU + 3], cmd[32], obs_carry[64];
   Key rng, bias_key[32];
   REAL nonfinite;
@@ -294,6 +294,22 @@ static void actuators_ctrl(const Task* t, Env* e, const REAL* ctrl_in, Key rng, 
   REAL action_scale = af[0];
   const REAL* an_f = af + 1; const REAL* tn_f = an_f + NOISE_NF;
   const REAL* kp = tn_f + NOISE_NF + 15; const REAL* kd = kp + nu; const REAL* clip = kd + nu;
+  if (t->act_type == ACT_POSITION_VELOCITY) {
+    /* PositionVelocityActuator.get_ctrl (actuators.py:261-293): split(rng, 3); action = [position | velocity] targets */
+    const int* vn_i = ai + 2 * NOISE_NI + 5;
+    const REAL* vn_f = clip + nu;
+    Key pos_rng = key_split(rng, 0), vel_rng = key_split(rng, 1), tor_rng = key_split(rng, 2);
+    for (int i = 0; i < nu; i++) {
+      REAL tp = noise_apply(an_i, an_f, ctrl_in[i], pos_rng, i, level);
+      REAL tv = noise_apply(vn_i, vn_f, ctrl_in[nu + i], vel_rng, i, level);
+      REAL c = kp[i] * (tp - (d->qpos[7 + i] - e->zero_off[i])) + kd[i] * (tv - d->qvel[6 + i]);
+      c = noise_apply(tn_i, tn_f, c, tor_rng, i, level);
+      if (c < -clip[i]) c = -clip[i];
+      if (c > clip[i]) c = clip[i];
+      torque[i] = c;
+    }
+    return;
+  }
   const REAL* action_bias = e->act_state; const REAL* torque_bias = e->act_state + nu;
   REAL kp_scale = e->act_state[2 * nu], kd_scale = e->act_state[2 * nu + 1], tl_scale = e->act_state[2 * nu + 2];
   Key pos_rng = key_split(rng, 0), tor_rng = key_split(rng, 1);
@@ -1152,6 +1168,13 @@ static void env_rewards(const Task* t, const REAL* rec, size_t tstride, int T, R
     int DN = ti[TI_R_DONE], SC = ti[TI_R_SUCCESS];
     int na = ti[TI_ACTION_SIZE];
     switch (type) {
+      case REW_AMP: /* ksim/task/amp.py:100-112 */
+        for (int s = 0; s < T; s++) {
+          REAL dd = REC(s, ti[TI_R_AUX] + xi[0]) - 1;
+          REAL v = 1 - (REAL)0.25 * dd * dd;
+          out[0][s] = v > 0 ? v : 0;
+        }
+        break;
       case REW_STAY_ALIVE:
         for (int s = 0; s < T; s++) {
           REAL alive = (REAL)1 / xf[0];

@@ -95,3 +95,30 @@ def test_trajectory_metrics_match_the_reference_formulas(walking_spec, walking_r
     cm = comps.cpu().numpy()
     for i, name in enumerate(p.reward_components):
         np.testing.assert_allclose(got[f"reward/{name}"], cm[i].mean(), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_histogram_matches_numpy(walking_spec, walking_randomizers) -> None:  # noqa: ANN001
+    """RLTask.get_histogram (rl.py:1521-1541): jnp.histogram == numpy.histogram semantics (range [min, max], last bin closed,
+    +-0.5 when degenerate), limits = edges[1:], and the five scalar statistics."""
+    import torch
+
+    from ksim_b200.engine import B200Engine
+
+    eng = B200Engine(walking_spec, 8, randomizers=walking_randomizers, seed=0)
+    r = np.random.RandomState(0)
+    for data, bins in ((r.randn(4096, 64).astype(np.float32), 100), (r.rand(1000).astype(np.float32) ** 3, 7),
+                       (np.full(333, 2.5, np.float32), 100), (np.arange(101, dtype=np.float32), 100),
+                       (np.concatenate([r.randn(10_000), [50.0]]).astype(np.float32), 1024)):
+        got = {k: v.cpu().numpy() for k, v in eng.get_histogram(torch.from_numpy(data).cuda(), bins).items()}
+        flat = data.reshape(-1)
+        counts, edges = np.histogram(flat.astype(np.float64), bins=bins)
+        assert got["counts"].sum() == flat.size
+        # fp32 edges can move a value sitting on a float64 edge into the neighbouring bin: compare cumulative counts loosely
+        assert np.abs(np.cumsum(got["counts"]) - np.cumsum(counts)).max() <= max(2, flat.size // 5000)
+        np.testing.assert_allclose(got["limits"], edges[1:], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose([got["min"], got["max"]], [flat.min(), flat.max()], rtol=0, atol=0)
+        f64 = flat.astype(np.float64)
+        np.testing.assert_allclose([got["sum"], got["sum_squares"], got["mean"]], [f64.sum(), (f64 * f64).sum(), f64.mean()], rtol=1e-5, atol=1e-4)
+    exact = eng.get_histogram(torch.arange(100, dtype=torch.float32, device="cuda"), 10)["counts"].cpu().numpy()
+    np.testing.assert_array_equal(exact, np.histogram(np.arange(100), bins=10)[0])
