@@ -177,34 +177,79 @@ class MixtureOfGaussians:
 
 
 # ---------------------------------------------------------------------------------------------------------- networks
+_ONES: dict[tuple, torch.Tensor] = {}
+
+
+def _ones_row(n: int, device: torch.device) -> torch.Tensor:
+    """``[1, n]`` bf16 ones (cached): column sums as a tensor-core GEMM, ``ones @ dy``, instead of a strided reduction."""
+    key = (n, str(device))
+    if key not in _ONES:
+        _ONES[key] = torch.ones((1, n), dtype=torch.bfloat16, device=device)
+    return _ONES[key]
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
 class _AffineFn(torch.autograd.Function):
     """``y = x W^T + b`` with bf16 tensor-core operands and fp32 accumulation; ``W`` read from its bf16 shadow.  Gradients:
-    ``dW = dy^T x`` and ``db`` in fp32 (they land in the fp32 flat gradient buffer), ``dx`` in bf16."""
+    ``dW = dy^T x`` and ``db`` in fp32 (they land in the fp32 flat gradient buffer), ``dx`` in bf16.  Operand widths that are
+    not a multiple of 8 elements (the 43 actor inputs, the 510 mixture outputs) are zero-padded so that the library picks its
+    16-byte-aligned tensor-core kernels; a single output column (the critic's value head) is a matrix-vector product."""
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, out_fp32: bool) -> torch.Tensor:  # noqa: ANN001
-        x16 = x.detach().to(torch.bfloat16).reshape(-1, x.shape[-1])
+        k, n_out = int(x.shape[-1]), int(weight.shape[0])
+        x16 = x.detach().to(torch.bfloat16).reshape(-1, k)
         w16 = shadow(weight)
-        if out_fp32:
+        kp, np_ = _pad8(k), (n_out if n_out == 1 else _pad8(n_out))
+        if kp != k:
+            x16 = F.pad(x16, (0, kp - k))
+        if kp != k or np_ != n_out:
+            w16 = F.pad(w16, (0, kp - k, 0, np_ - n_out))
+        if n_out == 1:
+            y = torch.mv(x16, w16[0]).unsqueeze(-1)
+            y = y.float() if out_fp32 else y
+            if bias is not None:
+                y = y + (bias.detach() if out_fp32 else shadow(bias))
+        elif out_fp32:
             y = torch.mm(x16, w16.t(), out_dtype=torch.float32)
             if bias is not None:
-                y += bias.detach()
+                y[:, :n_out] += bias.detach()
         elif bias is not None:
-            y = torch.addmm(shadow(bias), x16, w16.t())
+            b16 = shadow(bias)
+            y = torch.addmm(b16 if np_ == n_out else F.pad(b16, (0, np_ - n_out)), x16, w16.t())
         else:
             y = torch.mm(x16, w16.t())
+        if np_ != n_out:
+            y = y[:, :n_out].contiguous()
         ctx.save_for_backward(x16, w16)
-        ctx.has_bias, ctx.x_shape, ctx.x_dtype = bias is not None, x.shape, x.dtype
-        return y.view(*x.shape[:-1], weight.shape[0])
+        ctx.has_bias, ctx.x_shape, ctx.x_dtype, ctx.dims = bias is not None, x.shape, x.dtype, (k, kp, n_out, np_)
+        return y.view(*x.shape[:-1], n_out)
 
     @staticmethod
     def backward(ctx, dy: torch.Tensor):  # noqa: ANN001, ANN205
         x16, w16 = ctx.saved_tensors
-        dy16 = dy.to(torch.bfloat16).reshape(-1, dy.shape[-1])
-        dx = torch.mm(dy16, w16).view(ctx.x_shape).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
-        dw = torch.mm(dy16.t(), x16, out_dtype=torch.float32)
-        db = dy16.sum(0, dtype=torch.float32) if ctx.has_bias else None
-        return dx, dw, db, None
+        k, kp, n_out, np_ = ctx.dims
+        dy16 = dy.to(torch.bfloat16).reshape(-1, n_out)
+        rows = dy16.shape[0]
+        db = None
+        if n_out == 1:
+            dx = (dy16 * w16) if ctx.needs_input_grad[0] else None        # outer product [rows, 1] x [1, kp]
+            dw = torch.mv(x16.t(), dy16[:, 0]).float().unsqueeze(0)
+            if ctx.has_bias:
+                db = dy16.sum(0, dtype=torch.float32)
+        else:
+            if np_ != n_out:
+                dy16 = F.pad(dy16, (0, np_ - n_out))
+            dx = torch.mm(dy16, w16) if ctx.needs_input_grad[0] else None
+            dw = torch.mm(dy16.t(), x16, out_dtype=torch.float32)[:n_out]
+            if ctx.has_bias:
+                db = torch.mm(_ones_row(rows, dy16.device), dy16, out_dtype=torch.float32)[0, :n_out]
+        if dx is not None:
+            dx = (dx[:, :k] if kp != k else dx).reshape(ctx.x_shape).to(ctx.x_dtype)
+        return dx, (dw[:, :k] if kp != k else dw), db, None
 
 
 class Linear(nn.Module):

@@ -79,6 +79,16 @@ def shadow(p: torch.Tensor) -> torch.Tensor:
     return s if s is not None else p.detach().to(torch.bfloat16)
 
 
+_ONES: dict[tuple, torch.Tensor] = {}
+
+
+def _ones_col(n: int, device: torch.device) -> torch.Tensor:
+    key = (n, str(device))
+    if key not in _ONES:
+        _ONES[key] = torch.ones((n, 8), dtype=torch.bfloat16, device=device)   # 8 columns: a 16-byte-aligned operand
+    return _ONES[key]
+
+
 def _mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """bf16 x bf16 -> fp32 library GEMM."""
     return torch.mm(a, b, out_dtype=torch.float32)
@@ -239,8 +249,9 @@ class _GruStacksFn(torch.autograd.Function):
                 hst_r = hst.t()  # [T B, H] operand
                 g_w_ih = _mm(dgi, x_in.t())
                 g_w_hh = torch.cat([_mm(dgi[: 2 * hd], hst_r), _mm(dghn, hst_r)], dim=0)
-                g_b = dgi.sum(1, dtype=torch.float32)
-                g_bn = dghn.sum(1, dtype=torch.float32)
+                ones = _ones_col(tb, dev)               # row sums as tensor-core GEMVs
+                g_b = _mm(dgi, ones)[:, 0]
+                g_bn = _mm(dghn, ones)[:, 0]
                 pgrads[s][layer * 4 : layer * 4 + 4] = [g_w_ih, g_w_hh, g_b, g_bn]
                 if layer > 0:
                     dy[s] = _mm(w_ih16.t(), dgi)  # [H, T B]: gradient w.r.t. the layer below's feature-major output
