@@ -41,8 +41,6 @@ constexpr int NCH = H / U;           // CTAs (= state chunks) per group
 constexpr int MT = 128;              // batch rows per group = UMMA M
 constexpr int NEPI = 256;            // epilogue threads: warps 0-7; warp w reads TMEM lanes 32 (w % 4).., units 16 (w / 4)..
 constexpr int NTHREADS = NEPI + 64;  // backward: + warp 8 (bulk-copy producer) + warp 9 (MMA issuer, TMEM owner)
-constexpr int FULL_CH = 16;                    // forward: state chunks per arrival barrier (the MMA issuer waits NCH / FULL_CH times a step)
-constexpr int NFULL = NCH / FULL_CH;
 constexpr int FWD_THREADS = NEPI + 32;  // forward: + warp 8 (MMA issuer, TMEM owner); chunks arrive by multicast, no producer
 constexpr uint32_t SPIN = 1u << 22;  // bounded waits: a lost signal ends the kernel with an error code, not a hung GPU
 
@@ -129,39 +127,52 @@ __device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo, uint32_t s
 }
 
 // ------------------------------------------------------------------------------------------------------ forward
-// One thread-block CLUSTER of 16 CTAs = one group.  State exchange per step, with no flags and no polling of global memory:
-//   * the epilogue threads of CTA c store the CTA's bf16 chunk of the next state to the exchange buffer (L2), and one thread
-//     then issues ONE multicast bulk copy of that chunk (cp.async.bulk ... .multicast::cluster) which lands at sA + c * FWD_CH
-//     in all 16 CTAs and completes on full[c] of each of them: one L2 read feeds 16 SMs, the arrival is the signal;
-//   * before overwriting the peers' state tiles the sender waits for `peers_done`, on which the MMA issuer of every CTA of
-//     the cluster arrives (tcgen05.commit ... .multicast::cluster) when its MMAs of the previous step have completed.
+// One thread-block CLUSTER of 16 CTAs runs a PAIR of groups (two 128-row tiles of the same GRU layer, which share the weight
+// slices) interleaved step by step: while the tensor cores of the cluster multiply one tile's state, the epilogue warps apply
+// the other tile's gates and put its next state on its way, so the exchange latency of one tile hides behind the other's MMAs
+// (only 7 sixteen-CTA clusters are co-resident on a B200: a pair per cluster also lets 4 clusters cover the 8 tiles of a
+// 512-row minibatch of two networks in one round).  State exchange, with no flags and no polling of global memory:
+//   * the epilogue threads of CTA c store the CTA's bf16 chunk of a tile's next state to the exchange buffer (L2), and one
+//     thread then issues ONE multicast bulk copy of that chunk (cp.async.bulk ... .multicast::cluster) which lands at
+//     sA + c * FWD_CH in all 16 CTAs and completes on `full` of each of them: one L2 read feeds 16 SMs, the arrival is the signal;
+//   * the state tile sA is shared by the two tiles in turn (micro-step m = t * NG + g): before overwriting it the sender waits
+//     for `peers_done`, on which the MMA issuer of every CTA of the cluster arrives (tcgen05.commit ... .multicast::cluster)
+//     when its MMAs of the previous micro-step have completed;
+//   * two accumulators in TMEM (columns 0.. and 128..), one per tile, each with its own ready / drained barrier.
+struct FwdEpi {   // per-tile epilogue state of one thread: (row, 16 hidden units)
+  float h[16];
+  int grow, mt;
+  bool live;
+};
+
 __global__ void __launch_bounds__(FWD_THREADS, 1) k_gru_fwd(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sB = smem;
   uint8_t* sA = smem + W_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + W_BYTES + FWD_A);  // [NFULL]: chunks FULL_CH q .. FULL_CH q + FULL_CH - 1
-  uint64_t* acc_full = full + NCH;
-  uint64_t* tmem_empty = full + NCH + 1;
-  uint64_t* peers_done = full + NCH + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(full + NCH + 3);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + W_BYTES + FWD_A);  // all 16 chunks of a micro-step
+  uint64_t* acc_full = full + 1;      // [2]
+  uint64_t* tmem_empty = full + 3;    // [2]
+  uint64_t* peers_done = full + 5;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(full + 6);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   float* s_bias = reinterpret_cast<float*>(smem + W_BYTES + FWD_A + 256);  // b_i slice [3][U], b_hn slice [U]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = (int)cluster_ctarank(), slot = (int)cluster_id_x(), n_slots = (int)cluster_count_x();
-  const int n_groups = p.n_problems * p.n_mt, T = p.T, B = p.B;
+  const int T = p.T, B = p.B;
+  const int pairs_per_problem = (p.n_mt + 1) / 2, n_pairs = p.n_problems * pairs_per_problem;
   const size_t TB = (size_t)T * B;
   constexpr uint16_t ALL = (uint16_t)((1u << NCH) - 1);
+  constexpr uint32_t ACC_STRIDE = 128;  // TMEM columns between the two tiles' accumulators
 
   if (tid == 0) {
-    for (int i = 0; i < NFULL; i++) mbar_init(&full[i], 1);
-    mbar_init(acc_full, 1);
-    mbar_init(tmem_empty, NEPI);
+    mbar_init(full, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&tmem_empty[i], NEPI); }
     mbar_init(peers_done, NCH);
     *s_abort = 0;
     mbar_fence_init();
-    for (int i = 0; i < NFULL; i++) mbar_arrive_expect_tx(&full[i], FULL_CH * FWD_CH);  // phase 0 armed: FULL_CH chunks per phase
+    mbar_arrive_expect_tx(full, NCH * FWD_CH);  // phase 0 armed: every micro-step takes the 16 chunks of one state tile
   }
-  if (warp == 8) tmem_alloc(s_tmem, 128);
+  if (warp == 8) tmem_alloc(s_tmem, 256);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peers' barriers exist before anything is sent to them
@@ -170,9 +181,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_gru_fwd(const FwdParams p) {
   constexpr uint32_t IDESC = idesc_bf16(MT, 3 * U);
 
   int loaded = -1;
-  uint32_t base = 0;  // steps this CTA has run so far (mbarrier phase bookkeeping, identical in every role and every CTA)
-  for (int g = slot; g < n_groups; g += n_slots, base += T) {
-    const int pi = g / p.n_mt, mt = g % p.n_mt;
+  // phase bookkeeping, identical in every role and every CTA of the cluster: micro-steps run so far (full, peers_done) and steps
+  // run so far on each accumulator (acc_full[g], tmem_empty[g])
+  uint32_t mu_base = 0, st_base[2] = {0, 0};
+  for (int pr = slot; pr < n_pairs; pr += n_slots) {
+    const int pi = pr / pairs_per_problem, mt0 = 2 * (pr % pairs_per_problem);
+    const int NG = (mt0 + 1 < p.n_mt) ? 2 : 1;
     const FwdProblem& q = p.pr[pi];
     if (pi != loaded) {
       __syncthreads();
@@ -191,41 +205,47 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_gru_fwd(const FwdParams p) {
     if (warp < 8) {
       // ------------------------------------------------------------------ epilogue: gates, state, outputs
       const int row = (warp & 3) * 32 + lane, half = warp >> 2, j0 = half * 16;
-      const int grow = mt * MT + row;
-      const bool live = grow < B;
       const size_t ucol = (size_t)c * U + j0;
-      float h[16];
+      FwdEpi e[2];
 #pragma unroll
-      for (int i = 0; i < 16; i++) h[i] = 0.0f;
-      if (live && q.h0) {
+      for (int g = 0; g < 2; g++) {
+        e[g].mt = mt0 + g;
+        e[g].grow = e[g].mt * MT + row;
+        e[g].live = g < NG && e[g].grow < B;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float4 v = *reinterpret_cast<const float4*>(q.h0 + (size_t)grow * H + ucol + 4 * i);
-          h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+        for (int i = 0; i < 16; i++) e[g].h[i] = 0.0f;
+        if (e[g].live && q.h0) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float4 v = *reinterpret_cast<const float4*>(q.h0 + (size_t)e[g].grow * H + ucol + 4 * i);
+            e[g].h[4 * i] = v.x; e[g].h[4 * i + 1] = v.y; e[g].h[4 * i + 2] = v.z; e[g].h[4 * i + 3] = v.w;
+          }
         }
       }
-      // state s (the state step s starts from) goes out first; the step's bulky outputs (y, hst, saved) are stored afterwards
+      // state s of tile g (what step s starts from) goes out first; the step's bulky outputs are stored afterwards
       uint4 v0, v1;
-      auto publish = [&](int s) {
-        v0 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-        v1 = make_uint4(pack_bf16(h[8], h[9]), pack_bf16(h[10], h[11]), pack_bf16(h[12], h[13]), pack_bf16(h[14], h[15]));
-        bf16* dst = q.xchg + (((size_t)s * p.n_mt + mt) * NCH + c) * (FWD_CH / 2);
+      auto publish = [&](FwdEpi& st, int g, int s) {
+        v0 = make_uint4(pack_bf16(st.h[0], st.h[1]), pack_bf16(st.h[2], st.h[3]), pack_bf16(st.h[4], st.h[5]), pack_bf16(st.h[6], st.h[7]));
+        v1 = make_uint4(pack_bf16(st.h[8], st.h[9]), pack_bf16(st.h[10], st.h[11]), pack_bf16(st.h[12], st.h[13]), pack_bf16(st.h[14], st.h[15]));
+        bf16* dst = q.xchg + (((size_t)s * p.n_mt + st.mt) * NCH + c) * (FWD_CH / 2);
         *reinterpret_cast<uint4*>(dst + ((2 * half) * MT + row) * 8) = v0;
         *reinterpret_cast<uint4*>(dst + ((2 * half + 1) * MT + row) * 8) = v1;
         __syncwarp();
         named_bar_sync(1, NEPI);
         if (tid == 0 && !(p.lbo_sbo_swap & 2)) {
-          // every CTA of the cluster has finished the MMAs that read the previous state: the tiles may be overwritten
-          if (s > 0) TRACE(s - 1, 3);
-          if (base + s > 0) wait_bar(peers_done, (base + s - 1) & 1, s_abort, p.status, B2S_GRU_ERR_PEERS);
-          if (s > 0) TRACE(s - 1, 7);
           fence_proxy_async();  // the chunk was written through the generic proxy; the bulk copy reads it through the async proxy
-          bulk_g2s_multicast(sA + c * FWD_CH, dst, FWD_CH, &full[c / FULL_CH], ALL);
+          // the micro-step that consumes this state is mc: every CTA of the cluster must have finished the MMAs of micro-step
+          // mc - 1 (they read the state tile this copy overwrites)
+          const uint32_t mc = mu_base + (uint32_t)(s * NG + g);
+          if (g == 0 && s > 0) TRACE(s - 1, 3);
+          if (mc > 0) wait_bar(peers_done, (mc - 1) & 1, s_abort, p.status, B2S_GRU_ERR_PEERS);
+          if (g == 0 && s > 0) TRACE(s - 1, 7);
+          bulk_g2s_multicast(sA + c * FWD_CH, dst, FWD_CH, full, ALL);
         }
       };
-      auto store_cols = [&](bf16* base_ptr, int s, const uint4& a, const uint4& b) {  // feature-major [H][T B], lanes = batch rows
-        if (live) {
-          uint16_t* o = reinterpret_cast<uint16_t*>(base_ptr) + (size_t)ucol * TB + (size_t)s * B + grow;
+      auto store_cols = [&](const FwdEpi& st, bf16* base_ptr, int s, const uint4& a, const uint4& b) {  // feature-major [H][T B]
+        if (st.live) {
+          uint16_t* o = reinterpret_cast<uint16_t*>(base_ptr) + (size_t)ucol * TB + (size_t)s * B + st.grow;
           const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
           for (int i = 0; i < 8; i++) {
@@ -234,114 +254,128 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) k_gru_fwd(const FwdParams p) {
           }
         }
       };
-      auto store_hst = [&](int s) { if (!(p.lbo_sbo_swap & 4)) store_cols(q.hst, s, v0, v1); };
-      publish(0);
-      store_hst(0);
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        if (g < NG) {
+          publish(e[g], g, 0);
+          if (!(p.lbo_sbo_swap & (4 | 16))) store_cols(e[g], q.hst, 0, v0, v1);
+        }
+      }
       for (int t = 0; t < T; t++) {
-        float gr[16], gz[16], gn[16];
-        float kp = 1.0f;
-        if (live && !(p.lbo_sbo_swap & 8)) {
-          // feature-major gi [3H][T B]: consecutive lanes (batch rows) read consecutive addresses
-          const float* gp = q.gi + (size_t)ucol * TB + (size_t)t * B + grow;
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+          if (g >= NG) continue;
+          FwdEpi& st = e[g];
+          float gr[16], gz[16], gn[16];
+          float kp = 1.0f;
+          if (st.live && !(p.lbo_sbo_swap & 8)) {
+            // feature-major gi [3H][T B]: consecutive lanes (batch rows) read consecutive addresses
+            const float* gp = q.gi + (size_t)ucol * TB + (size_t)t * B + st.grow;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              gr[i] = ld_stream_f32(gp + (size_t)i * TB);
+              gz[i] = ld_stream_f32(gp + (size_t)(H + i) * TB);
+              gn[i] = ld_stream_f32(gp + (size_t)(2 * H + i) * TB);
+            }
+            if (p.keep) kp = p.keep[(size_t)t * B + st.grow];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) gr[i] = gz[i] = gn[i] = 0.0f;
+          }
+          if (lane == 0) wait_bar(&acc_full[g], (st_base[g] + t) & 1, s_abort, p.status, B2S_GRU_ERR_ACC);  // one poller per warp
+          if (tid == 0 && g == 0) TRACE(t, 0);
+          __syncwarp();
+          tc_fence_after();
+          const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * ACC_STRIDE + j0);
+          float a[16];
+          tmem_ld16(ta, a);
+#pragma unroll
+          for (int i = 0; i < 16; i++) gr[i] = sigmoid_fast(gr[i] + a[i] + s_bias[j0 + i]);
+          tmem_ld16(ta + U, a);
+#pragma unroll
+          for (int i = 0; i < 16; i++) gz[i] = sigmoid_fast(gz[i] + a[i] + s_bias[U + j0 + i]);
+          tmem_ld16(ta + 2 * U, a);
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[g]);
 #pragma unroll
           for (int i = 0; i < 16; i++) {
-            gr[i] = ld_stream_f32(gp + (size_t)i * TB);
-            gz[i] = ld_stream_f32(gp + (size_t)(H + i) * TB);
-            gn[i] = ld_stream_f32(gp + (size_t)(2 * H + i) * TB);
+            a[i] += s_bias[3 * U + j0 + i];                                   // hn = gh_n + b_hn
+            gn[i] = tanh_fast(gn[i] + s_bias[2 * U + j0 + i] + gr[i] * a[i]);  // n
           }
-          if (p.keep) kp = p.keep[(size_t)t * B + grow];
-        } else {
+          float hm[16];   // h - n (saved for the backward pass)
 #pragma unroll
-          for (int i = 0; i < 16; i++) gr[i] = gz[i] = gn[i] = 0.0f;
-        }
-        if (lane == 0) wait_bar(acc_full, (base + t) & 1, s_abort, p.status, B2S_GRU_ERR_ACC);  // one poller per warp
-        if (tid == 0) TRACE(t, 0);
-        __syncwarp();
-        tc_fence_after();
-        const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)j0;
-        float a[16];
-        tmem_ld16(ta, a);
+          for (int i = 0; i < 16; i++) { hm[i] = st.h[i] - gn[i]; st.h[i] = fmaf(gz[i], hm[i], gn[i]); }  // h' = n + z (h - n)
+          const uint4 y0 = make_uint4(pack_bf16(st.h[0], st.h[1]), pack_bf16(st.h[2], st.h[3]), pack_bf16(st.h[4], st.h[5]), pack_bf16(st.h[6], st.h[7]));
+          const uint4 y1 = make_uint4(pack_bf16(st.h[8], st.h[9]), pack_bf16(st.h[10], st.h[11]), pack_bf16(st.h[12], st.h[13]), pack_bf16(st.h[14], st.h[15]));
 #pragma unroll
-        for (int i = 0; i < 16; i++) gr[i] = sigmoid_fast(gr[i] + a[i] + s_bias[j0 + i]);
-        tmem_ld16(ta + U, a);
+          for (int i = 0; i < 16; i++) st.h[i] *= kp;  // the carry restarts from zero after a terminal step
+          if (tid == 0 && g == 0) TRACE(t, 1);
+          if (t + 1 < T) {
+            publish(st, g, t + 1);
+            if (tid == 0 && g == 0) TRACE(t, 2);
+            if (!(p.lbo_sbo_swap & (4 | 16))) store_cols(st, q.hst, t + 1, v0, v1);
+          }
+          if (!(p.lbo_sbo_swap & (4 | 64))) store_cols(st, q.y, t, y0, y1);
+          if (q.saved && !(p.lbo_sbo_swap & (4 | 32))) {
+            float* sv = q.saved + (((size_t)t * p.n_mt + st.mt) * NCH + c) * SAVED_BLOCK;
 #pragma unroll
-        for (int i = 0; i < 16; i++) gz[i] = sigmoid_fast(gz[i] + a[i] + s_bias[U + j0 + i]);
-        tmem_ld16(ta + 2 * U, a);
-        tc_fence_before();
-        mbar_arrive(tmem_empty);
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          a[i] += s_bias[3 * U + j0 + i];                                   // hn = gh_n + b_hn
-          gn[i] = tanh_fast(gn[i] + s_bias[2 * U + j0 + i] + gr[i] * a[i]);  // n
-        }
-        float hm[16];   // h - n (saved for the backward pass)
-#pragma unroll
-        for (int i = 0; i < 16; i++) { hm[i] = h[i] - gn[i]; h[i] = fmaf(gz[i], hm[i], gn[i]); }  // h' = n + z (h - n)
-        const uint4 y0 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-        const uint4 y1 = make_uint4(pack_bf16(h[8], h[9]), pack_bf16(h[10], h[11]), pack_bf16(h[12], h[13]), pack_bf16(h[14], h[15]));
-#pragma unroll
-        for (int i = 0; i < 16; i++) h[i] *= kp;  // the carry restarts from zero after a terminal step
-        if (tid == 0) TRACE(t, 1);
-        if (t + 1 < T) {
-          publish(t + 1);
-          if (tid == 0) TRACE(t, 2);
-          store_hst(t + 1);
-        }
-        if (!(p.lbo_sbo_swap & 4)) store_cols(q.y, t, y0, y1);
-        if (q.saved && !(p.lbo_sbo_swap & 4)) {
-          float* sv = q.saved + (((size_t)t * p.n_mt + mt) * NCH + c) * SAVED_BLOCK;
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int o = ((half * 4 + i) * MT + row) * 4;
-            __stcs(reinterpret_cast<float4*>(sv + o), make_float4(gr[4 * i], gr[4 * i + 1], gr[4 * i + 2], gr[4 * i + 3]));
-            __stcs(reinterpret_cast<float4*>(sv + MT * U + o), make_float4(gz[4 * i], gz[4 * i + 1], gz[4 * i + 2], gz[4 * i + 3]));
-            __stcs(reinterpret_cast<float4*>(sv + 2 * MT * U + o), make_float4(gn[4 * i], gn[4 * i + 1], gn[4 * i + 2], gn[4 * i + 3]));
-            __stcs(reinterpret_cast<float4*>(sv + 3 * MT * U + o), make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]));
-            __stcs(reinterpret_cast<float4*>(sv + 4 * MT * U + o), make_float4(hm[4 * i], hm[4 * i + 1], hm[4 * i + 2], hm[4 * i + 3]));
+            for (int i = 0; i < 4; i++) {
+              const int o = ((half * 4 + i) * MT + row) * 4;
+              __stcs(reinterpret_cast<float4*>(sv + o), make_float4(gr[4 * i], gr[4 * i + 1], gr[4 * i + 2], gr[4 * i + 3]));
+              __stcs(reinterpret_cast<float4*>(sv + MT * U + o), make_float4(gz[4 * i], gz[4 * i + 1], gz[4 * i + 2], gz[4 * i + 3]));
+              __stcs(reinterpret_cast<float4*>(sv + 2 * MT * U + o), make_float4(gn[4 * i], gn[4 * i + 1], gn[4 * i + 2], gn[4 * i + 3]));
+              __stcs(reinterpret_cast<float4*>(sv + 3 * MT * U + o), make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]));
+              __stcs(reinterpret_cast<float4*>(sv + 4 * MT * U + o), make_float4(hm[4 * i], hm[4 * i + 1], hm[4 * i + 2], hm[4 * i + 3]));
+            }
           }
         }
       }
-      if (live && q.h_last) {
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-          *reinterpret_cast<float4*>(q.h_last + (size_t)grow * H + ucol + 4 * i) = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      for (int g = 0; g < 2; g++) {
+        if (e[g].live && q.h_last) {
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            *reinterpret_cast<float4*>(q.h_last + (size_t)e[g].grow * H + ucol + 4 * i) =
+                make_float4(e[g].h[4 * i], e[g].h[4 * i + 1], e[g].h[4 * i + 2], e[g].h[4 * i + 3]);
+        }
       }
     } else if (lane == 0) {
       // ------------------------------------------------------------------ MMA issuer: gh_t[128 x 96] = h_{t-1}[128 x 512] W^T
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
       for (int t = 0; t < T; t++) {
-        const uint32_t gs = base + t;
-        if (gs > 0) wait_bar(tmem_empty, (gs - 1) & 1, s_abort, p.status, B2S_GRU_ERR_TMEM);
-        tc_fence_after();
-        for (int ch = 0; ch < NCH; ch++) {
-          if (ch % FULL_CH == 0 && !(p.lbo_sbo_swap & 2)) {
-            TRACE_CH0(t, ch);
-            wait_bar(&full[ch / FULL_CH], gs & 1, s_abort, p.status, B2S_GRU_ERR_FULL);
-            mbar_arrive_expect_tx(&full[ch / FULL_CH], FULL_CH * FWD_CH);  // arms the next phase (the next step's chunks)
-            if (ch == 0) TRACE(t, 4);
-            if (ch == NCH - FULL_CH) TRACE(t, 5);
-            TRACE_CH(t, ch);
-            tc_fence_after();
+        for (int g = 0; g < NG; g++) {
+          const uint32_t gm = mu_base + (uint32_t)(t * NG + g), gs = st_base[g] + t;
+          if (gs > 0) wait_bar(&tmem_empty[g], (gs - 1) & 1, s_abort, p.status, B2S_GRU_ERR_TMEM);
+          if (!(p.lbo_sbo_swap & 2)) {
+            if (g == 0) TRACE_CH0(t, 0);
+            wait_bar(full, gm & 1, s_abort, p.status, B2S_GRU_ERR_FULL);
+            mbar_arrive_expect_tx(full, NCH * FWD_CH);  // arms the next phase (the next micro-step's chunks)
+            if (g == 0) { TRACE(t, 4); TRACE(t, 5); TRACE_CH(t, 0); }
           }
+          tc_fence_after();
+          for (int ch = 0; ch < NCH; ch++) {
 #pragma unroll
-          for (int k2 = 0; k2 < U / 16; k2++) {
-            const uint64_t da = desc(a0 + ch * FWD_CH + k2 * 2 * (MT * 16), MT * 16, 128, p.lbo_sbo_swap);
-            const uint64_t db = desc(b0 + (ch * (U / 8) + k2 * 2) * (3 * U * 16), 3 * U * 16, 128, p.lbo_sbo_swap);
-            mma_bf16_ss(tmem, da, db, IDESC, (ch | k2) != 0);
+            for (int k2 = 0; k2 < U / 16; k2++) {
+              const uint64_t da = desc(a0 + ch * FWD_CH + k2 * 2 * (MT * 16), MT * 16, 128, p.lbo_sbo_swap);
+              const uint64_t db = desc(b0 + (ch * (U / 8) + k2 * 2) * (3 * U * 16), 3 * U * 16, 128, p.lbo_sbo_swap);
+              mma_bf16_ss(tmem + g * ACC_STRIDE, da, db, IDESC, (ch | k2) != 0);
+            }
           }
-          if (ch % FULL_CH != 0) TRACE_CH0(t, ch);   // after this chunk's MMAs were issued
+          mma_commit(&acc_full[g]);
+          if (!(p.lbo_sbo_swap & 2)) mma_commit_multicast(peers_done, ALL);
+          if (g == 0) TRACE(t, 6);
         }
-        mma_commit(acc_full);
-        if (!(p.lbo_sbo_swap & 2)) mma_commit_multicast(peers_done, ALL);
-        TRACE(t, 6);
       }
     }
     __syncwarp();  // roles reconverge before the next CTA-wide barrier
+    mu_base += (uint32_t)(NG * T);
+    st_base[0] += T;
+    if (NG == 2) st_base[1] += T;
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
-  if (warp == 8) tmem_dealloc(tmem, 128);
+  if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
 // ----------------------------------------------------------------------------------------------------- backward
@@ -629,7 +663,8 @@ extern "C" int b200sim_gru_forward(void* stream, int n_problems, const b200sim_g
   FwdParams prm{};
   prm.n_problems = n_problems; prm.T = n_steps; prm.B = batch; prm.n_mt = (batch + MT - 1) / MT; prm.keep = keep;
   prm.lbo_sbo_swap = (getenv("B2S_GRU_SWAP") ? 1 : 0) | (getenv("B2S_GRU_NOXCHG") ? 2 : 0) | (getenv("B2S_GRU_NOSTORE") ? 4 : 0) |
-                     (getenv("B2S_GRU_NOLOAD") ? 8 : 0);  // debug / timing experiments only
+                     (getenv("B2S_GRU_NOLOAD") ? 8 : 0) | (getenv("B2S_GRU_NOHST") ? 16 : 0) | (getenv("B2S_GRU_NOSAVED") ? 32 : 0) |
+                     (getenv("B2S_GRU_NOY") ? 64 : 0);  // debug / timing experiments only
   uint8_t* ws = (uint8_t*)workspace;
   prm.status = (int*)ws;
   const size_t flag_bytes = align256((size_t)prm.n_mt * NCH * sizeof(int));
@@ -647,7 +682,7 @@ extern "C" int b200sim_gru_forward(void* stream, int n_problems, const b200sim_g
   }
   cudaError_t e = cudaMemsetAsync(ws, 0, 256 + (size_t)n_problems * flag_bytes, (cudaStream_t)stream);
   if (e != cudaSuccess) return gfail(B2S_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
-  return launch_fwd(prm, n_problems * prm.n_mt, stream);
+  return launch_fwd(prm, n_problems * ((prm.n_mt + 1) / 2), stream);  // work items: pairs of row tiles
 }
 
 extern "C" int b200sim_gru_backward(void* stream, int n_problems, const b200sim_gru_bwd* pr, int n_steps, int batch, const float* keep,
