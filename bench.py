@@ -362,9 +362,7 @@ def main() -> None:
 
     def hot_path(acts: torch.Tensor) -> torch.Tensor:
         eng.rollout(acts, rec)
-        total, _ = eng.rewards(rec, t)
-        dones, succ = eng.flags(rec, t)
-        adv, tgt, ret = eng.gae(values, total, dones, succ, GAMMA, LAM)
+        adv = eng.score(rec, t, values=values, gamma=GAMMA, lam=LAM)["advantages"]  # rewards + flags + GAE: one launch
         collective()
         return adv  # (the engine hands this rollout's final pre-step block to the next one itself)
 
@@ -406,9 +404,7 @@ def main() -> None:
         kev[i][0].record(stream)
         eng.rollout(actions, rec)
         kev[i][1].record(stream)
-        total, _ = eng.rewards(rec, t)
-        dones, succ = eng.flags(rec, t)
-        eng.gae(values, total, dones, succ, GAMMA, LAM)
+        eng.score(rec, t, values=values, gamma=GAMMA, lam=LAM)
         collective()
         sev[i][1].record(stream)
     ev[1].record(stream)
@@ -427,12 +423,10 @@ def main() -> None:
     def e2e_step() -> None:
         dev_actions.copy_(host_actions, non_blocking=True)
         eng.rollout(dev_actions, rec)
-        total, _ = eng.rewards(rec, t)
-        dones, succ = eng.flags(rec, t)
-        adv, _, _ = eng.gae(values, total, dones, succ, GAMMA, LAM)
+        scored = eng.score(rec, t, values=values, gamma=GAMMA, lam=LAM)
         collective()
-        host_adv.copy_(adv, non_blocking=True)
-        host_total.copy_(total, non_blocking=True)
+        host_adv.copy_(scored["advantages"], non_blocking=True)
+        host_total.copy_(scored["total"], non_blocking=True)
         torch.cuda.synchronize(device)  # the caller reads the result
 
     e2e_step()

@@ -20,6 +20,7 @@
  *   b200sim_rollout     RLTask._single_unroll's scan over T of the above with given actions (rl.py:1604-1665)
  *   b200sim_rewards     get_rewards vmapped over envs (ksim/task/rl.py:189-245, 1663; ksim/rewards.py)
  *   b200sim_gae         compute_ppo_inputs (ksim/task/ppo.py:54-121)
+ *   b200sim_score       the three above fused: rewards + done / success flags + compute_ppo_inputs in one launch
  *   b200sim_ppo_loss    compute_ppo_loss + the mean over (B, T) of the summed terms, and that mean's gradient with respect to
  *                       the new policy's log-probs / values / entropy (ksim/task/ppo.py:149-246, 471-488; the backward
  *                       pass jax.grad derives from it at ppo.py:521-534)
@@ -77,6 +78,15 @@ int b200sim_rollout(const b200sim_model* model, void* stream, int n_envs, int n_
 /* rec[T][N][R]; levels[N]; carry[N][C] in/out; total[N][T]; comps[K][N][T]. */
 int b200sim_rewards(const b200sim_model* model, void* stream, int n_envs, int n_steps, const float* rec,
                     const float* levels, float* carry, float* total, float* comps);
+
+/* The scoring pass of a rollout in one launch: get_rewards (ksim/task/rl.py:189-245, 1663), the done / success flags of the
+ * records, and -- when `values` is given -- compute_ppo_inputs on them (ksim/task/ppo.py:54-121; what the three calls
+ * b200sim_rewards, b200sim_extract_flags, b200sim_gae produce).  rec[T][N][R]; levels[N]; carry[N][C] in/out; values[N][T] or
+ * NULL; total[N][T]; comps[K][N][T]; dones / successes [N][T] bytes (either may be NULL); adv / targets / returns [N][T]
+ * (required with values).  flags as for b200sim_gae. */
+int b200sim_score(const b200sim_model* model, void* stream, int n_envs, int n_steps, const float* rec, const float* levels,
+                  float* carry, const float* values, float gamma, float lam, int flags, float* total, float* comps,
+                  uint8_t* dones, uint8_t* successes, float* adv, float* targets, float* returns);
 
 /* all arrays [B][T]; flags: GAE_NORMALIZE_ADVANTAGES | GAE_MONTE_CARLO_RETURNS (include/b200sim_codes.h). */
 int b200sim_gae(void* stream, int batch, int n_steps, const float* values, const float* rewards,

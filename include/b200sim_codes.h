@@ -87,6 +87,9 @@
                                 postprocess_trajectory hook between rollout and rewards, never by the kernels */
 #define TI_AUX_SIZE 66
 #define TI_S_XFRC 64         /* 6 floats wrench + body id handled via event params; -1 if unused */
+#define TI_SCORE_NSEG 67     /* scoring read-set: the record columns the rewards read, as TI_SCORE_NSEG 16-byte aligned segments */
+#define TI_SCORE_SEG 68      /* offset in ti of the segments: (first column, columns) pairs, ascending, disjoint */
+#define TI_SCORE_WIDTH 69    /* floats per staged row (sum of the segments' columns, padded so that width / 4 is odd) */
 #define TI_HEADER_SIZE 72
 
 /* ---- plugin table entry: 8 ints each ---- */

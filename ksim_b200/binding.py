@@ -16,7 +16,7 @@ _LIB: ctypes.CDLL | None = None
 # every symbol include/b200sim.h declares (tests assert the library exports exactly these)
 EXPORTS = (
     "b200sim_model_create", "b200sim_model_destroy", "b200sim_model_info", "b200sim_model_set_option", "b200sim_last_error", "b200sim_init_envs",
-    "b200sim_step_ctrl", "b200sim_rollout", "b200sim_rewards", "b200sim_gae", "b200sim_extract_flags", "b200sim_dataset_pack",
+    "b200sim_step_ctrl", "b200sim_rollout", "b200sim_rewards", "b200sim_gae", "b200sim_extract_flags", "b200sim_score", "b200sim_dataset_pack",
     "b200sim_metrics", "b200sim_ppo_loss",
     "b200sim_gru_workspace_bytes", "b200sim_gru_saved_floats", "b200sim_gru_forward", "b200sim_gru_backward", "b200sim_gru_last_error",
     "b200sim_mixture_logprob", "b200sim_mixture_logprob_backward", "b200sim_mixture_sample", "b200sim_policy_last_error",
@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
         cdll.b200sim_rollout.restype = ci
         cdll.b200sim_rewards.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
         cdll.b200sim_rewards.restype = ci
+        cdll.b200sim_score.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, cf, cf, ci, vp, vp, vp, vp, vp, vp, vp]
+        cdll.b200sim_score.restype = ci
         cdll.b200sim_gae.argtypes = [vp, ci, ci, vp, vp, vp, vp, cf, cf, ci, vp, vp, vp]
         cdll.b200sim_gae.restype = ci
         cdll.b200sim_extract_flags.argtypes = [vp, vp, ci, ci, vp, vp, vp]

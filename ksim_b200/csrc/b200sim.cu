@@ -11,6 +11,7 @@
 #include "b2s_engine.cuh"
 #include "b2s_rewards.cuh"
 #include "b2s_host.cuh"
+#include "b2s_tc.cuh"
 
 using namespace b2s;
 
@@ -90,16 +91,112 @@ __global__ void __launch_bounds__(launch_threads<D>()) k_rollout(const Mdl mp, i
 #endif
 }
 
-__global__ void __launch_bounds__(256) k_rewards(const Mdl m, int n_envs, int n_steps, const float* __restrict__ rec,
-                                                 const float* __restrict__ levels, float* __restrict__ carry,
-                                                 float* __restrict__ total, float* __restrict__ comps) {
-  const int lane = threadIdx.x & 31;
-  const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (env >= n_envs) return;
+// Scoring pass of a rollout in ONE launch (north_star: "fuse reward/termination evaluation and the reverse-time GAE scan"):
+// get_rewards (rl.py:189-245), the done / success flags, and -- when values are given -- compute_ppo_inputs (ppo.py:54-121).
+// One CTA per environment:
+//   * the env's T records are rows of rec[T][N][R], N R floats apart.  The columns the rewards read (the program's scoring
+//     read-set: TI_SCORE_SEG) are STAGED in shared memory by bulk async copies (cp.async.bulk, one per row and segment, all in
+//     flight at once, completing on one mbarrier): HBM sees full-segment sequential reads instead of one 4-byte field per
+//     32-byte sector per lane, and the stateful rewards' serial scans over time (one lane walking T steps) run out of shared
+//     memory instead of paying a DRAM round trip per dependent load -- that serial chain was what the round-1 kernel's time was;
+//   * the env's rewards are spread over the CTA's warps (reward r on warp r mod SCORE_WARPS; carries of different rewards are
+//     disjoint); after a CTA barrier the threads turn to time steps: total = ordered sum of the components, flags and the
+//     values row, coalesced along [N][T]; one thread runs the reverse-time recurrence out of shared memory (T dependent steps in
+//     the oracle's order of operations) and the CTA writes advantages / targets / returns coalesced.
+// Unstaged (staged == 0: the default, see b200sim_score; also when T staged rows do not fit the SM) the same code reads the
+// records from global memory through L1.
+constexpr int SCORE_WARPS_MAX = 8;  // CTA size is a launch parameter (SCORE_WARPS_MAX warps at most): fewer warps per CTA = more envs per SM
+__global__ void __launch_bounds__(SCORE_WARPS_MAX * 32) k_score(const Mdl m, int n_envs, int n_steps, int staged, const float* rec,
+                                                            const float* __restrict__ levels, float* carry, const float* __restrict__ values,
+                                                            float gamma, float lam, int flags, float* total, float* comps,
+                                                            uint8_t* __restrict__ dones, uint8_t* __restrict__ successes,
+                                                            float* __restrict__ adv, float* __restrict__ targets, float* __restrict__ returns) {
+  extern __shared__ __align__(16) unsigned char sc_raw[];  // [mbarrier][staged rows T x width][6 T floats for the scan][carries][column table R]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NT = blockDim.x, SCORE_WARPS = NT >> 5;
+  const int env = blockIdx.x;
   const int* ti = m.ti;
-  const size_t R = ti[TI_REC_SIZE], C = ti[TI_REW_CARRY_SIZE];
-  env_rewards(m, rec + env * R, (size_t)n_envs * R, n_steps, levels[env], carry + env * C, total + (size_t)env * n_steps,
-              comps + (size_t)env * n_steps, (size_t)n_envs * n_steps, lane);
+  const int R = ti[TI_REC_SIZE];
+  const size_t C = ti[TI_REW_CARRY_SIZE];
+  const int T = n_steps;
+  const size_t cstride = (size_t)n_envs * T, row = (size_t)env * T, tstride = (size_t)n_envs * R;
+  const float* erec = rec + (size_t)env * R;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sc_raw);
+  float* srec = reinterpret_cast<float*>(sc_raw + 16);
+  const int width = staged ? ti[TI_SCORE_WIDTH] : 0;
+  float* s_scan = srec + (size_t)T * width;
+  float* s_carry = s_scan + (values ? 6 * T : 0);  // the rewards' carries: their scans are read-modify-write chains over T steps
+  unsigned short* s_col = reinterpret_cast<unsigned short*>(s_carry + ((C + 3) & ~(size_t)3));
+  for (int k = tid; k < (int)C; k += NT) s_carry[k] = carry[env * C + k];
+  RecStage stage = {srec, s_col, width};
+  if (staged) {
+    const int nseg = ti[TI_SCORE_NSEG];
+    const int* seg = ti + ti[TI_SCORE_SEG];
+    if (warp == 0) {
+      if (lane == 0) {
+        b2s_tc::mbar_init(bar, 1);
+        b2s_tc::mbar_fence_init();
+        int cols = 0;
+        for (int g = 0; g < nseg; g++) cols += seg[2 * g + 1];
+        b2s_tc::mbar_arrive_expect_tx(bar, (uint32_t)((size_t)T * cols * sizeof(float)));
+      }
+      __syncwarp();
+      for (int idx = lane; idx < T * nseg; idx += 32) {
+        const int t = idx / nseg, g = idx - t * nseg;
+        int dst = 0;
+        for (int k = 0; k < g; k++) dst += seg[2 * k + 1];
+        b2s_tc::bulk_g2s(srec + (size_t)t * width + dst, erec + (size_t)t * tstride + seg[2 * g], (uint32_t)(seg[2 * g + 1] * sizeof(float)), bar);
+      }
+    }
+    for (int c = tid; c < R; c += NT) {  // column table, built while the copies fly
+      unsigned short pos = 0xFFFFu;
+      int dst = 0;
+      for (int g = 0; g < nseg; g++) {
+        if (c >= seg[2 * g] && c < seg[2 * g] + seg[2 * g + 1]) pos = (unsigned short)(dst + c - seg[2 * g]);
+        dst += seg[2 * g + 1];
+      }
+      s_col[c] = pos;
+    }
+    __syncthreads();  // the barrier is initialised and the table complete for every thread
+    if (!b2s_tc::mbar_wait(bar, 0, 1u << 26)) __trap();  // a lost bulk copy ends the launch with an error, not a hang
+  }
+  const RecStage* stg = staged ? &stage : nullptr;
+  __syncthreads();
+  env_rewards(m, erec, tstride, T, levels[env], s_carry, nullptr, comps + row, cstride, lane, warp, SCORE_WARPS, false, stg);
+  __syncthreads();
+  for (int k = tid; k < (int)C; k += NT) carry[env * C + k] = s_carry[k];
+  float* s_rew = s_scan, *s_val = s_scan + T, *s_mask = s_scan + 2 * T, *s_trunc = s_scan + 3 * T;
+  float* s_adv = s_scan + 4 * T, *s_ret = s_scan + 5 * T;
+  const int DN = ti[TI_R_DONE], SC = ti[TI_R_SUCCESS];
+  for (int s = tid; s < T; s += NT) {
+    const float tot = env_total(m, comps + row, cstride, s);
+    total[row + s] = tot;
+    const bool d = rec_at(erec, tstride, stg, s, DN) != 0.0f, su = rec_at(erec, tstride, stg, s, SC) != 0.0f;
+    if (dones) dones[row + s] = d;
+    if (successes) successes[row + s] = su;
+    if (values) { s_rew[s] = tot; s_val[s] = values[row + s]; s_mask[s] = d ? 0.0f : 1.0f; s_trunc[s] = su ? 1.0f : 0.0f; }
+  }
+  if (!values) return;
+  __syncthreads();
+  if (tid == 0) {
+    float ret_next = 0.0f, adv_next = 0.0f, v_next = s_val[T - 1];
+    for (int s = T - 1; s >= 0; s--) {
+      const float v = s_val[s], mask = s_mask[s];
+      const float br = __fadd_rn(__fmul_rn(1.0f - gamma, s_rew[s]), __fmul_rn(__fmul_rn(gamma, v), s_trunc[s]));
+      const float delta = __fsub_rn(__fadd_rn(br, __fmul_rn(__fmul_rn(gamma, v_next), mask)), v);
+      const float ret = __fadd_rn(br, __fmul_rn(__fmul_rn(gamma, mask), ret_next));
+      const float a = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gamma, lam), mask), adv_next));
+      s_ret[s] = ret; s_adv[s] = a;
+      ret_next = ret; adv_next = a; v_next = v;
+    }
+  }
+  __syncthreads();
+  for (int s = tid; s < T; s += NT) {
+    const float a = s_adv[s], ret = s_ret[s];
+    returns[row + s] = ret;
+    adv[row + s] = a;
+    targets[row + s] = (flags & GAE_MONTE_CARLO_RETURNS) ? ret : __fadd_rn(a, s_val[s]);
+  }
 }
 
 __global__ void k_extract_flags(int n_envs, int n_steps, size_t R, int off_done, int off_success,
@@ -112,27 +209,46 @@ __global__ void k_extract_flags(int n_envs, int n_steps, size_t R, int off_done,
   successes[idx] = r[off_success] != 0.0f;
 }
 
-// compute_ppo_inputs (ksim/task/ppo.py:54-121): reverse-time scan, one thread per trajectory row.
-__global__ void k_gae(int batch, int n_steps, const float* __restrict__ values, const float* __restrict__ rewards,
+// compute_ppo_inputs (ksim/task/ppo.py:54-121) on its own (the PPO update recomputes it from the new values, ppo.py:597-601):
+// one warp per trajectory row.  The row's inputs are read coalesced ([B][T]: lanes along time) into shared memory, lane 0 runs
+// the reverse-time recurrence there (T dependent steps in the oracle's order of operations), the warp writes the three outputs
+// coalesced.  (The round-1 kernel ran one THREAD per row: every access had stride T.)
+constexpr int GAE_WARPS = 4;
+__global__ void __launch_bounds__(GAE_WARPS * 32) k_gae(int batch, int n_steps, const float* __restrict__ values, const float* __restrict__ rewards,
                       const uint8_t* __restrict__ dones, const uint8_t* __restrict__ successes, float gamma, float lam,
                       int flags, float* __restrict__ adv, float* __restrict__ targets, float* __restrict__ returns) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ float gae_smem[];  // per warp [5][T]: br, value, gamma * mask | advantage, return
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * GAE_WARPS + warp;
   if (b >= batch) return;
-  const size_t base = (size_t)b * n_steps;
-  float ret_next = 0.0f, adv_next = 0.0f;
-  float v_next = values[base + n_steps - 1];
-  for (int s = n_steps - 1; s >= 0; s--) {
+  const int T = n_steps;
+  float* s_br = gae_smem + (size_t)warp * 5 * T, *s_val = s_br + T, *s_gm = s_br + 2 * T, *s_adv = s_br + 3 * T, *s_ret = s_br + 4 * T;
+  const size_t base = (size_t)b * T;
+  for (int s = lane; s < T; s += 32) {
     const float v = values[base + s];
     const float trunc = successes[base + s] ? 1.0f : 0.0f;
-    const float mask = dones[base + s] ? 0.0f : 1.0f;
-    const float br = __fadd_rn(__fmul_rn(1.0f - gamma, rewards[base + s]), __fmul_rn(__fmul_rn(gamma, v), trunc));
-    const float delta = __fsub_rn(__fadd_rn(br, __fmul_rn(__fmul_rn(gamma, v_next), mask)), v);
-    const float ret = __fadd_rn(br, __fmul_rn(__fmul_rn(gamma, mask), ret_next));
-    const float a = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gamma, lam), mask), adv_next));
+    s_br[s] = __fadd_rn(__fmul_rn(1.0f - gamma, rewards[base + s]), __fmul_rn(__fmul_rn(gamma, v), trunc));
+    s_val[s] = v;
+    s_gm[s] = dones[base + s] ? 0.0f : 1.0f;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    float ret_next = 0.0f, adv_next = 0.0f, v_next = s_val[T - 1];
+    for (int s = T - 1; s >= 0; s--) {
+      const float v = s_val[s], mask = s_gm[s], br = s_br[s];
+      const float delta = __fsub_rn(__fadd_rn(br, __fmul_rn(__fmul_rn(gamma, v_next), mask)), v);
+      const float ret = __fadd_rn(br, __fmul_rn(__fmul_rn(gamma, mask), ret_next));
+      const float a = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gamma, lam), mask), adv_next));
+      s_ret[s] = ret; s_adv[s] = a;
+      ret_next = ret; adv_next = a; v_next = v;
+    }
+  }
+  __syncwarp();
+  for (int s = lane; s < T; s += 32) {
+    const float a = s_adv[s], ret = s_ret[s];
     returns[base + s] = ret;
     adv[base + s] = a;
-    targets[base + s] = (flags & GAE_MONTE_CARLO_RETURNS) ? ret : __fadd_rn(a, v);
-    ret_next = ret; adv_next = a; v_next = v;
+    targets[base + s] = (flags & GAE_MONTE_CARLO_RETURNS) ? ret : __fadd_rn(a, s_val[s]);
   }
 }
 
@@ -533,16 +649,50 @@ extern "C" int b200sim_rollout(const b200sim_model* mo, void* stream, int n_envs
   return launch_rollout(mo, stream, n_envs, n_steps, actions, rand, state, keys, rec, nullptr, nullptr);
 }
 
-extern "C" int b200sim_rewards(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* rec,
-                               const float* levels, float* carry, float* total, float* comps) {
+// dynamic shared memory of the scoring kernels grows with T: opt in above the 48 KB default, refuse beyond the SM
+template <class K>
+static int scoring_smem(K kernel, size_t bytes, const char* what) {
+  if (bytes > kSmemBudget) return fail(B2S_ERR_BAD_ARG, std::string(what) + ": n_steps too large for the shared-memory scan");
+  if (bytes > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return B2S_OK;
+}
+
+extern "C" int b200sim_score(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* rec, const float* levels,
+                             float* carry, const float* values, float gamma, float lam, int flags, float* total, float* comps,
+                             uint8_t* dones, uint8_t* successes, float* adv, float* targets, float* returns) {
   if (!mo || n_envs < 0 || n_steps < 0 || !rec || !levels || !total || !comps) return fail(B2S_ERR_BAD_ARG, "null argument");
+  if (values && (!adv || !targets || !returns)) return fail(B2S_ERR_BAD_ARG, "values given without adv / targets / returns");
+  if (flags & GAE_NORMALIZE_ADVANTAGES && !values) return fail(B2S_ERR_BAD_ARG, "normalisation asked for without values");
   if (n_envs == 0 || n_steps == 0) return B2S_OK;
   if (!carry && mo->ti_host[TI_REW_CARRY_SIZE] > 0) return fail(B2S_ERR_BAD_ARG, "carry is required for this task");
-  const int threads = 256;
-  const dim3 grid(((size_t)n_envs * 32 + threads - 1) / threads);
-  k_rewards<<<grid, threads, 0, (cudaStream_t)stream>>>(mo->mdl, n_envs, n_steps, rec, levels, carry, total, comps);
+  // shared memory: [16 B barrier][staged rows][scan arrays][column table]; staging needs 16-byte aligned rows and has to fit the SM
+  const int* ti = mo->ti_host.data();
+  const size_t scan = (values ? 6 * (size_t)n_steps : 0) * sizeof(float) + (((size_t)ti[TI_REW_CARRY_SIZE] + 3) & ~(size_t)3) * sizeof(float);
+  const size_t rows = (size_t)n_steps * ti[TI_SCORE_WIDTH] * sizeof(float), table = ((size_t)ti[TI_REC_SIZE] * 2 + 15) & ~(size_t)15;
+  int staged = ti[TI_SCORE_NSEG] > 0 && ti[TI_REC_SIZE] % 4 == 0 && (reinterpret_cast<uintptr_t>(rec) & 15) == 0 &&
+               16 + rows + scan + table <= kSmemBudget;
+  // Measured (gpurun_out/r02h_score_sweep.txt, humanoid 4096 x 64): staging costs more than it saves at this shape -- the rows'
+  // sectors are re-read through L1 (98 % hit rate) and 63 KB of shared memory per CTA caps the SM at 3 environments, so the
+  // copy latency is not hidden: 0.48 ms staged vs 0.22 ms unstaged at 2 warps per CTA.  Opt-in (B2S_SCORE_STAGE=1).
+  if (!getenv("B2S_SCORE_STAGE")) staged = 0;
+  const size_t smem = 16 + (staged ? rows + table : 0) + scan;
+  if (int rc = scoring_smem(k_score, smem, "b200sim_score")) return rc;
+  int warps = 2;  // measured best of 1 / 2 / 4 / 8: the stateful scans are the critical path, more CTAs per SM hide them better
+  if (const char* e = getenv("B2S_SCORE_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= SCORE_WARPS_MAX) warps = v; }  // tuning experiments
+  k_score<<<n_envs, warps * 32, smem, (cudaStream_t)stream>>>(mo->mdl, n_envs, n_steps, staged, rec, levels, carry, values, gamma, lam,
+                                                                     flags, total, comps, dones, successes, adv, targets, returns);
   CUDA_OK(cudaGetLastError());
+  if (flags & GAE_NORMALIZE_ADVANTAGES) {
+    k_gae_normalize<<<1, 1024, 0, (cudaStream_t)stream>>>((size_t)n_envs * n_steps, adv);
+    CUDA_OK(cudaGetLastError());
+  }
   return B2S_OK;
+}
+
+extern "C" int b200sim_rewards(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* rec,
+                               const float* levels, float* carry, float* total, float* comps) {
+  return b200sim_score(mo, stream, n_envs, n_steps, rec, levels, carry, nullptr, 0.0f, 0.0f, 0, total, comps, nullptr, nullptr, nullptr,
+                       nullptr, nullptr);
 }
 
 extern "C" int b200sim_extract_flags(const b200sim_model* mo, void* stream, int n_envs, int n_steps, const float* rec,
@@ -563,8 +713,10 @@ extern "C" int b200sim_gae(void* stream, int batch, int n_steps, const float* va
   if (batch < 0 || n_steps < 0 || !values || !rewards || !dones || !successes || !adv || !targets || !returns)
     return fail(B2S_ERR_BAD_ARG, "null argument");
   if (batch == 0 || n_steps == 0) return B2S_OK;
-  k_gae<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(batch, n_steps, values, rewards, dones, successes, gamma, lam,
-                                                               flags, adv, targets, returns);
+  const size_t smem = (size_t)GAE_WARPS * 5 * n_steps * sizeof(float);
+  if (int rc = scoring_smem(k_gae, smem, "b200sim_gae")) return rc;
+  k_gae<<<(batch + GAE_WARPS - 1) / GAE_WARPS, GAE_WARPS * 32, smem, (cudaStream_t)stream>>>(batch, n_steps, values, rewards, dones, successes,
+                                                                                            gamma, lam, flags, adv, targets, returns);
   CUDA_OK(cudaGetLastError());
   if (flags & GAE_NORMALIZE_ADVANTAGES) {
     k_gae_normalize<<<1, 1024, 0, (cudaStream_t)stream>>>((size_t)batch * n_steps, adv);

@@ -20,8 +20,29 @@ DEV float exp_kernel_pen(float x, float scale, float sq, float ab) {
 DEV float exp_kernel(float x, float scale) { return expf(-(x * x) / (2 * scale * scale)); }
 DEV float norm_fn(float x, int l2) { return l2 ? x * x : fabsf(x); }
 
+// Staged copy of an environment's records (b200sim_score): row t of the read-set columns at srec + t * width; col[c] = position of
+// record column c in a staged row, or 0xFFFF when the column is not staged (it is then read from global memory).
+struct RecStage {
+  const float* srec;
+  const unsigned short* col;
+  int width;
+};
+
+DEV const float& rec_at(const float* rec, size_t tstride, const RecStage* stg, int tt, int off) {
+  if (stg) {
+    const unsigned c = stg->col[off];
+    if (c != 0xFFFFu) return stg->srec[tt * stg->width + (int)c];
+  }
+  return rec[(size_t)tt * tstride + off];
+}
+
+// Rewards r0, r0 + rstride, ... of one environment (one warp).  with_total: this warp runs every reward and also forms the clipped
+// total (the single-warp pass of the host build and the oracle's order); otherwise only the scaled components are written and
+// the caller sums them in component order with env_total (the fused scoring kernel: the rewards of an env are spread over the
+// warps of a CTA; carries of different rewards are disjoint).
 DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, float level, float* carry, float* total,
-                     float* comps, size_t cstride, LANE_ARG) {
+                     float* comps, size_t cstride, LANE_ARG, int r0 = 0, int rstride = 1, bool with_total = true,
+                     const RecStage* stg = nullptr) {
   const int* ti = m.ti;
   const float* tf = m.tf;
   const float* ef = tf + ti[TI_ENGINE_FOFF];
@@ -30,10 +51,10 @@ DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, floa
   const int QP = ti[TI_R_QPOS], QV = ti[TI_R_QVEL], OB = ti[TI_R_OBS], CM = ti[TI_R_CMD], AC = ti[TI_R_ACTION];
   const int DN = ti[TI_R_DONE], SC = ti[TI_R_SUCCESS], LV = ti[TI_R_LEVEL];
   const int na = ti[TI_ACTION_SIZE];
-#define REC(tt, off) rec[(size_t)(tt) * tstride + (off)]
+#define REC(tt, off) rec_at(rec, tstride, stg, (tt), (off))
   const int done_last = REC(T - 1, DN) != 0.0f;
-  LANE_FOR(s, T) total[s] = 0.0f;
-  for (int r = 0; r < nrew; r++) {
+  if (with_total) { LANE_FOR(s, T) total[s] = 0.0f; }
+  for (int r = r0; r < nrew; r += rstride) {
     const int type = TAB(ti, TI_REW_TAB, r, TAB_TYPE);
     const int* xi = ti + TAB(ti, TI_REW_TAB, r, TAB_IOFF) + SCALE_NI;
     const float* xf = tf + TAB(ti, TI_REW_TAB, r, TAB_FOFF) + SCALE_NF;
@@ -90,6 +111,104 @@ DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, floa
           OUT(1, s) = rs == cs ? 1.0f : -1.0f;
         }
         break;
+#if B2S_DEVICE
+      // The two stateful scans of the walking task.  What is serial in them is only the per-foot counters / running maxima; the
+      // per-step inputs (gait period, moving / not-moving flags: square roots, scale look-ups, a dozen record reads) are computed by
+      // the 32 lanes for 32 steps at once and handed to the scan by shuffle.  Every lane runs the (cheap) scan redundantly on the
+      // broadcast inputs, lane j keeps step j's result, and the outputs leave as coalesced rows.  Same operations on the same
+      // values in the same order as the one-lane loop of the host build below.
+      case REW_FEET_AIR_TIME: {
+        const int coffs = xi[0], nf = xi[1], rows = xi[2], lcmd = xi[3], acmd = xi[4], gp_kind = xi[5];
+        const float air_pct = xf[0], ctrl_dt = xf[1], bias = xf[2], gpen = xf[4], lthr = xf[5], athr = xf[6];
+        for (int s0 = 0; s0 < T; s0 += 32) {
+          const int s = s0 + lane;
+          float air_steps = 1.0f, gnd_steps = 1.0f;
+          int moving = 0;
+          unsigned cmask = 0;  // bit f: foot f in contact (nf <= 32: one bit per foot; more feet take the per-step reads below)
+          if (s < T) {
+            const float gp = scale_get(gp_kind, xf + 7, REC(s, LV));
+            air_steps = rintf(gp * air_pct / ctrl_dt); gnd_steps = rintf(gp * (1.0f - air_pct) / ctrl_dt);
+            const bool mlin = lcmd < 0 ? (sqrtf(REC(s, QV) * REC(s, QV) + REC(s, QV + 1) * REC(s, QV + 1)) > lthr)
+                                       : (fabsf(REC(s, CM + lcmd)) > lthr);
+            const bool mang = acmd < 0 ? (REC(s, QV + 5) > athr) : (fabsf(REC(s, CM + acmd)) > athr);
+            moving = (mlin || mang) && !(REC(s, DN) != 0.0f);
+            for (int f = 0; f < nf && f < 32; f++) {
+              bool contact = false;
+              for (int rr = 0; rr < rows; rr++) contact |= REC(s, OB + coffs + rr * nf + f) > 0.5f;
+              cmask |= (unsigned)contact << f;
+            }
+          }
+          float o_air = 0.0f, o_gnd = 0.0f, o_st = 0.0f;
+          const int cnt = T - s0 < 32 ? T - s0 : 32;
+          for (int j = 0; j < cnt; j++) {
+            const float as = __shfl_sync(0xffffffffu, air_steps, j), gs = __shfl_sync(0xffffffffu, gnd_steps, j);
+            const unsigned cm = __shfl_sync(0xffffffffu, cmask, j);
+            const bool mv = __shfl_sync(0xffffffffu, moving, j) != 0;
+            float air_r = -INFINITY, gnd_r = -INFINITY, st_r = -INFINITY;
+            for (int f = 0; f < nf; f++) {
+              bool contact;
+              if (f < 32) contact = (cm >> f) & 1u;
+              else { contact = false; for (int rr = 0; rr < rows; rr++) contact |= REC(s0 + j, OB + coffs + rr * nf + f) > 0.5f; }
+              float air = cr[f], gnd = cr[nf + f], stg = cr[2 * nf + f];
+              air = (!contact && mv) ? air + 1 : 0.0f;
+              gnd = (contact && mv) ? gnd + 1 : 0.0f;
+              stg = (contact && !mv) ? stg + 1 : 0.0f;
+              WSYNC();
+              IF_LANE0 { cr[f] = air; cr[nf + f] = gnd; cr[2 * nf + f] = stg; }
+              WSYNC();
+              const float a = air < as ? air / as + bias : 0.0f;
+              const float g = gnd < gs ? gnd / gs + bias : -gpen;
+              const float q = clipf(stg / gs, 0.0f, 1.0f) + bias;
+              air_r = fmaxf(air_r, a); gnd_r = fmaxf(gnd_r, g); st_r = fmaxf(st_r, q);
+            }
+            if (lane == j) { o_air = air_r; o_gnd = gnd_r; o_st = st_r; }
+          }
+          if (s < T) { OUT(0, s) = o_air; OUT(1, s) = o_gnd; OUT(2, s) = o_st; }
+        }
+      } break;
+      case REW_SPARSE_TARGET_HEIGHT: {
+        const int coffs = xi[0], poff = xi[1], nbd = xi[2], rows = xi[3];
+        for (int s0 = 0; s0 < T; s0 += 32) {
+          const int s = s0 + lane;
+          int not_moving = 0;
+          unsigned cmask = 0;
+          if (s < T) {
+            const bool nm_lin = sqrtf(REC(s, QV) * REC(s, QV) + REC(s, QV + 1) * REC(s, QV + 1)) < xf[1];
+            const bool nm_ang = REC(s, QV + 5) < xf[2];
+            not_moving = (nm_lin && nm_ang) || (REC(s, DN) != 0.0f);
+            for (int b = 0; b < nbd && b < 32; b++) {
+              bool contact = false;
+              for (int rr = 0; rr < rows; rr++) contact |= REC(s, OB + coffs + rr * nbd + b) > 0.5f;
+              cmask |= (unsigned)contact << b;
+            }
+          }
+          float o_best = 0.0f;
+          const int cnt = T - s0 < 32 ? T - s0 : 32;
+          for (int j = 0; j < cnt; j++) {
+            const unsigned cm = __shfl_sync(0xffffffffu, cmask, j);
+            const bool nm = __shfl_sync(0xffffffffu, not_moving, j) != 0;
+            float best = -INFINITY;
+            for (int b = 0; b < nbd; b++) {
+              bool contact;
+              if (b < 32) contact = (cm >> b) & 1u;
+              else { contact = false; for (int rr = 0; rr < rows; rr++) contact |= REC(s0 + j, OB + coffs + rr * nbd + b) > 0.5f; }
+              const float h = REC(s0 + j, OB + poff + 3 * b + 2);
+              const float cur = cr[b];
+              float rw = contact ? cur : 0.0f;
+              if (rw > xf[0]) rw = xf[0];
+              float mh = cur > h ? cur : h;
+              if (nm || contact) mh = 0.0f;
+              WSYNC();
+              IF_LANE0 cr[b] = mh;
+              WSYNC();
+              best = fmaxf(best, rw);
+            }
+            if (lane == j) o_best = best;
+          }
+          if (s < T) OUT(0, s) = o_best;
+        }
+      } break;
+#else
       case REW_FEET_AIR_TIME:
         IF_LANE0 {
           const int coffs = xi[0], nf = xi[1], rows = xi[2], lcmd = xi[3], acmd = xi[4], gp_kind = xi[5];
@@ -142,6 +261,7 @@ DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, floa
           }
         }
         break;
+#endif
       case REW_FORCE_PENALTY:
         LANE_FOR(s, T) {
           float best = -INFINITY;
@@ -523,19 +643,34 @@ DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, floa
       LANE_FOR(s, T) {
         const float v = OUT(c, s) * scale;
         OUT(c, s) = v;
-        total[s] += v;
+        if (with_total) total[s] += v;
       }
     }
     WSYNC();
 #undef OUT
   }
-  LANE_FOR(s, T) {
-    float sum = total[s];
-    if (ef[7] == ef[7] && sum < ef[7]) sum = ef[7];
-    if (ef[8] == ef[8] && sum > ef[8]) sum = ef[8];
-    total[s] = sum;
+  if (with_total) {
+    LANE_FOR(s, T) {
+      float sum = total[s];
+      if (ef[7] == ef[7] && sum < ef[7]) sum = ef[7];
+      if (ef[8] == ef[8] && sum > ef[8]) sum = ef[8];
+      total[s] = sum;
+    }
   }
 #undef REC
+}
+
+// Total reward of step s from the scaled components, summed in component (= reward, then component) order from 0.0f and clipped:
+// the same order of additions as env_rewards(with_total).
+DEV float env_total(const Mdl& m, const float* comps, size_t cstride, int s) {
+  const int* ti = m.ti;
+  const float* ef = m.tf + ti[TI_ENGINE_FOFF];
+  const int ncomp = ti[TI_N_REW_COMP];
+  float sum = 0.0f;
+  for (int k = 0; k < ncomp; k++) sum += comps[(size_t)k * cstride + s];
+  if (ef[7] == ef[7] && sum < ef[7]) sum = ef[7];
+  if (ef[8] == ef[8] && sum > ef[8]) sum = ef[8];
+  return sum;
 }
 
 }  // namespace b2s

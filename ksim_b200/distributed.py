@@ -43,18 +43,21 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank, local, world
 
 
-def _reduce(value: float, op: dist.ReduceOp, device: torch.device | str) -> float:
+def _reduce(value: float, op: dist.ReduceOp, device: torch.device | str | None) -> float:
+    if device is None:  # NCCL reduces device tensors only: follow the backend, not a fixed default
+        nccl = dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+        device = torch.device("cuda", torch.cuda.current_device()) if nccl else "cpu"
     t = torch.tensor([value], dtype=torch.float64, device=device)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=op)
     return float(t.item())
 
 
-def max_over_ranks(value: float, device: torch.device | str = "cpu") -> float:
+def max_over_ranks(value: float, device: torch.device | str | None = None) -> float:
     return _reduce(value, dist.ReduceOp.MAX, device)
 
 
-def sum_over_ranks(value: float, device: torch.device | str = "cpu") -> float:
+def sum_over_ranks(value: float, device: torch.device | str | None = None) -> float:
     return _reduce(value, dist.ReduceOp.SUM, device)
 
 

@@ -470,6 +470,33 @@ class B200Engine:
         # t + 1 at the end of step t), a one-step lag at the iteration boundary that the reference does not have
         self.first_rec[:, self.program["TI_R_LEVEL"]].fill_(float(level))
 
+    def score(self, rec: torch.Tensor, n_steps: int | None = None, values: torch.Tensor | None = None, gamma: float = 0.0,
+              lam: float = 0.0, normalize_advantages: bool = False, monte_carlo_returns: bool = False) -> dict[str, torch.Tensor]:
+        """The scoring pass after a rollout as ONE launch (``b200sim_score``): ``get_rewards`` (rl.py:189-245), the done / success
+        flags and -- with ``values`` [N][T] -- ``compute_ppo_inputs`` (ppo.py:54-121).  Same results as ``rewards`` + ``flags`` +
+        ``gae``; updates the reward carry.  Returns total, comps, dones, successes (+ advantages, targets, returns)."""
+        t = self._scored_steps(rec, n_steps)
+        n, k = self.num_envs, self.program["TI_N_REW_COMP"]
+        dev = self.device
+        out = {"total": torch.empty((n, t), dtype=torch.float32, device=dev),
+               "comps": torch.empty((max(k, 1), n, t), dtype=torch.float32, device=dev),
+               "dones": torch.empty((n, t), dtype=torch.uint8, device=dev),
+               "successes": torch.empty((n, t), dtype=torch.uint8, device=dev)}
+        gae_out = [None, None, None]
+        if values is not None:
+            self._chk(values, (n, t), torch.float32, "values")
+            for name in ("advantages", "targets", "returns"):
+                out[name] = torch.empty((n, t), dtype=torch.float32, device=dev)
+            gae_out = [_ptr(out["advantages"]), _ptr(out["targets"]), _ptr(out["returns"])]
+        flags = (C.GAE_NORMALIZE_ADVANTAGES if normalize_advantages else 0) | (C.GAE_MONTE_CARLO_RETURNS if monte_carlo_returns else 0)
+        with torch.cuda.device(dev):
+            binding.check(self.lib.b200sim_score(self._handle, self._stream(), n, t, _ptr(rec), _ptr(self.levels), _ptr(self.reward_carry),
+                                                 _ptr(values) if values is not None else None, ctypes.c_float(gamma), ctypes.c_float(lam),
+                                                 flags, _ptr(out["total"]), _ptr(out["comps"]), _ptr(out["dones"]), _ptr(out["successes"]),
+                                                 *gae_out), "b200sim_score")
+        self.launches += 2 if (normalize_advantages and values is not None) else 1
+        return out
+
     def flags(self, rec: torch.Tensor, n_steps: int) -> tuple[torch.Tensor, torch.Tensor]:
         n = self.num_envs
         dones = torch.empty((n, n_steps), dtype=torch.uint8, device=self.device)

@@ -159,6 +159,7 @@ class _Ctx:
     def __init__(self, model: Model, obs: dict[str, tuple[int, int, tuple[int, ...]]], cmds: Mapping[str, Command],
                  cmd_slices: dict[str, tuple[int, int]], aux_slices: dict[str, tuple[int, int]] | None = None) -> None:
         self.model, self.obs, self.cmds, self.cmd_slices, self.aux_slices = model, obs, cmds, cmd_slices, aux_slices or {}
+        self.used_obs: set[tuple[int, int]] = set()  # (offset, dim) of every observation a reward asked for
 
     def aux_offset(self, name: str) -> int:
         """Float offset of an aux output inside a record's aux region."""
@@ -169,6 +170,7 @@ class _Ctx:
     def obs_offset(self, name: str) -> int:
         if name not in self.obs:
             raise KeyError(f"observation '{name}' not found; choices: {sorted(self.obs)}")
+        self.used_obs.add((int(self.obs[name][0]), int(self.obs[name][1])))
         return self.obs[name][0]
 
     def obs_shape(self, name: str) -> tuple[int, ...]:
@@ -372,6 +374,24 @@ def build_program(spec: TaskSpec) -> TaskProgram:
     alloc(C.TI_R_AUX, aoff)
     ints[C.TI_AUX_SIZE] = aoff
     ints[C.TI_REC_SIZE] = _pad4(off)
+
+    # Scoring read-set (b200sim_score stages these columns of an env's T records in shared memory with bulk copies): the row from
+    # the command block to its end (commands, level, qpos, qvel, ..., action, flags, aux outputs) plus every observation a reward
+    # named through ctx.obs_offset, as 16-byte aligned, merged segments.  A column outside the set is still read correctly (from
+    # global memory); the set only decides what is fast.
+    rsize = ints[C.TI_REC_SIZE]
+    spans = sorted([(ints[C.TI_R_CMD] & ~3, rsize)] + [((ints[C.TI_R_OBS] + o) & ~3, min(_pad4(ints[C.TI_R_OBS] + o + d), rsize))
+                                                      for o, d in ctx.used_obs])
+    segs: list[list[int]] = []
+    for lo, hi in spans:
+        if segs and lo <= segs[-1][1]:
+            segs[-1][1] = max(segs[-1][1], hi)
+        else:
+            segs.append([lo, hi])
+    width = sum(hi - lo for lo, hi in segs)
+    ints[C.TI_SCORE_NSEG] = len(segs)
+    ints[C.TI_SCORE_SEG], _ = put([v for lo, hi in segs for v in (lo, hi - lo)], [])
+    ints[C.TI_SCORE_WIDTH] = width if (width // 4) % 2 == 1 else width + 4  # width / 4 odd: 4-way instead of 8-way bank conflicts
 
     tf = np.array(floats, dtype=np.float64)
     tf32 = tf.astype(np.float32)

@@ -164,7 +164,53 @@ def test_rewards_and_flags_parity(ctx) -> None:  # noqa: ANN001
     assert _np(dones).sum() > 0
 
 
-@pytest.mark.parametrize("b,t", [(1, 1), (7, 3), (512, 24), (4096, 64)])
+@pytest.mark.parametrize("task,staged", [("walking", False), ("kbot", False), ("walking", True), ("kbot", True)])
+def test_fused_scoring_pass(ctx, kbot_spec, kbot_randomizers, monkeypatch, task, staged) -> None:  # noqa: ANN001
+    """b200sim_score (one launch) == get_rewards + flags + compute_ppo_inputs of the oracle on identical records: rewards 1e-5,
+    flags bit-exact, and the GAE outputs bit-exact given the kernel's own totals (same fp32 operation order as the oracle)."""
+    spec, rz = ctx if task == "walking" else (kbot_spec, kbot_randomizers)
+    if staged:  # the opt-in variant that stages the read-set columns in shared memory with bulk copies
+        monkeypatch.setenv("B2S_SCORE_STAGE", "1")
+    n, t = 37, 45
+    eng = _engine(spec, rz, n, level=0.7, seed=11)
+    ora, st, keys, rec0, _ = _oracle_init(eng)
+    twin = _engine(spec, rz, n, level=0.7, seed=11)   # same records scored by the three separate launches
+    actions = torch.from_numpy((0.4 * np.random.RandomState(12).randn(t, n, eng.NA)).astype(np.float32)).cuda()
+    carry = np.zeros((n, eng.program["TI_REW_CARRY_SIZE"]), np.float32)
+    d, sc = eng.program["TI_R_DONE"], eng.program["TI_R_SUCCESS"]
+    for it in range(2):  # two rollouts: the stateful carries cross a boundary
+        rec = eng.rollout(actions)
+        rec_np = _np(rec)[:t]
+        values = torch.from_numpy(np.random.RandomState(13 + it).randn(n, t).astype(np.float32)).cuda()
+        out = eng.score(rec, t, values=values, gamma=0.97, lam=0.95)
+        total_o, comps_o = ora.rewards(rec_np, eng.env_init.levels, carry)
+        np.testing.assert_allclose(_np(out["comps"]), comps_o, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(_np(out["total"]), total_o, rtol=1e-5, atol=1e-4)
+        np.testing.assert_array_equal(_np(eng.reward_carry), carry)
+        np.testing.assert_array_equal(_np(out["dones"]), (rec_np[:, :, d] != 0).T)
+        np.testing.assert_array_equal(_np(out["successes"]), (rec_np[:, :, sc] != 0).T)
+        oa, ot, orr = ora.gae(_np(values), _np(out["total"]), _np(out["dones"]) != 0, _np(out["successes"]) != 0, 0.97, 0.95, 0)
+        np.testing.assert_array_equal(_np(out["advantages"]), oa)
+        np.testing.assert_array_equal(_np(out["targets"]), ot)
+        np.testing.assert_array_equal(_np(out["returns"]), orr)
+        # the three separate entry points on the same records (the twin's carry has followed the same history)
+        tot2, comps2 = twin.rewards(rec, t)
+        dn2, su2 = twin.flags(rec, t)
+        adv2, tgt2, ret2 = twin.gae(values, tot2, dn2, su2, 0.97, 0.95)
+        for a, b in ((out["total"], tot2), (out["comps"], comps2), (out["dones"], dn2), (out["successes"], su2), (out["advantages"], adv2),
+                     (out["targets"], tgt2), (out["returns"], ret2)):
+            assert torch.equal(a, b)
+        assert torch.equal(eng.reward_carry, twin.reward_carry)
+    assert _np(out["dones"]).sum() > 0
+    mc = eng.score(rec, t, values=values, gamma=0.97, lam=0.95, monte_carlo_returns=True, normalize_advantages=True)
+    assert torch.equal(mc["targets"], mc["returns"])
+    a = _np(mc["advantages"])
+    assert abs(a.mean()) < 1e-4 and abs(a.std() - 1.0) < 1e-3
+    no_values = eng.score(rec, t)
+    assert "advantages" not in no_values and no_values["total"].shape == (n, t)
+
+
+@pytest.mark.parametrize("b,t", [(1, 1), (7, 3), (512, 24), (4096, 64), (3, 700)])
 def test_gae_bit_exact(ctx, b, t) -> None:  # noqa: ANN001
     from oracle import OracleEngine
 

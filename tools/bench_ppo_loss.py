@@ -80,7 +80,9 @@ def scoring(args: argparse.Namespace, peak: float) -> None:
     values = torch.zeros_like(total)
     k = int(comps.shape[0])
     cases = {
-        "k_rewards": (lambda: eng.rewards(rec, t), 4 * n * t * (eng.R + 1 + k)),
+        "k_score (rewards + flags + GAE, one launch)": (lambda: eng.score(rec, t, values=values, gamma=0.97, lam=0.95),
+                                                        n * t * (4 * (eng.R + 1 + k) + 2 + 16)),
+        "k_score (rewards only)": (lambda: eng.rewards(rec, t), 4 * n * t * (eng.R + 1 + k)),
         "k_extract_flags": (lambda: eng.flags(rec, t), n * t * (8 + 2)),
         "k_gae": (lambda: eng.gae(values, total, dones, succ, 0.97, 0.95), n * t * 22),
         "k_gae+k_gae_normalize": (lambda: eng.gae(values, total, dones, succ, 0.97, 0.95, normalize_advantages=True), n * t * (22 + 12)),
