@@ -32,6 +32,7 @@ L2_NOTE = ""  # set by main(): inputs larger than L2, or an explicit flush betwe
 METRIC = "humanoid env-steps/sec"
 UNIT = "env-steps/s"
 GAMMA, LAM = 0.97, 0.95
+KBOT_SOLVER: str | None = None
 WORKLOAD = "humanoid"  # --workload kbot: BASELINE.json configs[2] (K-Bot, 8192 envs x 100), a secondary measurement
 
 
@@ -39,6 +40,9 @@ def _task():  # noqa: ANN202
     """(make_spec, RANDOMIZERS) of the selected workload."""
     if WORKLOAD == "kbot":
         from ksim_b200.examples import kbot as task
+
+        if KBOT_SOLVER is not None:  # --kbot-solver fast: the opt-in solver (the task ships "reference", examples/kbot.py)
+            return (lambda: task.make_spec(task.KbotConfig(solver=KBOT_SOLVER))), task.RANDOMIZERS
     else:
         from ksim_b200.examples import walking as task
     return task.make_spec, task.RANDOMIZERS
@@ -287,9 +291,12 @@ def _mjx_baseline() -> dict:
         return {"impl": "mjx", "unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
-def _secondary_kbot(args: argparse.Namespace) -> dict | None:
-    """The K-Bot line (BASELINE.json configs[2]) from a child process of the same script, attached to the humanoid line."""
+def _secondary_kbot(args: argparse.Namespace, solver: str | None = None) -> dict | None:
+    """The K-Bot line (BASELINE.json configs[2]) from a child process of the same script, attached to the humanoid line.
+    ``solver`` None: the task as it ships (reference-shaped capped Newton iteration); "fast": the opt-in solver."""
     cmd = [sys.executable, str(ROOT / "bench.py"), "--workload", "kbot", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-extras"]
+    if solver is not None:
+        cmd += ["--kbot-solver", solver]
     try:
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
         line = json.loads(res.stdout.strip().splitlines()[-1])
@@ -314,9 +321,11 @@ def main() -> None:
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (env-count sweeps, BASELINE.json configs[4]); "
                     "the default is the configuration the metric is quoted on")
     ap.add_argument("--rollout", type=int, default=None, help="control steps per rollout")
+    ap.add_argument("--kbot-solver", default=None, choices=["fast", "reference"], help="K-Bot workload: override the task's solver option")
     ap.add_argument("--no-extras", action="store_true", help="skip the closed-loop, PPO-iteration and K-Bot secondary measurements")
     args = ap.parse_args()
-    global WORKLOAD, ENVS_PER_GPU, ROLLOUT, METRIC, GAMMA, LAM
+    global WORKLOAD, ENVS_PER_GPU, ROLLOUT, METRIC, GAMMA, LAM, KBOT_SOLVER
+    KBOT_SOLVER = args.kbot_solver
     if args.workload == "kbot":
         WORKLOAD, ENVS_PER_GPU, ROLLOUT, METRIC, GAMMA, LAM = "kbot", 8192, 100, "kbot env-steps/sec", 0.94, 0.94
     if args.envs is not None:
@@ -485,6 +494,9 @@ def main() -> None:
         del eng
         torch.cuda.empty_cache()
         out["secondary"] = _secondary_kbot(args)
+        fast = _secondary_kbot(args, "fast")
+        out["secondary_fast_solver"] = {k: fast[k] for k in ("value", "unit", "ms_per_step", "error") if k in fast} | {
+            "what": "same K-Bot workload with EngineConfig.solver='fast' (opt-in; departs from the reference's capped iterate, DESIGN.md 2)"}
     _emit(json.dumps(out))
     D.shutdown()
 

@@ -168,10 +168,15 @@
 #define OBS_FEET_FORCE 18
 #define OBS_FEET_TORQUE 19
 #define OBS_TIMESTEP 20
-#define OBS_CONTACT 21
+#define OBS_CONTACT 21           /* observation.py:452-478: ints [n, geom ids]; out[i] = any_j colliding(g_i, g_j) */
 #define OBS_FEET_POSITION 22     /* examples/kbot/train.py:653-689: feet relative to the base, in the base's yaw frame */
 #define OBS_BASE_HEIGHT 23       /* examples/kbot/train.py:693-697: xpos[1][2] */
 #define OBS_COM_DISTANCE 24      /* examples/kbot/train.py:500-649: |hull centroid of the contact points - subtree_com[2]| */
+#define OBS_DELAYED_JOINT_POSITION 25  /* observation.py:229-252: ints [delay_steps]; carry = delay_steps x (nq - 7) ring of qpos[7:] */
+#define OBS_DELAYED_JOINT_VELOCITY 26  /* observation.py:261-283: ints [delay_steps]; carry = delay_steps x (nv - 6) ring of qvel[6:] */
+#define OBS_BODY_ORIENTATION 27  /* observation.py:619-642 (+ FeetOrientationObservation 672-703): ints [n, body ids]; xquat rows */
+#define OBS_SITE_ORIENTATION 28  /* observation.py:645-669: ints [n, site ids]; first two rows of site_xmat (6-D rotation) */
+#define OBS_ACT_POS 29           /* observation.py:717-747: ints [ctrl_idx, qpos_idx]; (last_ctrl[ctrl_idx], qpos[qpos_idx]) */
 
 /* ---- terminations (ksim/terminations.py) ---- */
 #define TERM_NOT_UPRIGHT 1

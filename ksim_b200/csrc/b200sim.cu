@@ -481,9 +481,11 @@ static int fail(int code, const std::string& msg) { g_last_error = msg; return c
 extern "C" int b200sim_model_set_option(b200sim_model* mo, int option, int value) {
   if (!mo) return fail(B2S_ERR_BAD_ARG, "null model");
   if (option == B2S_OPT_SOLVER && (value == B2S_SOLVER_FAST || value == B2S_SOLVER_REFERENCE)) {
-    // bits 8 / 9 / 10 of sync_mask: constraint-space Newton off, factor-reusing dof-space Newton off, exact line search off
-    // (b2s_physics.cuh: dual_enabled / newton_dof_enabled / exact_ls_enabled) -> the reference-shaped solve_primal runs
-    const int ref_bits = (1 << 8) | (1 << 9) | (1 << 10);
+    // bits 8 / 10 / 11 of sync_mask: constraint-space Newton off, exact line search off, reference-shaped iteration in the
+    // factor-reusing dof-space Newton (b2s_physics.cuh: dual_enabled / exact_ls_enabled / newton_dof_refshape).  Models whose
+    // rows always fit the constraint-space path (humanoid) have no newton_dof and run solve_primal; the others run the same
+    // iteration through newton_dof's bookkeeping.  B2S_SYNC_MASK bit 9 (tuning) forces solve_primal everywhere.
+    const int ref_bits = (1 << 8) | (1 << 10) | (1 << 11);
     mo->mdl.sync_mask = value == B2S_SOLVER_REFERENCE ? (mo->mdl.sync_mask | ref_bits) : (mo->mdl.sync_mask & ~ref_bits);
     return B2S_OK;
   }
@@ -565,9 +567,9 @@ extern "C" int b200sim_model_create(const void* blob, size_t nbytes, b200sim_mod
   mo->mdl.poison_hi = getenv("B2S_POISON_HI") ? atoi(getenv("B2S_POISON_HI")) : 0;
 #endif
 #ifdef B2S_DEBUG_STOP
-  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0xff07ff;  // + DBG_STOP point
+  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0xff0fff;  // + DBG_STOP point
 #else
-  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0x7ff;  // tuning experiments
+  if (const char* e = getenv("B2S_SYNC_MASK")) mo->mdl.sync_mask = (int)strtol(e, nullptr, 0) & 0xfff;  // tuning experiments
 #endif
   int rc;
   const size_t words[4] = {ni, nf, nti, ntf};

@@ -44,7 +44,7 @@ DEV void apply_overrides(const Mdl& m, Work<D>& w, const float* rand, LANE_ARG) 
     for (int k = 0; k < 3; k++) { w.body_inertia[k][b] = inertia[3 * b + k]; w.body_ipos[k][b] = ipos[3 * b + k]; }
   }
   const int* pgeom[2] = {MI(m, MH_PAIR_GEOM1), MI(m, MH_PAIR_GEOM2)};
-  if constexpr (!D::EXACT) {
+  if constexpr (!D::SMALL) {
     const float* gpos = MF(m, MH_GEOM_POS);
     const float* gsize = MF(m, MH_GEOM_SIZE);
     LANE_FOR(p, DIM(NPAIR, MH_NPAIR)) {
@@ -61,7 +61,7 @@ DEV void apply_overrides(const Mdl& m, Work<D>& w, const float* rand, LANE_ARG) 
   for (int r = 0; r < n; r++) {
     const int code = TAB(ti, TI_RAND_TAB, r, TAB_AUX0), cnt = TAB(ti, TI_RAND_TAB, r, TAB_AUX1);
     if (code == RAND_GEOM_SIZE || code == RAND_GEOM_POS) {
-      if constexpr (!D::EXACT) {
+      if constexpr (!D::SMALL) {
         LANE_FOR(p, DIM(NPAIR, MH_NPAIR)) {
 #pragma unroll
           for (int sd = 0; sd < 2; sd++)
@@ -634,6 +634,15 @@ DEV void obs_carry_initial(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG)
 #pragma unroll
       for (int k = 0; k < 3; k++) c[4 + k] = key_uniform(brng, k, -of[5], of[5]);
     }
+  } else if (type == OBS_DELAYED_JOINT_POSITION || type == OBS_DELAYED_JOINT_VELOCITY) {
+    // observation.py:232-236 / 264-268: every row of the ring starts as the joint state right after the reset
+    const int dim = TAB(ti, TI_OBS_TAB, idx, TAB_OUT_DIM);
+    const int delay = (ti + TAB(ti, TI_OBS_TAB, idx, TAB_IOFF) + NOISE_NI + BIAS_NI)[0];
+    const bool pos = type == OBS_DELAYED_JOINT_POSITION;
+    LANE_FOR(k, dim) {
+      const float cur = pos ? w.qpos[7 + k] : w.qvel[6 + k];
+      for (int r = 0; r < delay; r++) c[r * dim + k] = cur;
+    }
   }
 }
 
@@ -769,6 +778,20 @@ DEVNI void observe(const Mdl& m, Work<D>& w, Key rng, float* out, LANE_ARG) {
         } break;
         case OBS_BASE_HEIGHT: x = w.xpos[2][1]; break;
         case OBS_COM_DISTANCE: x = oi[0] ? com_distance(m, w) : -1.0f; break;
+        case OBS_DELAYED_JOINT_POSITION: case OBS_DELAYED_JOINT_VELOCITY: {
+          // observation.py:238-252 / 270-283: the oldest row is the reading, the ring shifts by one and takes the current
+          // state; lane k owns column k of the ring, so the shift needs no cross-lane ordering
+          float* c = w.obs_carry + coff;
+          const int delay = oi[0];
+          const bool pos = type == OBS_DELAYED_JOINT_POSITION;
+          x = pos ? c[k] - w.zero_off[k] : c[k];
+          for (int r = 0; r + 1 < delay; r++) c[r * dim + k] = c[(r + 1) * dim + k];
+          c[(delay - 1) * dim + k] = pos ? w.qpos[7 + k] : w.qvel[6 + k];
+        } break;
+        case OBS_CONTACT: x = (float)geoms_colliding(m, w, oi + 1 + k, 1, oi + 1, oi[0]); break;
+        case OBS_BODY_ORIENTATION: x = w.xquat[k & 3][oi[1 + (k >> 2)]]; break;
+        case OBS_SITE_ORIENTATION: x = w.site_xmat[k % 6][oi[1 + k / 6]]; break;  // rows 0 and 1 of the row-major 3x3
+        case OBS_ACT_POS: x = k == 0 ? w.last_ctrl[oi[0]] : w.qpos[oi[1]]; break;
         default: x = 0.0f; break;
       }
       v[k] = x;

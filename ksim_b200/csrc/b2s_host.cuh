@@ -55,7 +55,7 @@ constexpr int max_warps() {
 // 8-warp CTA leaves free (256 threads -> up to 255 registers); the humanoid kernel (14 warps) is 3 % faster when held
 // to 128 registers (bound 512) than with the 144 its 448 threads would allow.
 template <class D>
-constexpr int launch_threads() { return D::EXACT ? 512 : 32 * max_warps<D>(); }
+constexpr int launch_threads() { return D::SMALL ? 512 : 32 * max_warps<D>(); }
 
 // -DB2S_POISON_SMEM (debug): a workspace starts as whatever the previous kernel left in shared memory; filling a byte range
 // of it with 0xFF (NaN floats, -1 ints) makes a read of a field nobody wrote visible in the outputs (tools/debug_poison.py)

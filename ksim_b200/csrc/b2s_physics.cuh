@@ -479,6 +479,11 @@ DEV bool dual_path(const Mdl& m, const Work<D>& w, int ne) {
 }
 // bit 9 switches the factor-reusing dof-space Newton path (newton_dof) off: the reference-shaped solve_primal runs instead
 DEV bool newton_dof_enabled(const Mdl& m) { return !((m.sync_mask >> 9) & 1); }
+// bit 11: newton_dof() runs the REFERENCE-SHAPED iteration (B2S_SOLVER_REFERENCE on models whose rows exceed NDUAL): the
+// reference's bracketing line search, its iteration cap and its stopping rules, no early finish -- the same sequence of
+// iterates as solve_primal up to fp32 rounding, with newton_dof's bookkeeping (factor reuse while the active set stands,
+// delta form, per-dof scatters)
+DEV bool newton_dof_refshape(const Mdl& m) { return (m.sync_mask >> 11) & 1; }
 
 // Builds A (FS_MASS: M; FS_NEWTON: M + J^T diag(D*active) J; FS_IMPLICIT: M + dt*diag(damping)), factors it and
 // solves A x = b.  The three dense factorisations of a physics sub-step all go through here.
@@ -720,7 +725,7 @@ DEV void collision(const Mdl& m, Work<D>& w, LANE_ARG) {
     const int b1 = gbody[g1], b2 = gbody[g2];
     // geom_pos / geom_size: per-env copies where the instantiation carries them (CollisionBodyRandomizer)
     V3 gp1, gp2, gs1, gs2;
-    if constexpr (D::EXACT) {
+    if constexpr (D::SMALL) {
       gp1 = ldg3(gpos + 3 * g1); gp2 = ldg3(gpos + 3 * g2); gs1 = ldg3(gsize + 3 * g1); gs2 = ldg3(gsize + 3 * g2);
     } else {
       gp1 = v3(w.pair_gpos[0][0][p], w.pair_gpos[0][1][p], w.pair_gpos[0][2][p]);
@@ -1705,6 +1710,7 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
   const float tol = m.mf[MF_TOLERANCE];
   const float scale = 1.0f / (m.mf[MF_MEANINERTIA] * (float)(nv > 1 ? nv : 1));
   bool need_factor = true;
+  const bool refshape = newton_dof_refshape(m);
   // The exact line search and the factor reuse make an iteration cheap, and a cold start (after a reset) with many
   // contact rows can need more than the reference's cap to settle its active set: up to 2x `iterations` are allowed, so
   // that what is returned is the converged minimum rather than wherever the cap happened to stop the reference.
@@ -1712,7 +1718,8 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
 #define B2S_NDOF_ITER_NUM 2   // iteration cap = B2S_NDOF_ITER_NUM / B2S_NDOF_ITER_DEN x the model's `iterations`
 #define B2S_NDOF_ITER_DEN 1
 #endif
-  for (int niter = 0; niter < (B2S_NDOF_ITER_NUM * iterations) / B2S_NDOF_ITER_DEN; niter++) {
+  const int iter_cap = refshape ? iterations : (B2S_NDOF_ITER_NUM * iterations) / B2S_NDOF_ITER_DEN;
+  for (int niter = 0; niter < iter_cap; niter++) {
     float gn = 0.0f;
     LANE_FOR(i, nv) { const float g = w.s_Ma[i] - w.qfrc_constraint[i]; w.s_grad[i] = g; gn += g * g; }
     gn = sqrtf(wsum(gn));
@@ -1733,19 +1740,28 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
     }
     LANE_FOR(i, nv) w.s_search[i] = -w.s_Mgrad[i];
     WSYNC();
-    float qg1 = 0.0f, qg2 = 0.0f;
+    float qg1 = 0.0f, qg2 = 0.0f, sn = 0.0f;
     LANE_FOR(i, nv) {
       float s = 0.0f;
       for (int j = 0; j < nv; j++) s = fmaf(w.M[i][j], w.s_search[j], s);
       w.s_mv[i] = s;
       qg1 += w.s_search[i] * w.s_Ma[i];
       qg2 += w.s_search[i] * s;
+      sn += w.s_search[i] * w.s_search[i];
     }
     LANE_FOR(r, ne) w.efc_jv[r] = row_dot(w, r, nsparse, w.s_search, nv);
     qg1 = wsum(qg1);
     qg2 = 0.5f * wsum(qg2);
     WSYNC();
-    const float alpha = ls_newton(w, ne, qg1, qg2, LANE_PASS);
+    float alpha;
+    if (refshape) {
+      // the reference's line search (mjx solver._linesearch: bracketing on the derivative, <= ls_iterations rounds, a step
+      // is kept only if it lowers the cost); (M qacc - qfrc_smooth) . s == (M delta) . s because M qacc_smooth = qfrc_smooth
+      const float qg[3] = {gauss, qg1, qg2};
+      alpha = ls_bracket(m, w, nv, ne, qg, sqrtf(wsum(sn)), false, true, LANE_PASS);
+    } else {
+      alpha = ls_newton(w, ne, qg1, qg2, LANE_PASS);
+    }
     SUB_MARK(w, 20);
     if (alpha == 0.0f) break;
     LANE_FOR(i, nv) { w.s_qacc[i] = fmaf(alpha, w.s_search[i], w.s_qacc[i]); w.s_Ma[i] = fmaf(alpha, w.s_mv[i], w.s_Ma[i]); }
@@ -1757,7 +1773,7 @@ DEV void newton_dof(const Mdl& m, Work<D>& w, LANE_ARG) {
     constraint_force_scatter(w, nv, ne, nsparse, LANE_PASS);
     need_factor = changed != 0;
     SUB_MARK(w, 21);
-    if (!moved && fabsf(alpha - 1.0f) < 1e-3f) break;
+    if (!refshape && !moved && fabsf(alpha - 1.0f) < 1e-3f) break;
   }
   LANE_FOR(i, nv) { const float a = w.qacc_smooth[i] + w.s_qacc[i]; w.qacc[i] = a; w.warm[i] = a; }
   WSYNC();

@@ -12,9 +12,10 @@ constexpr int dims_asq(int n, int cap) { return n * (n | 1) <= cap ? n : dims_as
 // Size traits.  A kernel instantiation serves every model whose sizes are <= the traits' (exact match is
 // fastest because lane loops collapse to a single predicated pass).
 template <int NQ_, int NV_, int NB_, int NJ_, int NU_, int NS_, int NSD_, int NPAIR_, int NCON_, int NDENSE_, int NLIMIT_,
-          int NFRIC_, bool EXACT_>
+          int NFRIC_, bool EXACT_, bool SMALL_ = EXACT_>
 struct Dims {
   static constexpr bool EXACT = EXACT_;       // model sizes equal the traits: lane loops get compile-time bounds
+  static constexpr bool SMALL = SMALL_;       // task budgets of the walking example, no per-env pair geoms (fills the SM with 14 workspaces)
   static constexpr int NQ = NQ_, NV = NV_, NB = NB_, NJ = NJ_, NU = NU_, NS = NS_, NSD = NSD_;
   static constexpr int NPAIR = NPAIR_, NCON = NCON_, NDENSE = NDENSE_, NLIMIT = NLIMIT_, NFRIC = NFRIC_;
   // action size: PositionVelocityActuator doubles it; the exact-fit instantiation serves nu-sized actions only
@@ -22,13 +23,15 @@ struct Dims {
   static constexpr int NVP = NV_ | 1;         // odd row stride: conflict-free column access
   static constexpr int NSPARSE = NFRIC_ + NLIMIT_;
   static constexpr int NEFC = NFRIC_ + NLIMIT_ + NDENSE_;
-  // task-state budgets: the exact-fit instantiation is sized for the walking task (2 event floats, 8 command floats)
+  // task-state budgets: the SMALL instantiation is sized for the walking task (2 event floats, 8 command floats)
   // so that the model AND the task program fit in shared memory next to 14 workspaces
-  static constexpr int EVS = EXACT_ ? 4 : 16;  // event state floats
+  static constexpr int EVS = SMALL_ ? 4 : 16;  // event state floats
   static constexpr int ACS = 2 * NU_ + 3;     // PositionActuators state
-  static constexpr int CMDS = EXACT_ ? 8 : 24;  // command floats
-  static constexpr int OCS = 16;              // observation carry floats (two projected-gravity observations: 14)
-  static constexpr int NOBS = EXACT_ ? 16 : 32;  // observation plugins (bias keys)
+  static constexpr int CMDS = SMALL_ ? 8 : 24;  // command floats
+  // observation carry floats: two projected-gravity observations (14) in the exact-fit instantiations; the generic one also
+  // has room for the delayed joint position / velocity rings (delay_steps x joints each)
+  static constexpr int OCS = EXACT_ ? 16 : 16 + 4 * NU_;
+  static constexpr int NOBS = SMALL_ ? 16 : 32;  // observation plugins (bias keys)
   // Dual (constraint-space) Newton path: at most NDUAL rows.  Z = M^-1 J^T lives in the storage of
   // crb/cacc/cfrc/cfrc_ext (28*NB floats, dead during the solve); A = J Z and the factor of the reduced Hessian
   // share the storage of W.  Rows beyond NDUAL fall back to the primal (dof-space) Newton path.
@@ -41,7 +44,8 @@ struct Dims {
 using DimsHumanoid = Dims<24, 23, 17, 18, 17, 3, 54, 2, 2, 2, 17, 0, true>;
 // examples/kbot/robot/kbot-headless/robot.mjcf: nq 27 nv 26 nbody 24 nu 20, 4 capsule-plane pairs condim 3
 // (8 contacts x 4 pyramid rows), 20 limited hinges, 20 frictionloss dofs.
-using DimsKbot = Dims<27, 26, 24, 21, 20, 4, 56, 4, 8, 32, 20, 20, false>;
+// Exact-fit as well (compile-time loop bounds), with the larger task budgets and per-env pair geoms of its task.
+using DimsKbot = Dims<27, 26, 24, 21, 20, 4, 56, 4, 8, 32, 20, 20, true, false>;
 // anything else that fits one dof / body per lane
 using DimsGeneric = Dims<33, 32, 32, 32, 32, 8, 96, 8, 16, 64, 32, 32, false>;
 
@@ -49,15 +53,15 @@ using DimsGeneric = Dims<33, 32, 32, 32, 32, 8, 96, 8, 16, 64, 32, 32, false>;
 #define DIM(X, H) (D::EXACT ? (int)D::X : m.h[H])
 
 // geom_pos / geom_size of the two geoms of every contact pair, per environment (CollisionBodyRandomizer,
-// randomization.py:380-442).  The exact-fit instantiation has no shared memory to spare (its workspaces, the model and the
+// randomization.py:380-442).  The humanoid (SMALL) instantiation has no shared memory to spare (its workspaces, the model and the
 // task program fill the SM) and its task has no such override: it reads the shared model instead and carries nothing.
-template <class D, bool EXACT>
+template <class D, bool SMALL>
 struct PairGeom { float pair_gpos[2][3][D::NPAIR], pair_gsize[2][3][D::NPAIR]; };
 template <class D>
 struct PairGeom<D, true> {};
 
 template <class D>
-struct Work : PairGeom<D, D::EXACT> {
+struct Work : PairGeom<D, D::SMALL> {
   // ---- persistent per-env state (mirrors the HBM state block) ----
   float qpos[D::NQ], qvel[D::NV], qacc[D::NV], warm[D::NV], ctrl[D::NU];
   float last_ctrl[D::NA], zero_off[D::NU], event[D::EVS], act_state[D::ACS], cmd[D::CMDS], obs_carry[D::OCS];

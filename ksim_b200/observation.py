@@ -14,7 +14,9 @@ __all__ = [
     "ActuatorForceObservation", "SensorObservation", "BaseLinearAccelerationObservation",
     "BaseAngularAccelerationObservation", "ActuatorAccelerationObservation", "ProjectedGravityObservation",
     "FeetContactObservation", "BodyPositionObservation", "BodyVelocityObservation", "FeetForceObservation",
-    "FeetTorqueObservation", "TimestepObservation",
+    "FeetTorqueObservation", "TimestepObservation", "DelayedJointPositionObservation", "DelayedJointVelocityObservation",
+    "ContactObservation", "BodyOrientationObservation", "SiteOrientationObservation", "FeetOrientationObservation",
+    "ActPosObservation",
 ]
 
 from abc import ABC, abstractmethod
@@ -90,8 +92,31 @@ class JointPositionObservation(Observation):
 
 
 @attrs.define(frozen=True, kw_only=True)
+class DelayedJointPositionObservation(StatefulObservation):
+    """``qpos[7:] - zero_offset`` as it was ``delay_steps`` observations ago (ksim/observation.py:229-252): the carry is a ring of
+    ``delay_steps`` rows, every row initialised to the joint positions right after the reset."""
+
+    delay_steps: int = attrs.field(default=1, validator=attrs.validators.ge(1))
+
+    def encode(self, model: Model) -> Encoded:
+        n = model.nq - 7
+        return C.OBS_DELAYED_JOINT_POSITION, [int(self.delay_steps)], [], n, int(self.delay_steps) * n
+
+
+@attrs.define(frozen=True, kw_only=True)
 class JointVelocityObservation(Observation):
     encode = _simple(C.OBS_JOINT_VELOCITY, lambda m: m.nv - 6)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class DelayedJointVelocityObservation(StatefulObservation):
+    """``qvel[6:]`` as it was ``delay_steps`` observations ago (ksim/observation.py:261-283)."""
+
+    delay_steps: int = attrs.field(default=1, validator=attrs.validators.ge(1))
+
+    def encode(self, model: Model) -> Encoded:
+        n = model.nv - 6
+        return C.OBS_DELAYED_JOINT_VELOCITY, [int(self.delay_steps)], [], n, int(self.delay_steps) * n
 
 
 @attrs.define(frozen=True, kw_only=True)
@@ -254,3 +279,92 @@ class FeetForceObservation(Observation):
 class FeetTorqueObservation(FeetForceObservation):
     def encode(self, model: Model) -> Encoded:
         return C.OBS_FEET_TORQUE, [self.foot_left, self.foot_right], [], 6, 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class ContactObservation(Observation):
+    """Per listed geom: is it in contact with any other listed geom (ksim/observation.py:452-478)."""
+
+    geom_idxs: tuple[int, ...] = attrs.field()
+    contact_group: str | None = attrs.field(default=None)
+
+    @classmethod
+    def create(cls, *, physics_model: Model, geom_names: str | Collection[str], contact_group: str | None = None,
+               noise: Noise | None = None) -> "ContactObservation":
+        return cls(geom_idxs=tuple(physics_model.id("geom", n) for n in _as_list(geom_names)), contact_group=contact_group, noise=noise)
+
+    def encode(self, model: Model) -> Encoded:
+        return C.OBS_CONTACT, [len(self.geom_idxs), *self.geom_idxs], [], len(self.geom_idxs), 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class BodyOrientationObservation(Observation):
+    """``xquat`` of the listed bodies (ksim/observation.py:619-642)."""
+
+    body_ids: tuple[int, ...] = attrs.field()
+    name: str = attrs.field(default="body_orientation")
+
+    @classmethod
+    def create(cls, *, physics_model: Model, body_names: Collection[str], noise: Noise | None = None):  # noqa: ANN206
+        ids = tuple(physics_model.id("body", n) for n in body_names)
+        snake = "".join("_" + ch.lower() if ch.isupper() else ch for ch in cls.__name__).lstrip("_")
+        return cls(body_ids=ids, name=f"{snake}_{'_'.join(body_names)}", noise=noise)
+
+    def encode(self, model: Model) -> Encoded:
+        return C.OBS_BODY_ORIENTATION, [len(self.body_ids), *self.body_ids], [], 4 * len(self.body_ids), 0
+
+    def shape(self, model: Model) -> tuple[int, ...]:
+        return (len(self.body_ids), 4)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class FeetOrientationObservation(BodyOrientationObservation):
+    """``BodyOrientationObservation`` of exactly two bodies, left then right (ksim/observation.py:672-703)."""
+
+    @classmethod
+    def create(cls, *, physics_model: Model, body_names: Collection[str], noise: Noise | None = None):  # noqa: ANN206
+        if len(body_names) != 2:
+            raise ValueError("FeetOrientationObservation expects exactly two body names (left and right foot).")
+        return super().create(physics_model=physics_model, body_names=body_names, noise=noise)
+
+    @classmethod
+    def create_from_feet(cls, *, physics_model: Model, foot_left_body_name: str, foot_right_body_name: str,
+                         noise: Noise | None = None):  # noqa: ANN206
+        return super().create(physics_model=physics_model, body_names=(foot_left_body_name, foot_right_body_name), noise=noise)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class SiteOrientationObservation(Observation):
+    """6-D rotation of the listed sites (ksim/observation.py:645-669).  ``xax.rotation_matrix_to_rotation6d`` is un-vendored; it
+    is restated from memory as the first two ROWS of the matrix, flattened (the Zhou et al. convention pytorch3d also uses)."""
+
+    site_ids: tuple[int, ...] = attrs.field()
+    name: str = attrs.field(default="site_orientation")
+
+    @classmethod
+    def create(cls, *, physics_model: Model, site_names: tuple[str, ...], noise: Noise | None = None) -> "SiteOrientationObservation":
+        ids = tuple(physics_model.id("site", n) for n in site_names)
+        return cls(site_ids=ids, name=f"site_orientation_observation_{'_'.join(site_names)}", noise=noise)
+
+    def encode(self, model: Model) -> Encoded:
+        return C.OBS_SITE_ORIENTATION, [len(self.site_ids), *self.site_ids], [], 6 * len(self.site_ids), 0
+
+    def shape(self, model: Model) -> tuple[int, ...]:
+        return (len(self.site_ids), 6)
+
+
+@attrs.define(frozen=True)
+class ActPosObservation(Observation):
+    """(last control of one actuator, position of its joint): the reference's debugging observation (ksim/observation.py:717-747)."""
+
+    joint_name: str = attrs.field()
+    ctrl_idx: int = attrs.field()
+    qpos_idx: int = attrs.field()
+
+    @classmethod
+    def create(cls, *, physics_model: Model, joint_name: str) -> "ActPosObservation":
+        qpos_idx = int(physics_model.jnt_qposadr[physics_model.id("joint", joint_name)])
+        return cls(joint_name=joint_name, ctrl_idx=physics_model.id("actuator", f"{joint_name}_ctrl"), qpos_idx=qpos_idx)
+
+    def encode(self, model: Model) -> Encoded:
+        return C.OBS_ACT_POS, [int(self.ctrl_idx), int(self.qpos_idx)], [], 2, 0

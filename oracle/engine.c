@@ -203,7 +203,7 @@ typedef struct {
   OData d;
   REAL level;
   REAL last_ctrl[2 * O_MAXNU], latency, zero_off[O_MAXNU];
-  REAL event[32], act_state[2 * O_MAXNU + 3], cmd[32], obs_carry[64];
+  REAL event[32], act_state[2 * O_MAXNU + 3], cmd[32], obs_carry[512];  /* delayed observations: delay_steps x joints each */
   Key rng, bias_key[32];
   REAL nonfinite;
 } Env;
@@ -755,6 +755,12 @@ static void obs_carry_initial(const Task* t, Env* e, int idx, Key rng) {
     c[0] = c[1] = c[2] = 0;
     c[3] = key_uniform(lrng, 0, of[3], of[4]);
     for (int k = 0; k < 3; k++) c[4 + k] = key_uniform(brng, k, -of[5], of[5]);
+  } else if (type == OBS_DELAYED_JOINT_POSITION || type == OBS_DELAYED_JOINT_VELOCITY) {
+    /* observation.py:232-236 / 264-268: jnp.tile(current[None, :], (delay_steps, 1)) */
+    int dim = TAB(t, TI_OBS_TAB, idx, TAB_OUT_DIM);
+    int delay = (t->ti + TAB(t, TI_OBS_TAB, idx, TAB_IOFF) + NOISE_NI + BIAS_NI)[0];
+    for (int r = 0; r < delay; r++)
+      for (int k = 0; k < dim; k++) c[r * dim + k] = type == OBS_DELAYED_JOINT_POSITION ? e->d.qpos[7 + k] : e->d.qvel[6 + k];
   }
 }
 
@@ -839,6 +845,24 @@ static void observe(const Task* t, Env* e, Key rng, REAL* out) {
         }
         v[0] = com_distance((const REAL (*)[2])pts, d->ncon, d->subtree_com[2]);
       } break;
+      case OBS_DELAYED_JOINT_POSITION: case OBS_DELAYED_JOINT_VELOCITY: {
+        /* observation.py:238-252 / 270-283: reading = carry[0] (- zero_offset); carry = roll(carry, -1).at[-1].set(current) */
+        REAL* c = e->obs_carry + coff;
+        int delay = oi[0], pos = type == OBS_DELAYED_JOINT_POSITION;
+        for (int k = 0; k < dim; k++) v[k] = pos ? c[k] - e->zero_off[k] : c[k];
+        for (int r = 0; r + 1 < delay; r++) for (int k = 0; k < dim; k++) c[r * dim + k] = c[(r + 1) * dim + k];
+        for (int k = 0; k < dim; k++) c[(delay - 1) * dim + k] = pos ? d->qpos[7 + k] : d->qvel[6 + k];
+      } break;
+      case OBS_CONTACT:
+        /* observation.py:474-478: geoms_colliding(data, idxs, idxs).any(axis=-1) */
+        for (int k = 0; k < oi[0]; k++) v[k] = (REAL)geoms_colliding(d, oi + 1 + k, 1, oi + 1, oi[0]);
+        break;
+      case OBS_BODY_ORIENTATION: for (int b = 0; b < oi[0]; b++) for (int k = 0; k < 4; k++) v[4 * b + k] = d->xquat[oi[1 + b]][k]; break;
+      case OBS_SITE_ORIENTATION:
+        /* observation.py:666-669; xax.rotation_matrix_to_rotation6d (un-vendored) restated as rows 0 and 1 of the matrix */
+        for (int b = 0; b < oi[0]; b++) for (int k = 0; k < 6; k++) v[6 * b + k] = d->site_xmat[oi[1 + b]][k];
+        break;
+      case OBS_ACT_POS: v[0] = e->last_ctrl[oi[0]]; v[1] = d->qpos[oi[1]]; break;
       default: for (int k = 0; k < dim; k++) v[k] = 0; break;
     }
     if (noff >= 0) {
