@@ -561,7 +561,12 @@ extern "C" int b200sim_model_create(const void* blob, size_t nbytes, b200sim_mod
   mo->mdl.mf = (const float*)(d + MH_SIZE + ni);
   mo->mdl.ti = d + MH_SIZE + ni + nf;
   mo->mdl.tf = (const float*)(d + MH_SIZE + ni + nf + nti);
-  mo->mdl.sync_mask = 0x7f;  // measured best on B200 (profiles/): a CTA barrier after every stage; votes inside the Newton loop (bit 7) are neutral since the solve became short
+  // Measured on B200 (profiles/r02k_barrier_masks.txt): the CTA barriers that pay are the ones after the two stages whose length
+  // varies per environment -- acceleration (bit 4: the Z solves depend on the row count) and the Newton solve (bit 5) -- plus the
+  // control-step one (bit 6, neutral); the barriers after the fixed-length stages (bits 0-3) cost 2.5 % on the humanoid kernel
+  // (33.9 -> 33.0 ms) now that the stages between them are short, and nothing either way on the K-Bot kernel.  Without bit 4 or 5
+  // the warps stay out of step through the following stages and every warp pays its own instruction-cache misses (+3 % / +33 %).
+  mo->mdl.sync_mask = 0x70;
 #ifdef B2S_POISON_SMEM
   mo->mdl.poison_lo = getenv("B2S_POISON_LO") ? atoi(getenv("B2S_POISON_LO")) : 0;
   mo->mdl.poison_hi = getenv("B2S_POISON_HI") ? atoi(getenv("B2S_POISON_HI")) : 0;

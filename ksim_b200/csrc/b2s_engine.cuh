@@ -413,6 +413,21 @@ DEV void reset_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
         w.qpos[2] = rf[0];
       }
       break;
+    case RESET_HFIELD_XY_POSITION:
+      // resets.py:56-89: xy like the plane reset, z read from the height field's cell under (x, y)
+      IF_LANE0 {
+        const Key kx = key_split(rng, 0), ky = key_split(rng, 1);
+        const float x = clipf(key_uniform(kx, 0, -rf[4], rf[4]), rf[6], rf[7]);
+        const float y = clipf(key_uniform(ky, 0, -rf[5], rf[5]), rf[8], rf[9]);
+        const int nx = ri[0], ny = ri[1];
+        int xi = (int)(((x + rf[0]) / (2.0f * rf[0])) * (float)(nx - 1));
+        int yi = (int)(((y + rf[1]) / (2.0f * rf[1])) * (float)(ny - 1));
+        xi = xi < 0 ? 0 : (xi > nx - 1 ? nx - 1 : xi);
+        yi = yi < 0 ? 0 : (yi > ny - 1 ? ny - 1 : yi);
+        w.qpos[0] = x; w.qpos[1] = y;
+        w.qpos[2] = rf[10 + xi * ny + yi] + rf[2] + rf[3];
+      }
+      break;
     case RESET_RANDOM_HEIGHT:
       IF_LANE0 w.qpos[2] += key_uniform(rng, 0, rf[0], rf[1]);
       break;

@@ -3,7 +3,7 @@
 from __future__ import annotations
 
 __all__ = [
-    "Reset", "PlaneXYPositionReset", "RandomJointPositionReset", "RandomJointVelocityReset",
+    "Reset", "PlaneXYPositionReset", "HFieldXYPositionReset", "RandomJointPositionReset", "RandomJointVelocityReset",
     "RandomBaseVelocityXYReset", "RandomHeadingReset", "RandomHeightReset", "RandomPitchRollReset",
     "get_xy_position_reset",
 ]
@@ -32,6 +32,31 @@ class PlaneXYPositionReset(Reset):
 
     def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
         return C.RESET_PLANE_XY_POSITION, [], [self.bounds[2] + self.robot_base_height, self.x_range, self.y_range, *self.padded_bounds]
+
+
+@attrs.define(frozen=True, kw_only=True, eq=False)
+class HFieldXYPositionReset(Reset):
+    """XY drawn like ``PlaneXYPositionReset``; z is the height-field cell under (x, y) plus ``z_top`` plus the base height
+    (ksim/resets.py:45-89).  ``hfield_data`` is the ``[nrow, ncol]`` elevation array the reference reads from
+    ``physics_model.hfield_data``; it travels in the task program, so the reset works whatever the collision floor is (height
+    -field *collision* is outside the supported model subset)."""
+
+    bounds: tuple[float, float, float, float]
+    padded_bounds: tuple[float, float, float, float]
+    x_range: float = attrs.field(default=5.0)
+    y_range: float = attrs.field(default=5.0)
+    hfield_data: object = attrs.field()
+    robot_base_height: float = attrs.field(default=0.0)
+
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
+        import numpy as np
+
+        data = np.asarray(getattr(self.hfield_data, "array", self.hfield_data), dtype=np.float32)
+        if data.ndim != 2 or data.size == 0:
+            raise ValueError("hfield_data must be a non-empty [nrow, ncol] array")
+        x_bound, y_bound, z_top, _ = self.bounds
+        floats = [x_bound, y_bound, z_top, self.robot_base_height, self.x_range, self.y_range, *self.padded_bounds]
+        return C.RESET_HFIELD_XY_POSITION, [int(data.shape[0]), int(data.shape[1])], [float(v) for v in floats] + data.reshape(-1).tolist()
 
 
 @attrs.define(frozen=True, kw_only=True)
@@ -115,7 +140,18 @@ class RandomPitchRollReset(Reset):
 
 def get_xy_position_reset(physics_model: Model, x_range: float = 5.0, y_range: float = 5.0, x_edge_padding: float = 5.0,
                           y_edge_padding: float = 5.0, robot_base_height: float = 0.0) -> Reset:
-    """Plane-floor variant of ksim/resets.py:210-280 (height fields are outside the supported subset)."""
+    """ksim/resets.py:210-280: a height-field reset when the model carries ``hfield_size`` / ``hfield_data`` (this repo's MJCF
+    compiler never produces them; a caller may attach the arrays to the model), else the plane reset."""
+    hsize = getattr(physics_model, "hfield_size", None)
+    if hsize is not None and len(hsize) > 0:
+        import numpy as np
+
+        x_bound, y_bound, z_top, z_bottom = (float(v) for v in np.asarray(hsize).reshape(-1)[:4])
+        nx, ny = int(np.asarray(physics_model.hfield_nrow).reshape(-1)[0]), int(np.asarray(physics_model.hfield_ncol).reshape(-1)[0])
+        padded = (-x_bound + x_edge_padding, x_bound - x_edge_padding, -y_bound + y_edge_padding, y_bound - y_edge_padding)
+        return HFieldXYPositionReset(bounds=(x_bound, y_bound, z_top, z_bottom), padded_bounds=padded, x_range=x_range, y_range=y_range,
+                                     hfield_data=np.asarray(physics_model.hfield_data, dtype=np.float32).reshape(nx, ny),
+                                     robot_base_height=robot_base_height)
     planes = [i for i, t in enumerate(physics_model.geom_type) if t == GEOM.PLANE]
     if not planes:
         raise ValueError("No heightfield or plane geom found in the model. MuJoCo scene missing floor!")

@@ -515,6 +515,21 @@ static void reset_apply(const Task* t, Env* e, int idx, Key rng) {
       if (y < rf[5]) y = rf[5]; if (y > rf[6]) y = rf[6];
       d->qpos[0] = x; d->qpos[1] = y; d->qpos[2] = rf[0];
     } break;
+    case RESET_HFIELD_XY_POSITION: {
+      /* resets.py:56-89; ints [nx, ny]; floats [x_bound, y_bound, z_top, base_height, x_range, y_range, lower_x, upper_x,
+         lower_y, upper_y, heights[nx][ny]] */
+      Key kx = key_split(rng, 0), ky = key_split(rng, 1);
+      REAL x = key_uniform(kx, 0, -rf[4], rf[4]), y = key_uniform(ky, 0, -rf[5], rf[5]);
+      if (x < rf[6]) x = rf[6]; if (x > rf[7]) x = rf[7];
+      if (y < rf[8]) y = rf[8]; if (y > rf[9]) y = rf[9];
+      int nx = ri[0], ny = ri[1];
+      int xi = (int)(((x + rf[0]) / ((REAL)2 * rf[0])) * (REAL)(nx - 1));
+      int yi = (int)(((y + rf[1]) / ((REAL)2 * rf[1])) * (REAL)(ny - 1));
+      xi = xi < 0 ? 0 : (xi > nx - 1 ? nx - 1 : xi);
+      yi = yi < 0 ? 0 : (yi > ny - 1 ? ny - 1 : yi);
+      d->qpos[0] = x; d->qpos[1] = y;
+      d->qpos[2] = rf[10 + xi * ny + yi] + rf[2] + rf[3];
+    } break;
     case RESET_RANDOM_HEIGHT: d->qpos[2] += key_uniform(rng, 0, rf[0], rf[1]); break;
     case RESET_RANDOM_PITCH_ROLL: {
       /* same key for pitch and roll draws (resets.py:346-347) */
