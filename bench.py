@@ -271,8 +271,38 @@ def _extras(eng, actions, rec, device, rank: int, world: int, args: argparse.Nam
                                             "final_loss": float(tr.loss)}
             del tr, model
             torch.cuda.empty_cache()
+        # the replay kernels alone: one eager update with CUDA events around every GRU launch (ksim_b200.replay.KERNEL_TIMES)
+        gru = None
+        try:
+            from ksim_b200 import replay
+
+            torch.manual_seed(0)
+            model = walking.make_model(eng.spec).to(device)
+            tr = PPOTrainer(eng, model, walking.network_columns(eng.program, walking.ACTOR_INPUTS),
+                            walking.network_columns(eng.program, walking.CRITIC_INPUTS),
+                            PPOConfig(batch_size=512, num_passes=4, rollout_length_frames=24), use_graphs=False, seed=rank)
+            tr.iteration()
+            tr.rollout(); tr.score()
+            torch.cuda.synchronize(device)
+            replay.KERNEL_TIMES = []
+            tr.update_model()
+            torch.cuda.synchronize(device)
+            times, replay.KERNEL_TIMES = replay.KERNEL_TIMES, None
+            peak_tf = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("bf16_tflops_sustained", 1385.4)) if (ROOT / "MEASURED_PEAKS.json").exists() else 1385.4
+            gru = {"peak": peak_tf, "unit": "TFLOP/s", "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)",
+                   "shape": "B = 512 rows x T = 24 steps x 2 networks per launch, GRU(512): 2 T B 3H H flops per network (the sequential h W_hh^T / dgh W_hh products only)"}
+            for d in ("fwd", "bwd"):
+                ms_ = [a.elapsed_time(b) for (dd, t_, b_, ns, a, b) in times if dd == d and b_ == 512]
+                if ms_:
+                    flops = 2.0 * 24 * 512 * 2 * (3 * 512) * 512
+                    m_ = float(np.median(ms_))
+                    gru[d] = {"launches": len(ms_), "ms_per_launch": m_, "achieved": flops / (m_ * 1e-3) / 1e12, "frac": flops / (m_ * 1e-3) / 1e12 / peak_tf}
+            del tr, model
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            gru = {"error": f"{type(e).__name__}: {e}"[:200]}
         out["ppo_iteration"] = {
-            **ppo_out, "unit": "ms", "envs_per_gpu": n, "batch_size": 512, "num_passes": 4, "updates_per_iteration": 4 * (n // 512),
+            **ppo_out, "gru_kernels": gru, "unit": "ms", "envs_per_gpu": n, "batch_size": 512, "num_passes": 4, "updates_per_iteration": 4 * (n // 512),
             "gradient_allreduce": (f"in-place NCCL all-reduce of the {PPO_GRAD_FLOATS * 4 / 1e6:.1f} MB flat gradient inside every captured "
                                    "minibatch step") if world > 1 else "none (single rank)",
             "ours": "engine step, rewards, flags, GAE, PPO loss fwd+bwd, GRU sequence kernels (tcgen05), mixture head, optimiser step",

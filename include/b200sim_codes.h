@@ -193,6 +193,13 @@
 #define CMD_LINEAR_VELOCITY 1
 #define CMD_ANGULAR_VELOCITY 2
 #define CMD_FLOAT_VECTOR 3
+#define CMD_INT_VECTOR 5         /* commands.py:137-169: ints [lo, hi]*n; floats [switch_prob, zero_prob]; randint and the zero mask share the key */
+#define CMD_START_POSITION 6     /* commands.py:173-192: qpos[:3] at the reset, constant afterwards */
+#define CMD_START_QUATERNION 7   /* commands.py:195-214: qpos[3:7] at the reset, constant afterwards */
+#define CMD_BASE_HEIGHT 8        /* commands.py:773-796: floats [min, max, switch_prob]; the redraw and its switch share the key */
+#define CMD_CARTESIAN_COORDINATE 9  /* commands.py:537-692: state [current xyz, target xyz, speed]; floats [box_min 3, box_max 3, dt, min_speed, max_speed, switch_prob, jump_prob, curriculum_scale] */
+#define CMD_SINUSOIDAL_GAIT 10   /* commands.py:703-770: state [moving_flag, phase, height[num_feet]]; ints [num_feet]; floats [gait_period, ctrl_dt, max_height, height_offset, stance_ratio, moving_threshold] */
+#define CMD_JOINT_POSITION 11    /* commands.py:799-880: state [start n, target n, total_time, num_steps, step_id]; ints [n, indices]; floats [lo, hi]*n, ctrl_dt, min_time, max_time */
 #define CMD_UNIFIED 4            /* examples/kbot/train.py:701-775: [vx vy wz bh rx ry arms[10]], 6-way mode switch */
 
 /* ---- rewards (ksim/rewards.py) ---- */
@@ -228,6 +235,10 @@
 #define REW_SYMMETRY 39
 #define REW_PAIRWISE_SYMMETRY 40
 #define REW_AMP 41               /* ksim/task/amp.py:100-112: max(0, 1 - 0.25 (logit - 1)^2) of an aux output; ints [aux offset] */
+#define REW_POSITION_TRACKING 42  /* rewards.py:704-744: ints [tracked body, base body, command offset, l2]; floats [kernel_scale] */
+#define REW_SINUSOIDAL_GAIT 43   /* rewards.py:1320-1348: ints [position obs offset, num_feet, command height offset]; floats [max_height] */
+#define REW_JOINT_POSITION 44    /* rewards.py:1352-1414: ints [n, command offset, indices]; floats [pos_scale, vel_scale, sq_scale, abs_scale]; comps pos, vel */
+#define REW_INTERSECTION 45      /* rewards.py:1418-1430: ints [position obs offset, n]; floats [min_distance] */
 #define REW_KBOT_SINGLE_FOOT_CONTACT 16
 #define REW_KBOT_NO_CONTACT 17
 #define REW_KBOT_FEET_AIRTIME 18

@@ -214,6 +214,13 @@ DEV uint32_t key_randint(Key k, uint32_t span) {
   return ((hi % span) * mult + (lo % span)) % span;
 }
 DEV uint32_t randint3(Key k) { return key_randint(k, 3u); }
+// element i of jax.random.randint(key, (n,), lo, hi): offset in [0, span)
+DEV uint32_t key_randint_at(Key k, int i, uint32_t span) {
+  const Key ra = key_split(k, 0), rb = key_split(k, 1);
+  const uint32_t hi = key_bits(ra, i), lo = key_bits(rb, i);
+  const uint32_t mult = ((65536u % span) * (65536u % span)) % span;
+  return ((hi % span) * mult + (lo % span)) % span;
+}
 
 template <class D>
 DEVNI void event_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
@@ -555,6 +562,26 @@ DEVNI void cmd_unified_initial(const float* cf, Key rng, float* out) {
   }
 }
 
+// CartesianCoordinateCommand._sample_box (commands.py:557-581)
+DEV void cmd_cartesian_sample(const float* cf, float level, Key rng, float* out) {
+  const float sf = cf[11] * level + 1.0f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float center = (cf[k] + cf[3 + k]) / 2.0f, half = (cf[3 + k] - cf[k]) / 2.0f * sf;
+    out[k] = key_uniform(rng, k, center - half, center + half);
+  }
+}
+// SinusoidalGaitCommand._get_height (commands.py:712-733)
+DEV void cmd_gait_heights(const float* cf, int nf, float phase, float* out) {
+  const float max_h = cf[2], offset = cf[3], sr = cf[4];
+  for (int f = 0; f < nf; f++) {
+    float pf = phase + (float)f / (float)nf;
+    pf = pf - floorf(pf);
+    const float prog = clipf((pf - sr) / (1.0f - sr), 0.0f, 1.0f);
+    out[f] = (pf >= sr ? max_h * sinf(PI_F * prog) : 0.0f) + offset;
+  }
+}
+
 // lane 0 only
 template <class D>
 DEV void cmd_initial(const Mdl& m, Work<D>& w, int idx, Key rng) {
@@ -568,6 +595,29 @@ DEV void cmd_initial(const Mdl& m, Work<D>& w, int idx, Key rng) {
   else if (type == CMD_ANGULAR_VELOCITY) cmd_angvel_initial(ci, cf, w, rng, st);
   else if (type == CMD_FLOAT_VECTOR) cmd_floatvec_initial(cf, dim, rng, st);
   else if (type == CMD_UNIFIED) cmd_unified_initial(cf, rng, st);
+  else if (type == CMD_INT_VECTOR) {
+    const int zero = key_bernoulli(rng, 0, cf[1]);
+    for (int i = 0; i < dim; i++)
+      st[i] = zero ? 0.0f : (float)(ci[2 * i] + (int)key_randint_at(rng, i, (uint32_t)(ci[2 * i + 1] + 1 - ci[2 * i])));
+  } else if (type == CMD_START_POSITION) { st[0] = w.qpos[0]; st[1] = w.qpos[1]; st[2] = w.qpos[2]; }
+  else if (type == CMD_START_QUATERNION) { st[0] = w.qpos[3]; st[1] = w.qpos[4]; st[2] = w.qpos[5]; st[3] = w.qpos[6]; }
+  else if (type == CMD_BASE_HEIGHT) st[0] = key_uniform(rng, 0, cf[0], cf[1]);
+  else if (type == CMD_CARTESIAN_COORDINATE) {
+    float tg[3];
+    cmd_cartesian_sample(cf, w.level, key_split(rng, 0), tg);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { st[k] = tg[k]; st[3 + k] = tg[k]; }
+    st[6] = key_uniform(key_split(rng, 1), 0, cf[7], cf[8]);
+  } else if (type == CMD_SINUSOIDAL_GAIT) {
+    st[0] = 1.0f; st[1] = 0.0f;
+    cmd_gait_heights(cf, ci[0], 0.0f, st + 2);
+  } else if (type == CMD_JOINT_POSITION) {
+    const int n = ci[0];
+    const Key ra = key_split(rng, 0), rb = key_split(rng, 1);
+    for (int i = 0; i < n; i++) { st[i] = w.qpos[7 + ci[1 + i]]; st[n + i] = key_uniform(ra, i, cf[2 * i], cf[2 * i + 1]); }
+    const float tt = key_uniform(rb, 0, cf[2 * n + 1], cf[2 * n + 2]);
+    st[2 * n] = tt; st[2 * n + 1] = ceilf(tt / cf[2 * n]); st[2 * n + 2] = 0.0f;
+  }
 }
 
 // lane 0 only
@@ -611,6 +661,43 @@ DEV void cmd_update(const Mdl& m, Work<D>& w, int idx, Key rng) {
       cmd_floatvec_initial(cf, dim, key_split(rng, 1), fresh);
       for (int i = 0; i < dim; i++) st[i] = fresh[i];
     }
+  } else if (type == CMD_INT_VECTOR) {
+    if (key_bernoulli(ra, 0, cf[0])) cmd_initial(m, w, idx, key_split(rng, 1));
+  } else if (type == CMD_BASE_HEIGHT) {
+    // commands.py:790-796: the fresh height and the switch are drawn from the SAME (unsplit) key
+    if (key_bernoulli(rng, 0, cf[2])) st[0] = key_uniform(rng, 0, cf[0], cf[1]);
+  } else if (type == CMD_CARTESIAN_COORDINATE) {
+    // commands.py:599-643
+    const float dx = st[3] - st[0], dy = st[4] - st[1], dz = st[5] - st[2];
+    const float distance = sqrtf(dx * dx + dy * dy + dz * dz);
+    const Key rc = key_split(rng, 2);
+    const bool reached = distance < cf[6] * st[6] * 0.5f;
+    const bool change = (reached && key_bernoulli(rc, 0, cf[9])) || key_bernoulli(rc, 0, cf[10]);
+    if (change) {
+      cmd_cartesian_sample(cf, w.level, ra, st + 3);
+      st[6] = key_uniform(key_split(rng, 1), 0, cf[7], cf[8]);
+    }
+    const float step = st[6] * cf[6];
+    float d[3] = {st[3] - st[0], st[4] - st[1], st[5] - st[2]};
+    const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const float adv = fminf(step, distance);
+#pragma unroll
+    for (int k = 0; k < 3; k++) st[k] = st[k] + (dn > 0.0f ? d[k] / dn : d[k]) * adv;
+  } else if (type == CMD_SINUSOIDAL_GAIT) {
+    // commands.py:748-770: phase advances while the robot moves, restarts when it stops (the flag never comes back on)
+    const bool moving = st[0] != 0.0f;
+    float ph = st[1] + cf[1] / cf[0];
+    ph = moving ? ph - floorf(ph) : 0.0f;
+    const bool is_moving = sqrtf(w.qvel[0] * w.qvel[0] + w.qvel[1] * w.qvel[1]) > cf[5];
+    if (!is_moving) { st[0] = 0.0f; ph = 0.0f; }
+    st[1] = ph;
+    cmd_gait_heights(cf, ci[0], ph, st + 2);
+  } else if (type == CMD_JOINT_POSITION) {
+    // commands.py:853-880: a fresh command (same, unsplit key) once the step counter has passed num_steps
+    const int n = ci[0];
+    const float step_id = st[2 * n + 2] + 1.0f;
+    if (step_id > st[2 * n + 1]) cmd_initial(m, w, idx, rng);
+    else st[2 * n + 2] = step_id;
   } else if (type == CMD_UNIFIED) {
     if (key_bernoulli(ra, 0, cf[32])) cmd_unified_initial(cf, key_split(rng, 1), st);
   }

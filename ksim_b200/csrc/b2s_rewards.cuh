@@ -74,6 +74,56 @@ DEV void env_rewards(const Mdl& m, const float* rec, size_t tstride, int T, floa
           OUT(0, s) = fmaxf(0.0f, 1.0f - 0.25f * d * d);
         }
         break;
+      case REW_POSITION_TRACKING: {
+        // rewards.py:715-721: exp_kernel(sum_k norm((xpos[tracked] - xpos[base])_k - command[:3]_k)); command[:3] is the
+        // CURRENT point of the CartesianCoordinateCommand
+        const int XP = ti[TI_R_XPOS];
+        LANE_FOR(s, T) {
+          float err = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            err += norm_fn((REC(s, XP + 3 * xi[0] + k) - REC(s, XP + 3 * xi[1] + k)) - REC(s, CM + xi[2] + k), xi[3]);
+          OUT(0, s) = exp_kernel(err, xf[0]);
+        }
+      } break;
+      case REW_SINUSOIDAL_GAIT:
+        // rewards.py:1336-1340: 1 - sum_f |obs[f].z - cmd.height[f]| / max_height
+        LANE_FOR(s, T) {
+          float acc = 0.0f;
+          for (int f = 0; f < xi[1]; f++) acc += fabsf(REC(s, OB + xi[0] + 3 * f + 2) - REC(s, CM + xi[2] + f));
+          OUT(0, s) = 1.0f - acc / xf[0];
+        }
+        break;
+      case REW_JOINT_POSITION: {
+        // rewards.py:1370-1385 with JointPositionCommandValue.current_position / current_velocity (commands.py:806-820)
+        const int n = xi[0], c = CM + xi[1];
+        LANE_FOR(s, T) {
+          const float total_time = REC(s, c + 2 * n), num_steps = REC(s, c + 2 * n + 1), step_id = REC(s, c + 2 * n + 2);
+          float ap = 0.0f, av = 0.0f;
+          for (int i = 0; i < n; i++) {
+            const float st0 = REC(s, c + i), d = REC(s, c + n + i) - st0;
+            const float cpos = st0 + d * step_id / num_steps, cvel = d / total_time;
+            ap += exp_kernel_pen(cpos - REC(s, QP + 7 + xi[2 + i]), xf[0], xf[2], xf[3]);
+            av += exp_kernel_pen(cvel - REC(s, QV + 6 + xi[2 + i]), xf[1], xf[2], xf[3]);
+          }
+          OUT(0, s) = ap / (float)n;
+          OUT(1, s) = av / (float)n;
+        }
+      } break;
+      case REW_INTERSECTION:
+        // rewards.py:1424-1430: any pair (i > j) of the observed points closer than min_distance
+        LANE_FOR(s, T) {
+          bool close = false;
+          for (int i = 1; i < xi[1]; i++)
+            for (int j = 0; j < i; j++) {
+              const float dx = REC(s, OB + xi[0] + 3 * i) - REC(s, OB + xi[0] + 3 * j);
+              const float dy = REC(s, OB + xi[0] + 3 * i + 1) - REC(s, OB + xi[0] + 3 * j + 1);
+              const float dz = REC(s, OB + xi[0] + 3 * i + 2) - REC(s, OB + xi[0] + 3 * j + 2);
+              close |= sqrtf(dx * dx + dy * dy + dz * dz) < xf[0];
+            }
+          OUT(0, s) = close ? 1.0f : 0.0f;
+        }
+        break;
       case REW_STAY_ALIVE:
         LANE_FOR(s, T) {
           const float alive = 1.0f / xf[0];

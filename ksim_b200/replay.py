@@ -150,6 +150,22 @@ def gru_stack_reference(stack: GRUStack, x: torch.Tensor, carry: torch.Tensor | 
     return torch.stack(ys), torch.stack(h)
 
 
+# Measurement hook (bench.py): a list here makes every eager GRU kernel launch append (direction, T, B, stacks, start event, end
+# event), CUDA events recorded on the launch stream around the one launch.  None (the default) costs nothing.
+KERNEL_TIMES: list | None = None
+
+
+def _timed_launch(direction: str, t_: int, b_: int, n_stacks: int, dev: torch.device, launch) -> None:  # noqa: ANN001
+    if KERNEL_TIMES is None or torch.cuda.is_current_stream_capturing():
+        launch()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream(dev))
+    launch()
+    e1.record(torch.cuda.current_stream(dev))
+    KERNEL_TIMES.append((direction, t_, b_, n_stacks, e0, e1))
+
+
 class _GruStacksFn(torch.autograd.Function):
     """Up to ``B2S_GRU_MAX_PROBLEMS`` GRU stacks of equal depth over the same ``(T, B)`` batch, layer by layer; each layer of
     all stacks is one persistent kernel launch per direction.  Between the kernels and the library GEMMs every sequence array
@@ -198,7 +214,8 @@ class _GruStacksFn(torch.autograd.Function):
                 nxt.append(y)
                 saved_layers.append((cur[s], w_ih16, w_hh16, hst, sv))
             with torch.cuda.device(dev):
-                _check(lib.b200sim_gru_forward(stream, n_stacks, ctypes.byref(probs), t_, b_, _p(keep), _p(ws), ws.numel()), "b200sim_gru_forward")
+                _timed_launch("fwd", t_, b_, n_stacks, dev, lambda: _check(
+                    lib.b200sim_gru_forward(stream, n_stacks, ctypes.byref(probs), t_, b_, _p(keep), _p(ws), ws.numel()), "b200sim_gru_forward"))
             del hold  # stream-ordered allocator: the memory is not reused before the launch has run
             cur = nxt
         ctx.n_stacks, ctx.depth, ctx.shape, ctx.keep = n_stacks, depth, (t_, b_), keep
@@ -241,7 +258,8 @@ class _GruStacksFn(torch.autograd.Function):
                 outs.append((dgi, dghn))
                 hold += [w_hh_t, dy[s]]
             with torch.cuda.device(dev):
-                _check(lib.b200sim_gru_backward(stream, n_stacks, ctypes.byref(probs), t_, b_, _p(keep), _p(ws), ws.numel()), "b200sim_gru_backward")
+                _timed_launch("bwd", t_, b_, n_stacks, dev, lambda: _check(
+                    lib.b200sim_gru_backward(stream, n_stacks, ctypes.byref(probs), t_, b_, _p(keep), _p(ws), ws.numel()), "b200sim_gru_backward"))
             del hold
             for s in range(n_stacks):
                 x_in, w_ih16, w_hh16, hst, sv = ctx.saved_layers[layer * n_stacks + s]

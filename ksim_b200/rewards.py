@@ -15,7 +15,8 @@ __all__ = ["AMPReward", "DISCRIMINATOR_OUTPUT_KEY",
     "BaseHeightRangeReward", "OffAxisVelocityReward", "SmallJointVelocityReward", "SmallJointAccelerationReward",
     "SmallJointJerkReward", "AvoidLimitsPenalty", "TorquePenalty", "EnergyPenalty", "JointDeviationPenalty", "FlatBodyReward",
     "NoRollReward", "LinkAccelerationPenalty", "LinkJerkPenalty", "FeetSlipPenalty", "ReachabilityPenalty", "SymmetryReward",
-    "PairwiseSymmetryReward", "exp_kernel", "exp_kernel_with_penalty",
+    "PairwiseSymmetryReward", "PositionTrackingReward", "SinusoidalGaitReward", "JointPositionReward", "IntersectionPenalty",
+    "exp_kernel", "exp_kernel_with_penalty",
 ]
 
 import math
@@ -529,3 +530,84 @@ class PairwiseSymmetryReward(StatefulReward):
         adr = physics_model.jnt_qposadr
         return cls(left_joint_index=int(adr[physics_model.id("joint", left_joint_name)]) - 7,
                    right_joint_index=int(adr[physics_model.id("joint", right_joint_name)]) - 7, **kw)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class PositionTrackingReward(Reward):
+    """Closeness of a body (relative to a base body) to the current point of a ``CartesianCoordinateCommand``
+    (ksim/rewards.py:704-744)."""
+
+    tracked_body_idx: int = attrs.field()
+    base_body_idx: int = attrs.field()
+    command_name: str = attrs.field()
+    body_name: str = attrs.field(default="")
+    norm: str = attrs.field(default="l1")
+    kernel_scale: float = attrs.field(default=0.25)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        ints = [int(self.tracked_body_idx), int(self.base_body_idx), ctx.cmd_offset(self.command_name), _norm_flag(self.norm)]
+        return C.REW_POSITION_TRACKING, ints, [float(self.kernel_scale)], [""], 0
+
+    @classmethod
+    def create(cls, model, command_name: str, tracked_body_name: str, base_body_name: str, norm: str = "l1", kernel_scale: float = 0.25,  # noqa: ANN001, ANN206
+               scale: float | Scale = 1.0):
+        return cls(tracked_body_idx=model.id("body", tracked_body_name), base_body_idx=model.id("body", base_body_name), norm=norm,
+                   command_name=command_name, body_name=tracked_body_name, scale=scale, kernel_scale=kernel_scale)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class SinusoidalGaitReward(Reward):
+    """``1 - sum_f |foot height - commanded height| / max_height`` (ksim/rewards.py:1320-1348)."""
+
+    ctrl_dt: float = attrs.field()
+    max_height: float = attrs.field()
+    pos_obs: str = attrs.field()
+    pos_cmd: str = attrs.field()
+    num_feet: int = attrs.field(default=2)
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        if ctx.obs_shape(self.pos_obs) != (self.num_feet, 3):
+            raise ValueError(f"position observation {self.pos_obs} must have shape ({self.num_feet}, 3)")
+        ints = [ctx.obs_offset(self.pos_obs), int(self.num_feet), ctx.cmd_offset(self.pos_cmd, "height")]
+        return C.REW_SINUSOIDAL_GAIT, ints, [float(self.max_height)], [""], 0
+
+
+@attrs.define(frozen=True, kw_only=True)
+class JointPositionReward(Reward):
+    """Tracking of a ``JointPositionCommand``'s interpolated position and constant velocity (ksim/rewards.py:1352-1414)."""
+
+    command_name: str = attrs.field()
+    indices: tuple[int, ...] = attrs.field()
+    pos_scale: float = attrs.field(default=0.25)
+    vel_scale: float = attrs.field(default=0.25)
+    sq_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+    abs_scale: float = attrs.field(default=0.1, validator=attrs.validators.gt(0.0))
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        ints = [len(self.indices), ctx.cmd_offset(self.command_name), *[int(i) for i in self.indices]]
+        floats = [self.pos_scale, self.vel_scale, self.sq_scale, self.abs_scale]
+        return C.REW_JOINT_POSITION, ints, [float(f) for f in floats], ["pos", "vel"], 0
+
+    @classmethod
+    def create(cls, physics_model, joint_names, command_name: str, pos_scale: float = 0.25, vel_scale: float = 0.25,  # noqa: ANN001, ANN206
+               sq_scale: float = 0.1, abs_scale: float = 0.1, scale: float | Scale = 1.0):
+        all_names = physics_model.names["joint"][1:]
+        for name in joint_names:
+            if name not in all_names:
+                raise ValueError(f"Joint {name} not found in the model! Options are: {all_names}")
+        return cls(indices=tuple(all_names.index(n) for n in joint_names), command_name=command_name, pos_scale=pos_scale,
+                   vel_scale=vel_scale, sq_scale=sq_scale, abs_scale=abs_scale, scale=scale)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class IntersectionPenalty(Reward):
+    """1 when any two of the observed points are closer than ``min_distance`` (ksim/rewards.py:1418-1430)."""
+
+    position_obs: str = attrs.field()
+    min_distance: float = attrs.field()
+
+    def encode(self, ctx: EncodeContext) -> Encoded:
+        shape = ctx.obs_shape(self.position_obs)
+        if len(shape) != 2 or shape[1] != 3:
+            raise ValueError(f"position observation {self.position_obs} must have shape (n, 3)")
+        return C.REW_INTERSECTION, [ctx.obs_offset(self.position_obs), int(shape[0])], [float(self.min_distance)], [""], 0

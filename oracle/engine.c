@@ -26,6 +26,8 @@
 #if defined(ORACLE_F32)
 #define SQRT sqrtf
 #define SIN sinf
+#define FLOOR floorf
+#define CEIL ceilf
 #define COS cosf
 #define FABS fabsf
 #define EXP expf
@@ -37,6 +39,8 @@
 #else
 #define SQRT sqrt
 #define SIN sin
+#define FLOOR floor
+#define CEIL ceil
 #define COS cos
 #define FABS fabs
 #define EXP exp
@@ -587,6 +591,36 @@ static uint32_t key_randint(Key k, uint32_t span) {
   return ((hi % span) * mult + (lo % span)) % span;
 }
 
+/* CartesianCoordinateCommand._sample_box (commands.py:557-581); floats [box_min 3, box_max 3, dt, min_speed, max_speed,
+   switch_prob, jump_prob, curriculum_scale] */
+static void cmd_cartesian_sample(const REAL* cf, REAL level, Key rng, REAL* out) {
+  REAL sf = cf[11] * level + (REAL)1;
+  for (int k = 0; k < 3; k++) {
+    REAL center = (cf[k] + cf[3 + k]) / (REAL)2, half = (cf[3 + k] - cf[k]) / (REAL)2 * sf;
+    out[k] = key_uniform(rng, k, center - half, center + half);
+  }
+}
+/* SinusoidalGaitCommand._get_height (commands.py:712-733); floats [gait_period, ctrl_dt, max_height, height_offset,
+   stance_ratio, moving_threshold] */
+static void cmd_gait_heights(const REAL* cf, int nf, REAL phase, REAL* out) {
+  REAL max_h = cf[2], offset = cf[3], sr = cf[4];
+  for (int f = 0; f < nf; f++) {
+    REAL pf = phase + (REAL)f / (REAL)nf;
+    pf = pf - FLOOR(pf);
+    REAL prog = (pf - sr) / ((REAL)1 - sr);
+    prog = prog < 0 ? 0 : (prog > 1 ? 1 : prog);
+    out[f] = (pf >= sr ? max_h * SIN((REAL)3.14159265358979323846 * prog) : 0) + offset;
+  }
+}
+
+/* element i of jax.random.randint(key, (n,), lo, hi): offset in [0, span) */
+static uint32_t key_randint_at(Key k, int i, uint32_t span) {
+  Key ra = key_split(k, 0), rb = key_split(k, 1);
+  uint32_t hi = key_bits(ra, i), lo = key_bits(rb, i);
+  uint32_t mult = (uint32_t)((65536u % span) * (65536u % span)) % span;
+  return ((hi % span) * mult + (lo % span)) % span;
+}
+
 /* UnifiedCommand.initial_command (examples/kbot/train.py:714-756).  floats: 6 x [lo, hi] (vx vy wz bh rx ry),
  * arms lo[10], arms hi[10], switch_prob.  The arm draw and its 50 % mask share one key (train.py:725-728). */
 static void cmd_unified_initial(const REAL* cf, Key rng, REAL* out) {
@@ -699,6 +733,33 @@ static void cmd_initial(const Task* t, Env* e, int idx, Key rng) {
     int zero = key_bernoulli(rng, 0, cf[2 * dim + 1]);
     for (int i = 0; i < dim; i++) st[i] = zero ? 0 : key_uniform(rng, i, cf[2 * i], cf[2 * i + 1]);
   } else if (type == CMD_UNIFIED) cmd_unified_initial(cf, rng, st);
+  else if (type == CMD_INT_VECTOR) {
+    /* commands.py:147-157: jnp.where(bernoulli(rng, zero_prob), 0.0, randint(rng, (n,), lo, hi + 1)); ints [lo, hi]*n,
+       floats [switch_prob, zero_prob] */
+    int zero = key_bernoulli(rng, 0, cf[1]);
+    for (int i = 0; i < dim; i++)
+      st[i] = zero ? 0 : (REAL)(ci[2 * i] + (int)key_randint_at(rng, i, (uint32_t)(ci[2 * i + 1] + 1 - ci[2 * i])));
+  } else if (type == CMD_START_POSITION) { for (int k = 0; k < 3; k++) st[k] = e->d.qpos[k]; }      /* commands.py:176-182 */
+  else if (type == CMD_START_QUATERNION) { for (int k = 0; k < 4; k++) st[k] = e->d.qpos[3 + k]; }  /* commands.py:198-204 */
+  else if (type == CMD_BASE_HEIGHT) st[0] = key_uniform(rng, 0, cf[0], cf[1]);                       /* commands.py:778-784 */
+  else if (type == CMD_CARTESIAN_COORDINATE) {
+    /* commands.py:583-597: [target, target, speed] */
+    REAL tg[3];
+    cmd_cartesian_sample(cf, e->level, key_split(rng, 0), tg);
+    for (int k = 0; k < 3; k++) { st[k] = tg[k]; st[3 + k] = tg[k]; }
+    st[6] = key_uniform(key_split(rng, 1), 0, cf[7], cf[8]);
+  } else if (type == CMD_SINUSOIDAL_GAIT) {
+    /* commands.py:735-746 */
+    st[0] = 1; st[1] = 0;
+    cmd_gait_heights(cf, ci[0], 0, st + 2);
+  } else if (type == CMD_JOINT_POSITION) {
+    /* commands.py:834-851; ints [n, indices]; floats [lo, hi]*n, ctrl_dt, min_time, max_time */
+    int n = ci[0];
+    Key ra = key_split(rng, 0), rb = key_split(rng, 1);
+    for (int i = 0; i < n; i++) { st[i] = e->d.qpos[7 + ci[1 + i]]; st[n + i] = key_uniform(ra, i, cf[2 * i], cf[2 * i + 1]); }
+    REAL tt = key_uniform(rb, 0, cf[2 * n + 1], cf[2 * n + 2]);
+    st[2 * n] = tt; st[2 * n + 1] = CEIL(tt / cf[2 * n]); st[2 * n + 2] = 0;
+  }
 }
 
 static void cmd_update(const Task* t, Env* e, int idx, Key rng) {
@@ -735,6 +796,47 @@ static void cmd_update(const Task* t, Env* e, int idx, Key rng) {
     int sw = key_bernoulli(ra, 0, cf[2 * dim]);
     cmd_initial(t, e, idx, rb);
     if (!sw) for (int i = 0; i < dim; i++) st[i] = prev[i];
+  } else if (type == CMD_INT_VECTOR) {
+    /* commands.py:159-169 */
+    REAL prev[32];
+    for (int i = 0; i < dim; i++) prev[i] = st[i];
+    int sw = key_bernoulli(ra, 0, cf[0]);
+    cmd_initial(t, e, idx, rb);
+    if (!sw) for (int i = 0; i < dim; i++) st[i] = prev[i];
+  } else if (type == CMD_BASE_HEIGHT) {
+    /* commands.py:786-796: new height and switch from the same, unsplit key */
+    REAL fresh = key_uniform(rng, 0, cf[0], cf[1]);
+    if (key_bernoulli(rng, 0, cf[2])) st[0] = fresh;
+  } else if (type == CMD_CARTESIAN_COORDINATE) {
+    /* commands.py:599-643 */
+    REAL dx = st[3] - st[0], dy = st[4] - st[1], dz = st[5] - st[2];
+    REAL distance = SQRT(dx * dx + dy * dy + dz * dz);
+    Key rc = key_split(rng, 2);
+    int reached = distance < cf[6] * st[6] * (REAL)0.5;
+    REAL ntg[3], nsp = key_uniform(rb, 0, cf[7], cf[8]);
+    cmd_cartesian_sample(cf, e->level, ra, ntg);
+    int change = (reached && key_bernoulli(rc, 0, cf[9])) || key_bernoulli(rc, 0, cf[10]);
+    if (change) { for (int k = 0; k < 3; k++) st[3 + k] = ntg[k]; st[6] = nsp; }
+    REAL step = st[6] * cf[6];
+    REAL dd[3] = {st[3] - st[0], st[4] - st[1], st[5] - st[2]};
+    REAL dn = SQRT(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+    REAL adv = step < distance ? step : distance;
+    for (int k = 0; k < 3; k++) st[k] = st[k] + (dn > 0 ? dd[k] / dn : dd[k]) * adv;
+  } else if (type == CMD_SINUSOIDAL_GAIT) {
+    /* commands.py:748-770; physics_data is the post-step (post-reset) state */
+    int moving = st[0] != 0;
+    REAL ph = st[1] + cf[1] / cf[0];
+    ph = moving ? ph - FLOOR(ph) : 0;
+    int is_moving = SQRT(e->d.qvel[0] * e->d.qvel[0] + e->d.qvel[1] * e->d.qvel[1]) > cf[5];
+    if (!is_moving) { st[0] = 0; ph = 0; }
+    st[1] = ph;
+    cmd_gait_heights(cf, ci[0], ph, st + 2);
+  } else if (type == CMD_JOINT_POSITION) {
+    /* commands.py:853-880: jax.tree.map(where(at_target, new, next)) with new = initial_command(rng) */
+    int n = ci[0];
+    REAL step_id = st[2 * n + 2] + 1;
+    if (step_id > st[2 * n + 1]) cmd_initial(t, e, idx, rng);
+    else st[2 * n + 2] = step_id;
   } else if (type == CMD_UNIFIED) {
     /* train.py:758-775 */
     REAL fresh[16];
@@ -1212,6 +1314,56 @@ static void env_rewards(const Task* t, const REAL* rec, size_t tstride, int T, R
           REAL dd = REC(s, ti[TI_R_AUX] + xi[0]) - 1;
           REAL v = 1 - (REAL)0.25 * dd * dd;
           out[0][s] = v > 0 ? v : 0;
+        }
+        break;
+      case REW_POSITION_TRACKING: {
+        /* rewards.py:715-721; ints [tracked body, base body, command offset, l2]; floats [kernel_scale] */
+        int XP = ti[TI_R_XPOS];
+        for (int s = 0; s < T; s++) {
+          REAL err = 0;
+          for (int k = 0; k < 3; k++) {
+            REAL v = (REC(s, XP + 3 * xi[0] + k) - REC(s, XP + 3 * xi[1] + k)) - REC(s, CM + xi[2] + k);
+            err += xi[3] ? v * v : FABS(v);
+          }
+          out[0][s] = exp_kernel(err, xf[0]);
+        }
+      } break;
+      case REW_SINUSOIDAL_GAIT:
+        /* rewards.py:1336-1340; ints [position obs offset, num_feet, command height offset]; floats [max_height] */
+        for (int s = 0; s < T; s++) {
+          REAL acc = 0;
+          for (int f = 0; f < xi[1]; f++) acc += FABS(REC(s, OB + xi[0] + 3 * f + 2) - REC(s, CM + xi[2] + f));
+          out[0][s] = (REAL)1 - acc / xf[0];
+        }
+        break;
+      case REW_JOINT_POSITION: {
+        /* rewards.py:1370-1385, commands.py:806-820; ints [n, command offset, indices]; floats [pos_scale, vel_scale, sq, abs] */
+        int n = xi[0], c = CM + xi[1];
+        for (int s = 0; s < T; s++) {
+          REAL total_time = REC(s, c + 2 * n), num_steps = REC(s, c + 2 * n + 1), step_id = REC(s, c + 2 * n + 2);
+          REAL ap = 0, av = 0;
+          for (int i = 0; i < n; i++) {
+            REAL st0 = REC(s, c + i), dd = REC(s, c + n + i) - st0;
+            REAL cpos = st0 + dd * step_id / num_steps, cvel = dd / total_time;
+            ap += exp_kernel_pen(cpos - REC(s, QP + 7 + xi[2 + i]), xf[0], xf[2], xf[3]);
+            av += exp_kernel_pen(cvel - REC(s, QV + 6 + xi[2 + i]), xf[1], xf[2], xf[3]);
+          }
+          out[0][s] = ap / (REAL)n;
+          out[1][s] = av / (REAL)n;
+        }
+      } break;
+      case REW_INTERSECTION:
+        /* rewards.py:1424-1430: the upper triangle (incl. the diagonal) is pushed beyond the threshold */
+        for (int s = 0; s < T; s++) {
+          int close = 0;
+          for (int i = 1; i < xi[1]; i++)
+            for (int j = 0; j < i; j++) {
+              REAL dx = REC(s, OB + xi[0] + 3 * i) - REC(s, OB + xi[0] + 3 * j);
+              REAL dy = REC(s, OB + xi[0] + 3 * i + 1) - REC(s, OB + xi[0] + 3 * j + 1);
+              REAL dz = REC(s, OB + xi[0] + 3 * i + 2) - REC(s, OB + xi[0] + 3 * j + 2);
+              close |= SQRT(dx * dx + dy * dy + dz * dz) < xf[0];
+            }
+          out[0][s] = close ? 1 : 0;
         }
         break;
       case REW_STAY_ALIVE:
