@@ -525,18 +525,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
           *reinterpret_cast<float4*>(q.dh0 + (size_t)grow * H + ucol + 4 * i) = make_float4(dhs[4 * i], dhs[4 * i + 1], dhs[4 * i + 2], dhs[4 * i + 3]);
       }
     } else if (warp == 8) {
-      if (lane == 0) {
-        uint32_t use = base * NCH;
-        for (int s = 0; s < T; s++) {
-          for (int ch = 0; ch < NCH; ch++, use++) {
-            const uint32_t st = use % BWD_STAGES, nuse = use / BWD_STAGES;
+      // Producer.  The 16 peers' flags are polled AT ONCE, one lane each, and the generic -> async proxy fence is paid once per
+      // step: one thread polling them in turn (an L2 round trip each) with a fence per chunk was the longest serial chain of a
+      // step (profiles/r02m_gru_bwd.txt: the producer warp never waited for a free stage).  The polling lanes' acquires are
+      // ordered before lane 0's copies by the warp barrier; lane 0 then only waits for free stages.
+      uint32_t use = base * NCH;
+      for (int s = 0; s < T; s++) {
+        if (lane < NCH) {
+          wait_flag(&flags[lane], s + 1, s_abort, p.status, B2S_GRU_ERR_FLAG);
+          fence_proxy_async();
+        }
+        __syncwarp();
+        if (lane == 0) {
+          fence_proxy_async();
+          for (int ch = 0; ch < NCH; ch++) {
+            const uint32_t u = use + ch, st = u % BWD_STAGES, nuse = u / BWD_STAGES;
             if (nuse > 0) wait_bar(&empty[st], (nuse - 1) & 1, s_abort, p.status, B2S_GRU_ERR_EMPTY);
-            wait_flag(&flags[ch], s + 1, s_abort, p.status, B2S_GRU_ERR_FLAG);
-            fence_proxy_async();
             mbar_arrive_expect_tx(&full[st], BWD_CH);
             bulk_g2s(sA + st * BWD_CH, q.xchg + (((size_t)s * p.n_mt + mt) * NCH + ch) * (BWD_CH / 2), BWD_CH, &full[st]);
           }
         }
+        use += NCH;
+        __syncwarp();
       }
     } else if (lane == 0) {
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
