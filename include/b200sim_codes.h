@@ -260,6 +260,8 @@
 #define RAND_BODY_IPOS 6
 #define RAND_GEOM_SIZE 7         /* [ngeom][3]; the engine keeps the rows of the geoms that appear in contact pairs */
 #define RAND_GEOM_POS 8          /* [ngeom][3] */
+#define RAND_SITE_QUAT 9         /* [nsite][4] (IMUAlignmentRandomizer, randomization.py:245-283) */
+#define RAND_SITE_POS 10         /* [nsite][3] */
 
 /* ---- GAE flags (ksim/task/ppo.py:54-121) ---- */
 #define GAE_NORMALIZE_ADVANTAGES 1

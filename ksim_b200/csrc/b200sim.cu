@@ -510,10 +510,21 @@ static bool fits(const int* h) {
          h[MH_NSITE] <= D::NS && h[MH_NSENSORDATA] <= D::NSD && h[MH_NPAIR] <= D::NPAIR && h[MH_NCON] <= D::NCON &&
          h[MH_NEFC_DENSE] <= D::NDENSE && h[MH_NLIMIT] <= D::NLIMIT && h[MH_NFRICTION] <= D::NFRIC;
 }
+// per-env geom / site overrides live only in the workspaces of the non-SMALL instantiations (b2s_work.cuh: PairGeom): a task
+// that randomises them must not be served by the humanoid instantiation, which would silently ignore the override
+static bool needs_env_geometry(const int* ti) {
+  for (int r = 0; r < ti[TI_N_RAND]; r++) {
+    const int code = TAB(ti, TI_RAND_TAB, r, TAB_AUX0);
+    if (code == RAND_GEOM_SIZE || code == RAND_GEOM_POS || code == RAND_SITE_QUAT || code == RAND_SITE_POS) return true;
+  }
+  return false;
+}
+
 template <class D>
 static bool task_fits(const int* ti) {
   return ti[TI_EVENT_SIZE] <= D::EVS && ti[TI_ACT_STATE_SIZE] <= D::ACS && ti[TI_CMD_SIZE] <= D::CMDS &&
-         ti[TI_OBS_CARRY_SIZE] <= D::OCS && ti[TI_N_OBS] <= D::NOBS && ti[TI_ACTION_SIZE] <= D::NA;
+         ti[TI_OBS_CARRY_SIZE] <= D::OCS && ti[TI_N_OBS] <= D::NOBS && ti[TI_ACTION_SIZE] <= D::NA &&
+         !(D::SMALL && needs_env_geometry(ti));
 }
 
 template <class D>

@@ -53,6 +53,14 @@ DEV void apply_overrides(const Mdl& m, Work<D>& w, const float* rand, LANE_ARG) 
 #pragma unroll
         for (int k = 0; k < 3; k++) { w.pair_gpos[sd][k][p] = gpos[3 * pgeom[sd][p] + k]; w.pair_gsize[sd][k][p] = gsize[3 * pgeom[sd][p] + k]; }
     }
+    const float* spos = MF(m, MH_SITE_POS);
+    const float* squat = MF(m, MH_SITE_QUAT);
+    LANE_FOR(s, DIM(NS, MH_NSITE)) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) w.site_pos[k][s] = spos[3 * s + k];
+#pragma unroll
+      for (int k = 0; k < 4; k++) w.site_quat[k][s] = squat[4 * s + k];
+    }
   }
   WSYNC();
   const int* ti = m.ti;
@@ -70,6 +78,15 @@ DEV void apply_overrides(const Mdl& m, Work<D>& w, const float* rand, LANE_ARG) 
               const float v = rand[off + 3 * pgeom[sd][p] + k];
               if (code == RAND_GEOM_SIZE) w.pair_gsize[sd][k][p] = v; else w.pair_gpos[sd][k][p] = v;
             }
+        }
+      }
+      off += cnt;
+      continue;
+    }
+    if (code == RAND_SITE_QUAT || code == RAND_SITE_POS) {
+      if constexpr (!D::SMALL) {
+        LANE_FOR(k, cnt) {
+          if (code == RAND_SITE_QUAT) w.site_quat[k & 3][k >> 2] = rand[off + k]; else w.site_pos[k % 3][k / 3] = rand[off + k];
         }
       }
       off += cnt;

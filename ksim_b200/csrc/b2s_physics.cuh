@@ -248,9 +248,12 @@ DEV void kinematics(const Mdl& m, Work<D>& w, LANE_ARG) {
   const float* site_quat = MF(m, MH_SITE_QUAT);
   LANE_FOR(s, ns) {
     const int b = site_body[s];
-    V3 p = LD3(w.xpos, b) + mulv(ldm9(w.xmat, b), ldg3(site_pos + 3 * s));
+    V3 sp; Q4 sq;
+    if constexpr (D::SMALL) { sp = ldg3(site_pos + 3 * s); sq = ldgq(site_quat + 4 * s); }
+    else { sp = LD3(w.site_pos, s); sq = LDQ(w.site_quat, s); }  // per-env copies (IMUAlignmentRandomizer)
+    V3 p = LD3(w.xpos, b) + mulv(ldm9(w.xmat, b), sp);
     ST3(w.site_xpos, s, p);
-    stm9(w.site_xmat, s, q2mat(qmul(LDQ(w.xquat, b), ldgq(site_quat + 4 * s))));
+    stm9(w.site_xmat, s, q2mat(qmul(LDQ(w.xquat, b), sq)));
   }
   WSYNC();
   SUB_MARK(w, 27);
@@ -2362,7 +2365,9 @@ DEV void sensors_pos_vel(const Mdl& m, Work<D>& w, LANE_ARG) {
       if (t == SENS_FRAMEPOS) { out[0] = pos.x; out[1] = pos.y; out[2] = pos.z; }
       else if (t == SENS_FRAMEQUAT) {
         Q4 q = LDQ(w.xquat, body);
-        if (ot == OBJ_SITE) q = qmul(q, ldgq(MF(m, MH_SITE_QUAT) + 4 * id));
+        if (ot == OBJ_SITE) {
+          if constexpr (D::SMALL) q = qmul(q, ldgq(MF(m, MH_SITE_QUAT) + 4 * id)); else q = qmul(q, LDQ(w.site_quat, id));
+        }
         else if (ot == OBJ_BODY) q = qmul(q, ldgq(MF(m, MH_BODY_IQUAT) + 4 * id));
         out[0] = q.w; out[1] = q.x; out[2] = q.y; out[3] = q.z;
       } else {

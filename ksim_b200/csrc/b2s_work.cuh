@@ -56,7 +56,10 @@ using DimsGeneric = Dims<33, 32, 32, 32, 32, 8, 96, 8, 16, 64, 32, 32, false>;
 // randomization.py:380-442).  The humanoid (SMALL) instantiation has no shared memory to spare (its workspaces, the model and the
 // task program fill the SM) and its task has no such override: it reads the shared model instead and carries nothing.
 template <class D, bool SMALL>
-struct PairGeom { float pair_gpos[2][3][D::NPAIR], pair_gsize[2][3][D::NPAIR]; };
+struct PairGeom {
+  float pair_gpos[2][3][D::NPAIR], pair_gsize[2][3][D::NPAIR];
+  float site_pos[3][D::NS], site_quat[4][D::NS];  // per-env site frames (IMUAlignmentRandomizer, randomization.py:245-283)
+};
 template <class D>
 struct PairGeom<D, true> {};
 

@@ -335,7 +335,8 @@ def build_program(spec: TaskSpec) -> TaskProgram:
 
     # per-env model overrides
     field_sizes = {"dof_frictionloss": m.nv, "dof_armature": m.nv, "dof_damping": m.nv, "body_mass": m.nbody,
-                   "body_inertia": 3 * m.nbody, "body_ipos": 3 * m.nbody, "geom_size": 3 * m.ngeom, "geom_pos": 3 * m.ngeom}
+                   "body_inertia": 3 * m.nbody, "body_ipos": 3 * m.nbody, "geom_size": 3 * m.ngeom, "geom_pos": 3 * m.ngeom,
+                   "site_quat": 4 * m.nsite, "site_pos": 3 * m.nsite}
     ints[C.TI_N_RAND] = len(spec.randomized_fields)
     ints[C.TI_RAND_TAB] = base = table(len(spec.randomized_fields))
     rand_slices: dict[str, tuple[int, int]] = {}

@@ -13,9 +13,10 @@ __all__ = [
     "PhysicsRandomizer", "StaticFrictionRandomizer", "ArmatureRandomizer", "MassAdditionRandomizer",
     "MassMultiplicationRandomizer", "AllBodiesMassMultiplicationRandomizer", "JointDampingRandomizer",
     "COMRandomizer", "AllBodiesCOMRandomizer", "AllBodiesInertiaRandomizer", "FloorFrictionRandomizer",
-    "CollisionBodyRandomizer", "FIELD_CODES", "pair_friction_unaffected",
+    "CollisionBodyRandomizer", "IMUAlignmentRandomizer", "FIELD_CODES", "pair_friction_unaffected",
 ]
 
+import math
 from abc import ABC, abstractmethod
 
 import attrs
@@ -35,6 +36,8 @@ FIELD_CODES = {
     "body_ipos": C.RAND_BODY_IPOS,
     "geom_size": C.RAND_GEOM_SIZE,
     "geom_pos": C.RAND_GEOM_POS,
+    "site_quat": C.RAND_SITE_QUAT,
+    "site_pos": C.RAND_SITE_POS,
 }
 
 _F32 = np.float32
@@ -139,6 +142,53 @@ class AllBodiesMassMultiplicationRandomizer(PhysicsRandomizer):
 
     def __call__(self, model: Model, rng: np.ndarray) -> dict[str, np.ndarray]:
         return {"body_mass": (model.body_mass.astype(_F32)[None] * _u(rng, model.nbody, self.scale_lower, self.scale_upper)).astype(_F32)}
+
+
+def _quat_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Hamilton product, wxyz, float32 (xax.quat_mul)."""
+    w1, x1, y1, z1 = (a[..., i] for i in range(4))
+    w2, x2, y2, z2 = (b[..., i] for i in range(4))
+    return np.stack([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                     w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2], axis=-1).astype(_F32)
+
+
+@attrs.define(frozen=True, kw_only=True)
+class IMUAlignmentRandomizer(PhysicsRandomizer):
+    """Small random rotation (and optional translation) of one site's frame in its body (ksim/randomization.py:245-283):
+    roll / pitch ~ N(0, tilt_std), optional yaw, composed as Z Y X of small-angle quaternions and normalised."""
+
+    site_name: str = attrs.field(default="imu_site")
+    tilt_std_rad: float = attrs.field(default=math.radians(2))
+    yaw_std_rad: float | None = attrs.field(default=None)
+    translate_std_m: float | None = attrs.field(default=None)
+
+    def __call__(self, model: Model, rng: np.ndarray) -> dict[str, np.ndarray]:
+        n = rng.shape[0]
+        pair = R.split(rng, 2)
+        rng, sub = pair[:, 0], pair[:, 1]
+        rxy = R.normal(sub, 2) * _F32(self.tilt_std_rad)
+        rz = np.zeros(n, _F32)
+        if self.yaw_std_rad is not None:
+            pair = R.split(rng, 2)
+            rng, sub = pair[:, 0], pair[:, 1]
+            rz = R.normal(sub, 1)[:, 0] * _F32(self.yaw_std_rad)
+        h, one, zero = _F32(0.5), np.ones(n, _F32), np.zeros(n, _F32)
+        qx = np.stack([one, rxy[:, 0] * h, zero, zero], axis=-1)
+        qy = np.stack([one, zero, rxy[:, 1] * h, zero], axis=-1)
+        qz = np.stack([one, zero, zero, rz * h], axis=-1)
+        q = _quat_mul(qz, _quat_mul(qy, qx))
+        q = (q / np.sqrt((q * q).sum(axis=-1, dtype=_F32), dtype=_F32)[:, None]).astype(_F32)
+        site = model.id("site", self.site_name)
+        site_quat = np.broadcast_to(model.site_quat.astype(_F32)[None], (n, model.nsite, 4)).copy()
+        site_quat[:, site] = _quat_mul(q, site_quat[:, site])
+        out = {"site_quat": site_quat}
+        if self.translate_std_m is not None and self.translate_std_m > 0.0:
+            pair = R.split(rng, 2)
+            rng, sub = pair[:, 0], pair[:, 1]
+            site_pos = np.broadcast_to(model.site_pos.astype(_F32)[None], (n, model.nsite, 3)).copy()
+            site_pos[:, site] = site_pos[:, site] + R.normal(sub, 3) * _F32(self.translate_std_m)
+            out["site_pos"] = site_pos
+        return out
 
 
 @attrs.define(frozen=True, kw_only=True)

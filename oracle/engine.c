@@ -227,6 +227,8 @@ static void apply_overrides(const Task* t, const OModel* base, OModel* m, const 
       case RAND_BODY_IPOS: dst = &m->body_ipos[0][0]; break;
       case RAND_GEOM_SIZE: dst = &m->geom_size[0][0]; break;
       case RAND_GEOM_POS: dst = &m->geom_pos[0][0]; break;
+      case RAND_SITE_QUAT: dst = &m->site_quat[0][0]; break;  /* IMUAlignmentRandomizer, randomization.py:245-283 */
+      case RAND_SITE_POS: dst = &m->site_pos[0][0]; break;
     }
     if (dst) for (int k = 0; k < cnt; k++) dst[k] = rand[off + k];
     off += cnt;
