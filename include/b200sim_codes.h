@@ -146,6 +146,7 @@
 #define RESET_PLANE_XY_POSITION 5
 #define RESET_RANDOM_HEIGHT 6
 #define RESET_RANDOM_PITCH_ROLL 7
+#define RESET_INITIAL_MOTION_STATE 9 /* resets.py:284-304: ints [num_frames, nq]; floats [ctrl_dt, qpos frames*nq, qvel frames*nq (nq wide, as MotionReferenceData stores it)] */
 #define RESET_HFIELD_XY_POSITION 8  /* resets.py:45-89: ints [nx, ny]; floats [x_bound, y_bound, z_top, base_height, x_range, y_range, lower_x, upper_x, lower_y, upper_y, heights nx*ny] */
 
 /* ---- observations (ksim/observation.py) ---- */

@@ -231,14 +231,6 @@ DEV uint32_t key_randint(Key k, uint32_t span) {
   return ((hi % span) * mult + (lo % span)) % span;
 }
 DEV uint32_t randint3(Key k) { return key_randint(k, 3u); }
-// element i of jax.random.randint(key, (n,), lo, hi): offset in [0, span)
-DEV uint32_t key_randint_at(Key k, int i, uint32_t span) {
-  const Key ra = key_split(k, 0), rb = key_split(k, 1);
-  const uint32_t hi = key_bits(ra, i), lo = key_bits(rb, i);
-  const uint32_t mult = ((65536u % span) * (65536u % span)) % span;
-  return ((hi % span) * mult + (lo % span)) % span;
-}
-
 template <class D>
 DEVNI void event_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
   const int* ti = m.ti;
@@ -394,6 +386,14 @@ DEV void engine_step(const Mdl& m, Work<D>& w, Key rng, LANE_ARG) {
   WSYNC();
 }
 
+// element i of jax.random.randint(key, (n,), lo, hi): offset in [0, span)
+DEV uint32_t key_randint_at(Key k, int i, uint32_t span) {
+  const Key ra = key_split(k, 0), rb = key_split(k, 1);
+  const uint32_t hi = key_bits(ra, i), lo = key_bits(rb, i);
+  const uint32_t mult = ((65536u % span) * (65536u % span)) % span;
+  return ((hi % span) * mult + (lo % span)) % span;
+}
+
 template <class D>
 DEV void reset_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
   const int* ti = m.ti;
@@ -452,6 +452,16 @@ DEV void reset_apply(const Mdl& m, Work<D>& w, int idx, Key rng, LANE_ARG) {
         w.qpos[2] = rf[10 + xi * ny + yi] + rf[2] + rf[3];
       }
       break;
+    case RESET_INITIAL_MOTION_STATE: {
+      // resets.py:290-304 (freejoint = False): joints from a random frame of the motion bank, the base is left alone; the
+      // bank stores qvel nq wide, the joints' velocities are its columns 7.. ; time = frame * ctrl_dt
+      const int frames = ri[0], wq = ri[1];
+      const int frame = (int)key_randint_at(rng, 0, (uint32_t)frames);
+      const float* qp = rf + 1 + frame * wq;
+      const float* qv = rf + 1 + (frames + frame) * wq;
+      LANE_FOR(i, nj) { w.qpos[7 + i] = qp[7 + i]; w.qvel[6 + i] = qv[7 + i]; }
+      IF_LANE0 w.time = (float)frame * rf[0];
+    } break;
     case RESET_RANDOM_HEIGHT:
       IF_LANE0 w.qpos[2] += key_uniform(rng, 0, rf[0], rf[1]);
       break;

@@ -3,7 +3,7 @@
 from __future__ import annotations
 
 __all__ = [
-    "Reset", "PlaneXYPositionReset", "HFieldXYPositionReset", "RandomJointPositionReset", "RandomJointVelocityReset",
+    "Reset", "PlaneXYPositionReset", "HFieldXYPositionReset", "InitialMotionStateReset", "MotionReferenceData", "RandomJointPositionReset", "RandomJointVelocityReset",
     "RandomBaseVelocityXYReset", "RandomHeadingReset", "RandomHeightReset", "RandomPitchRollReset",
     "get_xy_position_reset",
 ]
@@ -57,6 +57,44 @@ class HFieldXYPositionReset(Reset):
         x_bound, y_bound, z_top, _ = self.bounds
         floats = [x_bound, y_bound, z_top, self.robot_base_height, self.x_range, self.y_range, *self.padded_bounds]
         return C.RESET_HFIELD_XY_POSITION, [int(data.shape[0]), int(data.shape[1])], [float(v) for v in floats] + data.reshape(-1).tolist()
+
+
+@attrs.define(frozen=True, kw_only=True, eq=False)
+class MotionReferenceData:
+    """The fields of ``ksim.utils.priors.MotionReferenceData`` (priors.py:53-91) the reset reads: ``qpos`` and ``qvel`` are both
+    ``[T, nq]`` (the reference stores the velocities nq wide), ``ctrl_dt`` the frame period."""
+
+    qpos: object = attrs.field()
+    qvel: object = attrs.field()
+    ctrl_dt: float = attrs.field()
+
+    @property
+    def num_frames(self) -> int:
+        import numpy as np
+
+        return int(np.asarray(getattr(self.qpos, "array", self.qpos)).shape[0])
+
+
+@attrs.define(frozen=True, kw_only=True, eq=False)
+class InitialMotionStateReset(Reset):
+    """Joint positions / velocities of a random frame of a motion bank, ``time = frame * ctrl_dt`` (ksim/resets.py:284-304).
+    ``freejoint=True`` is refused: the reference then writes the bank's nq-wide ``qvel`` row into the nv-wide ``data.qvel``,
+    which does not trace."""
+
+    reference_motion: MotionReferenceData = attrs.field()
+    freejoint: bool = attrs.field(default=False)
+
+    def encode(self, model: Model) -> tuple[int, list[int], list[float]]:
+        import numpy as np
+
+        if self.freejoint:
+            raise NotImplementedError("InitialMotionStateReset(freejoint=True) is shape-inconsistent in the reference (qvel is [T, nq])")
+        qpos = np.asarray(getattr(self.reference_motion.qpos, "array", self.reference_motion.qpos), dtype=np.float32)
+        qvel = np.asarray(getattr(self.reference_motion.qvel, "array", self.reference_motion.qvel), dtype=np.float32)
+        if qpos.ndim != 2 or qpos.shape != qvel.shape or qpos.shape[1] != model.nq or qpos.shape[0] < 1:
+            raise ValueError(f"reference motion must hold qpos and qvel of shape [T, nq = {model.nq}]")
+        floats = [float(self.reference_motion.ctrl_dt)] + qpos.reshape(-1).tolist() + qvel.reshape(-1).tolist()
+        return C.RESET_INITIAL_MOTION_STATE, [int(qpos.shape[0]), int(model.nq)], floats
 
 
 @attrs.define(frozen=True, kw_only=True)

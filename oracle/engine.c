@@ -476,6 +476,14 @@ static void engine_step(const Task* t, Env* e, const REAL* action, Key rng) {
   for (int i = 0; i < na; i++) e->last_ctrl[i] = action[i];
 }
 
+/* element i of jax.random.randint(key, (n,), lo, hi): offset in [0, span) */
+static uint32_t key_randint_at(Key k, int i, uint32_t span) {
+  Key ra = key_split(k, 0), rb = key_split(k, 1);
+  uint32_t hi = key_bits(ra, i), lo = key_bits(rb, i);
+  uint32_t mult = (uint32_t)((65536u % span) * (65536u % span)) % span;
+  return ((hi % span) * mult + (lo % span)) % span;
+}
+
 static void reset_apply(const Task* t, Env* e, int idx, Key rng) {
   int type = TAB(t, TI_RESET_TAB, idx, TAB_TYPE);
   const int* ri = t->ti + TAB(t, TI_RESET_TAB, idx, TAB_IOFF);
@@ -535,6 +543,15 @@ static void reset_apply(const Task* t, Env* e, int idx, Key rng) {
       yi = yi < 0 ? 0 : (yi > ny - 1 ? ny - 1 : yi);
       d->qpos[0] = x; d->qpos[1] = y;
       d->qpos[2] = rf[10 + xi * ny + yi] + rf[2] + rf[3];
+    } break;
+    case RESET_INITIAL_MOTION_STATE: {
+      /* resets.py:290-304, freejoint = False; ints [num_frames, nq]; floats [ctrl_dt, qpos[frames][nq], qvel[frames][nq]] */
+      int frames = ri[0], wq = ri[1];
+      int frame = (int)key_randint_at(rng, 0, (uint32_t)frames);
+      const REAL* qp = rf + 1 + frame * wq;
+      const REAL* qv = rf + 1 + (frames + frame) * wq;
+      for (int i = 0; i < nj; i++) { d->qpos[7 + i] = qp[7 + i]; d->qvel[6 + i] = qv[7 + i]; }
+      d->time = (REAL)frame * rf[0];
     } break;
     case RESET_RANDOM_HEIGHT: d->qpos[2] += key_uniform(rng, 0, rf[0], rf[1]); break;
     case RESET_RANDOM_PITCH_ROLL: {
@@ -613,14 +630,6 @@ static void cmd_gait_heights(const REAL* cf, int nf, REAL phase, REAL* out) {
     prog = prog < 0 ? 0 : (prog > 1 ? 1 : prog);
     out[f] = (pf >= sr ? max_h * SIN((REAL)3.14159265358979323846 * prog) : 0) + offset;
   }
-}
-
-/* element i of jax.random.randint(key, (n,), lo, hi): offset in [0, span) */
-static uint32_t key_randint_at(Key k, int i, uint32_t span) {
-  Key ra = key_split(k, 0), rb = key_split(k, 1);
-  uint32_t hi = key_bits(ra, i), lo = key_bits(rb, i);
-  uint32_t mult = (uint32_t)((65536u % span) * (65536u % span)) % span;
-  return ((hi % span) * mult + (lo % span)) % span;
 }
 
 /* UnifiedCommand.initial_command (examples/kbot/train.py:714-756).  floats: 6 x [lo, hi] (vx vy wz bh rx ry),

@@ -121,3 +121,62 @@ def test_cuda_matches_oracle(oracle_built) -> None:  # noqa: ANN001
     e = np.nonzero(rec_o[t - 1, :, prog["TI_R_DONE"]] != 0)[0]
     assert e.size > 0
     np.testing.assert_array_equal(got[e, q : q + 3], st[e, q : q + 3])
+
+
+# ------------------------------------------------------------------------------------------ InitialMotionStateReset
+def _motion_spec():  # noqa: ANN202
+    model = tripod_model()
+    frames = 37
+    rs = np.random.RandomState(0)
+    bank = resets.MotionReferenceData(qpos=rs.uniform(-0.4, 0.4, (frames, model.nq)).astype(np.float32),
+                                      qvel=rs.uniform(-1.0, 1.0, (frames, model.nq)).astype(np.float32), ctrl_dt=0.02)
+    spec = tripod_spec(terminations={"episode_length": terminations.EpisodeLengthTermination(max_length_sec=100.0)})
+    spec.resets = [resets.InitialMotionStateReset(reference_motion=bank)]
+    return spec, bank
+
+
+def test_initial_motion_state_reset(emu, oracle_built) -> None:  # noqa: ANN001, F811
+    """resets.py:284-304 against a numpy transcription on the repo's threefry: frame = randint(rng, (1,), 0, T)[0]; joints from the
+    bank, base untouched, time = frame * ctrl_dt (the engine zeroes qvel after its forward pass, engine.py:216-219)."""
+    from ksim_b200 import rng as R
+    from ksim_b200.blob import pack_blob
+
+    spec, bank = _motion_spec()
+    n = 48
+    prog, init, st0, k0, *_ = _oracle(spec, n, 2)
+    q, tm = prog["TI_S_QPOS"], prog["TI_S_TIME"]
+    frames = np.zeros(n, np.int64)
+    for e in range(n):
+        reset_rng = R.split(init.init_keys[e, 0:2], 2)[1]    # rng, reset_rng = split(rng) for the first (only) reset
+        k1, k2 = R.split(reset_rng, 2)
+        span = np.uint32(bank.num_frames)
+        mult = ((np.uint32(65536) % span) * (np.uint32(65536) % span)) % span
+        frames[e] = int(((R.bits(k1, 1)[0] % span) * mult + R.bits(k2, 1)[0] % span) % span)
+    assert np.unique(frames).size > 15
+    np.testing.assert_array_equal(st0[:, q + 7 : q + 10], np.asarray(bank.qpos)[frames, 7:10])
+    np.testing.assert_array_equal(st0[:, tm], frames.astype(np.float32) * np.float32(0.02))
+    model = spec.model
+    np.testing.assert_allclose(st0[:, q : q + 7], np.broadcast_to(model.qpos0[:7].astype(np.float32), (n, 7)), atol=1e-7)
+    blob = np.frombuffer(pack_blob(spec.model, prog.ti, prog.tf), dtype=np.uint8).copy()
+    st_e, k_e = np.zeros_like(st0), np.zeros_like(k0)
+    rec0 = np.zeros((n, prog.rec_size), np.float32)
+    ak = np.zeros((n, 2), np.uint32)
+    emu.emu_init_envs(_p(blob), n, _p(init.init_keys), _p(init.levels), _p(init.rand), _p(st_e), _p(k_e), _p(rec0), _p(ak))
+    np.testing.assert_array_equal(st_e[:, q + 7 : q + 10], st0[:, q + 7 : q + 10])
+    np.testing.assert_array_equal(st_e[:, tm], st0[:, tm])
+    with pytest.raises(NotImplementedError):
+        resets.InitialMotionStateReset(reference_motion=bank, freejoint=True).encode(model)
+
+
+@pytest.mark.gpu
+def test_initial_motion_state_reset_cuda(oracle_built) -> None:  # noqa: ANN001
+    from ksim_b200.engine import B200Engine
+
+    spec, _ = _motion_spec()
+    n = 48
+    prog, init, st0, *_ = _oracle(spec, n, 2)
+    eng = B200Engine(spec, n, device="cuda:0", seed=5, curriculum_level=1.0)
+    q, tm = prog["TI_S_QPOS"], prog["TI_S_TIME"]
+    got = eng.state.cpu().numpy()
+    np.testing.assert_array_equal(got[:, q : q + 10], st0[:, q : q + 10])
+    np.testing.assert_array_equal(got[:, tm], st0[:, tm])
