@@ -494,9 +494,9 @@ def main() -> None:
     bytes_per_env_step = 4 * (p.action_size + p.rec_size) + per_launch_env / t
     peak, peak_src = _peaks()
     achieved = n * t * bytes_per_env_step / (kernel_ms * 1e-3) / 1e9
-    # measured DRAM bytes of one launch of this configuration (one ncu capture per round, profiles/r01_traffic.json)
+    # measured DRAM bytes of one launch of this configuration (one ncu capture per round, profiles/r02_traffic.json)
     traffic = None
-    tpath = ROOT / "profiles" / "r01_traffic.json"
+    tpath = ROOT / "profiles" / "r02_traffic.json"
     if tpath.exists():
         rec_t = json.loads(tpath.read_text()).get(WORKLOAD)
         if rec_t and rec_t["envs"] == n and rec_t["rollout"] == t:
@@ -509,7 +509,7 @@ def main() -> None:
                 "d2h_bytes_per_step": int((host_adv.numel() + host_total.numel()) * 4), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": "profiles/r01_traffic.json (one ncu capture of this configuration, committed; not measured in this run)" if traffic else None,
+                     "traffic_source": "profiles/r02_traffic.json (one ncu capture of this configuration, committed; not measured in this run)" if traffic else None,
                      "algorithmic_bytes_per_launch": n * t * bytes_per_env_step,
                      "kernel": "k_rollout<DimsKbot>" if WORKLOAD == "kbot" else "k_rollout<DimsHumanoid>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms,
                      "algorithmic_bytes_per_env_step": bytes_per_env_step, "peak_source": peak_src,
