@@ -91,7 +91,6 @@ struct BwdParams {
   const float* keep;
   int* status;
   uint32_t lbo_sbo_swap;
-  int pair;            // work items are pairs of row tiles, interleaved step by step (k_gru_bwd)
 };
 
 #ifdef B2S_GRU_TRACE
@@ -390,26 +389,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
   uint8_t* sA = smem + W_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + W_BYTES + BWD_STAGES * BWD_CH);  // [BWD_STAGES]
   uint64_t* empty = full + BWD_STAGES;
-  uint64_t* acc_full = full + 2 * BWD_STAGES;  // [2]: one accumulator per interleaved tile
-  uint64_t* tmem_empty = acc_full + 2;         // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* acc_full = full + 2 * BWD_STAGES;
+  uint64_t* tmem_empty = acc_full + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tmem_empty + 1);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = blockIdx.x % NCH, slot = blockIdx.x / NCH, n_slots = gridDim.x / NCH;
-  const int T = p.T, B = p.B;
-  // Work item = one row tile, or (p.pair) TWO row tiles of the same layer interleaved step by step like the forward kernel: while
-  // the chunks of one tile travel and its MMAs run, the epilogue warps compute the other tile's gate gradients.
-  const int tpi = p.pair ? 2 : 1;
-  const int items_per_problem = (p.n_mt + tpi - 1) / tpi, n_items = p.n_problems * items_per_problem;
+  const int n_groups = p.n_problems * p.n_mt, T = p.T, B = p.B;
 
   const size_t TB = (size_t)T * B;
   if (tid == 0) {
     for (int i = 0; i < BWD_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&tmem_empty[i], NEPI); }
+    mbar_init(acc_full, 1);
+    mbar_init(tmem_empty, NEPI);
     *s_abort = 0;
     mbar_fence_init();
   }
-  if (warp == 9) tmem_alloc(s_tmem, 64);
+  if (warp == 9) tmem_alloc(s_tmem, 32);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -418,11 +414,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
   constexpr int KC = 3 * H / 8;  // 192 core-matrix columns of K
 
   int loaded = -1;
-  // phase bookkeeping, identical in every role: ring uses (chunks) so far, steps run so far on each accumulator
-  uint32_t use_base = 0, st_base[2] = {0, 0};
-  for (int it = slot; it < n_items; it += n_slots) {
-    const int pi = it / items_per_problem, mt0 = (it % items_per_problem) * tpi;
-    const int NG = (tpi == 2 && mt0 + 1 < p.n_mt) ? 2 : 1;
+  uint32_t base = 0;
+  for (int g = slot; g < n_groups; g += n_slots, base += T) {
+    const int pi = g / p.n_mt, mt = g % p.n_mt;
     const BwdProblem& q = p.pr[pi];
     if (pi != loaded) {
       __syncthreads();
@@ -437,20 +431,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
       __syncthreads();
       loaded = pi;
     }
+    int* flags = q.flags + mt * NCH;
     if (warp < 8) {
       const int row = (warp & 3) * 32 + lane, half = warp >> 2, j0 = half * 16;
+      const int grow = mt * MT + row;
+      const bool live = grow < B;
       const size_t ucol = (size_t)c * U + j0;
-      float dhs[2][16];
+      float dhs[16];
 #pragma unroll
-      for (int g = 0; g < 2; g++)
-#pragma unroll
-        for (int i = 0; i < 16; i++) dhs[g][i] = 0.0f;
-      // front half of step s of one tile: gate gradients from dh = dy_t + keep_t dhs, the chunk for the peers, then the outputs
-      auto front = [&](float* dh_state, int mt, int s) {
+      for (int i = 0; i < 16; i++) dhs[i] = 0.0f;
+      for (int s = 0; s < T; s++) {
         const int t = T - 1 - s;
-        const int grow = mt * MT + row;
-        const bool live = grow < B;
-        int* flags = q.flags + mt * NCH;
         float r[16], z[16], n[16], hn[16], hmn[16], dy[16];
         float kp = 1.0f;
         const float* sv = q.saved + (((size_t)t * p.n_mt + mt) * NCH + c) * SAVED_BLOCK;
@@ -480,13 +471,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
         float dr_[16], dz_[16], dn_[16], dg_[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-          const float dh = fmaf(kp, dh_state[i], dy[i]);
+          const float dh = fmaf(kp, dhs[i], dy[i]);
           const float dnp = dh * (1.0f - z[i]) * (1.0f - n[i] * n[i]);
           dn_[i] = dnp;
           dg_[i] = dnp * r[i];
           dz_[i] = dh * hmn[i] * z[i] * (1.0f - z[i]);
           dr_[i] = dnp * hn[i] * r[i] * (1.0f - r[i]);
-          dh_state[i] = dh * z[i];  // the direct path; the GEMM term is added by back()
+          dhs[i] = dh * z[i];  // the direct path; the GEMM term is added below
         }
         auto pk = [](const float* v, int o) { return make_uint4(pack_bf16(v[o], v[o + 1]), pack_bf16(v[o + 2], v[o + 3]), pack_bf16(v[o + 4], v[o + 5]), pack_bf16(v[o + 6], v[o + 7])); };
         const uint4 r0 = pk(dr_, 0), r1 = pk(dr_, 8), z0 = pk(dz_, 0), z1 = pk(dz_, 8), n0 = pk(dn_, 0), n1 = pk(dn_, 8), g0 = pk(dg_, 0), g1 = pk(dg_, 8);
@@ -518,99 +509,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_bwd(const BwdParams p) {
             og[(size_t)(2 * i) * TB] = (uint16_t)(wg[i] & 0xffffu);             og[(size_t)(2 * i + 1) * TB] = (uint16_t)(wg[i] >> 16);
           }
         }
-      };
-      // back half: the step's GEMM term dgh_t W_hh from the tile's accumulator
-      auto back = [&](float* dh_state, int g, int s) {
-        if (lane == 0) wait_bar(&acc_full[g], (st_base[g] + s) & 1, s_abort, p.status, B2S_GRU_ERR_ACC);  // one poller per warp
+        if (lane == 0) wait_bar(acc_full, (base + s) & 1, s_abort, p.status, B2S_GRU_ERR_ACC);  // one poller per warp
         __syncwarp();
         tc_fence_after();
         float a[16];
-        tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * U + j0), a);
+        tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)j0, a);
         tc_fence_before();
-        mbar_arrive(&tmem_empty[g]);
+        mbar_arrive(tmem_empty);
 #pragma unroll
-        for (int i = 0; i < 16; i++) dh_state[i] += a[i];
-      };
-#pragma unroll
-      for (int g = 0; g < 2; g++)
-        if (g < NG) front(dhs[g], mt0 + g, 0);
-      for (int s = 0; s < T; s++) {
-#pragma unroll
-        for (int g = 0; g < 2; g++) {
-          if (g >= NG) continue;
-          back(dhs[g], g, s);
-          if (s + 1 < T) front(dhs[g], mt0 + g, s + 1);
-        }
+        for (int i = 0; i < 16; i++) dhs[i] += a[i];
       }
+      if (live && q.dh0) {
 #pragma unroll
-      for (int g = 0; g < 2; g++) {
-        const int grow = (mt0 + g) * MT + row;
-        if (g < NG && grow < B && q.dh0) {
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-            *reinterpret_cast<float4*>(q.dh0 + (size_t)grow * H + ucol + 4 * i) = make_float4(dhs[g][4 * i], dhs[g][4 * i + 1], dhs[g][4 * i + 2], dhs[g][4 * i + 3]);
-        }
+        for (int i = 0; i < 4; i++)
+          *reinterpret_cast<float4*>(q.dh0 + (size_t)grow * H + ucol + 4 * i) = make_float4(dhs[4 * i], dhs[4 * i + 1], dhs[4 * i + 2], dhs[4 * i + 3]);
       }
     } else if (warp == 8) {
       // Producer.  The 16 peers' flags are polled AT ONCE, one lane each, and the generic -> async proxy fence is paid once per
       // step: one thread polling them in turn (an L2 round trip each) with a fence per chunk was the longest serial chain of a
       // step (profiles/r02m_gru_bwd.txt: the producer warp never waited for a free stage).  The polling lanes' acquires are
       // ordered before lane 0's copies by the warp barrier; lane 0 then only waits for free stages.
-      uint32_t use = use_base;
+      uint32_t use = base * NCH;
       for (int s = 0; s < T; s++) {
-        for (int g = 0; g < NG; g++) {
-          const int mt = mt0 + g;
-          const int* flags = q.flags + mt * NCH;
-          if (lane < NCH) {
-            wait_flag(&flags[lane], s + 1, s_abort, p.status, B2S_GRU_ERR_FLAG);
-            fence_proxy_async();
-          }
-          __syncwarp();
-          if (lane == 0) {
-            fence_proxy_async();
-            for (int ch = 0; ch < NCH; ch++) {
-              const uint32_t u = use + ch, st = u % BWD_STAGES, nuse = u / BWD_STAGES;
-              if (nuse > 0) wait_bar(&empty[st], (nuse - 1) & 1, s_abort, p.status, B2S_GRU_ERR_EMPTY);
-              mbar_arrive_expect_tx(&full[st], BWD_CH);
-              bulk_g2s(sA + st * BWD_CH, q.xchg + (((size_t)s * p.n_mt + mt) * NCH + ch) * (BWD_CH / 2), BWD_CH, &full[st]);
-            }
-          }
-          use += NCH;
-          __syncwarp();
+        if (lane < NCH) {
+          wait_flag(&flags[lane], s + 1, s_abort, p.status, B2S_GRU_ERR_FLAG);
+          fence_proxy_async();
         }
+        __syncwarp();
+        if (lane == 0) {
+          fence_proxy_async();
+          for (int ch = 0; ch < NCH; ch++) {
+            const uint32_t u = use + ch, st = u % BWD_STAGES, nuse = u / BWD_STAGES;
+            if (nuse > 0) wait_bar(&empty[st], (nuse - 1) & 1, s_abort, p.status, B2S_GRU_ERR_EMPTY);
+            mbar_arrive_expect_tx(&full[st], BWD_CH);
+            bulk_g2s(sA + st * BWD_CH, q.xchg + (((size_t)s * p.n_mt + mt) * NCH + ch) * (BWD_CH / 2), BWD_CH, &full[st]);
+          }
+        }
+        use += NCH;
+        __syncwarp();
       }
     } else if (lane == 0) {
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-      uint32_t use = use_base;
+      uint32_t use = base * NCH;
       for (int s = 0; s < T; s++) {
-        for (int g = 0; g < NG; g++) {
-          const uint32_t gs = st_base[g] + s;
-          if (gs > 0) wait_bar(&tmem_empty[g], (gs - 1) & 1, s_abort, p.status, B2S_GRU_ERR_TMEM);
+        const uint32_t gs = base + s;
+        if (gs > 0) wait_bar(tmem_empty, (gs - 1) & 1, s_abort, p.status, B2S_GRU_ERR_TMEM);
+        tc_fence_after();
+        for (int ch = 0; ch < NCH; ch++, use++) {
+          const uint32_t st = use % BWD_STAGES, nuse = use / BWD_STAGES;
+          wait_bar(&full[st], nuse & 1, s_abort, p.status, B2S_GRU_ERR_FULL);
           tc_fence_after();
-          for (int ch = 0; ch < NCH; ch++, use++) {
-            const uint32_t st = use % BWD_STAGES, nuse = use / BWD_STAGES;
-            wait_bar(&full[st], nuse & 1, s_abort, p.status, B2S_GRU_ERR_FULL);
-            tc_fence_after();
 #pragma unroll
-            for (int k6 = 0; k6 < 3 * U / 16; k6++) {
-              const uint64_t da = desc(a0 + st * BWD_CH + k6 * 2 * (MT * 16), MT * 16, 128, p.lbo_sbo_swap);
-              const uint64_t db = desc(b0 + (ch * 12 + k6 * 2) * (U * 16), U * 16, 128, p.lbo_sbo_swap);
-              mma_bf16_ss(tmem + (uint32_t)(g * U), da, db, IDESC, (ch | k6) != 0);
-            }
-            mma_commit(&empty[st]);
+          for (int k6 = 0; k6 < 3 * U / 16; k6++) {
+            const uint64_t da = desc(a0 + st * BWD_CH + k6 * 2 * (MT * 16), MT * 16, 128, p.lbo_sbo_swap);
+            const uint64_t db = desc(b0 + (ch * 12 + k6 * 2) * (U * 16), U * 16, 128, p.lbo_sbo_swap);
+            mma_bf16_ss(tmem, da, db, IDESC, (ch | k6) != 0);
           }
-          mma_commit(&acc_full[g]);
+          mma_commit(&empty[st]);
         }
+        mma_commit(acc_full);
       }
     }
     __syncwarp();
-    use_base += (uint32_t)(NG * T * NCH);
-    st_base[0] += T;
-    if (NG == 2) st_base[1] += T;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, 64);
+  if (warp == 9) tmem_dealloc(tmem, 32);
 }
 
 // -------------------------------------------------------------------------------------------------------- host
@@ -755,9 +719,7 @@ extern "C" int b200sim_gru_backward(void* stream, int n_problems, const b200sim_
   }
   cudaError_t e = cudaMemsetAsync(ws, 0, 256 + (size_t)n_problems * flag_bytes, (cudaStream_t)stream);
   if (e != cudaSuccess) return gfail(B2S_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
-  // two row tiles per work item, interleaved (B2S_GRU_BWD_SINGLE=1: one tile per work item, twice as many CTAs)
-  prm.pair = getenv("B2S_GRU_BWD_SINGLE") ? 0 : (prm.n_mt > 1);
-  return launch<BwdParams>(k_gru_bwd, prm, BWD_SMEM, prm.pair ? n_problems * ((prm.n_mt + 1) / 2) : n_problems * prm.n_mt, stream);
+  return launch<BwdParams>(k_gru_bwd, prm, BWD_SMEM, n_problems * prm.n_mt, stream);
 }
 
 extern "C" size_t b200sim_gru_saved_floats(int n_steps, int batch) {
