@@ -213,6 +213,9 @@ const char* b200sim_policy_last_error(void);
  * int32; limits[bins] = the upper edge of every bin (edges[1:], as the reference stores them); stats[5] = {min, max, sum,
  * sum_squares, mean}; scratch: b200sim_histogram_scratch_bytes() bytes.  bins <= 1024.  Counts are exact and deterministic. */
 size_t b200sim_histogram_scratch_bytes(void);
+/* out[r] = sum over the columns of row r of a row-major bf16 matrix x[rows][cols], fp32 accumulation in a fixed order: the bias
+ * gradients of the GRU replay (the reference gets them from jax.grad through `+ bias`, equinox.nn.GRUCell). */
+int b200sim_row_sums(void* stream, int rows, int cols, const void* x, float* out);
 int b200sim_histogram(void* stream, size_t n, const float* x, int bins, int32_t* counts, float* limits, float* stats, void* scratch);
 
 /* ---- Optimiser step of the PPO update (ksim/task/ppo.py:536-565 apply_gradients_with_clipping -> optax chain of

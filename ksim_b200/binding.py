@@ -21,7 +21,7 @@ EXPORTS = (
     "b200sim_gru_workspace_bytes", "b200sim_gru_saved_floats", "b200sim_gru_forward", "b200sim_gru_backward", "b200sim_gru_last_error",
     "b200sim_mixture_logprob", "b200sim_mixture_logprob_backward", "b200sim_mixture_sample", "b200sim_policy_last_error",
     "b200sim_data_layout", "b200sim_engine_reset", "b200sim_engine_step", "b200sim_terminations", "b200sim_engine_last_error",
-    "b200sim_histogram_scratch_bytes", "b200sim_histogram",
+    "b200sim_histogram_scratch_bytes", "b200sim_histogram", "b200sim_row_sums",
     "b200sim_optimizer_scratch_bytes", "b200sim_optimizer_step", "b200sim_optimizer_last_error",
 )
 
@@ -97,6 +97,7 @@ def lib() -> ctypes.CDLL:
         cdll.b200sim_engine_last_error.argtypes, cdll.b200sim_engine_last_error.restype = [], ctypes.c_char_p
         cdll.b200sim_histogram_scratch_bytes.argtypes, cdll.b200sim_histogram_scratch_bytes.restype = [], sz
         cdll.b200sim_histogram.argtypes, cdll.b200sim_histogram.restype = [vp, sz, vp, ci, vp, vp, vp, vp], ci
+        cdll.b200sim_row_sums.argtypes, cdll.b200sim_row_sums.restype = [vp, ci, ci, vp, vp], ci
         cdll.b200sim_optimizer_scratch_bytes.argtypes, cdll.b200sim_optimizer_scratch_bytes.restype = [], sz
         cdll.b200sim_optimizer_step.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, cf, cf, cf, ci, cf, cf, cf, cf, cf, vp, vp]
         cdll.b200sim_optimizer_step.restype = ci

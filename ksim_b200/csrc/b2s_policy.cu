@@ -295,7 +295,45 @@ __global__ void __launch_bounds__(HNT) k_hist_count(size_t n, const float* __res
     if (s_cnt[b]) atomicAdd(&counts[b], s_cnt[b]);
 }
 
+// Row sums of a row-major bf16 matrix, fp32 accumulation in a fixed order: the bias gradients of the GRU replay (sum over the T B
+// columns of the feature-major gate gradients).  HBM-bound: one CTA per row, 128-bit loads, 2 bytes read per element.
+constexpr int RS_NT = 256;
+__global__ void __launch_bounds__(RS_NT) k_row_sums_bf16(int cols, const __nv_bfloat16* __restrict__ x, float* __restrict__ out) {
+  const __nv_bfloat16* row = x + (size_t)blockIdx.x * cols;
+  float acc = 0.0f;
+  if ((cols & 7) == 0 && ((size_t)row & 15) == 0) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+    for (int i = threadIdx.x; i < cols / 8; i += RS_NT) {
+      const uint4 v = __ldcs(r4 + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc += __uint_as_float(w[k] << 16) + __uint_as_float(w[k] & 0xffff0000u);
+    }
+  } else {
+    for (int i = threadIdx.x; i < cols; i += RS_NT) acc += __bfloat162float(row[i]);
+  }
+  __shared__ float s_part[RS_NT / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < RS_NT / 32; k++) t += s_part[k];
+    out[blockIdx.x] = t;
+  }
+}
+
 }  // namespace
+
+extern "C" int b200sim_row_sums(void* stream, int rows, int cols, const void* x, float* out) {
+  if (rows < 0 || cols < 0 || (rows > 0 && (!x || !out))) return pfail(B2S_ERR_BAD_ARG, "row_sums: null argument");
+  if (rows == 0) return B2S_OK;
+  k_row_sums_bf16<<<rows, RS_NT, 0, (cudaStream_t)stream>>>(cols, (const __nv_bfloat16*)x, out);
+  LAUNCH_OK();
+  return B2S_OK;
+}
 
 extern "C" size_t b200sim_histogram_scratch_bytes(void) { return (size_t)B2S_HIST_MAX_CTAS * 6 * sizeof(float); }
 

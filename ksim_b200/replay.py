@@ -89,6 +89,16 @@ def _ones_col(n: int, device: torch.device) -> torch.Tensor:
     return _ONES[key]
 
 
+def _row_sums(x: torch.Tensor) -> torch.Tensor:
+    """fp32 sums over the columns of a contiguous bf16 ``[rows, cols]`` matrix (``b200sim_row_sums``)."""
+    rows, cols = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(_lib().b200sim_row_sums(ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream), rows, cols, _p(x), _p(out)),
+               "b200sim_row_sums")
+    return out
+
+
 def _mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """bf16 x bf16 -> fp32 library GEMM."""
     return torch.mm(a, b, out_dtype=torch.float32)
@@ -267,9 +277,7 @@ class _GruStacksFn(torch.autograd.Function):
                 hst_r = hst.t()  # [T B, H] operand
                 g_w_ih = _mm(dgi, x_in.t())
                 g_w_hh = torch.cat([_mm(dgi[: 2 * hd], hst_r), _mm(dghn, hst_r)], dim=0)
-                ones = _ones_col(tb, dev)               # row sums as tensor-core GEMVs
-                g_b = _mm(dgi, ones)[:, 0]
-                g_bn = _mm(dghn, ones)[:, 0]
+                g_b, g_bn = _row_sums(dgi), _row_sums(dghn)   # bias gradients: HBM-bound row sums of the gate gradients
                 pgrads[s][layer * 4 : layer * 4 + 4] = [g_w_ih, g_w_hh, g_b, g_bn]
                 if layer > 0:
                     dy[s] = _mm(w_ih16.t(), dgi)  # [H, T B]: gradient w.r.t. the layer below's feature-major output

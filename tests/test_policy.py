@@ -307,3 +307,18 @@ def test_ppo_iteration_runs(walking_spec, walking_randomizers, use_graphs):
     assert float(tr.actions.abs().sum()) > 0
     # the clipped means keep sampled actions near the joint ranges (std <= 1)
     assert float(tr.data["logp_on"].max()) < 10.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols", [(1536, 12288), (512, 24 * 512), (7, 1000), (3, 13)])
+def test_row_sums_match_torch(rows, cols):
+    """``b200sim_row_sums`` (the GRU replay's bias gradients): fp32 sums of bf16 rows, against torch in float64; deterministic."""
+    from ksim_b200.replay import _row_sums
+
+    torch.manual_seed(5)
+    x = (torch.randn(rows, cols, device="cuda:0") * 0.3).to(torch.bfloat16)
+    got = _row_sums(x)
+    want = x.double().sum(dim=1)
+    scale = x.double().abs().sum(dim=1)
+    assert float(((got.double() - want).abs() / scale).max()) < 2e-6
+    assert torch.equal(got, _row_sums(x))
