@@ -372,7 +372,7 @@ def main() -> None:
     from ksim_b200.engine import B200Engine
 
     make_spec, RANDOMIZERS = _task()
-    rank, local, world = D.init_from_env()
+    rank, local, world = D.init_from_env(timeout_s=240.0)  # a collective mismatch fails within minutes instead of the default 10
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     device = torch.device("cuda", local)
@@ -399,10 +399,11 @@ def main() -> None:
             for _ in range(PPO_UPDATES_PER_STEP):
                 torch.distributed.all_reduce(grad)
 
-    def hot_path(acts: torch.Tensor) -> torch.Tensor:
+    def hot_path(acts: torch.Tensor, with_collective: bool = True) -> torch.Tensor:
         eng.rollout(acts, rec)
         adv = eng.score(rec, t, values=values, gamma=GAMMA, lam=LAM)["advantages"]  # rewards + flags + GAE: one launch
-        collective()
+        if with_collective:
+            collective()
         return adv  # (the engine hands this rollout's final pre-step block to the next one itself)
 
     def barrier() -> None:
@@ -416,9 +417,14 @@ def main() -> None:
     for _ in range(max(args.warmup, 3)):
         hot_path(actions)
     t_wait = time.perf_counter()
-    while sampler.proc is not None and not sampler.samples and time.perf_counter() - t_wait < 3.0:
-        hot_path(actions)  # extra untimed warm-up until nvidia-smi has printed its first sample (rank 0 only)
+    forced = int(os.environ.get("B2S_BENCH_FORCE_WAIT_STEPS", "0"))  # test hook: make the rank-0-only wait loop run
+    while sampler.proc is not None and ((not sampler.samples and time.perf_counter() - t_wait < 3.0) or forced > 0):
+        # extra untimed warm-up until nvidia-smi has printed its first sample.  RANK 0 ONLY, so it must not contain a collective:
+        # the other ranks are already waiting at the barrier below (with the all-reduces in it this loop deadlocked an 8-GPU run
+        # whenever nvidia-smi was slow to start)
+        hot_path(actions, with_collective=False)
         torch.cuda.synchronize(device)
+        forced -= 1
     # ---- device-resident timing (value) + dominant-kernel timing (roofline) ----
     barrier()
     sampler.mark()

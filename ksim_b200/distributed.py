@@ -11,6 +11,7 @@ from __future__ import annotations
 
 __all__ = ["shard_range", "init_from_env", "shutdown", "max_over_ranks", "sum_over_ranks", "global_mean_std", "allreduce_mean_"]
 
+import datetime
 import os
 
 import torch
@@ -26,8 +27,9 @@ def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
-    """(rank, local_rank, world) from torchrun's environment; initialises the process group when world > 1."""
+def init_from_env(backend: str | None = None, timeout_s: float | None = None) -> tuple[int, int, int]:
+    """(rank, local_rank, world) from torchrun's environment; initialises the process group when world > 1.  ``timeout_s``: the
+    collective watchdog's timeout (a benchmark wants a mismatched collective to fail in minutes, not after the default 10)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -35,11 +37,12 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {} if timeout_s is None else {"timeout": datetime.timedelta(seconds=float(timeout_s))}
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend, device_id=torch.device("cuda", local), **kw)
         else:
-            dist.init_process_group(backend)
+            dist.init_process_group(backend, **kw)
     return rank, local, world
 
 
