@@ -32,3 +32,22 @@ def test_reference_arm_line_and_thread_count() -> None:
 def test_reference_arm_other_ranks_exit_quietly() -> None:
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_rank0_only_wait_loop_has_no_collective() -> None:
+    """The extra warm-up steps bench.py runs while it waits for nvidia-smi's first sample execute on rank 0 ONLY: a collective
+    inside them leaves the other ranks with fewer enqueued all-reduces and deadlocks the run (it did, at 8 GPUs).  Static check
+    of the source: the loop body calls the collective-free form of the step."""
+    import ast
+    from pathlib import Path
+
+    src = (Path(__file__).resolve().parent.parent / "bench.py").read_text()
+    tree = ast.parse(src)
+    loops = [n for n in ast.walk(tree) if isinstance(n, ast.While) and "sampler.samples" in ast.unparse(n.test)]
+    assert len(loops) == 1
+    calls = [c for c in ast.walk(loops[0]) if isinstance(c, ast.Call) and getattr(c.func, "id", "") == "hot_path"]
+    assert calls, "the wait loop should still step the hot path"
+    for c in calls:
+        kw = {k.arg: ast.unparse(k.value) for k in c.keywords}
+        assert kw.get("with_collective") == "False", ast.unparse(c)
+    assert "collective()" not in ast.unparse(loops[0])
