@@ -138,3 +138,136 @@ def test_f32_oracle_tracks_f64_over_one_control_step(oracle_mod) -> None:  # noq
             d.step()
         out[precision] = d.get("qpos", model.nq)
     np.testing.assert_allclose(out["f32"], out["f64"], atol=2e-5)
+
+
+# ------------------------------------------------------------------------------- more analytic pins (round 2)
+def _incline_ball(theta: float, mu: float) -> str:
+    """A sphere on a plane with gravity tilted by theta about y (== a plane inclined by theta), pyramidal friction mu."""
+    g = 9.81
+    return f"""
+<mujoco model="incline">
+  <option timestep="0.001" integrator="implicitfast" gravity="{g * math.sin(theta)} 0 {-g * math.cos(theta)}"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="50 5 0.1" contype="0" conaffinity="0"/>
+    <body name="ball" pos="0 0 0.0995">
+      <freejoint name="root"/>
+      <geom name="ball" type="sphere" size="0.1" density="1000" contype="0" conaffinity="0"/>
+    </body>
+  </worldbody>
+  <contact>
+    <pair geom1="ball" geom2="floor" condim="3" friction="{mu} {mu} 0.005 0.0001 0.0001"/>
+  </contact>
+</mujoco>
+"""
+
+
+def _accel_along_x(oracle_mod, xml: str, settle: int = 400, span: int = 400) -> float:  # noqa: ANN001
+    model = load_mjcf_string(xml)
+    d = oracle_mod.OracleData(oracle_mod.OracleModel(model, "f64"))
+    for _ in range(settle):
+        d.step()
+    v0 = d.get("qvel", 6)[0]
+    for _ in range(span):
+        d.step()
+    return float((d.get("qvel", 6)[0] - v0) / (span * model.opt.timestep))
+
+
+def test_sphere_rolls_without_slipping_down_an_incline(oracle_mod) -> None:  # noqa: ANN001
+    """Enough friction: a solid sphere (I = 2/5 m r^2) rolls with a = 5/7 g sin(theta); the friction force needed is
+    2/7 m g sin(theta), far inside the cone at mu = 1."""
+    theta = math.radians(15.0)
+    a = _accel_along_x(oracle_mod, _incline_ball(theta, 1.0))
+    assert a == pytest.approx(5.0 / 7.0 * 9.81 * math.sin(theta), rel=0.02)
+
+
+def test_sphere_slides_when_friction_is_too_small(oracle_mod) -> None:  # noqa: ANN001
+    """mu < 2/7 tan(theta): the contact slips and the centre accelerates with g (sin(theta) - mu cos(theta)); the slip is along
+    one axis of the friction pyramid, where the pyramidal and the elliptic cone agree."""
+    theta, mu = math.radians(20.0), 0.05
+    assert mu < 2.0 / 7.0 * math.tan(theta)
+    a = _accel_along_x(oracle_mod, _incline_ball(theta, mu))
+    assert a == pytest.approx(9.81 * (math.sin(theta) - mu * math.cos(theta)), rel=0.02)
+
+
+def _loss_pendulum(frictionloss: float) -> str:
+    return f"""
+<mujoco model="loss_pendulum">
+  <option timestep="0.001" integrator="implicitfast"/>
+  <worldbody>
+    <body name="bob" pos="0 0 1">
+      <joint name="pivot" type="hinge" axis="0 1 0" damping="0" frictionloss="{frictionloss}"/>
+      <geom name="rod" type="sphere" size="0.05" pos="0 0 -0.5" density="1000" contype="0" conaffinity="0"/>
+    </body>
+  </worldbody>
+</mujoco>
+"""
+
+
+def test_dry_joint_friction_holds_below_its_limit_and_slips_above(oracle_mod) -> None:  # noqa: ANN001
+    """frictionloss is a force-limited SOFT constraint (MuJoCo's friction rows: quadratic zone, then constant force): a pendulum
+    held horizontal with m g l < frictionloss is carried by a constraint force equal to the gravity torque and only creeps at a
+    small terminal speed; above the limit the force saturates at frictionloss and the pendulum starts with angular acceleration
+    (m g l - frictionloss) / I."""
+    model = load_mjcf_string(_loss_pendulum(0.0))
+    m = float(model.body_mass[1])
+    gravity_torque = m * 9.81 * 0.5
+    inertia = m * 0.5**2 + 0.4 * m * 0.05**2     # point mass at 0.5 m + the sphere's own 2/5 m r^2
+    free_speed_after_20 = gravity_torque / inertia * 0.02
+    for floss, holds in ((1.5 * gravity_torque, True), (0.4 * gravity_torque, False)):
+        model = load_mjcf_string(_loss_pendulum(floss))
+        d = oracle_mod.OracleData(oracle_mod.OracleModel(model, "f64"))
+        d.set("qpos", [math.pi / 2])
+        for _ in range(20):
+            d.step()
+        w20 = float(d.get("qvel", 1)[0])
+        assert int(d.get("nefc", 1)[0]) == 1
+        if holds:
+            for _ in range(180):
+                d.step()
+            w200 = float(d.get("qvel", 1)[0])
+            for _ in range(200):
+                d.step()
+            w400 = float(d.get("qvel", 1)[0])
+            assert abs(w20) < 0.06 * free_speed_after_20 and abs(w400) < 0.03          # a creep, not a fall
+            assert abs(w400 - w200) < 1e-5                                              # terminal speed reached
+            assert abs(d.get("efc_force", 1)[0]) == pytest.approx(gravity_torque, rel=1e-3)
+        else:
+            assert abs(d.get("efc_force", 1)[0]) == pytest.approx(floss, rel=1e-9)      # saturated
+            assert abs(w20) == pytest.approx((gravity_torque - floss) / inertia * 20 * model.opt.timestep, rel=0.01)
+
+
+CAPSULE = """
+<mujoco model="capsule">
+  <option timestep="0.002" integrator="implicitfast"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="5 5 0.1" contype="0" conaffinity="0"/>
+    <body name="log" pos="0 0 0.3">
+      <freejoint name="root"/>
+      <geom name="log" type="capsule" fromto="-0.2 0 0 0.2 0 0" size="0.05" density="1000" contype="0" conaffinity="0"/>
+    </body>
+  </worldbody>
+  <contact>
+    <pair geom1="log" geom2="floor" condim="3"/>
+  </contact>
+</mujoco>
+"""
+
+
+def test_capsule_rests_on_its_two_end_contacts(oracle_mod) -> None:  # noqa: ANN001
+    """A capsule lying on a plane: two contacts (one under each end of the segment), the axis stays horizontal at one radius
+    (minus the soft penetration) and the normal forces carry the weight."""
+    model = load_mjcf_string(CAPSULE)
+    d = oracle_mod.OracleData(oracle_mod.OracleModel(model, "f64"))
+    for _ in range(2500):
+        d.step()
+    q, v = d.get("qpos", 7), d.get("qvel", 6)
+    assert np.abs(v).max() < 1e-3
+    assert 0.049 < q[2] < 0.0501
+    np.testing.assert_allclose(q[3:7] / np.linalg.norm(q[3:7]), [1, 0, 0, 0], atol=1e-4)
+    assert int(d.get("ncon", 1)[0]) == 2
+    ne = int(d.get("nefc", 1)[0])
+    assert ne == 8   # two contacts x four pyramid edges
+    f = d.get("efc_force", ne)
+    # pyramid edge forces: the normal force of a contact is the sum of its four edge forces
+    assert f.sum() == pytest.approx(float(model.body_mass[1]) * 9.81, rel=5e-3)
+    assert f[:4].sum() == pytest.approx(f[4:].sum(), rel=1e-3)
