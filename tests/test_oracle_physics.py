@@ -271,3 +271,67 @@ def test_capsule_rests_on_its_two_end_contacts(oracle_mod) -> None:  # noqa: ANN
     # pyramid edge forces: the normal force of a contact is the sum of its four edge forces
     assert f.sum() == pytest.approx(float(model.body_mass[1]) * 9.81, rel=5e-3)
     assert f[:4].sum() == pytest.approx(f[4:].sum(), rel=1e-3)
+
+
+def _momenta(model, d) -> tuple[np.ndarray, np.ndarray, np.ndarray]:  # noqa: ANN001
+    """(total mass centre C, linear momentum P, angular momentum L about C) of the whole tree from the per-body quantities the
+    oracle exposes: cvel = [omega, v at subtree_com[root]] (MuJoCo's convention), xipos / ximat, body mass / inertia."""
+    nb = model.nbody
+    mass = np.asarray(model.body_mass, np.float64)
+    inertia = np.asarray(model.body_inertia, np.float64)
+    r = d.get("xipos", 3 * nb).reshape(nb, 3)
+    rot = d.get("ximat", 9 * nb).reshape(nb, 3, 3)
+    cvel = d.get("cvel", 6 * nb).reshape(nb, 6)
+    c0 = d.get("subtree_com", 3 * nb).reshape(nb, 3)[1]
+    om, v = cvel[:, :3], cvel[:, 3:] + np.cross(cvel[:, :3], r - c0)
+    com = (mass[:, None] * r).sum(0) / mass.sum()
+    p = (mass[:, None] * v).sum(0)
+    spin = np.einsum("bij,bj,bkj,bk->bi", rot, inertia, rot, om)
+    ang = (mass[:, None] * np.cross(r - com, v)).sum(0) + spin.sum(0)
+    return com, p, ang
+
+
+@pytest.mark.parametrize("robot", ["humanoid", "kbot"])
+def test_robot_in_free_flight_conserves_momentum(oracle_mod, robot) -> None:  # noqa: ANN001
+    """The articulated robot (the humanoid; the K-Bot with its dry joint friction and armatures) thrown into the air with spinning limbs and its motors fighting each other: joint torques,
+    damping, armature and joint limits are internal, so the linear momentum changes by M g t only and the angular momentum about
+    the mass centre stays constant.  The semi-implicit Euler step is first-order accurate, so the test checks CONVERGENCE: the
+    deviation from the conservation laws halves with the time step, and the Richardson extrapolation of the dt / 2 and dt / 4
+    runs meets them to 1e-3.  Pins the composite-inertia mass matrix, the bias (Coriolis / gravity) forces, the damping and the
+    actuator transmission of the real model against each other -- a wrong term would leave an error that does not vanish with dt."""
+    import copy
+
+    flight = 0.24
+    res = {}
+    for dt_scale in (1.0, 0.5, 0.25):
+        if robot == "kbot":
+            from ksim_b200.examples.kbot import make_spec as make_kbot
+
+            model = copy.deepcopy(make_kbot().model)
+        else:
+            model = copy.deepcopy(make_spec().model)
+        model.opt.timestep = model.opt.timestep * dt_scale
+        d = oracle_mod.OracleData(oracle_mod.OracleModel(model, "f64"))
+        rs = np.random.RandomState(0)
+        qpos = np.asarray(model.qpos0, np.float64).copy()
+        qpos[2] = 5.0                                   # far above the floor: no contact during the flight
+        qpos[7:] += rs.uniform(-0.2, 0.2, model.nq - 7)
+        qvel = np.concatenate([[0.4, -0.3, 2.0], rs.uniform(-2, 2, 3), rs.uniform(-4, 4, model.nv - 6)])
+        d.set("qpos", qpos); d.set("qvel", qvel); d.set("ctrl", rs.uniform(-0.4, 0.4, model.nu))
+        d.forward()
+        _, p0, l0 = _momenta(model, d)
+        n = int(round(flight / model.opt.timestep))
+        for _ in range(n):
+            d.step()
+        assert int(d.get("ncon", 1)[0]) == 0 or d.get("qpos", 3)[2] > 2.0   # still in the air
+        d.forward()
+        _, p1, l1 = _momenta(model, d)
+        total_mass = float(np.sum(model.body_mass))
+        res[dt_scale] = (p1 - (p0 + total_mass * np.asarray(model.opt.gravity) * n * model.opt.timestep), l1 - l0)
+    scale_p, scale_l = total_mass * 2.0, float(np.linalg.norm(l0))
+    assert scale_l > 2.0
+    for k, scale in ((0, scale_p), (1, scale_l)):
+        e1, e2, e4 = (np.linalg.norm(res[s_][k]) / scale for s_ in (1.0, 0.5, 0.25))
+        assert e1 < 0.06 and 0.35 < e2 / e1 < 0.65 and 0.35 < e4 / e2 < 0.65, (k, e1, e2, e4)
+        extrapolated = np.linalg.norm(2.0 * res[0.25][k] - res[0.5][k]) / scale
+        assert extrapolated < 1e-3, (k, extrapolated)
