@@ -6,6 +6,11 @@
  * and the MJX module layout (smooth / passive / collision_primitive / constraint / solver / sensor /
  * forward).  Dense mass matrix + Cholesky as MJX uses for nv < 60; Newton solver with MJX's bracketing
  * line search; pyramidal cones; implicitfast integrator with Euler damping disabled (ksim/task/rl.py:717-748).
+ *
+ * PARITY UNPINNED: neither mujoco nor mujoco-mjx can be imported or built in this repository's image and the reference holds
+ * no physics test vectors, so this file is pinned only by the analytic cases of tests/test_oracle_physics.py (closed forms,
+ * friction / contact equilibria, momentum-conservation convergence of both robots).  scripts/gen_mjx_fixtures.py +
+ * tests/test_oracle_vs_mjx_fixtures.py pin it against MJX on a machine that has jax + mujoco-mjx.
  */
 #include "oracle.h"
 
