@@ -274,6 +274,8 @@ def _extras(eng, actions, rec, device, rank: int, world: int, args: argparse.Nam
         # the replay kernels alone: one eager update with CUDA events around every GRU launch (ksim_b200.replay.KERNEL_TIMES)
         gru = None
         try:
+            if world > 1:
+                raise RuntimeError("measured at N = 1 only (a per-kernel figure; keeps the N > 1 run free of eager collectives)")
             from ksim_b200 import replay
 
             torch.manual_seed(0)
